@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""Benchmark of the TEDM hot path on B200 (see BASELINE.json / DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+Workload (config.workload = "tedm_seg_inference"): BASELINE.json configs[3] -- TEDM shared-weight
+timestep-ensembled segmentation inference at config.py defaults: 1x128x128 images, S = 8 timesteps
+[1,10,25,50,200,400,600,800], UNet dim 64 / mults (1,2,4,8), B = 16 images per GPU per step
+(config.py:58).  One step = B images -> B masks = 8B UNet forwards + heads + ensemble.  Weights are
+random-init (seeded), images synthetic.  Printed line: whole-job images/s (`value`, inputs resident
+in HBM), the same through host buffers (`e2e`), the conv kernel's tensor roofline, and the CPU
+baseline (the oracle port of the reference's path timed on this box's cores).
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+STEPS_TEDM = [1, 10, 25, 50, 200, 400, 600, 800]
+IMG = 128
+GFLOP_UNET_FWD = 58.97          # per image, reference form
+GFLOP_TEDM_REF = 505.0          # per image: 8 x (58.97 + 4.16)
+GFLOP_TEDM_MIN = 436.1          # per image: 8 x (53.87 + 0.64)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"],
+                "tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            self.thr.join(timeout=2)
+
+    def summary(self):
+        sm = sorted(int(float(r[0])) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic model / data (identical on every arm)
+# ------------------------------------------------------------------------------------------------
+def synth_state(n_steps: int):
+    from oracle import tedm_oracle as O          # shapes only (bench.py may use oracle/ for its CPU legs)
+    from tests.golden.synth import synth_state_dict
+    shapes = {**O.unet_param_shapes(prefix="diffusion_model.model."), **O.head_param_shapes(n_steps, True)}
+    return synth_state_dict(shapes, 0)
+
+
+def synth_batch(b: int, seed: int):
+    import torch
+    g = torch.Generator().manual_seed(1234 + seed)
+    return torch.rand(b, 1, IMG, IMG, generator=g)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs: the oracle port of the reference's path
+# ------------------------------------------------------------------------------------------------
+def cpu_tedm_images_per_s(n_images: int, repeats: int = 1):
+    import torch
+    from oracle import tedm_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth_state(len(STEPS_TEDM))
+    sd.update(O.schedule_tables())
+    x0 = synth_batch(n_images, 99)
+    noises = [torch.randn(n_images, 1, IMG, IMG, generator=torch.Generator().manual_seed(7 + i)) for i in range(len(STEPS_TEDM))]
+    best = None
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            O.tedm_segment(sd, x0, STEPS_TEDM, noises, shared=True)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return n_images / best, best
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  /root/reference is pure Python
+    with no packaging (no setup.py / pyproject: `pip install /root/reference` has nothing to build) and does not
+    exist on the GPU box, so this arm times the oracle port (oracle/tedm_oracle.py, pinned to the live reference
+    by tests/golden) with all host threads, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_img = 2
+    vals = []
+    for _ in range(max(1, args.warmup and 1)):
+        cpu_tedm_images_per_s(1)
+    t_all = 0.0
+    for _ in range(args.steps):
+        v, dt = cpu_tedm_images_per_s(n_img)
+        vals.append(v)
+        t_all += dt
+    value = n_img * args.steps / t_all
+    line = {"metric": "tedm_seg_images_per_s", "value": value, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "reference",
+            "config": {"workload": "tedm_seg_inference", "img_size": IMG, "t_steps": STEPS_TEDM, "unet_dim": 64,
+                       "dim_mults": [1, 2, 4, 8], "batch_per_step": n_img},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"{n_img} images x 8 timesteps per step, {args.steps} steps (oracle port, torch CPU fp32)"},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from argparse import Namespace
+    from tedm_b200 import native as N
+    from tedm_b200.models import DatasetDM, tedm_classifier
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device: tedm_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N.load()
+
+    B, S = args.batch, len(STEPS_TEDM)
+    model = DatasetDM(Namespace(normalize=True, saved_diffusion_model="", t_steps_to_save=STEPS_TEDM))
+    model.classifier = tedm_classifier(S)
+    model.load_state_dict(synth_state(S), strict=False)
+    model = model.eval().to(dev)
+
+    # inputs: a ring of distinct batches (activations per step ~ several GB >> 126 MB L2, so no L2 flush needed)
+    n_ring = 4
+    host = [synth_batch(B, rank * 100 + i).pin_memory() for i in range(n_ring)]
+    resident = [h.to(dev) for h in host]
+    noise = [torch.randn(B, 1, IMG, IMG, device=dev, generator=torch.Generator(device=dev).manual_seed(5 + i)) for i in range(n_ring)]
+    mask_host = torch.empty(B, 1, IMG, IMG, dtype=torch.bool).pin_memory()
+
+    def step_resident(i):
+        return model.segment(resident[i % n_ring], noise[i % n_ring])[0]
+
+    def step_e2e(i):
+        x = host[i % n_ring].to(dev, non_blocking=True)
+        mask = model.segment(x, noise[i % n_ring])[0]
+        mask_host.copy_(mask, non_blocking=True)
+        return mask
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    for i in range(args.warmup):
+        step_resident(i)
+    l0, f0 = N.launches, N.conv_flops
+    with ClockSampler(local) as clocks:
+        ms = timed(step_resident, args.steps)
+    launches = N.launches - l0
+    conv_flops_step = (N.conv_flops - f0) / args.steps
+    for i in range(min(args.warmup, 2)):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+
+    value = world * B * args.steps / (ms * 1e-3)
+    e2e = world * B * args.steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv): CUDA events around every launch ----
+    records = []
+
+    @contextlib.contextmanager
+    def conv_timer(flops):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        yield
+        b.record()
+        records.append((flops, a, b))
+
+    N.conv_timer = conv_timer
+    try:
+        step_resident(0)
+    finally:
+        N.conv_timer = None
+    torch.cuda.synchronize()
+    conv_ms = sum(a.elapsed_time(b) for _, a, b in records)
+    conv_fl = sum(f for f, _, _ in records)
+    pk = peaks()
+    achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (all conv launches of one step)", "achieved": achieved,
+                "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
+                "peak_source": pk["source"] + " (sustained cuBLAS bf16)", "traffic": None,
+                "conv_launches_per_step": len(records), "conv_ms_per_step": conv_ms,
+                "conv_share_of_step": conv_ms / (ms / args.steps) if ms > 0 else None,
+                "conv_gflop_per_step": conv_fl / 1e9}
+
+    line = {"metric": "tedm_seg_images_per_s", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "tedm_seg_inference", "img_size": IMG, "t_steps": STEPS_TEDM, "unet_dim": 64,
+                       "dim_mults": [1, 2, 4, 8], "batch_per_gpu_per_step": B, "global_batch": B * world,
+                       "parallelism": f"dp{world} (image x timestep shards, no collective)",
+                       "l2": "working set per step (GBs of activations) >> 126 MB L2; 4 distinct input batches cycled"},
+            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * IMG * IMG * 4,
+                    "d2h_bytes_per_step": B * IMG * IMG, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "tflops": {"unet_fwd_reference_form": value * GFLOP_TEDM_REF / 1e3, "minimal_form": value * GFLOP_TEDM_MIN / 1e3,
+                       "executed_conv_gflop_per_image": conv_flops_step / B / 1e9,
+                       "frac_of_sustained_peak_minimal_form": value * GFLOP_TEDM_MIN / 1e3 / (pk["tflops_sustained"] * world)},
+            "roofline": roofline, "clocks": clocks.summary()}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            v, dt = cpu_tedm_images_per_s(2)
+            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"2 images x 8 timesteps, one pass ({dt:.1f} s), oracle port on torch CPU fp32"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="images per GPU per step (config.py:58 default 16)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,206 @@
+/* tedm_b200 -- C ABI of the B200-native TEDM hot path (libtedm_b200.so).
+ *
+ * The reference (mmr12/TEDM) is pure Python: its boundary for this path is the nn.Module surface
+ * of models/unet_model.py, models/diffusion_model.py and models/datasetDM_model.py, and every
+ * arithmetic step is a PyTorch library call.  This header is what replaces those library calls:
+ * one entry point per fused op.  Each comment cites the reference lines the entry point replaces.
+ *
+ * Conventions
+ *   - plain pointers + sizes; no torch types.  All pointers are DEVICE pointers unless stated.
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t) and never synchronises, so call
+ *     sequences can be captured in a CUDA graph.
+ *   - activations: NHWC bf16.  conv weights: [Cout][kh][kw][Cin] bf16 ("KRSC").  Statistics, loss,
+ *     schedule tables, time embeddings: fp32.  Timesteps: int64.  Public image tensors (x_0, x_t,
+ *     noise, UNet output, logits): NCHW fp32 exactly as the reference.
+ *   - return 0 on success, <0 on error (TEDM_ERR_*); tedm_last_error() gives the message of the
+ *     last failing call on this thread.  Unsupported shapes are hard errors: there is no fallback.
+ */
+#ifndef TEDM_B200_H
+#define TEDM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TEDM_ABI_VERSION 1
+#define TEDM_ERR_ARG (-1)
+#define TEDM_ERR_CUDA (-2)
+#define TEDM_ERR_UNSUPPORTED (-3)
+
+typedef void* tedm_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define TEDM_API __attribute__((visibility("default")))
+#else
+#define TEDM_API
+#endif
+
+TEDM_API int tedm_version(void);
+TEDM_API const char* tedm_last_error(void);
+
+/* ---- DDPM arithmetic ------------------------------------------------------------------- */
+
+/* x_t = sa[t_b] * x0' + sb[t_b] * noise, x0' = normalize ? x0*2-1 : x0.  fp32, bit-exact with the
+ * reference's unfused mul/mul/add.  Replaces DiffusionModel.forward_diffusion_model
+ * (models/diffusion_model.py:176-203), get_index_from_list (trainers/utils.py:48-59) and
+ * normalize_to_neg_one_to_one (trainers/utils.py:28-29, models/diffusion_model.py:169-170). */
+TEDM_API int tedm_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sqrt_ac,
+                  const float* sqrt_1m_ac, float* x_t, int batch, int chw, int T, int normalize,
+                  tedm_stream_t stream);
+
+/* per-image mean |pred-target| * w[t_b] -> loss_per_image[b]; mean over b -> loss[0].
+ * grad (nullable) = d loss / d pred = sign(pred-target) * w[t_b] / (chw * batch).
+ * Replaces F.l1_loss + reduce + p2 weighting (models/diffusion_model.py:138-143). */
+TEDM_API int tedm_l1_loss(const float* pred, const float* target, const int64_t* t, const float* p2_weight,
+                 float* loss_per_image, float* loss, float* grad, int batch, int chw, int T,
+                 tedm_stream_t stream);
+
+/* One reverse-diffusion update after the UNet call: x0_hat = sqrt_recip_ac*x_t - sqrt_recipm1_ac*eps;
+ * dynamic thresholding by the EXACT per-image quantile of |x0_hat| (radix select of the order
+ * statistics k_lo and k_lo+1, then torch.quantile's lerp with weight q_weight; the host derives
+ * k_lo/q_weight from the percentile exactly as torch does: rank = float32(q) * (chw-1));
+ * s = max(s,1); x0_hat = clip(x0_hat,-s,s)/s; x_prev = coef1*x0_hat + coef2*x_t (+ sigma*z when z is
+ * not NULL; pass NULL at t==0).  All images share the timestep, so the schedule values are scalars.
+ * x0_hat and s_out (per-image threshold) are optional outputs.
+ * Replaces sample_timestep / p_mean_variance / predict_x_0_from_noise / q_posterior
+ * (models/diffusion_model.py:205-286). */
+TEDM_API int tedm_sampler_step(const float* x_t, const float* eps, const float* z, float* x_prev,
+                      float* x0_hat /*nullable*/, float* s_out /*nullable*/, float sqrt_recip_ac,
+                      float sqrt_recipm1_ac, float coef1, float coef2, float sigma, int k_lo,
+                      float q_weight, int batch, int chw, tedm_stream_t stream);
+
+/* ---- UNet pieces ------------------------------------------------------------------------- */
+
+/* SinusoidalPosEmb(dim) -> Linear(dim,tdim) -> GELU(erf) -> Linear(tdim,tdim); fp32.
+ * freq: [dim/2] fp32, the reference's exp(arange(dim/2) * -log(1e4)/(dim/2-1)) table.
+ * Replaces models/unet_model.py:76-93 and Unet.time_mlp (:287-292). */
+TEDM_API int tedm_time_embed(const int64_t* t, const float* freq, const float* w1, const float* b1,
+                    const float* w2, const float* b2, float* temb, int batch, int dim, int tdim,
+                    tedm_stream_t stream);
+
+/* out[b][j] = sum_k W[j][k] * silu(temb[b][k]) + bias[j] for the concatenation of every
+ * ResnetBlock.time_mlp of the net (models/unet_model.py:150-152,168-171). */
+TEDM_API int tedm_time_proj(const float* temb, const float* w_cat, const float* b_cat, float* out, int batch,
+                   int tdim, int total, tedm_stream_t stream);
+
+/* 7x7 pad-3 stem conv on the fp32 NCHW network input -> NHWC bf16 (Unet.init_conv,
+ * models/unet_model.py:267,334).  weight fp32 [Cout][Cin][7][7]. */
+TEDM_API int tedm_stem_conv7x7(const float* x, const float* weight, const float* bias, void* out, int batch,
+                      int cin, int height, int width, int cout, tedm_stream_t stream);
+
+/* Implicit-GEMM convolution on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
+ *   mode 0: 1x1            (res_conv, to_qkv, to_out, head layer 1: unet_model.py:157,185,188,226,227)
+ *   mode 1: 3x3 pad 1      (Block.proj, last-level down/up conv: :122,307-308,323-324)
+ *   mode 2: 4x4 stride 2 pad 1 (Downsample: :47-49)
+ *   mode 3: nearest-x2 upsample folded into 3x3 pad 1 (Upsample: :39-44); weight is the
+ *           parity-combined [4][Cout][2][2][Cin] tensor made by tedm_fold_upsample_weight.
+ * K runs over src0's channels then src1's (the skip concat of Unet.forward, :356,359,365, is
+ * never materialised).  Epilogue: + bias, + residual, bf16 store, optional per-(image, group)
+ * partial sum / sum-of-squares of the fp32 accumulators for the GroupNorm that follows. */
+typedef struct {
+  const void* src0;      /* [B][H][W][c0] bf16 */
+  const void* src1;      /* [B][H][W][c1] bf16 or NULL */
+  const void* weight;    /* bf16 KRSC, K = taps*(c0+c1) */
+  const float* bias;     /* [cout] or NULL */
+  const void* residual;  /* [B][Ho][Wo][cout] bf16 or NULL */
+  void* out;             /* [B][Ho][Wo][cout] bf16 */
+  float* gn_partial;     /* NULL or [B][gn_parts][gn_groups][2] fp32 (sum, sum of squares) */
+  int batch, height, width; /* input extent */
+  int c0, c1, cout;
+  int mode;
+  int gn_groups;         /* number of GroupNorm groups (0 when gn_partial is NULL) */
+  int64_t src0_image_stride, src1_image_stride, out_image_stride; /* elements; 0 = dense */
+} tedm_conv_args;
+TEDM_API int tedm_conv_igemm_fwd(const tedm_conv_args* args, tedm_stream_t stream);
+/* number of partial-statistics slots per image that tedm_conv_igemm_fwd writes for this output extent */
+TEDM_API int tedm_conv_gn_parts(int out_height, int out_width);
+/* tuning/debug: force the N tile (64/128/256; 0 = automatic) of tedm_conv_igemm_fwd */
+TEDM_API int tedm_conv_set_tile_n(int bn);
+
+/* fp32 OIHW [Cout][Cin][kh][kw] -> bf16 KRSC [Cout][kh][kw][Cin] (derived weight cache). */
+TEDM_API int tedm_weight_to_krsc(const float* w_oihw, void* w_krsc, int cout, int cin, int kh, int kw,
+                        tedm_stream_t stream);
+/* fp32 OIHW 3x3 -> bf16 [4 parities][Cout][2][2][Cin] for mode 3. */
+TEDM_API int tedm_fold_upsample_weight(const float* w_oihw, void* w_folded, int cout, int cin, tedm_stream_t stream);
+
+/* GroupNorm finalise + affine + optional (scale+1)/shift + SiLU (+ residual), one pass.
+ * Replaces Block.forward after the conv (models/unet_model.py:126-135) and the residual add of
+ * ResnetBlock.forward (:175).  scale_shift: fp32 [B][ss_stride], scale at ss_offset, shift at
+ * ss_offset + C (the chunk(2) of :171), or NULL. */
+TEDM_API int tedm_gn_silu_fwd(const void* x, const float* gn_partial, int gn_parts, const float* gamma,
+                     const float* beta, const float* scale_shift, int ss_stride, int ss_offset,
+                     const void* residual, void* out, int batch, int hw, int channels, int groups,
+                     float eps, tedm_stream_t stream);
+
+/* Per-pixel channel LayerNorm with gain only (+ residual): models/unet_model.py:52-61, and the
+ * Residual wrapper (:29-36) when `residual` is given. */
+TEDM_API int tedm_layernorm_fwd(const void* x, const float* g, const void* residual, void* out, int64_t npix,
+                       int channels, float eps, tedm_stream_t stream);
+
+/* LinearAttention core between to_qkv and to_out (models/unet_model.py:197-209):
+ * qkv [B][n][3*heads*dh] bf16 -> out [B][n][heads*dh] bf16.  workspace: fp32,
+ * tedm_linear_attention_workspace(batch, n, heads, dh) elements. */
+TEDM_API int64_t tedm_linear_attention_workspace(int batch, int n, int heads, int dim_head);
+TEDM_API int tedm_linear_attention_fwd(const void* qkv, void* out, float* workspace, int batch, int n, int heads,
+                              int dim_head, float scale, tedm_stream_t stream);
+
+/* Attention core of the mid block (models/unet_model.py:229-240): q,k L2-normalised along n,
+ * sim*scale, softmax, @v.  n <= 256. */
+TEDM_API int tedm_attention_fwd(const void* qkv, void* out, int batch, int n, int heads, int dim_head, float scale,
+                       tedm_stream_t stream);
+
+/* nearest x2 (nn.Upsample, models/unet_model.py:42) on NHWC bf16. */
+TEDM_API int tedm_upsample2x(const void* x, void* out, int batch, int height, int width, int channels,
+                    tedm_stream_t stream);
+
+/* final 1x1 conv C -> out_dim, NHWC bf16 -> NCHW fp32 (Unet.final_conv, models/unet_model.py:331,368). */
+TEDM_API int tedm_final_conv1x1(const void* x, const float* weight, const float* bias, float* out, int batch, int hw,
+                       int channels, int out_dim, tedm_stream_t stream);
+
+/* layout conversion at the module boundary */
+TEDM_API int tedm_nchw_f32_to_nhwc_bf16(const float* x, void* out, int batch, int channels, int hw, tedm_stream_t stream);
+TEDM_API int tedm_nhwc_bf16_to_nchw_f32(const void* x, float* out, int batch, int channels, int hw, tedm_stream_t stream);
+
+/* ---- TEDM / LEDM head ---------------------------------------------------------------------- */
+
+/* Per-pixel MLP tail after the per-level layer-1 GEMMs (commuted form of the reference's
+ * upsample+concat+conv1x1): z1 = b1 + sum_{s<n_sum} sum_l g_l[img*n_sum+s][y>>sh_l][x>>sh_l];
+ * ReLU; BN1 (folded affine a1,c1); W2,b2; ReLU; BN2 (a2,c2); w3,b3 -> logits fp32 [n_img][H][W].
+ * Replaces F.interpolate + cat + classifier (models/datasetDM_model.py:57-64,80-88;
+ * trainers/train_datasetDM.py:30-42), eval-mode BatchNorm. */
+typedef struct {
+  const void* g[4];      /* level l: [n_img*n_sum][H>>shift[l]][W>>shift[l]][c1] bf16 */
+  int shift[4];
+  int n_levels;
+  int n_sum;             /* 1 for TEDM (shared head), S for LEDM/LEDMe */
+  int n_img, height, width;
+  int c1, c2;            /* 128, 32 */
+  const float* b1; const float* bn1_a; const float* bn1_c;   /* [c1] */
+  const float* w2;       /* [c2][c1] fp32 */
+  const float* b2; const float* bn2_a; const float* bn2_c;   /* [c2] */
+  const float* w3;       /* [c2] */
+  float b3;
+  float* logits;
+} tedm_head_args;
+TEDM_API int tedm_head_infer(const tedm_head_args* args, tedm_stream_t stream);
+
+/* prob[b] = mean_s sigmoid(logits[b*S+s]); mask = prob > 0.5
+ * (auxiliary/postprocessing/testing_shared_weights.py:113,120,133-138; app.py:79). */
+TEDM_API int tedm_ensemble_mask(const float* logits, float* prob, uint8_t* mask, int batch, int n_steps, int hw,
+                       tedm_stream_t stream);
+
+/* ---- test-only ----------------------------------------------------------------------------- */
+
+/* Hardware probe used by tests/test_umma_probe.py: runs 128x64x64 UMMAs whose A descriptor start
+ * is shifted by shifts[v] 128-byte rows (descriptor base_offset field = base_offsets[v]) over a
+ * TMA-written 384-row buffer.  shifts/base_offsets are HOST arrays; A [384][64] bf16, Bm [64][64]
+ * bf16 and out [nvar][128][64] fp32 are device pointers. */
+TEDM_API int tedm_debug_umma_probe(const void* A, const void* Bm, const int* shifts, const int* base_offsets,
+                                   int nvar, float* out, tedm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEDM_B200_H */

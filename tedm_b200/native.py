@@ -1,0 +1,359 @@
+"""ctypes binding of libtedm_b200.so -- the C ABI declared in include/tedm_b200.h.
+
+PyTorch owns every tensor; this module only passes raw device pointers, sizes and the current
+CUDA stream.  There is no fallback: if the library is missing or a call fails, a RuntimeError
+with tedm_last_error() is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtedm_b200.so")
+
+_p, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+
+
+class ConvArgs(C.Structure):  # tedm_conv_args
+    _fields_ = [("src0", _p), ("src1", _p), ("weight", _p), ("bias", _p), ("residual", _p), ("out", _p),
+                ("gn_partial", _p), ("batch", _i), ("height", _i), ("width", _i), ("c0", _i), ("c1", _i),
+                ("cout", _i), ("mode", _i), ("gn_groups", _i), ("src0_image_stride", _i64),
+                ("src1_image_stride", _i64), ("out_image_stride", _i64)]
+
+
+class HeadArgs(C.Structure):  # tedm_head_args
+    _fields_ = [("g", _p * 4), ("shift", _i * 4), ("n_levels", _i), ("n_sum", _i), ("n_img", _i), ("height", _i),
+                ("width", _i), ("c1", _i), ("c2", _i), ("b1", _p), ("bn1_a", _p), ("bn1_c", _p), ("w2", _p),
+                ("b2", _p), ("bn2_a", _p), ("bn2_c", _p), ("w3", _p), ("b3", _f), ("logits", _p)]
+
+
+# name -> (restype, argtypes); must list every symbol include/tedm_b200.h declares
+SIGNATURES = {
+    "tedm_version": (_i, []),
+    "tedm_last_error": (C.c_char_p, []),
+    "tedm_q_sample": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "tedm_l1_loss": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "tedm_sampler_step": (_i, [_p, _p, _p, _p, _p, _p, _f, _f, _f, _f, _f, _i, _f, _i, _i, _p]),
+    "tedm_time_embed": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "tedm_time_proj": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "tedm_stem_conv7x7": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "tedm_conv_igemm_fwd": (_i, [C.POINTER(ConvArgs), _p]),
+    "tedm_conv_gn_parts": (_i, [_i, _i]),
+    "tedm_conv_set_tile_n": (_i, [_i]),
+    "tedm_weight_to_krsc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "tedm_fold_upsample_weight": (_i, [_p, _p, _i, _i, _p]),
+    "tedm_gn_silu_fwd": (_i, [_p, _p, _i, _p, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _f, _p]),
+    "tedm_layernorm_fwd": (_i, [_p, _p, _p, _p, _i64, _i, _f, _p]),
+    "tedm_linear_attention_workspace": (_i64, [_i, _i, _i, _i]),
+    "tedm_linear_attention_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _p]),
+    "tedm_attention_fwd": (_i, [_p, _p, _i, _i, _i, _i, _f, _p]),
+    "tedm_upsample2x": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "tedm_final_conv1x1": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "tedm_nchw_f32_to_nhwc_bf16": (_i, [_p, _p, _i, _i, _i, _p]),
+    "tedm_nhwc_bf16_to_nchw_f32": (_i, [_p, _p, _i, _i, _i, _p]),
+    "tedm_head_infer": (_i, [C.POINTER(HeadArgs), _p]),
+    "tedm_ensemble_mask": (_i, [_p, _p, _p, _i, _i, _i, _p]),
+    "tedm_debug_umma_probe": (_i, [_p, _p, C.POINTER(_i), C.POINTER(_i), _i, _p, _p]),
+}
+
+_lib: Optional[C.CDLL] = None
+launches = 0  # kernels-launching C calls made so far (bench.py reads this for its gpu_launches claim)
+conv_flops = 0  # executed conv MACs*2 so far (minimal form: the folded upsample conv counts 4 taps, not 9)
+conv_timer = None  # bench.py instrumentation: callable(flops) -> context manager bracketing one conv launch
+
+
+def load() -> C.CDLL:
+    """dlopen the library and bind every declared symbol (fails loudly if one is missing)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} not found: build it with `python -m tedm_b200._build` "
+                               "(tedm_b200 has no non-CUDA fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the .so does not export it
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().tedm_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def _ptr(t: Optional[torch.Tensor], dtype=None, name="tensor") -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (tedm_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t.data_ptr()
+
+
+def _call(name: str, *args) -> None:
+    global launches
+    launches += 1
+    _check(getattr(load(), name)(*args), name)
+
+
+# ------------------------------------------------------------------------------------------------
+# DDPM arithmetic
+# ------------------------------------------------------------------------------------------------
+def q_sample(x0: torch.Tensor, noise: torch.Tensor, t: torch.Tensor, sqrt_ac: torch.Tensor,
+             sqrt_1m_ac: torch.Tensor, normalize: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    b = x0.shape[0]
+    chw = x0[0].numel()
+    if noise.shape != x0.shape or t.shape != (b,):
+        raise ValueError("q_sample: shape mismatch")
+    out = torch.empty_like(x0) if out is None else out
+    _call("tedm_q_sample", _ptr(x0, torch.float32, "x0"), _ptr(noise, torch.float32, "noise"),
+          _ptr(t, torch.int64, "t"), _ptr(sqrt_ac, torch.float32), _ptr(sqrt_1m_ac, torch.float32),
+          _ptr(out, torch.float32, "out"), b, chw, sqrt_ac.numel(), int(normalize), _stream())
+    return out
+
+
+def l1_loss(pred, target, t, p2_weight, want_grad: bool = False):
+    b, chw = pred.shape[0], pred[0].numel()
+    per_img = torch.empty(b, device=pred.device, dtype=torch.float32)
+    loss = torch.empty(1, device=pred.device, dtype=torch.float32)
+    grad = torch.empty_like(pred) if want_grad else None
+    _call("tedm_l1_loss", _ptr(pred, torch.float32, "pred"), _ptr(target, torch.float32, "target"),
+          _ptr(t, torch.int64, "t"), _ptr(p2_weight, torch.float32), _ptr(per_img), _ptr(loss), _ptr(grad), b, chw,
+          p2_weight.numel(), _stream())
+    return loss[0], per_img, grad
+
+
+def sampler_step(x_t, eps, z, c_recip: float, c_recipm1: float, coef1: float, coef2: float, sigma: float,
+                 k_lo: int, q_weight: float, want_x0: bool = False):
+    b, chw = x_t.shape[0], x_t[0].numel()
+    out = torch.empty_like(x_t)
+    x0h = torch.empty_like(x_t) if want_x0 else None
+    s = torch.empty(b, device=x_t.device, dtype=torch.float32)
+    _call("tedm_sampler_step", _ptr(x_t, torch.float32, "x_t"), _ptr(eps, torch.float32, "eps"),
+          _ptr(z, torch.float32, "z"), _ptr(out), _ptr(x0h), _ptr(s), c_recip, c_recipm1, coef1, coef2, sigma,
+          k_lo, q_weight, b, chw, _stream())
+    return out, x0h, s
+
+
+# ------------------------------------------------------------------------------------------------
+# UNet pieces (activations: NHWC bf16 tensors of shape (B, H, W, C))
+# ------------------------------------------------------------------------------------------------
+def time_embed(t, freq, w1, b1, w2, b2):
+    b, dim, tdim = t.shape[0], w1.shape[1], w1.shape[0]
+    out = torch.empty(b, tdim, device=t.device, dtype=torch.float32)
+    _call("tedm_time_embed", _ptr(t, torch.int64, "t"), _ptr(freq, torch.float32), _ptr(w1, torch.float32),
+          _ptr(b1, torch.float32), _ptr(w2, torch.float32), _ptr(b2, torch.float32), _ptr(out), b, dim, tdim, _stream())
+    return out
+
+
+def time_proj(temb, w_cat, b_cat):
+    b, tdim, total = temb.shape[0], temb.shape[1], w_cat.shape[0]
+    out = torch.empty(b, total, device=temb.device, dtype=torch.float32)
+    _call("tedm_time_proj", _ptr(temb, torch.float32), _ptr(w_cat, torch.float32), _ptr(b_cat, torch.float32),
+          _ptr(out), b, tdim, total, _stream())
+    return out
+
+
+def stem_conv7x7(x, weight, bias):
+    b, cin, h, w = x.shape
+    cout = weight.shape[0]
+    out = torch.empty(b, h, w, cout, device=x.device, dtype=torch.bfloat16)
+    _call("tedm_stem_conv7x7", _ptr(x, torch.float32, "x"), _ptr(weight, torch.float32), _ptr(bias, torch.float32),
+          _ptr(out), b, cin, h, w, cout, _stream())
+    return out
+
+
+def weight_to_krsc(w: torch.Tensor) -> torch.Tensor:
+    cout, cin, kh, kw = w.shape
+    out = torch.empty(cout, kh, kw, cin, device=w.device, dtype=torch.bfloat16)
+    _call("tedm_weight_to_krsc", _ptr(w.contiguous(), torch.float32, "weight"), _ptr(out), cout, cin, kh, kw, _stream())
+    return out
+
+
+def fold_upsample_weight(w: torch.Tensor) -> torch.Tensor:
+    cout, cin, kh, kw = w.shape
+    if (kh, kw) != (3, 3):
+        raise ValueError("fold_upsample_weight expects a 3x3 kernel")
+    out = torch.empty(4, cout, 2, 2, cin, device=w.device, dtype=torch.bfloat16)
+    _call("tedm_fold_upsample_weight", _ptr(w.contiguous(), torch.float32, "weight"), _ptr(out), cout, cin, _stream())
+    return out
+
+
+MODE_1X1, MODE_3X3, MODE_4X4S2, MODE_UP3X3 = 0, 1, 2, 3
+
+
+def conv_gn_parts(oh: int, ow: int) -> int:
+    return load().tedm_conv_gn_parts(oh, ow)
+
+
+def _nhwc(t: Optional[torch.Tensor], name: str):
+    """(pointer, image stride in elements) of an NHWC bf16 tensor whose batch axis may be strided."""
+    if t is None:
+        return None, 0
+    if not t.is_cuda or t.dtype != torch.bfloat16 or t.dim() != 4:
+        raise TypeError(f"{name} must be a 4-D CUDA bf16 tensor (B, H, W, C)")
+    b, h, w, c = t.shape
+    if t.stride(3) != 1 or t.stride(2) != c or t.stride(1) != w * c:
+        raise ValueError(f"{name} must be NHWC-contiguous within each image")
+    return t.data_ptr(), t.stride(0)
+
+
+def conv_igemm(src0: torch.Tensor, weight: torch.Tensor, mode: int, cout: int, bias=None, src1=None, residual=None,
+               gn_groups: int = 0, out: Optional[torch.Tensor] = None):
+    """Returns out (B, Ho, Wo, cout) bf16 [, gn_partial (B, parts, groups, 2) fp32 if gn_groups > 0].
+    src0/src1/out may be batch-strided views (e.g. x[s::S]); residual must share out's strides."""
+    b, h, w, c0 = src0.shape
+    c1 = src1.shape[3] if src1 is not None else 0
+    if src1 is not None and src1.shape[:3] != src0.shape[:3]:
+        raise ValueError("conv_igemm: src0/src1 extent mismatch")
+    oh, ow = (h // 2, w // 2) if mode == MODE_4X4S2 else ((2 * h, 2 * w) if mode == MODE_UP3X3 else (h, w))
+    taps = {MODE_1X1: 1, MODE_3X3: 9, MODE_4X4S2: 16, MODE_UP3X3: 16}[mode]
+    if weight.numel() != cout * taps * (c0 + c1):
+        raise ValueError(f"conv_igemm: weight has {weight.numel()} elements, expected {cout * taps * (c0 + c1)}")
+    if out is None:
+        out = torch.empty(b, oh, ow, cout, device=src0.device, dtype=torch.bfloat16)
+    elif tuple(out.shape) != (b, oh, ow, cout):
+        raise ValueError(f"conv_igemm: out has shape {tuple(out.shape)}, expected {(b, oh, ow, cout)}")
+    gnp = None
+    if gn_groups:
+        gnp = torch.empty(b, conv_gn_parts(oh, ow), gn_groups, 2, device=src0.device, dtype=torch.float32)
+    p0, s0 = _nhwc(src0, "src0")
+    p1, s1 = _nhwc(src1, "src1")
+    po, so = _nhwc(out, "out")
+    pr, sr = _nhwc(residual, "residual")
+    if residual is not None and (sr != so or residual.shape != out.shape):
+        raise ValueError("conv_igemm: residual must have out's shape and strides")
+    a = ConvArgs(p0, p1, _ptr(weight, torch.bfloat16, "weight"), _ptr(bias, torch.float32, "bias"), pr, po, _ptr(gnp),
+                 b, h, w, c0, c1, cout, mode, gn_groups, s0, s1, so)
+    global conv_flops
+    flops = 2 * b * (h * w if mode == MODE_UP3X3 else oh * ow) * cout * taps * (c0 + c1)
+    conv_flops += flops
+    if conv_timer is not None:
+        with conv_timer(flops):
+            _call("tedm_conv_igemm_fwd", C.byref(a), _stream())
+    else:
+        _call("tedm_conv_igemm_fwd", C.byref(a), _stream())
+    return (out, gnp) if gn_groups else out
+
+
+def gn_silu(x, gn_partial, gamma, beta, groups: int, eps: float = 1e-5, scale_shift=None, ss_offset: int = 0,
+            residual=None):
+    b, h, w, c = x.shape
+    out = torch.empty_like(x)
+    _call("tedm_gn_silu_fwd", _ptr(x, torch.bfloat16, "x"), _ptr(gn_partial, torch.float32), gn_partial.shape[1],
+          _ptr(gamma, torch.float32), _ptr(beta, torch.float32), _ptr(scale_shift, torch.float32),
+          scale_shift.shape[1] if scale_shift is not None else 0, ss_offset, _ptr(residual, torch.bfloat16, "residual"),
+          _ptr(out), b, h * w, c, groups, eps, _stream())
+    return out
+
+
+def layernorm(x, g, eps: float = 1e-5, residual=None):
+    c = x.shape[-1]
+    out = torch.empty_like(x)
+    _call("tedm_layernorm_fwd", _ptr(x, torch.bfloat16, "x"), _ptr(g, torch.float32), _ptr(residual, torch.bfloat16),
+          _ptr(out), x.numel() // c, c, eps, _stream())
+    return out
+
+
+def linear_attention(qkv, heads: int = 4, dim_head: int = 32, scale: Optional[float] = None):
+    b, h, w, c3 = qkv.shape
+    n = h * w
+    ws_n = load().tedm_linear_attention_workspace(b, n, heads, dim_head)
+    if ws_n < 0:
+        raise RuntimeError("linear_attention: unsupported configuration")
+    ws = torch.empty(ws_n, device=qkv.device, dtype=torch.float32)
+    out = torch.empty(b, h, w, heads * dim_head, device=qkv.device, dtype=torch.bfloat16)
+    _call("tedm_linear_attention_fwd", _ptr(qkv, torch.bfloat16, "qkv"), _ptr(out), _ptr(ws), b, n, heads, dim_head,
+          float(dim_head ** -0.5 if scale is None else scale), _stream())
+    return out
+
+
+def attention(qkv, heads: int = 4, dim_head: int = 32, scale: float = 16.0):
+    b, h, w, c3 = qkv.shape
+    out = torch.empty(b, h, w, heads * dim_head, device=qkv.device, dtype=torch.bfloat16)
+    _call("tedm_attention_fwd", _ptr(qkv, torch.bfloat16, "qkv"), _ptr(out), b, h * w, heads, dim_head, float(scale),
+          _stream())
+    return out
+
+
+def upsample2x(x):
+    b, h, w, c = x.shape
+    out = torch.empty(b, 2 * h, 2 * w, c, device=x.device, dtype=torch.bfloat16)
+    _call("tedm_upsample2x", _ptr(x, torch.bfloat16, "x"), _ptr(out), b, h, w, c, _stream())
+    return out
+
+
+def final_conv1x1(x, weight, bias):
+    b, h, w, c = x.shape
+    od = weight.shape[0]
+    out = torch.empty(b, od, h, w, device=x.device, dtype=torch.float32)
+    _call("tedm_final_conv1x1", _ptr(x, torch.bfloat16, "x"), _ptr(weight, torch.float32), _ptr(bias, torch.float32),
+          _ptr(out), b, h * w, c, od, _stream())
+    return out
+
+
+def nchw_to_nhwc_bf16(x):
+    b, c, h, w = x.shape
+    out = torch.empty(b, h, w, c, device=x.device, dtype=torch.bfloat16)
+    _call("tedm_nchw_f32_to_nhwc_bf16", _ptr(x, torch.float32, "x"), _ptr(out), b, c, h * w, _stream())
+    return out
+
+
+def nhwc_to_nchw_f32(x):
+    b, h, w, c = x.shape
+    out = torch.empty(b, c, h, w, device=x.device, dtype=torch.float32)
+    _call("tedm_nhwc_bf16_to_nchw_f32", _ptr(x, torch.bfloat16, "x"), _ptr(out), b, c, h * w, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# head
+# ------------------------------------------------------------------------------------------------
+def head_infer(g_maps: Sequence[torch.Tensor], shifts: Sequence[int], n_sum: int, n_img: int, height: int, width: int,
+               b1, bn1_a, bn1_c, w2, b2, bn2_a, bn2_c, w3, b3: float):
+    a = HeadArgs()
+    for l, (g, s) in enumerate(zip(g_maps, shifts)):
+        a.g[l] = _ptr(g, torch.bfloat16, f"g[{l}]")
+        a.shift[l] = s
+    a.n_levels, a.n_sum, a.n_img, a.height, a.width = len(g_maps), n_sum, n_img, height, width
+    a.c1, a.c2 = b1.numel(), b2.numel()
+    a.b1, a.bn1_a, a.bn1_c = _ptr(b1, torch.float32), _ptr(bn1_a, torch.float32), _ptr(bn1_c, torch.float32)
+    a.w2, a.b2, a.bn2_a, a.bn2_c = (_ptr(w2, torch.float32), _ptr(b2, torch.float32), _ptr(bn2_a, torch.float32),
+                                    _ptr(bn2_c, torch.float32))
+    a.w3, a.b3 = _ptr(w3, torch.float32), float(b3)
+    logits = torch.empty(n_img, 1, height, width, device=g_maps[0].device, dtype=torch.float32)
+    a.logits = _ptr(logits)
+    _call("tedm_head_infer", C.byref(a), _stream())
+    return logits
+
+
+def ensemble_mask(logits: torch.Tensor, n_steps: int):
+    bs, c, h, w = logits.shape
+    b = bs // n_steps
+    prob = torch.empty(b, c, h, w, device=logits.device, dtype=torch.float32)
+    mask = torch.empty(b, c, h, w, device=logits.device, dtype=torch.uint8)
+    _call("tedm_ensemble_mask", _ptr(logits, torch.float32, "logits"), _ptr(prob), _ptr(mask), b, n_steps, c * h * w,
+          _stream())
+    return mask.bool(), prob
+
+
+def umma_probe(A, Bm, shifts: Sequence[int], base_offsets: Sequence[int]):
+    n = len(shifts)
+    out = torch.zeros(n, 128, 64, device=A.device, dtype=torch.float32)
+    sh = (C.c_int * n)(*shifts)
+    bo = (C.c_int * n)(*base_offsets)
+    _call("tedm_debug_umma_probe", _ptr(A, torch.bfloat16), _ptr(Bm, torch.bfloat16), sh, bo, n, _ptr(out), _stream())
+    return out

@@ -16,6 +16,9 @@ def pytest_configure(config):
 
 def pytest_collection_modifyitems(config, items):
     import torch
+    # references computed with torch on the GPU must be true fp32 (no TF32 shortcuts)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     if torch.cuda.is_available():
         return
     skip = pytest.mark.skip(reason="no CUDA device")

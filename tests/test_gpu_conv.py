@@ -1,0 +1,113 @@
+"""tcgen05 implicit-GEMM convolution against F.conv2d on the same bf16-rounded operands."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale)
+
+
+def _nhwc(x):  # NCHW fp32 -> NHWC bf16 cuda
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+
+
+def _ref_conv(xs, w, b, mode):
+    x = torch.cat([t.to(torch.bfloat16).float() for t in xs], dim=1).cuda()
+    wq = w.to(torch.bfloat16).float().cuda()
+    bb = b.cuda() if b is not None else None
+    if mode == 0:
+        return F.conv2d(x, wq, bb)
+    if mode == 1:
+        return F.conv2d(x, wq, bb, padding=1)
+    if mode == 2:
+        return F.conv2d(x, wq, bb, stride=2, padding=1)
+    return F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), wq, bb, padding=1)
+
+
+CASES = [
+    # (B, H, W, c0, c1, cout, mode, bias, residual, gn, force_bn)
+    (2, 16, 16, 64, 0, 64, 0, True, False, 0, 0),
+    (2, 16, 16, 64, 0, 64, 1, True, False, 8, 0),
+    (1, 128, 128, 64, 0, 64, 1, True, False, 8, 0),
+    (3, 32, 32, 128, 64, 128, 1, True, False, 8, 0),
+    (2, 8, 8, 256, 128, 256, 1, True, False, 8, 0),
+    (5, 4, 4, 512, 256, 512, 1, True, False, 8, 0),
+    (5, 4, 4, 512, 0, 512, 1, True, False, 8, 128),
+    (5, 4, 4, 512, 0, 512, 1, True, False, 8, 256),
+    (2, 64, 64, 64, 0, 128, 2, True, False, 0, 0),
+    (3, 8, 8, 128, 0, 256, 2, True, False, 0, 0),
+    (2, 16, 16, 128, 0, 64, 3, True, False, 0, 0),
+    (1, 64, 64, 128, 0, 64, 3, True, False, 0, 0),
+    (2, 16, 16, 128, 0, 512, 0, True, True, 0, 0),
+    (2, 32, 32, 64, 0, 384, 0, False, False, 0, 0),
+    (2, 32, 32, 192, 64, 128, 0, True, False, 0, 0),
+    (9, 8, 8, 64, 0, 64, 1, True, False, 8, 0),
+    (2, 16, 16, 64, 0, 256, 1, True, False, 8, 256),
+    (2, 16, 16, 64, 0, 128, 1, True, False, 8, 128),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
+def test_conv_igemm(case):
+    from tedm_b200 import native as N
+    B, H, W, c0, c1, cout, mode, use_bias, use_res, gn, force_bn = case
+    kh = {0: 1, 1: 3, 2: 4, 3: 3}[mode]
+    x0 = _rand((B, c0, H, W), 1)
+    x1 = _rand((B, c1, H, W), 2) if c1 else None
+    cin = c0 + c1
+    w = _rand((cout, cin, kh, kh), 3, scale=(cin * kh * kh) ** -0.5)
+    b = _rand((cout,), 4, 0.1) if use_bias else None
+    ref = _ref_conv([x0] + ([x1] if c1 else []), w, b, mode)
+    res = None
+    if use_res:
+        res = _rand(tuple(ref.shape), 5)
+        ref = ref + res.to(torch.bfloat16).float().cuda()
+    wk = N.fold_upsample_weight(w.cuda()) if mode == 3 else N.weight_to_krsc(w.cuda())
+    N.load().tedm_conv_set_tile_n(force_bn)
+    try:
+        got = N.conv_igemm(_nhwc(x0), wk, mode, cout, bias=b.cuda() if b is not None else None,
+                           src1=_nhwc(x1) if c1 else None, residual=_nhwc(res) if use_res else None, gn_groups=gn)
+    finally:
+        N.load().tedm_conv_set_tile_n(0)
+    torch.cuda.synchronize()
+    if gn:
+        got, part = got
+        stats = part.double().sum(dim=1)                     # (B, groups, 2)
+        r = ref.double().reshape(B, gn, -1)
+        assert _rel(stats[..., 0], r.sum(-1)) < 2e-3 or (stats[..., 0] - r.sum(-1)).abs().max() < 0.5
+        assert _rel(stats[..., 1], (r * r).sum(-1)) < 1e-3
+    out = got.float().permute(0, 3, 1, 2)
+    tol = 8e-3 if mode != 3 else 1.2e-2   # mode 3 sums taps in fp32 before the bf16 rounding of the weights
+    assert _rel(out, ref) < tol, _rel(out, ref)
+
+
+def test_conv_batch_strided_views():
+    from tedm_b200 import native as N
+    S, B, H, W, C, cout = 3, 2, 8, 8, 64, 128
+    x = _rand((B * S, C, H, W), 7)
+    xs = _nhwc(x)
+    out = torch.zeros(B * S, H, W, cout, dtype=torch.bfloat16, device="cuda")
+    ws = [_rand((cout, C, 1, 1), 10 + s, C ** -0.5) for s in range(S)]
+    for s in range(S):
+        N.conv_igemm(xs[s::S], N.weight_to_krsc(ws[s].cuda()), 0, cout, out=out[s::S])
+    torch.cuda.synchronize()
+    for s in range(S):
+        ref = _ref_conv([x[s::S]], ws[s], None, 0)
+        assert _rel(out[s::S].float().permute(0, 3, 1, 2), ref) < 8e-3
+
+
+def test_conv_rejects_unsupported_shapes():
+    from tedm_b200 import native as N
+    x = torch.zeros(1, 8, 8, 48, dtype=torch.bfloat16, device="cuda")
+    w = torch.zeros(64, 3, 3, 48, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(RuntimeError, match="multiples of 64"):
+        N.conv_igemm(x, w, 1, 64)

@@ -1,0 +1,169 @@
+"""End-to-end parity of the CUDA path against the committed outputs of the live reference
+(tests/golden/*.npz, made by tests/golden/make_golden.py) and against the oracle.
+
+Tolerances (BASELINE.json north_star): schedule / q_sample / indices bit-exact; UNet activations and
+features <= 2e-2 relative (bf16 compute); argmax masks agree on >= 99.9 % of pixels."""
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tedm_oracle as O
+from tests.golden.synth import synth_noise, synth_state_dict
+
+pytestmark = pytest.mark.gpu
+T = lambda a: torch.from_numpy(np.asarray(a))
+TOL = 2e-2
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _nchw(f):
+    return f.float().permute(0, 3, 1, 2).cpu()
+
+
+@pytest.fixture(scope="module")
+def ddpm():
+    from tedm_b200.models import DiffusionModel
+    m = DiffusionModel(Namespace(normalize=True)).eval()
+    sd = synth_state_dict(O.unet_param_shapes(prefix="model."), 0)
+    missing = m.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys and all(not k.startswith("model.") for k in missing.missing_keys)
+    return m.cuda()
+
+
+def test_unet_forward_small(golden, ddpm):
+    g = golden["ddpm_small"]
+    x_t, t = T(g["x_t"]).cuda(), T(g["t"]).cuda()
+    with torch.no_grad():
+        out, feats = ddpm.model.engine.forward(x_t, t, want_features=True)
+    errs = {"out": _rel(out, g["unet_out"]), **{f"feat{i}": _rel(_nchw(f), g[f"feat{i}"]) for i, f in enumerate(feats)}}
+    print("unet small rel errors:", errs)
+    assert max(errs.values()) < TOL, errs
+    with torch.no_grad():
+        out_none = ddpm.model(x_t, None)
+    assert _rel(out_none, g["unet_out_t_none"]) < TOL
+    # folded-upsample path and materialised-upsample path agree with each other too
+    ddpm.model.engine.fold_upsample = False
+    try:
+        with torch.no_grad():
+            out2 = ddpm.model(x_t, t)
+    finally:
+        ddpm.model.engine.fold_upsample = True
+    assert _rel(out2, g["unet_out"]) < TOL and _rel(out2, out) < TOL
+
+
+def test_q_sample_loss_and_sampler_small(golden, ddpm):
+    g = golden["ddpm_small"]
+    x0, t, nz = T(g["x0"]).cuda(), T(g["t"]).cuda(), T(g["noise"]).cuda()
+    x_t, _ = ddpm.forward_diffusion_model(x0 * 2 - 1, t, nz)
+    assert np.array_equal(x_t.cpu().numpy(), g["x_t"])                       # bit-exact
+    with torch.no_grad():
+        loss = ddpm.train_step(x0, t=t, noise=nz)
+    assert abs(loss.item() - float(g["ddpm_loss"])) < TOL * float(g["ddpm_loss"])
+    z = synth_noise(g["x0"].shape, 1, "z").cuda()
+    for ts in (500, 999, 0):
+        got = ddpm.sample_timestep(T(g["x_t"]).cuda(), ts, noise=z)
+        assert _rel(got, g[f"sample_t{ts}"]) < TOL, ts
+
+
+def _tedm(n_steps, shared, steps):
+    from tedm_b200.models import DatasetDM, tedm_classifier
+    m = DatasetDM(Namespace(normalize=True, saved_diffusion_model="/nonexistent", t_steps_to_save=steps))
+    if shared:
+        m.classifier = tedm_classifier(n_steps)
+    shapes = {**O.unet_param_shapes(prefix="diffusion_model.model."), **O.head_param_shapes(n_steps, shared)}
+    missing = m.load_state_dict(synth_state_dict(shapes, 0), strict=False)
+    assert not missing.unexpected_keys
+    return m.eval().cuda()
+
+
+class FixedNoise:
+    def __init__(self, tensors):
+        self.q = list(tensors)
+    def __enter__(self):
+        self.orig = torch.randn_like
+        torch.randn_like = lambda x, **kw: self.q.pop(0).to(device=x.device, dtype=x.dtype)
+        return self
+    def __exit__(self, *a):
+        torch.randn_like = self.orig
+
+
+def _interleaved(noises, b):
+    """per-step noise tensors (S x (B,1,H,W)) -> (B*S,1,H,W) in '(b step)' order"""
+    return torch.stack(noises, dim=1).reshape(b * len(noises), *noises[0].shape[1:])
+
+
+def test_tedm_and_ledm_small(golden):
+    g = golden["tedm_small"]
+    steps = g["steps"].tolist()
+    x0 = T(g["x0"]).cuda()
+    noises = [T(g[f"noise{i}"]) for i in range(len(steps))]
+    ted = _tedm(len(steps), True, steps)
+    with FixedNoise([_interleaved(noises, x0.shape[0])]):
+        mask, prob, logits = ted.segment(x0)
+    assert logits.shape == (x0.shape[0] * len(steps), 1, 32, 32)
+    print("tedm small logits rel:", _rel(logits, g["tedm_logits"]))
+    assert _rel(logits, g["tedm_logits"]) < TOL
+    assert _rel(prob, g["tedm_prob"]) < TOL
+    assert (mask.cpu().numpy() != g["tedm_mask"]).mean() <= 1e-3
+    with FixedNoise([_interleaved(noises, x0.shape[0])]):
+        assert _rel(ted(x0), g["tedm_logits"]) < TOL                          # nn.Module.__call__ path
+    led = _tedm(len(steps), False, steps)
+    with FixedNoise([_interleaved(noises, x0.shape[0])]):
+        ll = led(x0)
+    assert ll.shape == (x0.shape[0], 1, 32, 32)
+    print("ledm small logits rel:", _rel(ll, g["ledm_logits"]))
+    assert _rel(ll, g["ledm_logits"]) < TOL
+    # reference-format feature tensor (API compatibility)
+    with FixedNoise([_interleaved(noises, x0.shape[0])]):
+        feats = ted.extract_features(x0)
+    assert feats.shape == (2, 960 * 3, 32, 32)
+    sd = synth_state_dict({**O.unet_param_shapes(prefix="diffusion_model.model.")}, 0)
+    sd.update(O.schedule_tables())
+    with torch.no_grad():
+        ref_feats = O.concat_features(O.extract_feature_maps(sd, x0.cpu(), steps, noises), 32)
+    assert _rel(feats, ref_feats) < TOL
+
+
+def test_tedm_full_size(golden):
+    g = golden["tedm_full"]
+    steps = g["steps"].tolist()
+    x0 = T(g["x0"]).cuda()
+    noises = [synth_noise((1, 1, 128, 128), 20 + i, "tedm") for i in range(len(steps))]
+    ted = _tedm(len(steps), True, steps)
+    with FixedNoise([_interleaved(noises, 1)]):
+        mask, prob, logits = ted.segment(x0)
+    lr = _rel(logits, g["tedm_logits"])
+    agree = (mask.cpu().numpy() == g["tedm_mask"]).mean()
+    print(f"tedm full: logits rel {lr:.4g}, mask agreement {agree:.5f}")
+    assert lr < TOL
+    assert agree >= 0.999
+    # one full-size UNet forward with intermediate feature checks
+    dm = ted.diffusion_model
+    t = torch.tensor([400], device="cuda")
+    x_t, _ = dm.forward_diffusion_model(x0, t, noises[5].cuda())
+    with torch.no_grad():
+        out, feats = dm.model.engine.forward(x_t, t, want_features=True)
+    assert _rel(out, g["unet_out_t400"]) < TOL
+    for i, f in enumerate(feats):
+        fn = _nchw(f)
+        assert _rel(fn[:, :8], g[f"feat{i}_t400_first8ch"]) < TOL
+        assert abs(fn.norm().item() - float(g[f"feat{i}_t400_norm"])) < TOL * float(g[f"feat{i}_t400_norm"])
+        assert _rel(fn.mean(dim=(0, 2, 3)), g[f"feat{i}_t400_chmean"]) < 5e-2
+
+
+def test_batched_equals_per_image(ddpm):
+    """Size-independent property at BASELINE batch size: a batch of 16 gives the same per-image result
+    as 16 batches of 1 (no cross-image leakage in tiles that span images)."""
+    x = torch.rand(16, 1, 32, 32, generator=torch.Generator().manual_seed(5)).cuda()
+    t = torch.randint(0, 1000, (16,), generator=torch.Generator().manual_seed(6)).cuda()
+    with torch.no_grad():
+        full = ddpm.model(x, t)
+        for i in (0, 7, 15):
+            one = ddpm.model(x[i:i + 1], t[i:i + 1])
+            assert _rel(one, full[i:i + 1]) < 5e-3

@@ -1,0 +1,250 @@
+"""Memory-bound / small kernels against the oracle (CPU fp32) on identical seeded inputs."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import tedm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _rand(shape, seed, scale=1.0):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+
+
+def _nchw(y):
+    return y.float().permute(0, 3, 1, 2).cpu()
+
+
+# ---- DDPM arithmetic ---------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(2, 1, 32, 32), (16, 1, 128, 128), (3, 2, 5, 7), (0, 1, 4, 4)])
+@pytest.mark.parametrize("normalize", [False, True])
+def test_q_sample_bit_exact(shape, normalize):
+    from tedm_b200 import native as N
+    if shape[0] == 0:
+        pytest.skip("empty batch is rejected by the ABI (checked below)")
+    tb = O.schedule_tables()
+    x0, nz = torch.rand(shape, generator=torch.Generator().manual_seed(1)), _rand(shape, 2)
+    t = torch.randint(0, 1000, (shape[0],), generator=torch.Generator().manual_seed(3))
+    t[0] = 999
+    t[-1] = 0
+    ref = O.q_sample(tb, x0, t, nz, normalize=normalize)
+    got = N.q_sample(x0.cuda(), nz.cuda(), t.cuda(), tb["sqrt_alphas_cumprod"].cuda(),
+                     tb["sqrt_one_minus_alphas_cumprod"].cuda(), normalize=normalize)
+    assert np.array_equal(got.cpu().numpy(), ref.numpy())
+
+
+def test_q_sample_rejects_empty_batch():
+    from tedm_b200 import native as N
+    tb = O.schedule_tables()
+    z = torch.zeros(0, 1, 4, 4, device="cuda")
+    with pytest.raises(RuntimeError, match="bad sizes"):
+        N.q_sample(z, z, torch.zeros(0, dtype=torch.long, device="cuda"), tb["sqrt_alphas_cumprod"].cuda(),
+                   tb["sqrt_one_minus_alphas_cumprod"].cuda())
+
+
+def test_l1_loss_and_grad():
+    from tedm_b200 import native as N
+    tb = O.schedule_tables(p2_gamma=1.0)
+    pred, tgt = _rand((5, 1, 64, 64), 1), _rand((5, 1, 64, 64), 2)
+    t = torch.tensor([0, 10, 500, 998, 999])
+    ref = O.l1_p2_loss(pred, tgt, tb["p2_loss_weight"][t])
+    loss, per_img, grad = N.l1_loss(pred.cuda(), tgt.cuda(), t.cuda(), tb["p2_loss_weight"].cuda(), want_grad=True)
+    assert abs(loss.item() - ref.item()) <= 2e-6 * abs(ref.item())
+    p = pred.clone().requires_grad_(True)
+    O.l1_p2_loss(p, tgt, tb["p2_loss_weight"][t]).backward()
+    assert _rel(grad, p.grad) < 1e-6
+
+
+@pytest.mark.parametrize("t", [999, 500, 1, 0])
+def test_sampler_step_matches_oracle(t):
+    from tedm_b200 import native as N
+    tb = O.schedule_tables()
+    shape = (3, 1, 128, 128)
+    x_t, eps, z = _rand(shape, 1), _rand(shape, 2), _rand(shape, 3)
+    ref, x0_ref = O.sampler_update(tb, x_t, eps, t, z)
+    chw = x_t[0].numel()
+    rank = torch.tensor(0.995, dtype=torch.float32) * (chw - 1)
+    k_lo, wgt = int(torch.floor(rank)), float(rank - torch.floor(rank))
+    sigma = float((0.5 * tb["posterior_log_variance_clipped"][t]).exp())
+    got, x0h, s = N.sampler_step(x_t.cuda(), eps.cuda(), z.cuda() if t > 0 else None,
+                                 float(tb["sqrt_recip_alphas_cumprod"][t]), float(tb["sqrt_recipm1_alphas_cumprod"][t]),
+                                 float(tb["posterior_mean_coef1"][t]), float(tb["posterior_mean_coef2"][t]), sigma, k_lo,
+                                 wgt, want_x0=True)
+    x0_raw = tb["sqrt_recip_alphas_cumprod"][t] * x_t - tb["sqrt_recipm1_alphas_cumprod"][t] * eps
+    s_ref = torch.quantile(x0_raw.flatten(1).abs(), 0.995, dim=1).clamp_min(1.0)
+    assert torch.allclose(s.cpu(), s_ref, rtol=1e-6, atol=0), (s.cpu(), s_ref)
+    assert _rel(x0h, x0_ref) < 1e-6
+    assert _rel(got, ref) < 1e-6
+
+
+def test_sampler_quantile_with_ties_and_small_images():
+    from tedm_b200 import native as N
+    x_t = torch.zeros(2, 1, 4, 4)
+    x_t[0].view(-1)[:] = torch.tensor([3., 3, 3, 3, 1, 1, 1, 1, 2, 2, 2, 2, 5, 5, 5, 5])
+    x_t[1].view(-1)[:] = torch.arange(16.) * 0.25
+    eps = torch.zeros_like(x_t)
+    for q in (0.5, 0.995, 0.2, 1.0):
+        rank = torch.tensor(q, dtype=torch.float32) * 15
+        k_lo, wgt = int(torch.floor(rank)), float(rank - torch.floor(rank))
+        _, _, s = N.sampler_step(x_t.cuda(), eps.cuda(), None, 1.0, 0.0, 1.0, 0.0, 0.0, k_lo, wgt)
+        ref = torch.quantile(x_t.flatten(1).abs(), q, dim=1).clamp_min(1.0)
+        assert torch.allclose(s.cpu(), ref, rtol=1e-6), (q, s.cpu(), ref)
+
+
+# ---- UNet pieces ---------------------------------------------------------------------------------
+def test_time_embed_and_proj():
+    from tedm_b200 import native as N
+    from tedm_b200.models.unet_model import SinusoidalPosEmb
+    sd = {"time_mlp.1.weight": _rand((256, 64), 1, 0.125), "time_mlp.1.bias": _rand((256,), 2, 0.1),
+          "time_mlp.3.weight": _rand((256, 256), 3, 0.0625), "time_mlp.3.bias": _rand((256,), 4, 0.1)}
+    t = torch.tensor([0, 1, 10, 400, 999, 800, 50])
+    ref = O.time_embedding(sd, "", t, 64)
+    freq = SinusoidalPosEmb(64).frequencies("cpu").float()
+    got = N.time_embed(t.cuda(), freq.cuda(), *(sd[k].cuda() for k in sd))
+    assert _rel(got, ref) < 2e-5
+    wcat, bcat = _rand((1000, 256), 5, 0.0625), _rand((1000,), 6, 0.1)
+    ref2 = F.linear(F.silu(ref), wcat, bcat)
+    got2 = N.time_proj(got, wcat.cuda(), bcat.cuda())
+    assert _rel(got2, ref2) < 2e-5
+    big = _rand((70, 256), 7)
+    assert _rel(N.time_proj(big.cuda(), wcat.cuda(), bcat.cuda()), F.linear(F.silu(big), wcat, bcat)) < 2e-5
+
+
+@pytest.mark.parametrize("cin,cout,size", [(1, 64, 32), (1, 64, 128), (2, 64, 16)])
+def test_stem_conv(cin, cout, size):
+    from tedm_b200 import native as N
+    x, w, b = _rand((2, cin, size, size), 1), _rand((cout, cin, 7, 7), 2, 0.14), _rand((cout,), 3, 0.1)
+    ref = F.conv2d(x, w, b, padding=3)
+    got = N.stem_conv7x7(x.cuda(), w.cuda(), b.cuda())
+    assert _rel(_nchw(got), ref) < 4e-3
+
+
+@pytest.mark.parametrize("C,hw,B", [(64, 32, 2), (128, 16, 3), (256, 8, 2), (512, 4, 5), (64, 128, 1)])
+@pytest.mark.parametrize("with_ss,with_res", [(True, False), (False, True)])
+def test_gn_silu(C, hw, B, with_ss, with_res):
+    """GroupNorm statistics come from the conv epilogue; here they are produced by a 1x1 identity-free
+    conv so the test covers the partial-sum layout end to end."""
+    from tedm_b200 import native as N
+    x = _rand((B, C, hw, hw), 1, 1.5) + 0.3
+    w = _rand((C, C, 1, 1), 2, C ** -0.5)
+    bias = _rand((C,), 3, 0.1)
+    gamma, beta = 1 + _rand((C,), 4, 0.2), _rand((C,), 5, 0.1)
+    y, part = N.conv_igemm(_nhwc(x), N.weight_to_krsc(w.cuda()), 0, C, bias=bias.cuda(), gn_groups=8)
+    yref = F.conv2d(_bf(x), _bf(w), bias)
+    ss = _rand((B, 4 * C + 10), 6, 0.3) if with_ss else None
+    res = _rand((B, C, hw, hw), 7) if with_res else None
+    ref = F.group_norm(yref, 8, gamma, beta, eps=1e-5)
+    if with_ss:
+        ref = ref * (ss[:, 10:10 + C, None, None] + 1) + ss[:, 10 + C:10 + 2 * C, None, None]
+    ref = F.silu(ref)
+    if with_res:
+        ref = ref + _bf(res)
+    got = N.gn_silu(y, part, gamma.cuda(), beta.cuda(), 8, scale_shift=ss.cuda() if with_ss else None, ss_offset=10,
+                    residual=_nhwc(res) if with_res else None)
+    assert _rel(_nchw(got), ref) < 8e-3
+
+
+@pytest.mark.parametrize("C", [64, 128, 256, 512])
+def test_layernorm(C):
+    from tedm_b200 import native as N
+    x, g, res = _rand((3, C, 8, 8), 1, 2.0) + 0.5, 1 + _rand((1, C, 1, 1), 2, 0.2), _rand((3, C, 8, 8), 3)
+    ref = O._chan_layernorm(_bf(x), g, 1e-5)
+    got = N.layernorm(_nhwc(x), g.reshape(-1).cuda())
+    assert _rel(_nchw(got), ref) < 4e-3
+    got2 = N.layernorm(_nhwc(x), g.reshape(-1).cuda(), residual=_nhwc(res))
+    assert _rel(_nchw(got2), ref + _bf(res)) < 4e-3
+
+
+@pytest.mark.parametrize("hw,B", [(4, 2), (16, 3), (32, 2), (128, 1)])
+def test_linear_attention_core(hw, B):
+    from tedm_b200 import native as N
+    qkv = _rand((B, 384, hw, hw), 1, 1.5)
+    q, k, v = (z.reshape(B, 4, 32, hw * hw) for z in _bf(qkv).chunk(3, dim=1))
+    q = q.softmax(dim=-2) * 32 ** -0.5
+    k = k.softmax(dim=-1)
+    ctx = torch.einsum("bhdn,bhen->bhde", k, v / (hw * hw))
+    ref = torch.einsum("bhde,bhdn->bhen", ctx, q).reshape(B, 128, hw, hw)
+    got = N.linear_attention(_nhwc(qkv))
+    assert _rel(_nchw(got), ref) < 6e-3
+
+
+@pytest.mark.parametrize("hw,B", [(4, 2), (16, 3), (8, 1)])
+def test_mid_attention_core(hw, B):
+    from tedm_b200 import native as N
+    qkv = _rand((B, 384, hw, hw), 1, 1.0)
+    n = hw * hw
+    q, k, v = (z.reshape(B, 4, 32, n) for z in _bf(qkv).chunk(3, dim=1))
+    q, k = F.normalize(q, dim=-1), F.normalize(k, dim=-1)
+    att = (torch.einsum("bhdi,bhdj->bhij", q, k) * 16).softmax(dim=-1)
+    ref = torch.einsum("bhij,bhdj->bhid", att, v).permute(0, 1, 3, 2).reshape(B, 128, hw, hw)
+    got = N.attention(_nhwc(qkv))
+    assert _rel(_nchw(got), ref) < 6e-3
+
+
+def test_upsample_final_conv_and_layout():
+    from tedm_b200 import native as N
+    x = _rand((2, 64, 8, 8), 1)
+    xh = _nhwc(x)
+    assert torch.equal(_nchw(N.upsample2x(xh)), F.interpolate(_bf(x), scale_factor=2, mode="nearest"))
+    w, b = _rand((3, 64, 1, 1), 2, 0.125), _rand((3,), 3, 0.1)
+    assert _rel(N.final_conv1x1(xh, w.reshape(3, 64).cuda(), b.cuda()), F.conv2d(_bf(x), w, b)) < 1e-5
+    back = N.nhwc_to_nchw_f32(xh)
+    assert torch.equal(back.cpu(), _bf(x))
+    assert torch.equal(N.nchw_to_nhwc_bf16(x.cuda()), xh)
+
+
+def test_fold_upsample_weight_is_exact_in_fp32():
+    from tedm_b200 import native as N
+    w = _rand((8, 16, 3, 3), 1)
+    folded = N.fold_upsample_weight(w.cuda()).float().cpu()       # (4, cout, 2, 2, cin)
+    x = _rand((1, 16, 6, 6), 2)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, padding=1)
+    out = torch.zeros_like(ref)
+    xp = F.pad(x, (1, 1, 1, 1))
+    for py in range(2):
+        for px in range(2):
+            wk = folded[py * 2 + px].permute(0, 3, 1, 2)            # (cout, cin, 2, 2)
+            o = F.conv2d(xp[:, :, py:py + 7, px:px + 7], wk)       # source offsets (a-1+py, b-1+px)
+            out[:, :, py::2, px::2] = o[:, :, :6, :6]
+    assert _rel(out, ref) < 5e-3                                    # only the bf16 rounding of the folded taps
+
+
+def test_head_and_ensemble():
+    from tedm_b200 import native as N
+    B, S, size = 2, 3, 32
+    chans, sizes = [512, 256, 128, 64], [4, 8, 16, 32]
+    feats = [_rand((B * S, c, s, s), 10 + i) for i, (c, s) in enumerate(zip(chans, sizes))]
+    sd = {k: v for k, v in __import__("tests.golden.synth", fromlist=["x"]).synth_state_dict(O.head_param_shapes(S, True), 0).items()}
+    full = torch.cat([F.interpolate(_bf(f), size=[size, size]) for f in feats], dim=1).reshape(B, S * 960, size, size)
+    ref = O.head_forward(sd, full, S, True)
+    w1 = sd["classifier.1.weight"]
+    offs = [0, 512, 768, 896]
+    g = [N.conv_igemm(_nhwc(f), w1[:, o:o + c, 0, 0].to(torch.bfloat16).contiguous().cuda(), 0, 128)
+         for f, o, c in zip(feats, offs, chans)]
+    def fold(i):
+        a = sd[f"classifier.{i}.weight"] / torch.sqrt(sd[f"classifier.{i}.running_var"] + 1e-5)
+        return a.cuda(), (sd[f"classifier.{i}.bias"] - sd[f"classifier.{i}.running_mean"] * a).cuda()
+    a1, c1 = fold(3)
+    a2, c2 = fold(6)
+    logits = N.head_infer(g, [3, 2, 1, 0], 1, B * S, size, size, sd["classifier.1.bias"].cuda(), a1, c1,
+                          sd["classifier.4.weight"].reshape(32, 128).cuda(), sd["classifier.4.bias"].cuda(), a2, c2,
+                          sd["classifier.7.weight"].reshape(32).cuda(), float(sd["classifier.7.bias"]))
+    assert _rel(logits, ref) < 1e-2
+    mask, prob = N.ensemble_mask(logits, S)
+    mref, pref = O.ensemble_mask(logits.cpu(), S)
+    assert _rel(prob, pref) < 1e-6 and torch.equal(mask.cpu(), mref)
