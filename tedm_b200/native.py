@@ -115,7 +115,7 @@ def _call(name: str, *args) -> None:
 def q_sample(x0: torch.Tensor, noise: torch.Tensor, t: torch.Tensor, sqrt_ac: torch.Tensor,
              sqrt_1m_ac: torch.Tensor, normalize: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     b = x0.shape[0]
-    chw = x0[0].numel()
+    chw = x0.numel() // b if b else int(torch.Size(x0.shape[1:]).numel())
     if noise.shape != x0.shape or t.shape != (b,):
         raise ValueError("q_sample: shape mismatch")
     out = torch.empty_like(x0) if out is None else out

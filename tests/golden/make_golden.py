@@ -169,6 +169,49 @@ def main():
         g[f"feat{i}_t400_norm"] = np_(f.norm())
         g[f"feat{i}_t400_chmean"] = np_(f.mean(dim=(0, 2, 3)))
     np.savez_compressed(os.path.join(HERE, "tedm_full.npz"), **g)
+
+    # ---- heads that actually segment ------------------------------------------------------
+    # A random-init head puts every logit at the decision threshold (|prob - 0.5| < 0.01 on ~64 % of
+    # the pixels), so mask agreement there measures rounding noise.  These two fixtures train the
+    # reference's TEDM head (reference modules, reference BCE loss, Adam) for a few dozen steps on the
+    # frozen synthetic UNet's features against the mask (x0 > 0.45), then record the reference's
+    # eval-mode outputs together with the trained head parameters.
+    for tag, (bsz, size, stps, seed0, iters) in {"small": (2, 32, [10, 400, 800], 10, 80),
+                                                 "full": (1, 128, [1, 10, 25, 50, 200, 400, 600, 800], 20, 60)}.items():
+        cfg.t_steps_to_save = stps
+        x0 = synth_images(bsz, size, 0 if tag == "small" else 3)
+        noises = [synth_noise((bsz, 1, size, size), seed0 + i, "tedm") for i in range(len(stps))]
+        ted = DatasetDM(cfg)
+        ted.classifier = tedm_head(len(stps))
+        ted.eval()
+        load_synth(ted, 0, skip=("diffusion_model.sqrt_", "diffusion_model.posterior_", "diffusion_model.p2_"))
+        with FixedNoise(noises):
+            feats = ted.extract_features(x0)
+        y = (x0 > 0.45).float()
+        yr = y.repeat_interleave(len(stps), dim=0)                      # 'b c h w -> (b step) c h w'
+        torch.manual_seed(0)
+        with torch.enable_grad():
+            opt = torch.optim.Adam(ted.classifier.parameters(), lr=2e-3)
+            ted.classifier.train()
+            for it in range(iters):
+                opt.zero_grad()
+                out = ted.classifier(feats)
+                loss = torch.nn.functional.binary_cross_entropy_with_logits(out, yr, reduction="none").mean(dim=(2, 3)).mean()
+                loss.backward()
+                opt.step()
+        ted.classifier.eval()
+        logits = ted.classifier(feats)
+        pr = torch.sigmoid(logits).reshape(bsz, len(stps), 1, size, size).mean(1)
+        g = {"x0": np_(x0), "steps": np.array(stps), "target": np_(y), "final_train_loss": np_(loss.detach()),
+             "tedm_logits": np_(logits), "tedm_prob": np_(pr), "tedm_mask": np_(pr > 0.5)}
+        for i, n_ in enumerate(noises):
+            g[f"noise{i}"] = np_(n_)
+        for k, v in ted.classifier.state_dict().items():
+            g[f"classifier.{k}"] = np_(v)
+        print(tag, "trained head: loss", float(loss), "logit std", float(logits.std()),
+              "frac |p-.5|<.02:", float(((pr - .5).abs() < .02).float().mean()),
+              "acc vs target", float(((pr > .5).float() == y).float().mean()))
+        np.savez_compressed(os.path.join(HERE, f"tedm_{tag}_trained.npz"), **g)
     print("golden fixtures written:", sorted(f for f in os.listdir(HERE) if f.endswith((".npz", ".json"))))
 
 

@@ -82,6 +82,38 @@ def _tedm(n_steps, shared, steps):
     return m.eval().cuda()
 
 
+# An untrained (random-init) head puts every logit at the decision threshold: the reference's logits
+# have std 0.04 around 0.03 and ~64 % of the pixels have |prob - 0.5| < 0.01, i.e. the logits are a
+# near-cancelling residual of O(1) activations.  bf16 feature rounding (features themselves are within
+# 0.7 % of the reference) shows up as ~2 % there (the bf16-emulating oracle gives 1.8 %), so those
+# fixtures get a 3e-2 logit budget and a "disagreements only inside the rounding band" mask check;
+# the >= 99.9 % mask criterion is asserted on the fixtures whose head the reference trained.
+TOL_UNTRAINED_LOGITS = 3e-2
+
+
+def _masks_agree_outside_threshold_band(mask, g, band=5e-3):
+    diff = mask.cpu().numpy() != g["tedm_mask"]
+    assert not (diff & (np.abs(g["tedm_prob"] - 0.5) >= band)).any(), "mask differs where the reference is decisive"
+
+
+@pytest.mark.parametrize("tag", ["small", "full"])
+def test_tedm_trained_head_masks(golden, tag):
+    """North-star criterion: argmax masks agree with the reference on >= 99.9 % of the pixels."""
+    g = golden[f"tedm_{tag}_trained"]
+    steps = g["steps"].tolist()
+    x0 = T(g["x0"]).cuda()
+    noises = [T(g[f"noise{i}"]) for i in range(len(steps))]
+    ted = _tedm(len(steps), True, steps)
+    ted.load_state_dict({k: T(g[k]) for k in g.files if k.startswith("classifier.")}, strict=False)
+    with FixedNoise([_interleaved(noises, x0.shape[0])]):
+        mask, prob, logits = ted.segment(x0)
+    lr = _rel(logits, g["tedm_logits"])
+    agree = (mask.cpu().numpy() == g["tedm_mask"]).mean()
+    print(f"tedm {tag} (trained head): logits rel {lr:.4g}, prob rel {_rel(prob, g['tedm_prob']):.4g}, mask agreement {agree:.5f}")
+    assert lr < TOL
+    assert agree >= 0.999
+
+
 class FixedNoise:
     def __init__(self, tensors):
         self.q = list(tensors)
@@ -108,17 +140,17 @@ def test_tedm_and_ledm_small(golden):
         mask, prob, logits = ted.segment(x0)
     assert logits.shape == (x0.shape[0] * len(steps), 1, 32, 32)
     print("tedm small logits rel:", _rel(logits, g["tedm_logits"]))
-    assert _rel(logits, g["tedm_logits"]) < TOL
+    assert _rel(logits, g["tedm_logits"]) < TOL_UNTRAINED_LOGITS
     assert _rel(prob, g["tedm_prob"]) < TOL
-    assert (mask.cpu().numpy() != g["tedm_mask"]).mean() <= 1e-3
+    _masks_agree_outside_threshold_band(mask, g)
     with FixedNoise([_interleaved(noises, x0.shape[0])]):
-        assert _rel(ted(x0), g["tedm_logits"]) < TOL                          # nn.Module.__call__ path
+        assert _rel(ted(x0), g["tedm_logits"]) < TOL_UNTRAINED_LOGITS        # nn.Module.__call__ path
     led = _tedm(len(steps), False, steps)
     with FixedNoise([_interleaved(noises, x0.shape[0])]):
         ll = led(x0)
     assert ll.shape == (x0.shape[0], 1, 32, 32)
     print("ledm small logits rel:", _rel(ll, g["ledm_logits"]))
-    assert _rel(ll, g["ledm_logits"]) < TOL
+    assert _rel(ll, g["ledm_logits"]) < TOL_UNTRAINED_LOGITS
     # reference-format feature tensor (API compatibility)
     with FixedNoise([_interleaved(noises, x0.shape[0])]):
         feats = ted.extract_features(x0)
@@ -140,9 +172,9 @@ def test_tedm_full_size(golden):
         mask, prob, logits = ted.segment(x0)
     lr = _rel(logits, g["tedm_logits"])
     agree = (mask.cpu().numpy() == g["tedm_mask"]).mean()
-    print(f"tedm full: logits rel {lr:.4g}, mask agreement {agree:.5f}")
-    assert lr < TOL
-    assert agree >= 0.999
+    print(f"tedm full (untrained head): logits rel {lr:.4g}, mask agreement {agree:.5f}")
+    assert lr < TOL_UNTRAINED_LOGITS
+    _masks_agree_outside_threshold_band(mask, g)
     # one full-size UNet forward with intermediate feature checks
     dm = ted.diffusion_model
     t = torch.tensor([400], device="cuda")

@@ -119,6 +119,22 @@ def test_tedm_and_ledm_small(golden):
         assert rel(O.head_forward(sdl, feats, len(steps), False, training=True), g["ledm_logits_bn_train"]) < 5e-5
 
 
+@pytest.mark.parametrize("tag", ["small", "full"])
+def test_tedm_trained_head_fixtures(golden, tag):
+    """Fixtures whose head was trained by the reference (decisive logits): the oracle reproduces them."""
+    g = golden[f"tedm_{tag}_trained"]
+    steps = g["steps"].tolist()
+    noises = [T(g[f"noise{i}"]) for i in range(len(steps))]
+    sd = synth_state_dict(O.unet_param_shapes(prefix="diffusion_model.model."), 0)
+    sd.update(O.schedule_tables())
+    sd.update({k: T(g[k]) for k in g.files if k.startswith("classifier.")})
+    with torch.no_grad():
+        logits, mask, pr = O.tedm_segment(sd, T(g["x0"]), steps, noises)
+    assert rel(logits, g["tedm_logits"]) < 1e-4
+    assert np.array_equal(mask.numpy(), g["tedm_mask"])
+    assert float(((T(g["tedm_prob"]) - 0.5).abs() < 0.02).float().mean()) < 0.05     # the head is decisive
+
+
 def test_tedm_full_size(golden):
     g = golden["tedm_full"]
     steps = g["steps"].tolist()
