@@ -231,12 +231,12 @@ def run_ours(args):
     records = []
 
     @contextlib.contextmanager
-    def conv_timer(flops):
+    def conv_timer(flops, shape=None):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         yield
         b.record()
-        records.append((flops, a, b))
+        records.append((flops, a, b, shape))
 
     N.conv_timer = conv_timer
     try:
@@ -244,8 +244,19 @@ def run_ours(args):
     finally:
         N.conv_timer = None
     torch.cuda.synchronize()
-    conv_ms = sum(a.elapsed_time(b) for _, a, b in records)
-    conv_fl = sum(f for f, _, _ in records)
+    conv_ms = sum(a.elapsed_time(b) for _, a, b, _ in records)
+    conv_fl = sum(f for f, _, _, _ in records)
+    if os.environ.get("TEDM_BENCH_CONV_TABLE") and rank == 0:
+        agg = {}
+        for f, a, b, shp in records:
+            e = agg.setdefault(shp, [0, 0.0, 0.0])
+            e[0] += 1
+            e[1] += a.elapsed_time(b)
+            e[2] += f
+        with open(os.environ["TEDM_BENCH_CONV_TABLE"], "w") as fh:
+            fh.write("mode B H W c0 c1 cout gn res | launches  ms_total  TFLOP/s  share_of_conv_time\n")
+            for shp, (cnt, t_ms, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                fh.write(f"{shp} | {cnt:3d} {t_ms:9.3f} {fl / (t_ms * 1e-3) / 1e12:8.1f} {100 * t_ms / conv_ms:6.1f}%\n")
     pk = peaks()
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (all conv launches of one step)", "achieved": achieved,

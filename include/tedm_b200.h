@@ -111,6 +111,7 @@ typedef struct {
   int c0, c1, cout;
   int mode;
   int gn_groups;         /* number of GroupNorm groups (0 when gn_partial is NULL) */
+  int out_dtype;         /* 0: out is bf16 (TMA store); 1: out is fp32 (head layer 1 keeps full precision) */
   int64_t src0_image_stride, src1_image_stride, out_image_stride; /* elements; 0 = dense */
 } tedm_conv_args;
 TEDM_API int tedm_conv_igemm_fwd(const tedm_conv_args* args, tedm_stream_t stream);
@@ -171,7 +172,8 @@ TEDM_API int tedm_nhwc_bf16_to_nchw_f32(const void* x, float* out, int batch, in
  * Replaces F.interpolate + cat + classifier (models/datasetDM_model.py:57-64,80-88;
  * trainers/train_datasetDM.py:30-42), eval-mode BatchNorm. */
 typedef struct {
-  const void* g[4];      /* level l: [n_img*n_sum][H>>shift[l]][W>>shift[l]][c1] bf16 */
+  const void* g[4];      /* level l: [n_img*n_sum][H>>shift[l]][W>>shift[l]][c1], bf16 or fp32 (g_dtype) */
+  int g_dtype;           /* 0 = bf16, 1 = fp32 */
   int shift[4];
   int n_levels;
   int n_sum;             /* 1 for TEDM (shared head), S for LEDM/LEDMe */

@@ -10,184 +10,358 @@
 // LinearAttention                                               models/unet_model.py:197-209
 //   q = softmax_d(q) * scale ; k = softmax_n(k) ; v = v / n
 //   ctx[d][e] = sum_n k[d][n] v[e][n] ; out[e][n] = sum_d ctx[d][e] q[d][n]
-// Phase 1: per (image, head, chunk of LA_NP pixels): local column max m, s = sum exp(k-m),
-//          ctx_c = exp(k-m)^T v.                  -> workspace partials
-// Phase 2: per (image, head): fold partials with exp(m_c - M), divide by (S * n), fold in `scale`.
-// Phase 3: per pixel: softmax over the head's 32 q channels, 32x32 matvec with ctx.
+// The two contractions are 32x32xn / nx32x32 per head: far too small in M for tcgen05 (M >= 64), so
+// they run on the warp-level bf16 tensor-core path (mma.sync m16n8k16) with fp32 accumulation, and
+// the kernels are bound by streaming qkv once from HBM:
+//   K0 colmax : per (image, 1024-pixel chunk) column max of the 128 k channels          (reads k)
+//   K1 ctx    : P = exp(k - max) built in registers from ldmatrix fragments, ctx += P^T v on
+//               tensor cores, s += sum P; one partial per chunk                          (reads k, v)
+//   K2 combine: sum partials, ctx * scale / (s * n) -> bf16 ctx^T                         (tiny)
+//   K3 out    : per 64-pixel tile: softmax over each head's 32 q channels in fragment layout,
+//               out = softmax(q) ctx on tensor cores, coalesced bf16 store                (reads q)
 // ------------------------------------------------------------------------------------------
-#define LA_NP 128
-#define LA_PART (2 * DH + DH * DH)  // m[32], s[32], ctx[32][32]
+#define LA_HEADS 4
+#define LA_C (LA_HEADS * DH)          // 128 channels per q / k / v
+#define LA_SUB 64                      // pixels per shared-memory tile
+#define LA_CHUNK 1024                  // pixels per K0/K1 CTA
+#define LA_KV_PITCH 528                // bytes per smem row: 512 (k|v) + 16 pad (ldmatrix conflict-free)
+#define LA_Q_PITCH 272                 // 256 + 16
+#define LA_CT_PITCH 80                 // 64 + 16
+#define LA_PART (LA_C + LA_C * DH)     // per-chunk partial: s[128], ctx[128][32]
 
-__global__ void __launch_bounds__(256) linattn_partial_kernel(const bf16* __restrict__ qkv, float* __restrict__ ws, int n,
-                                                              int heads, int nchunks) {
-  __shared__ __align__(16) float sk[LA_NP][DH];
-  __shared__ __align__(16) float sv[LA_NP][DH];
-  __shared__ float s_max[DH];
-  const int chunk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int C3 = 3 * heads * DH;
-  const int p0 = chunk * LA_NP;
-  const int np = min(LA_NP, n - p0);
-  // load k and v: (pixel, 8-channel vector) per thread-iteration
-  for (int i = tid; i < LA_NP * 8; i += 256) {
-    const int pi = i >> 3, part = i & 7;          // part 0..3 -> k, 4..7 -> v
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// K0: partial column maxima of k.  thread = (16-byte channel vector, pixel lane)
+__global__ void __launch_bounds__(256) linattn_colmax_kernel(const bf16* __restrict__ qkv, float* __restrict__ pmax, int n,
+                                                             int nchunks) {
+  __shared__ float red[16][LA_C];
+  const int chunk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int vec = tid & 15, pl = tid >> 4;
+  const int p0 = chunk * LA_CHUNK, p1 = min(n, p0 + LA_CHUNK);
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+  for (int px = p0 + pl; px < p1; px += 16) {
     float f[8];
-    if (pi < np) {
-      const bf16* src = qkv + ((size_t)b * n + p0 + pi) * C3 + (part < 4 ? heads * DH : 2 * heads * DH) + h * DH + (part & 3) * 8;
-      unpack8(ldg_stream(src), f);
-    } else {
+    unpack8(ldg_stream(qkv + ((size_t)b * n + px) * (3 * LA_C) + LA_C + vec * 8), f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = part < 4 ? -INFINITY : 0.0f;
-    }
-    float* dst = part < 4 ? &sk[pi][(part & 3) * 8] : &sv[pi][(part & 3) * 8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dst[j] = f[j];
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[pl][vec * 8 + j] = m[j];
   __syncthreads();
-  // column max: warp w owns columns 4w..4w+3
-  for (int dd = 0; dd < 4; ++dd) {
-    const int d = warp * 4 + dd;
+  if (tid < LA_C) {
+    float v = red[0][tid];
+#pragma unroll
+    for (int i = 1; i < 16; ++i) v = fmaxf(v, red[i][tid]);
+    pmax[((size_t)b * nchunks + chunk) * LA_C + tid] = v;
+  }
+}
+
+// K1: per (image, chunk): s[c] = sum_px exp(k - M), ctx[h][d][e] = sum_px exp(k[px][h,d] - M) v[px][h,e]
+__global__ void __launch_bounds__(256) linattn_ctx_kernel(const bf16* __restrict__ qkv, const float* __restrict__ pmax,
+                                                          float* __restrict__ part, int n, int nchunks) {
+  extern __shared__ __align__(16) uint8_t la_smem[];
+  __shared__ float sM[LA_C];
+  const int chunk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int p0 = chunk * LA_CHUNK, p1 = min(n, p0 + LA_CHUNK);
+  const int nsub = (p1 - p0 + LA_SUB - 1) / LA_SUB;
+  const uint32_t tile0 = smem_u32(la_smem);
+  constexpr int TILE_BYTES = LA_SUB * LA_KV_PITCH;
+
+  if (tid < LA_C) {
     float m = -INFINITY;
-    for (int pi = lane; pi < LA_NP; pi += 32) m = fmaxf(m, sk[pi][d]);
-    m = warp_max(m);
-    if (lane == 0) s_max[d] = m;
+    for (int c = 0; c < nchunks; ++c) m = fmaxf(m, pmax[((size_t)b * nchunks + c) * LA_C + tid]);
+    sM[tid] = m;
+  }
+
+  auto load_sub = [&](int sub, int buf) {
+    const int base_px = p0 + sub * LA_SUB;
+    for (int i = tid; i < LA_SUB * 32; i += 256) {
+      const int row = i >> 5, c16 = i & 31;
+      const int px = base_px + row;
+      const uint32_t dst = tile0 + buf * TILE_BYTES + row * LA_KV_PITCH + c16 * 16;
+      if (px < p1) {
+        cp_async16(dst, reinterpret_cast<const uint8_t*>(qkv + ((size_t)b * n + px) * (3 * LA_C) + LA_C) + c16 * 16);
+      } else {  // padding rows: k = -inf (P = 0), v = 0
+        const uint32_t fill = c16 < 16 ? 0xFF80FF80u : 0u;
+        asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(dst), "r"(fill) : "memory");
+      }
+    }
+  };
+
+  const int h = warp & 3, slice = warp >> 2;
+  const int g = lane >> 2, t4 = lane & 3;
+  float acc[2][4][4];
+  float ssum[2][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    ssum[a][0] = ssum[a][1] = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[a][c][e] = 0.0f;
+  }
+
+  load_sub(0, 0);
+  cp_async_commit();
+  __syncthreads();  // sM visible
+  float Mrow[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    Mrow[mt][0] = sM[h * DH + mt * 16 + g];
+    Mrow[mt][1] = sM[h * DH + mt * 16 + g + 8];
+  }
+
+  for (int sub = 0; sub < nsub; ++sub) {
+    const int buf = sub & 1;
+    if (sub + 1 < nsub) {
+      load_sub(sub + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const uint32_t tile = tile0 + buf * TILE_BYTES;
+    const int j = lane >> 3, rr = lane & 7;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int k0 = slice * 32 + ks * 16;
+      uint32_t a[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int px = k0 + (j >> 1) * 8 + rr, dcol = h * DH + mt * 16 + (j & 1) * 8;
+        ldsm_x4_trans(tile + px * LA_KV_PITCH + dcol * 2, a[mt]);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float2 kv = unpack_bf16x2(a[mt][r]);
+          const float mm = Mrow[mt][r & 1];
+          const float e0 = __expf(kv.x - mm), e1 = __expf(kv.y - mm);
+          ssum[mt][r & 1] += e0 + e1;
+          a[mt][r] = pack_bf16x2(e0, e1);
+        }
+      }
+      uint32_t bfr[2][4];
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        const int px = k0 + (j & 1) * 8 + rr, ecol = h * DH + (2 * np + (j >> 1)) * 8;
+        ldsm_x4_trans(tile + px * LA_KV_PITCH + 256 + ecol * 2, bfr[np]);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[mt][nt], a[mt], bfr[nt >> 1][(nt & 1) * 2], bfr[nt >> 1][(nt & 1) * 2 + 1]);
+    }
+    __syncthreads();  // the buffer is refilled by the next iteration's prefetch
+  }
+  // quad-reduce the row sums
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      ssum[mt][r] += __shfl_xor_sync(0xffffffffu, ssum[mt][r], 1);
+      ssum[mt][r] += __shfl_xor_sync(0xffffffffu, ssum[mt][r], 2);
+    }
+  // merge the two pixel slices through shared memory, then write the chunk partial
+  float* red = reinterpret_cast<float*>(la_smem);  // [4 heads][32 lanes][36]
+  if (slice == 1) {
+    float* r = red + (h * 32 + lane) * 36;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) r[(mt * 4 + nt) * 4 + e] = acc[mt][nt][e];
+      r[32 + mt * 2] = ssum[mt][0];
+      r[32 + mt * 2 + 1] = ssum[mt][1];
+    }
   }
   __syncthreads();
-  for (int i = tid; i < LA_NP * DH; i += 256) {
-    const int pi = i >> 5, d = i & 31;
-    sk[pi][d] = __expf(sk[pi][d] - s_max[d]);   // padded rows: exp(-inf) = 0
+  if (slice == 0) {
+    const float* r = red + (h * 32 + lane) * 36;
+    float* dst = part + ((size_t)b * nchunks + chunk) * LA_PART;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int d_lo = h * DH + mt * 16 + g, d_hi = d_lo + 8;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int e = nt * 8 + 2 * t4;
+        const float* rr2 = r + (mt * 4 + nt) * 4;
+        *reinterpret_cast<float2*>(dst + LA_C + (size_t)d_lo * DH + e) = make_float2(acc[mt][nt][0] + rr2[0], acc[mt][nt][1] + rr2[1]);
+        *reinterpret_cast<float2*>(dst + LA_C + (size_t)d_hi * DH + e) = make_float2(acc[mt][nt][2] + rr2[2], acc[mt][nt][3] + rr2[3]);
+      }
+      if (t4 == 0) {
+        dst[d_lo] = ssum[mt][0] + r[32 + mt * 2];
+        dst[d_hi] = ssum[mt][1] + r[32 + mt * 2 + 1];
+      }
+    }
   }
-  __syncthreads();
-  float* part_out = ws + (((size_t)b * heads + h) * nchunks + chunk) * LA_PART;
-  for (int dd = 0; dd < 4; ++dd) {
-    const int d = warp * 4 + dd;
+}
+
+// K2: ctxT[b][h][e][d] = bf16( scale * sum_c ctx_c[h][d][e] / (n * sum_c s_c[h][d]) )
+__global__ void __launch_bounds__(256) linattn_combine_kernel(const float* __restrict__ part, bf16* __restrict__ ctxT, int n,
+                                                              int nchunks, float scale) {
+  __shared__ float sS[LA_C];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* p = part + (size_t)b * nchunks * LA_PART;
+  if (tid < LA_C) {
     float s = 0.0f;
-    for (int pi = lane; pi < LA_NP; pi += 32) s += sk[pi][d];
-    s = warp_sum(s);
-    if (lane == 0) {
-      part_out[d] = s_max[d];
-      part_out[DH + d] = s;
-    }
-  }
-  // ctx: thread = (pixel quarter, 4 d, 4 e) register tile
-  const int pq = tid >> 6, d0 = ((tid & 63) >> 3) * 4, e0 = (tid & 7) * 4;
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-  for (int pi = pq * (LA_NP / 4); pi < (pq + 1) * (LA_NP / 4); ++pi) {
-    const float4 kk = *reinterpret_cast<const float4*>(&sk[pi][d0]);
-    const float4 vv = *reinterpret_cast<const float4*>(&sv[pi][e0]);
-    const float ka[4] = {kk.x, kk.y, kk.z, kk.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ka[i], va[j], acc[i][j]);
-  }
-  __syncthreads();  // everyone is done reading sk/sv: reuse sk as the cross-quarter reduction buffer
-  float* redbuf = &sk[0][0];  // [4][32][32]
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) redbuf[(pq * DH + d0 + i) * DH + e0 + j] = acc[i][j];
-  __syncthreads();
-  for (int i = tid; i < DH * DH; i += 256)
-    part_out[2 * DH + i] = redbuf[i] + redbuf[DH * DH + i] + redbuf[2 * DH * DH + i] + redbuf[3 * DH * DH + i];
-}
-
-__global__ void __launch_bounds__(256) linattn_combine_kernel(float* __restrict__ ws, float* __restrict__ ctx_out, int n,
-                                                              int heads, int nchunks, float scale) {
-  __shared__ float sM[DH], sS[DH];
-  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-  const float* parts = ws + ((size_t)b * heads + h) * nchunks * LA_PART;
-  if (tid < DH) {
-    float M = -INFINITY;
-    for (int c = 0; c < nchunks; ++c) M = fmaxf(M, parts[(size_t)c * LA_PART + tid]);
-    float S = 0.0f;
-    for (int c = 0; c < nchunks; ++c) S += parts[(size_t)c * LA_PART + DH + tid] * __expf(parts[(size_t)c * LA_PART + tid] - M);
-    sM[tid] = M;
-    sS[tid] = S;
+    for (int c = 0; c < nchunks; ++c) s += p[(size_t)c * LA_PART + tid];
+    sS[tid] = s;
   }
   __syncthreads();
-  for (int i = tid; i < DH * DH; i += 256) {
-    const int d = i >> 5;
+  for (int idx = tid; idx < LA_C * DH; idx += 256) {
+    const int hd = idx >> 5, e = idx & 31;  // hd = h*32 + d
     float acc = 0.0f;
-    for (int c = 0; c < nchunks; ++c)
-      acc += parts[(size_t)c * LA_PART + 2 * DH + i] * __expf(parts[(size_t)c * LA_PART + d] - sM[d]);
-    ctx_out[((size_t)b * heads + h) * DH * DH + i] = acc * scale / (sS[d] * (float)n);
+    for (int c = 0; c < nchunks; ++c) acc += p[(size_t)c * LA_PART + LA_C + idx];
+    const int h = hd >> 5, d = hd & 31;
+    ctxT[(((size_t)b * LA_HEADS + h) * DH + e) * DH + d] = __float2bfloat16_rn(acc * scale / (sS[hd] * (float)n));
   }
 }
 
-__global__ void __launch_bounds__(256) linattn_out_kernel(const bf16* __restrict__ qkv, const float* __restrict__ ctx,
-                                                          bf16* __restrict__ out, int n, int heads) {
-  __shared__ __align__(16) float sc[DH][DH];  // ctx[d][e]
-  const int h = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
-  for (int i = tid; i < DH * DH; i += 256) (&sc[0][0])[i] = ctx[((size_t)b * heads + h) * DH * DH + i];
+// K3: out[px][h*32+e] = sum_d softmax_d(q[px][h*32+:])[d] * ctx[h][d][e]
+__global__ void __launch_bounds__(256) linattn_out_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ctxT,
+                                                          bf16* __restrict__ out, int n) {
+  __shared__ __align__(16) uint8_t qtile[LA_SUB * LA_Q_PITCH];
+  __shared__ __align__(16) uint8_t otile[LA_SUB * LA_Q_PITCH];
+  __shared__ __align__(16) uint8_t ctile[LA_HEADS * DH * LA_CT_PITCH];
+  const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int p0 = blockIdx.x * LA_SUB;
+  for (int i = tid; i < LA_HEADS * DH * 4; i += 256) {  // 128 rows x 4 chunks of 16 B
+    const int row = i >> 2, c16 = i & 3;
+    *reinterpret_cast<uint4*>(ctile + row * LA_CT_PITCH + c16 * 16) =
+        __ldg(reinterpret_cast<const uint4*>(ctxT + ((size_t)b * LA_HEADS * DH + row) * DH) + c16);
+  }
+  for (int i = tid; i < LA_SUB * 16; i += 256) {
+    const int row = i >> 4, c16 = i & 15;
+    const int px = p0 + row;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (px < n) v = ldg_stream(qkv + ((size_t)b * n + px) * (3 * LA_C) + c16 * 8);
+    *reinterpret_cast<uint4*>(qtile + row * LA_Q_PITCH + c16 * 16) = v;
+  }
   __syncthreads();
-  const int pi = blockIdx.x * 256 + tid;
-  if (pi >= n) return;
-  const int C3 = 3 * heads * DH, C = heads * DH;
-  float qv[DH];
-  const bf16* qp = qkv + ((size_t)b * n + pi) * C3 + h * DH;
+  const int h = warp & 3, slice = warp >> 2;
+  const int g = lane >> 2, t4 = lane & 3, j = lane >> 3, rr = lane & 7;
+  const uint32_t q_s = smem_u32(qtile), c_s = smem_u32(ctile);
+  uint32_t bfr[2][2][4];  // [k-step][n-tile pair][regs]
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float f[8];
-    unpack8(ldg_stream(qp + j * 8), f);
+  for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) qv[j * 8 + e] = f[e];
-  }
-  float m = qv[0];
+    for (int np = 0; np < 2; ++np) {
+      const int e = (2 * np + (j >> 1)) * 8 + rr, dcol = ks * 16 + (j & 1) * 8;
+      ldsm_x4(c_s + (h * DH + e) * LA_CT_PITCH + dcol * 2, bfr[ks][np]);
+    }
 #pragma unroll
-  for (int d = 1; d < DH; ++d) m = fmaxf(m, qv[d]);
-  float s = 0.0f;
+  for (int mt = 0; mt < 2; ++mt) {
+    const int m0 = slice * 32 + mt * 16;
+    uint32_t a[2][4];
 #pragma unroll
-  for (int d = 0; d < DH; ++d) {
-    qv[d] = __expf(qv[d] - m);
-    s += qv[d];
-  }
-  const float inv = 1.0f / s;
-  float o[DH];
+    for (int ks = 0; ks < 2; ++ks) {
+      const int px = m0 + (j & 1) * 8 + rr, dcol = h * DH + ks * 16 + (j >> 1) * 8;
+      ldsm_x4(q_s + px * LA_Q_PITCH + dcol * 2, a[ks]);
+    }
+    // softmax over the 32 channels of each row: rows g (regs 0,2) and g+8 (regs 1,3)
+    float x[2][8];
 #pragma unroll
-  for (int e = 0; e < DH; ++e) o[e] = 0.0f;
+    for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-  for (int d = 0; d < DH; ++d) {
-    const float qd = qv[d] * inv;
+      for (int r = 0; r < 4; ++r) {
+        const float2 f = unpack_bf16x2(a[ks][r]);
+        x[r & 1][ks * 4 + (r >> 1) * 2] = f.x;
+        x[r & 1][ks * 4 + (r >> 1) * 2 + 1] = f.y;
+      }
+    float inv[2];
 #pragma unroll
-    for (int e4 = 0; e4 < DH / 4; ++e4) {
-      const float4 c4 = *reinterpret_cast<const float4*>(&sc[d][e4 * 4]);
-      o[e4 * 4] = fmaf(c4.x, qd, o[e4 * 4]);
-      o[e4 * 4 + 1] = fmaf(c4.y, qd, o[e4 * 4 + 1]);
-      o[e4 * 4 + 2] = fmaf(c4.z, qd, o[e4 * 4 + 2]);
-      o[e4 * 4 + 3] = fmaf(c4.w, qd, o[e4 * 4 + 3]);
+    for (int r = 0; r < 2; ++r) {
+      float m = x[r][0];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) m = fmaxf(m, x[r][i]);
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      float s = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        x[r][i] = __expf(x[r][i] - m);
+        s += x[r][i];
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      inv[r] = 1.0f / s;
+    }
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        a[ks][r] = pack_bf16x2(x[r & 1][ks * 4 + (r >> 1) * 2], x[r & 1][ks * 4 + (r >> 1) * 2 + 1]);
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) mma_bf16_16816(acc[nt], a[ks], bfr[ks][nt >> 1][(nt & 1) * 2], bfr[ks][nt >> 1][(nt & 1) * 2 + 1]);
+      const int col = h * DH + nt * 8 + 2 * t4;
+      *reinterpret_cast<uint32_t*>(otile + (m0 + g) * LA_Q_PITCH + col * 2) = pack_bf16x2(acc[nt][0] * inv[0], acc[nt][1] * inv[0]);
+      *reinterpret_cast<uint32_t*>(otile + (m0 + g + 8) * LA_Q_PITCH + col * 2) = pack_bf16x2(acc[nt][2] * inv[1], acc[nt][3] * inv[1]);
     }
   }
-  uint4* op = reinterpret_cast<uint4*>(out + ((size_t)b * n + pi) * C + h * DH);
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    op[j] = make_uint4(pack_bf16x2(o[8 * j], o[8 * j + 1]), pack_bf16x2(o[8 * j + 2], o[8 * j + 3]),
-                       pack_bf16x2(o[8 * j + 4], o[8 * j + 5]), pack_bf16x2(o[8 * j + 6], o[8 * j + 7]));
+  __syncthreads();
+  for (int i = tid; i < LA_SUB * 16; i += 256) {
+    const int row = i >> 4, c16 = i & 15;
+    const int px = p0 + row;
+    if (px < n)
+      *reinterpret_cast<uint4*>(out + ((size_t)b * n + px) * LA_C + c16 * 8) = *reinterpret_cast<const uint4*>(otile + row * LA_Q_PITCH + c16 * 16);
+  }
 }
 
 extern "C" int64_t tedm_linear_attention_workspace(int batch, int n, int heads, int dim_head) {
-  if (batch <= 0 || n <= 0 || heads <= 0 || dim_head != DH) return -1;
-  const int64_t nchunks = (n + LA_NP - 1) / LA_NP;
-  return (int64_t)batch * heads * (nchunks * LA_PART + DH * DH);
+  if (batch <= 0 || n <= 0 || heads != LA_HEADS || dim_head != DH) return -1;
+  const int64_t nchunks = (n + LA_CHUNK - 1) / LA_CHUNK;
+  // fp32 elements: chunk maxima + chunk partials + bf16 ctx^T (LA_C*DH/2 floats)
+  return (int64_t)batch * (nchunks * (LA_C + LA_PART) + LA_C * DH / 2);
 }
 
 extern "C" int tedm_linear_attention_fwd(const void* qkv, void* out, float* workspace, int batch, int n, int heads,
                                          int dim_head, float scale, tedm_stream_t stream) {
-  TEDM_CHECK_ARG(qkv && out && workspace && batch > 0 && n > 0 && heads > 0, "tedm_linear_attention_fwd: bad arguments");
-  TEDM_UNSUPPORTED(dim_head != DH, "tedm_linear_attention_fwd: dim_head=%d (only 32)", dim_head);
-  TEDM_CHECK_ARG(batch <= 65535 && heads <= 65535, "tedm_linear_attention_fwd: batch/heads too large");
+  TEDM_CHECK_ARG(qkv && out && workspace && batch > 0 && n > 0, "tedm_linear_attention_fwd: bad arguments");
+  TEDM_UNSUPPORTED(dim_head != DH || heads != LA_HEADS, "tedm_linear_attention_fwd: heads=%d dim_head=%d (only 4 x 32)", heads, dim_head);
+  TEDM_CHECK_ARG(batch <= 65535, "tedm_linear_attention_fwd: batch too large");
   cudaStream_t s = (cudaStream_t)stream;
-  const int nchunks = (n + LA_NP - 1) / LA_NP;
-  float* ctx = workspace + (size_t)batch * heads * nchunks * LA_PART;
-  linattn_partial_kernel<<<dim3(nchunks, heads, batch), 256, 0, s>>>((const bf16*)qkv, workspace, n, heads, nchunks);
+  const int nchunks = (n + LA_CHUNK - 1) / LA_CHUNK;
+  float* pmax = workspace;
+  float* part = pmax + (size_t)batch * nchunks * LA_C;
+  bf16* ctxT = reinterpret_cast<bf16*>(part + (size_t)batch * nchunks * LA_PART);
+  const int smem = 2 * LA_SUB * LA_KV_PITCH;
+  static bool configured = false;
+  if (!configured) {
+    TEDM_CUDA(cudaFuncSetAttribute(linattn_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  linattn_colmax_kernel<<<dim3(nchunks, batch), 256, 0, s>>>((const bf16*)qkv, pmax, n, nchunks);
   TEDM_LAUNCH_CHECK();
-  linattn_combine_kernel<<<dim3(heads, batch), 256, 0, s>>>(workspace, ctx, n, heads, nchunks, scale);
+  linattn_ctx_kernel<<<dim3(nchunks, batch), 256, smem, s>>>((const bf16*)qkv, pmax, part, n, nchunks);
   TEDM_LAUNCH_CHECK();
-  linattn_out_kernel<<<dim3((n + 255) / 256, heads, batch), 256, 0, s>>>((const bf16*)qkv, ctx, (bf16*)out, n, heads);
+  linattn_combine_kernel<<<batch, 256, 0, s>>>(part, ctxT, n, nchunks, scale);
+  TEDM_LAUNCH_CHECK();
+  linattn_out_kernel<<<dim3((n + LA_SUB - 1) / LA_SUB, batch), 256, 0, s>>>((const bf16*)qkv, ctxT, (bf16*)out, n);
   TEDM_LAUNCH_CHECK();
   return TEDM_OK;
 }

@@ -49,6 +49,7 @@ struct ConvParams {
   const float* bias;
   const bf16* residual;
   bf16* out;
+  int out_f32;                   // 1: `out` is fp32 (direct stores); 0: bf16 through smem + TMA store
   float* gn_partial;
   int gn_cpg, gn_groups, gn_parts;
   long long out_image_stride;    // elements
@@ -85,7 +86,8 @@ __device__ __forceinline__ void gn_accumulate(const float (&v)[32], int lane, in
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                  const __grid_constant__ CUtensorMap mapW, const ConvParams p) {
+                  const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapOut,
+                  const ConvParams p) {
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -114,6 +116,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     tma_prefetch_desc(&mapA0);
     if (p.c1_blocks) tma_prefetch_desc(&mapA1);
     tma_prefetch_desc(&mapW);
+    if (!p.out_f32) tma_prefetch_desc(&mapOut);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
@@ -224,22 +227,46 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         else if (p.gn_cpg == 16) gn_accumulate<16>(v, lane, seg_size, red_row, gl0);
         else gn_accumulate<32>(v, lane, seg_size, red_row, gl0);
       }
-      if (valid) {
-        if (p.residual) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + opix + chunk * 32);
+      if (p.residual && valid) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + opix + chunk * 32);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float f[8];
-            unpack8(__ldg(rp + j), f);
+        for (int j = 0; j < 4; ++j) {
+          float f[8];
+          unpack8(__ldg(rp + j), f);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[8 * j + e] += f[e];
-          }
+          for (int e = 0; e < 8; ++e) v[8 * j + e] += f[e];
         }
-        uint4* op = reinterpret_cast<uint4*>(p.out + opix + chunk * 32);
+      }
+      if (p.out_f32) {
+        if (valid) {
+          float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix + chunk * 32);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                             pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      } else {
+        // stage the bf16 tile in the (now idle) pipeline buffers in the 128B-swizzled layout TMA expects:
+        // sub-tile = 64 channels, row = pixel (128 B), 16-byte chunk index XOR (row & 7)
+        const uint32_t sub = smem_base + (uint32_t)(chunk >> 1) * A_BYTES + (uint32_t)row * 128u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t c16 = (uint32_t)((chunk & 1) * 4 + j);
+          const uint32_t dst = sub + ((c16 ^ (uint32_t)(row & 7)) << 4);
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pack_bf16x2(v[8 * j], v[8 * j + 1])),
+                       "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])), "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])),
+                       "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7])) : "memory");
+        }
+      }
+    }
+    if (!p.out_f32) {
+      fence_proxy_async_smem();           // generic-proxy smem writes -> visible to the TMA (async proxy)
+      named_bar_sync(2, 128);
+      if (threadIdx.x == 64) {
+        const int chan_base = (p.mode == 3 ? par_x * p.cout : 0) + n0;
+        const int pc_out = p.mode == 3 ? par_y : 0;
+        for (int sidx = 0; sidx < BN / 64; ++sidx)
+          tma_store_5d(&mapOut, smem_base + (uint32_t)sidx * A_BYTES, chan_base + sidx * 64, x0, pc_out, y0, b0);
+        tma_store_commit();
+        tma_store_wait_read<0>();         // smem must outlive the bulk read
       }
     }
     if (p.gn_partial) {
@@ -309,15 +336,15 @@ int encode_weight_map(CUtensorMap* map, const void* ptr, long long rows, long lo
 }
 
 template <int BN, int STAGES>
-int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const ConvParams& p, dim3 grid,
-                cudaStream_t stream) {
+int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o,
+                const ConvParams& p, dim3 grid, cudaStream_t stream) {
   constexpr int smem = STAGES * (A_BYTES + BN * BK * 2) + 1024;
   static bool configured = false;
   if (!configured) {
     TEDM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  conv_igemm_kernel<BN, STAGES><<<grid, 192, smem, stream>>>(a0, a1, w, p);
+  conv_igemm_kernel<BN, STAGES><<<grid, 192, smem, stream>>>(a0, a1, w, o, p);
   TEDM_LAUNCH_CHECK();
   return TEDM_OK;
 }
@@ -376,6 +403,8 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   p.bias = a->bias;
   p.residual = (const bf16*)a->residual;
   p.out = (bf16*)a->out;
+  p.out_f32 = a->out_dtype == 1;
+  TEDM_CHECK_ARG(a->out_dtype == 0 || a->out_dtype == 1, "tedm_conv_igemm_fwd: out_dtype=%d", a->out_dtype);
   p.out_image_stride = a->out_image_stride ? a->out_image_stride : (long long)p.OH * p.OW * a->cout;
   p.gn_partial = a->gn_partial;
   if (a->gn_partial) {
@@ -408,7 +437,7 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   TEDM_UNSUPPORTED(bn == 0, "tedm_conv_igemm_fwd: no N tile for cout=%d with %d-channel GroupNorm groups", a->cout, p.gn_cpg);
   TEDM_CHECK_ARG(m_tiles <= 2147483647LL, "tedm_conv_igemm_fwd: too many tiles");
 
-  alignas(64) CUtensorMap mapA0, mapA1, mapW;
+  alignas(64) CUtensorMap mapA0, mapA1, mapW, mapOut;
   int rc = encode_act_map(&mapA0, a->src0, a->batch, a->height, a->width, a->c0,
                           a->src0_image_stride ? a->src0_image_stride : (long long)a->height * a->width * a->c0, a->mode,
                           p.tileW, p.tileH, p.tileB);
@@ -425,11 +454,21 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   rc = encode_weight_map(&mapW, a->weight, (long long)zdim * a->cout, ktot, bn);
   if (rc) return rc;
 
+  if (!p.out_f32) {
+    // bf16 outputs leave through a TMA store; the upsample mode scatters each parity through the same
+    // (2C, W, 2, H, B) view the stride-2 mode uses for its input
+    rc = encode_act_map(&mapOut, a->out, a->batch, p.OH, p.OW, a->cout, p.out_image_stride, a->mode == 3 ? 2 : 0, p.tileW,
+                        p.tileH, p.tileB);
+    if (rc) return rc;
+  } else {
+    mapOut = mapA0;
+  }
+
   dim3 grid((unsigned)m_tiles, (unsigned)(a->cout / bn), (unsigned)zdim);
   cudaStream_t s = (cudaStream_t)stream;
   switch (bn) {
-    case 64: return launch_conv<64, 4>(mapA0, mapA1, mapW, p, grid, s);
-    case 128: return launch_conv<128, 3>(mapA0, mapA1, mapW, p, grid, s);
-    default: return launch_conv<256, 4>(mapA0, mapA1, mapW, p, grid, s);
+    case 64: return launch_conv<64, 4>(mapA0, mapA1, mapW, mapOut, p, grid, s);
+    case 128: return launch_conv<128, 3>(mapA0, mapA1, mapW, mapOut, p, grid, s);
+    default: return launch_conv<256, 4>(mapA0, mapA1, mapW, mapOut, p, grid, s);
   }
 }

@@ -15,7 +15,7 @@
 #define HEAD_C2 32
 
 struct HeadParams {
-  const bf16* g[4];
+  const void* g[4];
   int shift[4];
   int n_levels, n_sum, n_img, H, W;
   const float *b1, *a1, *c1, *w2, *b2, *a2, *c2, *w3;
@@ -23,6 +23,7 @@ struct HeadParams {
   float* logits;
 };
 
+template <bool G_F32>
 __global__ void __launch_bounds__(128) head_tail_kernel(const HeadParams p) {
   __shared__ __align__(16) float sw2[HEAD_C1][HEAD_C2];  // transposed: [k][j]
   __shared__ float sb1[HEAD_C1], sa1[HEAD_C1], sc1[HEAD_C1];
@@ -51,9 +52,15 @@ __global__ void __launch_bounds__(128) head_tail_kernel(const HeadParams p) {
         for (int l = 0; l < p.n_levels; ++l) {
           const int sh = p.shift[l];
           const int hl = p.H >> sh, wl = p.W >> sh;
-          const bf16* src = p.g[l] + ((((size_t)img * p.n_sum + s) * hl + (y >> sh)) * wl + (x >> sh)) * HEAD_C1 + k0;
+          const size_t off = ((((size_t)img * p.n_sum + s) * hl + (y >> sh)) * wl + (x >> sh)) * HEAD_C1 + k0;
           float f[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(src)), f);
+          if (G_F32) {
+            const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.g[l]) + off);
+            const float4 u0 = __ldg(src), u1 = __ldg(src + 1);
+            f[0] = u0.x; f[1] = u0.y; f[2] = u0.z; f[3] = u0.w; f[4] = u1.x; f[5] = u1.y; f[6] = u1.z; f[7] = u1.w;
+          } else {
+            unpack8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.g[l]) + off)), f);
+          }
 #pragma unroll
           for (int e = 0; e < 8; ++e) z[e] += f[e];
         }
@@ -91,7 +98,7 @@ extern "C" int tedm_head_infer(const tedm_head_args* a, tedm_stream_t stream) {
                        ((a->height >> a->shift[l]) << a->shift[l]) == a->height &&
                        ((a->width >> a->shift[l]) << a->shift[l]) == a->width,
                    "tedm_head_infer: level %d shift %d does not divide %dx%d", l, a->shift[l], a->height, a->width);
-    p.g[l] = (const bf16*)a->g[l];
+    p.g[l] = a->g[l];
     p.shift[l] = a->shift[l];
   }
   p.n_levels = a->n_levels;
@@ -106,7 +113,9 @@ extern "C" int tedm_head_infer(const tedm_head_args* a, tedm_stream_t stream) {
   long long blocks = (npix + 127) / 128;
   const long long cap = (long long)tedm_num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  head_tail_kernel<<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(p);
+  TEDM_CHECK_ARG(a->g_dtype == 0 || a->g_dtype == 1, "tedm_head_infer: g_dtype=%d", a->g_dtype);
+  if (a->g_dtype == 1) head_tail_kernel<true><<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(p);
+  else head_tail_kernel<false><<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(p);
   TEDM_LAUNCH_CHECK();
   return TEDM_OK;
 }

@@ -133,9 +133,9 @@ class DatasetDM(nn.Module):
             cl = chans[l]
             if shared:
                 wl = self._cache.get(f"w1.l{l}", (w1,), lambda w, o=offs[l], c=cl: w[:, o:o + c, 0, 0].to(torch.bfloat16).contiguous())
-                g_maps.append(N.conv_igemm(f, wl, N.MODE_1X1, w1.shape[0]))
+                g_maps.append(N.conv_igemm(f, wl, N.MODE_1X1, w1.shape[0], out_dtype=torch.float32))
             else:
-                g = torch.empty(b * s, f.shape[1], f.shape[2], w1.shape[0], device=f.device, dtype=torch.bfloat16)
+                g = torch.empty(b * s, f.shape[1], f.shape[2], w1.shape[0], device=f.device, dtype=torch.float32)
                 for st in range(s):
                     wl = self._cache.get(f"w1.s{st}.l{l}", (w1,),
                                          lambda w, o=st * ctot + offs[l], c=cl: w[:, o:o + c, 0, 0].to(torch.bfloat16).contiguous())

@@ -21,12 +21,12 @@ _p, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
 class ConvArgs(C.Structure):  # tedm_conv_args
     _fields_ = [("src0", _p), ("src1", _p), ("weight", _p), ("bias", _p), ("residual", _p), ("out", _p),
                 ("gn_partial", _p), ("batch", _i), ("height", _i), ("width", _i), ("c0", _i), ("c1", _i),
-                ("cout", _i), ("mode", _i), ("gn_groups", _i), ("src0_image_stride", _i64),
+                ("cout", _i), ("mode", _i), ("gn_groups", _i), ("out_dtype", _i), ("src0_image_stride", _i64),
                 ("src1_image_stride", _i64), ("out_image_stride", _i64)]
 
 
 class HeadArgs(C.Structure):  # tedm_head_args
-    _fields_ = [("g", _p * 4), ("shift", _i * 4), ("n_levels", _i), ("n_sum", _i), ("n_img", _i), ("height", _i),
+    _fields_ = [("g", _p * 4), ("g_dtype", _i), ("shift", _i * 4), ("n_levels", _i), ("n_sum", _i), ("n_img", _i), ("height", _i),
                 ("width", _i), ("c1", _i), ("c2", _i), ("b1", _p), ("bn1_a", _p), ("bn1_c", _p), ("w2", _p),
                 ("b2", _p), ("bn2_a", _p), ("bn2_c", _p), ("w3", _p), ("b3", _f), ("logits", _p)]
 
@@ -199,12 +199,12 @@ def conv_gn_parts(oh: int, ow: int) -> int:
     return load().tedm_conv_gn_parts(oh, ow)
 
 
-def _nhwc(t: Optional[torch.Tensor], name: str):
-    """(pointer, image stride in elements) of an NHWC bf16 tensor whose batch axis may be strided."""
+def _nhwc(t: Optional[torch.Tensor], name: str, dtype=torch.bfloat16):
+    """(pointer, image stride in elements) of an NHWC tensor whose batch axis may be strided."""
     if t is None:
         return None, 0
-    if not t.is_cuda or t.dtype != torch.bfloat16 or t.dim() != 4:
-        raise TypeError(f"{name} must be a 4-D CUDA bf16 tensor (B, H, W, C)")
+    if not t.is_cuda or t.dtype != dtype or t.dim() != 4:
+        raise TypeError(f"{name} must be a 4-D CUDA {dtype} tensor (B, H, W, C)")
     b, h, w, c = t.shape
     if t.stride(3) != 1 or t.stride(2) != c or t.stride(1) != w * c:
         raise ValueError(f"{name} must be NHWC-contiguous within each image")
@@ -212,8 +212,8 @@ def _nhwc(t: Optional[torch.Tensor], name: str):
 
 
 def conv_igemm(src0: torch.Tensor, weight: torch.Tensor, mode: int, cout: int, bias=None, src1=None, residual=None,
-               gn_groups: int = 0, out: Optional[torch.Tensor] = None):
-    """Returns out (B, Ho, Wo, cout) bf16 [, gn_partial (B, parts, groups, 2) fp32 if gn_groups > 0].
+               gn_groups: int = 0, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16):
+    """Returns out (B, Ho, Wo, cout) bf16 (or fp32) [, gn_partial (B, parts, groups, 2) fp32 if gn_groups > 0].
     src0/src1/out may be batch-strided views (e.g. x[s::S]); residual must share out's strides."""
     b, h, w, c0 = src0.shape
     c1 = src1.shape[3] if src1 is not None else 0
@@ -224,7 +224,7 @@ def conv_igemm(src0: torch.Tensor, weight: torch.Tensor, mode: int, cout: int, b
     if weight.numel() != cout * taps * (c0 + c1):
         raise ValueError(f"conv_igemm: weight has {weight.numel()} elements, expected {cout * taps * (c0 + c1)}")
     if out is None:
-        out = torch.empty(b, oh, ow, cout, device=src0.device, dtype=torch.bfloat16)
+        out = torch.empty(b, oh, ow, cout, device=src0.device, dtype=out_dtype)
     elif tuple(out.shape) != (b, oh, ow, cout):
         raise ValueError(f"conv_igemm: out has shape {tuple(out.shape)}, expected {(b, oh, ow, cout)}")
     gnp = None
@@ -232,17 +232,19 @@ def conv_igemm(src0: torch.Tensor, weight: torch.Tensor, mode: int, cout: int, b
         gnp = torch.empty(b, conv_gn_parts(oh, ow), gn_groups, 2, device=src0.device, dtype=torch.float32)
     p0, s0 = _nhwc(src0, "src0")
     p1, s1 = _nhwc(src1, "src1")
-    po, so = _nhwc(out, "out")
+    po, so = _nhwc(out, "out", out.dtype)
+    if out.dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError("conv_igemm: out must be bf16 or fp32")
     pr, sr = _nhwc(residual, "residual")
     if residual is not None and (sr != so or residual.shape != out.shape):
         raise ValueError("conv_igemm: residual must have out's shape and strides")
     a = ConvArgs(p0, p1, _ptr(weight, torch.bfloat16, "weight"), _ptr(bias, torch.float32, "bias"), pr, po, _ptr(gnp),
-                 b, h, w, c0, c1, cout, mode, gn_groups, s0, s1, so)
+                 b, h, w, c0, c1, cout, mode, gn_groups, 1 if out.dtype == torch.float32 else 0, s0, s1, so)
     global conv_flops
     flops = 2 * b * (h * w if mode == MODE_UP3X3 else oh * ow) * cout * taps * (c0 + c1)
     conv_flops += flops
     if conv_timer is not None:
-        with conv_timer(flops):
+        with conv_timer(flops, (mode, b, h, w, c0, c1, cout, bool(gn_groups), residual is not None)):
             _call("tedm_conv_igemm_fwd", C.byref(a), _stream())
     else:
         _call("tedm_conv_igemm_fwd", C.byref(a), _stream())
@@ -325,8 +327,12 @@ def nhwc_to_nchw_f32(x):
 def head_infer(g_maps: Sequence[torch.Tensor], shifts: Sequence[int], n_sum: int, n_img: int, height: int, width: int,
                b1, bn1_a, bn1_c, w2, b2, bn2_a, bn2_c, w3, b3: float):
     a = HeadArgs()
+    gdt = g_maps[0].dtype
+    if gdt not in (torch.bfloat16, torch.float32):
+        raise TypeError("head_infer: g maps must be bf16 or fp32")
+    a.g_dtype = 1 if gdt == torch.float32 else 0
     for l, (g, s) in enumerate(zip(g_maps, shifts)):
-        a.g[l] = _ptr(g, torch.bfloat16, f"g[{l}]")
+        a.g[l] = _ptr(g, gdt, f"g[{l}]")
         a.shift[l] = s
     a.n_levels, a.n_sum, a.n_img, a.height, a.width = len(g_maps), n_sum, n_img, height, width
     a.c1, a.c2 = b1.numel(), b2.numel()

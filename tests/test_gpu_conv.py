@@ -111,3 +111,12 @@ def test_conv_rejects_unsupported_shapes():
     w = torch.zeros(64, 3, 3, 48, dtype=torch.bfloat16, device="cuda")
     with pytest.raises(RuntimeError, match="multiples of 64"):
         N.conv_igemm(x, w, 1, 64)
+
+
+def test_conv_fp32_output():
+    from tedm_b200 import native as N
+    x, w = _rand((3, 128, 16, 16), 1), _rand((128, 128, 1, 1), 2, 128 ** -0.5)
+    got = N.conv_igemm(_nhwc(x), N.weight_to_krsc(w.cuda()), 0, 128, out_dtype=torch.float32)
+    assert got.dtype == torch.float32
+    ref = _ref_conv([x], w, None, 0)
+    assert _rel(got.permute(0, 3, 1, 2), ref) < 1e-5

@@ -111,7 +111,13 @@ def test_tedm_trained_head_masks(golden, tag):
     agree = (mask.cpu().numpy() == g["tedm_mask"]).mean()
     print(f"tedm {tag} (trained head): logits rel {lr:.4g}, prob rel {_rel(prob, g['tedm_prob']):.4g}, mask agreement {agree:.5f}")
     assert lr < TOL
-    assert agree >= 0.999
+    if tag == "full":
+        assert agree >= 0.999                      # the north-star criterion, at the BASELINE image size
+    else:
+        # 2 x 32 x 32 = 2048 pixels: 0.1 % is two pixels, too coarse a grid for the percentage criterion;
+        # require >= 99.8 % and that every disagreement sits inside the rounding band around prob = 0.5
+        assert agree >= 0.998
+        _masks_agree_outside_threshold_band(mask, g, band=2e-2)
 
 
 class FixedNoise:
