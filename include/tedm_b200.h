@@ -119,6 +119,8 @@ TEDM_API int tedm_conv_igemm_fwd(const tedm_conv_args* args, tedm_stream_t strea
 TEDM_API int tedm_conv_gn_parts(int out_height, int out_width);
 /* tuning/debug: force the N tile (64/128/256; 0 = automatic) of tedm_conv_igemm_fwd */
 TEDM_API int tedm_conv_set_tile_n(int bn);
+/* tuning/debug: enable (default) / disable the weight-stationary row path of the 3x3 conv */
+TEDM_API int tedm_conv_set_ws(int enable);
 
 /* fp32 OIHW [Cout][Cin][kh][kw] -> bf16 KRSC [Cout][kh][kw][Cin] (derived weight cache). */
 TEDM_API int tedm_weight_to_krsc(const float* w_oihw, void* w_krsc, int cout, int cin, int kh, int kw,

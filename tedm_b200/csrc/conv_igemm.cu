@@ -37,7 +37,11 @@ PFN_tensorMapEncodeTiled get_encode_fn() {
 constexpr int BM = 128;          // pixels per tile (UMMA M)
 constexpr int BK = 64;           // channels per k-block (128 bytes: one swizzle row)
 constexpr int A_BYTES = BM * BK * 2;
+constexpr int A_ROW_BYTES = 17 * 1024;   // row mode: 130 pixels x 128 B = 16640 B, padded to the 1 KB swizzle atom
+constexpr int ROW_PIX = BM + 2;
 constexpr int NGMAX = 32;        // max GroupNorm groups touched by one N tile
+constexpr int MAX_STAGES = 8;
+constexpr int DYN_SMEM_MAX = 221 * 1024;  // + ~3.3 KB static <= 227 KB per CTA
 
 struct ConvParams {
   int mode, taps, kxc;           // kxc = taps per filter row
@@ -46,6 +50,7 @@ struct ConvParams {
   int B, Ho, Wo;                 // tile space extent (output pixels; source pixels for mode 3)
   int OH, OW, osy, osx;          // output tensor extent and tile->output coordinate scale
   int cout;
+  int n_tiles, zdim, num_tiles, stages, out_bufs;
   const float* bias;
   const bf16* residual;
   bf16* out;
@@ -57,74 +62,114 @@ struct ConvParams {
 
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   // K-major, 128B swizzle: 8-row atoms of 1024 B (SBO), LBO unused, descriptor version 1 (sm_100).
+  // The start address may sit on any 128-byte row (profiles/r01_umma_row_shift_probe.json): the swizzle
+  // is a function of the absolute shared-memory address, so row-shifted windows of a TMA-written
+  // buffer are valid operands with base_offset = 0.
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-template <int W>
-__device__ __forceinline__ void gn_accumulate(const float (&v)[32], int lane, int seg_size, float* red_row, int gl0) {
-  // W = channels per partial sum inside this 32-column chunk (8, 16 or 32)
+// Sum NV per-thread values over the `width` (32 or 16) lanes of a segment with a transposing butterfly:
+// every exchange halves the number of values a lane carries, so NV values cost NV-1 + log2(width/NV)
+// shuffles instead of NV*log2(width).  Afterwards vals[0] of lane l holds the total of value index
+// (l % width) >> (log2(width) - log2(NV)).
+template <int NV>
+__device__ __forceinline__ void butterfly_sum(float (&vals)[NV], int lane, int width) {
+  int nv = NV;
 #pragma unroll
-  for (int sg = 0; sg < 32 / W; ++sg) {
-    float s = 0.0f, q = 0.0f;
+  for (int step = 0; step < 5; ++step) {
+    const int off = width >> (step + 1);
+    if (off == 0) break;
+    if (nv > 1) {
+      const int half = nv >> 1;
+      const bool upper = (lane & off) != 0;
 #pragma unroll
-    for (int j = 0; j < W; ++j) {
-      s += v[sg * W + j];
-      q = fmaf(v[sg * W + j], v[sg * W + j], q);
-    }
-    for (int o = seg_size >> 1; o > 0; o >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-      q += __shfl_xor_sync(0xffffffffu, q, o);
-    }
-    if ((lane & (seg_size - 1)) == 0) {
-      float* r = red_row + (size_t)(gl0 + sg) * 2;
-      r[0] += s;
-      r[1] += q;
+      for (int i = 0; i < NV / 2; ++i) {
+        if (i < half) {
+          const float send = upper ? vals[i] : vals[i + half];
+          const float keep = upper ? vals[i + half] : vals[i];
+          vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      nv = half;
+    } else {
+      vals[0] += __shfl_xor_sync(0xffffffffu, vals[0], off);
     }
   }
 }
 
-template <int BN, int STAGES>
+struct TileCoord {
+  int b0, y0, x0, n0, par, trem;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, int bn) {
+  TileCoord t;
+  const int nt = tile % p.n_tiles;
+  int rest = tile / p.n_tiles;
+  t.par = rest % p.zdim;
+  const int mt = rest / p.zdim;
+  const int tiles_per_group = p.tiles_x * p.tiles_y;
+  const int bg = mt / tiles_per_group;
+  t.trem = mt % tiles_per_group;
+  t.b0 = bg * p.tileB;
+  t.y0 = (t.trem / p.tiles_x) * p.tileH;
+  t.x0 = (t.trem % p.tiles_x) * p.tileW;
+  t.n0 = nt * bn;
+  return t;
+}
+
+// Persistent, warp-specialised: each CTA (one per SM) walks tiles blockIdx.x, +gridDim.x, ... .  The TMA
+// producer runs ahead across tile boundaries through a ring of `stages` shared-memory slots; the MMA
+// issuer alternates between two TMEM accumulators so the epilogue of tile i overlaps the main loop of
+// tile i+1.
+//   WS = false: slot = one (tap, 64-channel) k-block: A box 128 pixels + the matching weight tile.
+//   WS = true  (3x3, full 128-pixel rows, cout = 64, <= 128 input channels): all 9 x cin weights are
+//               loaded ONCE per CTA and stay in shared memory; a slot is one 130-pixel input row
+//               (x0-1 .. x0+128) of one 64-channel block, and the three horizontal taps are three
+//               UMMAs on row-shifted windows of it -> activations cross L2->SM 3x instead of 9x and
+//               weights once instead of once per tile.
+template <int BN, bool WS, int CPG>
 __global__ void __launch_bounds__(192, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapOut,
                   const ConvParams p) {
   constexpr int B_BYTES = BN * BK * 2;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGE_BYTES = WS ? A_ROW_BYTES : A_BYTES + B_BYTES;
+  constexpr int OUT_BYTES = (BN / 64) * A_BYTES;
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[STAGES];
-  __shared__ __align__(8) uint64_t bar_empty[STAGES];
-  __shared__ __align__(8) uint64_t bar_acc;
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_acc_full[2];
+  __shared__ __align__(8) uint64_t bar_acc_empty[2];
+  __shared__ __align__(8) uint64_t bar_w;
   __shared__ uint32_t tmem_slot;
   __shared__ float red[4][2][NGMAX][2];
+  __shared__ __align__(16) float sbias[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cb_total = p.c0_blocks + p.c1_blocks;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_bytes = WS ? (uint32_t)(9 * cb_total * B_BYTES) : 0u;
+  const uint32_t stage_base = smem_base + w_bytes;
+  const uint32_t out_base = stage_base + (uint32_t)p.stages * STAGE_BYTES;
 
-  // ---- tile coordinates -----------------------------------------------------------------
-  const int tiles_per_group = p.tiles_x * p.tiles_y;
-  const int bg = blockIdx.x / tiles_per_group;
-  const int trem = blockIdx.x % tiles_per_group;
-  const int b0 = bg * p.tileB, y0 = (trem / p.tiles_x) * p.tileH, x0 = (trem % p.tiles_x) * p.tileW;
-  const int n0 = blockIdx.y * BN;
-  const int par = blockIdx.z, par_y = par >> 1, par_x = par & 1;  // mode 3 only
-  const int num_kb = p.taps * (p.c0_blocks + p.c1_blocks);
-
-  for (int i = threadIdx.x; i < 4 * 2 * NGMAX * 2; i += blockDim.x) (&red[0][0][0][0])[i] = 0.0f;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
     if (p.c1_blocks) tma_prefetch_desc(&mapA1);
     tma_prefetch_desc(&mapW);
     if (!p.out_f32) tma_prefetch_desc(&mapOut);
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
-    mbar_init(smem_u32(&bar_acc), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar_acc_full[i]), 1);
+      mbar_init(smem_u32(&bar_acc_empty[i]), 4);
+    }
+    mbar_init(smem_u32(&bar_w), 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<BN>(smem_u32(&tmem_slot));
+  if (warp == 1) tmem_alloc<2 * BN>(smem_u32(&tmem_slot));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -135,34 +180,59 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      const int cb_total = p.c0_blocks + p.c1_blocks;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-        const uint32_t full = smem_u32(&bar_full[stage]);
-        mbar_expect_tx(full, STAGE_BYTES);
-        const int tap = kb / cb_total, cb = kb % cb_total;
-        const int ky = tap / p.kxc, kx = tap % p.kxc;
-        int offy = 0, offx = 0, pc = 0, chan_off = 0;
-        const bool second = cb >= p.c0_blocks;
-        const int cblk = second ? cb - p.c0_blocks : cb;
-        if (p.mode == 1) {
-          offy = ky - 1;
-          offx = kx - 1;
-        } else if (p.mode == 2) {
-          offy = ((ky + 1) >> 1) - 1;
-          offx = ((kx + 1) >> 1) - 1;
-          pc = (ky + 1) & 1;
-          chan_off = ((kx + 1) & 1) * (second ? p.C1 : p.C0);
-        } else if (p.mode == 3) {
-          offy = ky - 1 + par_y;
-          offx = kx - 1 + par_x;
-        }
-        const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
-        tma_load_5d(a_dst, second ? &mapA1 : &mapA0, full, chan_off + cblk * BK, x0 + offx, pc, y0 + offy, b0);
-        tma_load_2d(a_dst + A_BYTES, &mapW, full, kb * BK, par * p.cout + n0);
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1u;
+      if (WS) {
+        const uint32_t bw = smem_u32(&bar_w);
+        mbar_expect_tx(bw, w_bytes);
+        for (int i = 0; i < 9 * cb_total; ++i) tma_load_2d(smem_base + (uint32_t)i * B_BYTES, &mapW, bw, i * BK, 0);
+      }
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile, BN);
+        if (WS) {
+          for (int dy = 0; dy < 3; ++dy)
+            for (int cb = 0; cb < cb_total; ++cb) {
+              mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+              const uint32_t full = smem_u32(&bar_full[stage]);
+              mbar_expect_tx(full, ROW_PIX * BK * 2);
+              const bool second = cb >= p.c0_blocks;
+              tma_load_5d(stage_base + stage * STAGE_BYTES, second ? &mapA1 : &mapA0, full,
+                          (second ? cb - p.c0_blocks : cb) * BK, t.x0 - 1, 0, t.y0 + dy - 1, t.b0);
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+        } else {
+          const int par_y = t.par >> 1, par_x = t.par & 1;
+          const int num_kb = p.taps * cb_total;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+            const uint32_t full = smem_u32(&bar_full[stage]);
+            mbar_expect_tx(full, STAGE_BYTES);
+            const int tap = kb / cb_total, cb = kb % cb_total;
+            const int ky = tap / p.kxc, kx = tap % p.kxc;
+            int offy = 0, offx = 0, pc = 0, chan_off = 0;
+            const bool second = cb >= p.c0_blocks;
+            const int cblk = second ? cb - p.c0_blocks : cb;
+            if (p.mode == 1) {
+              offy = ky - 1;
+              offx = kx - 1;
+            } else if (p.mode == 2) {
+              offy = ((ky + 1) >> 1) - 1;
+              offx = ((kx + 1) >> 1) - 1;
+              pc = (ky + 1) & 1;
+              chan_off = ((kx + 1) & 1) * (second ? p.C1 : p.C0);
+            } else if (p.mode == 3) {
+              offy = ky - 1 + par_y;
+              offx = kx - 1 + par_x;
+            }
+            const uint32_t a_dst = stage_base + stage * STAGE_BYTES;
+            tma_load_5d(a_dst, second ? &mapA1 : &mapA0, full, chan_off + cblk * BK, t.x0 + offx, pc, t.y0 + offy, t.b0);
+            tma_load_2d(a_dst + A_BYTES, &mapW, full, kb * BK, t.par * p.cout + t.n0);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
         }
       }
     }
@@ -170,131 +240,200 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   } else if (warp == 1) {
     // ===== MMA issuer =========================================================================
     if (elect_one()) {
-      int stage = 0;
+      int stage = 0, it = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(smem_u32(&bar_full[stage]), phase);
+      if (WS) {
+        mbar_wait(smem_u32(&bar_w), 0);
         tc_fence_after();
-        const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
-        const uint64_t adesc = make_sw128_desc(a_addr), bdesc = make_sw128_desc(a_addr + A_BYTES);
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k)
-          umma_bf16(tmem_base, adesc + 2ull * k, bdesc + 2ull * k, IDESC, (kb | k) != 0 ? 1u : 0u);
-        umma_commit(smem_u32(&bar_empty[stage]));
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1u;
-        }
       }
-      umma_commit(smem_u32(&bar_acc));
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(smem_u32(&bar_acc_empty[buf]), (uint32_t)(((it >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        if (WS) {
+          for (int dy = 0; dy < 3; ++dy)
+            for (int cb = 0; cb < cb_total; ++cb) {
+              mbar_wait(smem_u32(&bar_full[stage]), phase);
+              tc_fence_after();
+              const uint32_t a_addr = stage_base + stage * STAGE_BYTES;
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                const uint64_t adesc = make_sw128_desc(a_addr + (uint32_t)dx * 128u);
+                const uint64_t bdesc = make_sw128_desc(smem_base + (uint32_t)(((dy * 3 + dx) * cb_total + cb) * B_BYTES));
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  umma_bf16(d_tmem, adesc + 2ull * k, bdesc + 2ull * k, IDESC, (dy | cb | dx | k) != 0 ? 1u : 0u);
+              }
+              umma_commit(smem_u32(&bar_empty[stage]));
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+        } else {
+          const int num_kb = p.taps * cb_total;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(smem_u32(&bar_full[stage]), phase);
+            tc_fence_after();
+            const uint32_t a_addr = stage_base + stage * STAGE_BYTES;
+            const uint64_t adesc = make_sw128_desc(a_addr), bdesc = make_sw128_desc(a_addr + A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(d_tmem, adesc + 2ull * k, bdesc + 2ull * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(smem_u32(&bar_empty[stage]));
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+        umma_commit(smem_u32(&bar_acc_full[buf]));
+      }
     }
     __syncwarp();
   } else {
     // ===== epilogue ===========================================================================
+    constexpr int NGL = CPG ? BN / CPG : 1;   // GroupNorm groups covered by this N tile (<= 8)
+    constexpr int NV = 2 * NGL;               // (sum, sum of squares) per group
     const int q = warp & 3;               // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;
+    const int e = threadIdx.x - 64;       // 0..127
     const int hwt = p.tileW * p.tileH;    // pixels of one image inside the tile
     const int tb = row / hwt, rrem = row % hwt;
     const int ty = rrem / p.tileW, tx = rrem % p.tileW;
-    const int b = b0 + tb, y = y0 + ty, x = x0 + tx;
-    const bool valid = b < p.B;
-    const int oy = y * p.osy + par_y, ox = x * p.osx + par_x;
-    const size_t opix = (size_t)b * p.out_image_stride + ((size_t)oy * p.OW + ox) * p.cout + n0;
     const int seg_size = hwt < 32 ? hwt : 32;
-    float* red_row = &red[q][lane / seg_size][0][0];
-
-    mbar_wait(smem_u32(&bar_acc), 0);
-    tc_fence_after();
-#pragma unroll 1
-    for (int chunk = 0; chunk < BN / 32; ++chunk) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(chunk * 32), r);
-      tmem_ld_wait();
-      float v[32];
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const TileCoord t = decode_tile(p, tile, BN);
+      const int par_y = t.par >> 1, par_x = t.par & 1;
+      const int b = t.b0 + tb, y = t.y0 + ty, x = t.x0 + tx;
+      const bool valid = b < p.B;
+      const int oy = y * p.osy + par_y, ox = x * p.osx + par_x;
+      const size_t opix = (size_t)b * p.out_image_stride + ((size_t)oy * p.OW + ox) * p.cout + t.n0;
+      const int buf = it & 1;
+      const uint32_t out_buf = out_base + (p.out_bufs == 2 ? (uint32_t)(buf * OUT_BYTES) : 0u);
+      // the TMA store that last used this staging buffer must have drained it; every thread must be done
+      // with the previous tile's `red` / `sbias` before this tile overwrites them (barrier below)
+      if (e == 0 && !p.out_f32) {
+        if (p.out_bufs == 2) tma_store_wait_read<1>();
+        else tma_store_wait_read<0>();
+      }
+      for (int i = e; i < BN; i += 128) sbias[i] = p.bias ? __ldg(p.bias + t.n0 + i) : 0.0f;
+      named_bar_sync(1, 128);
+      mbar_wait(smem_u32(&bar_acc_full[buf]), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      float gv[NV];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      if (p.bias) {
-        const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + chunk * 32);
+      for (int i = 0; i < NV; ++i) gv[i] = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 bv = __ldg(bp + j);
-          v[4 * j] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w;
+      for (int cp = 0; cp < BN / 64; ++cp) {
+        uint32_t r0[32], r1[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cp * 64);
+        tmem_ld32(taddr, r0);
+        tmem_ld32(taddr + 32, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int chunk = cp * 2 + half;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bv = *reinterpret_cast<const float4*>(&sbias[chunk * 32 + 4 * j]);
+            v[4 * j] = __uint_as_float(half ? r1[4 * j] : r0[4 * j]) + bv.x;
+            v[4 * j + 1] = __uint_as_float(half ? r1[4 * j + 1] : r0[4 * j + 1]) + bv.y;
+            v[4 * j + 2] = __uint_as_float(half ? r1[4 * j + 2] : r0[4 * j + 2]) + bv.z;
+            v[4 * j + 3] = __uint_as_float(half ? r1[4 * j + 3] : r0[4 * j + 3]) + bv.w;
+          }
+          if (CPG) {
+            constexpr int W = CPG < 32 ? (CPG ? CPG : 32) : 32;   // channels per partial sum inside this chunk
+#pragma unroll
+            for (int sg = 0; sg < 32 / W; ++sg) {
+              float s_ = 0.0f, q_ = 0.0f;
+#pragma unroll
+              for (int j = 0; j < W; ++j) {
+                s_ += v[sg * W + j];
+                q_ = fmaf(v[sg * W + j], v[sg * W + j], q_);
+              }
+              const int gl = (chunk * 32 + sg * W) / (CPG ? CPG : 1);
+              gv[2 * gl] += s_;
+              gv[2 * gl + 1] += q_;
+            }
+          }
+          if (p.residual && valid) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + opix + chunk * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float f[8];
+              unpack8(__ldg(rp + j), f);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) v[8 * j + c] += f[c];
+            }
+          }
+          if (p.out_f32) {
+            if (valid) {
+              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix + chunk * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+          } else {
+            // stage the bf16 tile in the 128B-swizzled layout the TMA store expects: sub-tile = 64 channels,
+            // row = pixel (128 B), 16-byte chunk index XOR (row & 7)
+            const uint32_t sub = out_buf + (uint32_t)cp * A_BYTES + (uint32_t)row * 128u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t c16 = (uint32_t)(half * 4 + j);
+              const uint32_t dst = sub + ((c16 ^ (uint32_t)(row & 7)) << 4);
+              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pack_bf16x2(v[8 * j], v[8 * j + 1])),
+                           "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])), "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])),
+                           "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7])) : "memory");
+            }
+          }
         }
       }
-      if (p.gn_partial) {
-        const int gl0 = (chunk * 32) / p.gn_cpg;
-        if (p.gn_cpg == 8) gn_accumulate<8>(v, lane, seg_size, red_row, gl0);
-        else if (p.gn_cpg == 16) gn_accumulate<16>(v, lane, seg_size, red_row, gl0);
-        else gn_accumulate<32>(v, lane, seg_size, red_row, gl0);
+      // this accumulator buffer is free for the MMA issuer again
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[buf]));
+      if (CPG) {
+        butterfly_sum<NV>(gv, lane, seg_size);
+        const int ls = lane & (seg_size - 1);
+        const int keep_shift = (seg_size == 32 ? 5 : 4) - (NV == 16 ? 4 : NV == 8 ? 3 : NV == 4 ? 2 : 1);
+        if ((ls & ((1 << keep_shift) - 1)) == 0) (&red[q][lane / seg_size][0][0])[ls >> keep_shift] = gv[0];
       }
-      if (p.residual && valid) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + opix + chunk * 32);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float f[8];
-          unpack8(__ldg(rp + j), f);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[8 * j + e] += f[e];
-        }
-      }
-      if (p.out_f32) {
-        if (valid) {
-          float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix + chunk * 32);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-      } else {
-        // stage the bf16 tile in the (now idle) pipeline buffers in the 128B-swizzled layout TMA expects:
-        // sub-tile = 64 channels, row = pixel (128 B), 16-byte chunk index XOR (row & 7)
-        const uint32_t sub = smem_base + (uint32_t)(chunk >> 1) * A_BYTES + (uint32_t)row * 128u;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t c16 = (uint32_t)((chunk & 1) * 4 + j);
-          const uint32_t dst = sub + ((c16 ^ (uint32_t)(row & 7)) << 4);
-          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pack_bf16x2(v[8 * j], v[8 * j + 1])),
-                       "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])), "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])),
-                       "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7])) : "memory");
-        }
-      }
-    }
-    if (!p.out_f32) {
-      fence_proxy_async_smem();           // generic-proxy smem writes -> visible to the TMA (async proxy)
+      if (!p.out_f32) fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
       named_bar_sync(2, 128);
-      if (threadIdx.x == 64) {
-        const int chan_base = (p.mode == 3 ? par_x * p.cout : 0) + n0;
+      if (e == 0 && !p.out_f32) {
+        const int chan_base = (p.mode == 3 ? par_x * p.cout : 0) + t.n0;
         const int pc_out = p.mode == 3 ? par_y : 0;
         for (int sidx = 0; sidx < BN / 64; ++sidx)
-          tma_store_5d(&mapOut, smem_base + (uint32_t)sidx * A_BYTES, chan_base + sidx * 64, x0, pc_out, y0, b0);
+          tma_store_5d(&mapOut, out_buf + (uint32_t)sidx * A_BYTES, chan_base + sidx * 64, t.x0, pc_out, t.y0, t.b0);
         tma_store_commit();
-        tma_store_wait_read<0>();         // smem must outlive the bulk read
       }
-    }
-    if (p.gn_partial) {
-      named_bar_sync(1, 128);
-      const int e = threadIdx.x - 64;               // 0..127
-      const int ngl = BN / p.gn_cpg;                // groups covered by this N tile
-      const int segs_per_img = hwt / seg_size;      // 4, 2 or 1
-      const int nimg = p.tileB;
-      const int part = hwt == BM ? trem : 0;
-      for (int o = e; o < nimg * ngl; o += 128) {
-        const int img = o / ngl, gl = o % ngl;
-        if (b0 + img >= p.B) continue;
-        float s = 0.0f, qq = 0.0f;
-        for (int sgi = 0; sgi < segs_per_img; ++sgi) {
-          const int gseg = img * segs_per_img + sgi;       // global segment index in the tile
-          const int w = (gseg * seg_size) >> 5, sl = ((gseg * seg_size) & 31) / seg_size;
-          s += red[w][sl][gl][0];
-          qq += red[w][sl][gl][1];
+      if (CPG) {
+        const int segs_per_img = hwt / seg_size;      // 4, 2 or 1
+        const int part = hwt == BM ? t.trem : 0;
+        for (int o = e; o < p.tileB * NGL; o += 128) {
+          const int img = o / NGL, gl = o % NGL;
+          if (t.b0 + img >= p.B) continue;
+          float s_ = 0.0f, q_ = 0.0f;
+          for (int sgi = 0; sgi < segs_per_img; ++sgi) {
+            const int gseg = img * segs_per_img + sgi;       // global segment index in the tile
+            const int w = (gseg * seg_size) >> 5, sl = ((gseg * seg_size) & 31) / seg_size;
+            s_ += red[w][sl][gl][0];
+            q_ += red[w][sl][gl][1];
+          }
+          float* dst = p.gn_partial + (((size_t)(t.b0 + img) * p.gn_parts + part) * p.gn_groups + t.n0 / (CPG ? CPG : 1) + gl) * 2;
+          dst[0] = s_;
+          dst[1] = q_;
         }
-        float* dst = p.gn_partial + (((size_t)(b0 + img) * p.gn_parts + part) * p.gn_groups + n0 / p.gn_cpg + gl) * 2;
-        dst[0] = s;
-        dst[1] = qq;
       }
     }
+    if (e == 0 && !p.out_f32) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+  if (warp == 1) tmem_dealloc<2 * BN>(tmem_base);
 }
 
 int encode_act_map(CUtensorMap* map, const void* ptr, int B, int H, int W, int C, long long image_stride, int mode,
@@ -335,20 +474,54 @@ int encode_weight_map(CUtensorMap* map, const void* ptr, long long rows, long lo
   return TEDM_OK;
 }
 
-template <int BN, int STAGES>
-int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o,
-                const ConvParams& p, dim3 grid, cudaStream_t stream) {
-  constexpr int smem = STAGES * (A_BYTES + BN * BK * 2) + 1024;
-  static bool configured = false;
-  if (!configured) {
-    TEDM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+template <int BN, bool WS, int CPG>
+int launch_conv_cpg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o, ConvParams& p,
+                    cudaStream_t stream) {
+  const int cb_total = p.c0_blocks + p.c1_blocks;
+  const int stage_bytes = WS ? A_ROW_BYTES : A_BYTES + BN * BK * 2;
+  const int out_bytes = (BN / 64) * A_BYTES;
+  const int base = 1024 + (WS ? 9 * cb_total * BN * BK * 2 : 0);
+  // double-buffer the output staging tile when that still leaves >= 4 pipeline slots
+  p.out_bufs = (DYN_SMEM_MAX - base - 2 * out_bytes) / stage_bytes >= 4 ? 2 : 1;
+  const int fixed = base + p.out_bufs * out_bytes;
+  int stages = (DYN_SMEM_MAX - fixed) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  TEDM_UNSUPPORTED(stages < 2, "tedm_conv_igemm_fwd: shared memory too small for this shape");
+  p.stages = stages;
+  const int smem = fixed + stages * stage_bytes;
+  static int configured = 0;
+  if (configured < smem) {
+    TEDM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, WS, CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
   }
-  conv_igemm_kernel<BN, STAGES><<<grid, 192, smem, stream>>>(a0, a1, w, o, p);
+  int grid = p.num_tiles < tedm_num_sms() ? p.num_tiles : tedm_num_sms();
+  conv_igemm_kernel<BN, WS, CPG><<<grid, 192, smem, stream>>>(a0, a1, w, o, p);
   TEDM_LAUNCH_CHECK();
   return TEDM_OK;
 }
 
+template <int BN, bool WS>
+int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o, ConvParams& p,
+                cudaStream_t stream) {
+  const int cpg = p.gn_partial ? p.gn_cpg : 0;
+  if (cpg == 0) return launch_conv_cpg<BN, WS, 0>(a0, a1, w, o, p, stream);
+  if constexpr (BN / 8 <= 8) {
+    if (cpg == 8) return launch_conv_cpg<BN, WS, 8>(a0, a1, w, o, p, stream);
+  }
+  if constexpr (BN / 16 <= 8) {
+    if (cpg == 16) return launch_conv_cpg<BN, WS, 16>(a0, a1, w, o, p, stream);
+  }
+  if (cpg == 32) return launch_conv_cpg<BN, WS, 32>(a0, a1, w, o, p, stream);
+  if constexpr (BN >= 64) {
+    if (cpg == 64) return launch_conv_cpg<BN, WS, 64>(a0, a1, w, o, p, stream);
+  }
+  if constexpr (BN >= 128) {
+    if (cpg == 128) return launch_conv_cpg<BN, WS, 128>(a0, a1, w, o, p, stream);
+  }
+  return tedm_set_error(TEDM_ERR_UNSUPPORTED, "tedm_conv_igemm_fwd: %d channels per GroupNorm group with N tile %d", cpg, BN);
+}
+
+int g_enable_ws = 1;  // tedm_conv_set_ws
 int g_force_bn = 0;  // debug/tuning override (tedm_conv_set_tile_n)
 
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -358,6 +531,11 @@ bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 extern "C" int tedm_conv_set_tile_n(int bn) {
   TEDM_CHECK_ARG(bn == 0 || bn == 64 || bn == 128 || bn == 256, "tedm_conv_set_tile_n: bn=%d", bn);
   g_force_bn = bn;
+  return TEDM_OK;
+}
+
+extern "C" int tedm_conv_set_ws(int enable) {
+  g_enable_ws = enable != 0;
   return TEDM_OK;
 }
 
@@ -413,39 +591,44 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
     p.gn_groups = a->gn_groups;
     p.gn_cpg = a->cout / a->gn_groups;
     p.gn_parts = tedm_conv_gn_parts(p.Ho, p.Wo);
-    TEDM_UNSUPPORTED(p.gn_cpg % 8 != 0 || (p.gn_cpg < 32 && 32 % p.gn_cpg != 0) || (p.gn_cpg > 32 && p.gn_cpg % 32 != 0),
-                     "tedm_conv_igemm_fwd: %d channels per GroupNorm group unsupported", p.gn_cpg);
+    TEDM_UNSUPPORTED(p.gn_cpg != 8 && p.gn_cpg != 16 && p.gn_cpg != 32 && p.gn_cpg != 64 && p.gn_cpg != 128,
+                     "tedm_conv_igemm_fwd: %d channels per GroupNorm group unsupported (8/16/32/64/128)", p.gn_cpg);
   }
 
-  // ---- N tile: the widest that divides cout, covers whole GroupNorm groups and still fills the SMs
+  // ---- N tile: the widest that divides cout, covers whole GroupNorm groups and still gives every SM a tile
   const long long m_tiles = (long long)ceil_div(p.B, p.tileB) * p.tiles_x * p.tiles_y;
   const int zdim = a->mode == 3 ? 4 : 1;
+  auto legal = [&](int c) {
+    return a->cout % c == 0 && (!p.gn_partial || (c % p.gn_cpg == 0 && c / p.gn_cpg <= 8));
+  };
   int bn = 0;
   const int cands[3] = {256, 128, 64};
-  for (int i = 0; i < 3 && bn == 0; ++i) {
-    const int c = cands[i];
-    if (a->cout % c) continue;
-    if (p.gn_partial && (c % p.gn_cpg != 0 || c / p.gn_cpg > NGMAX)) continue;
-    if (m_tiles * zdim * (a->cout / c) >= tedm_num_sms() || c == 64) bn = c;
-  }
-  if (bn == 0) {  // nothing fills the machine: take the narrowest legal tile
-    for (int i = 2; i >= 0 && bn == 0; --i)
-      if (a->cout % cands[i] == 0 && (!p.gn_partial || (cands[i] % p.gn_cpg == 0 && cands[i] / p.gn_cpg <= NGMAX))) bn = cands[i];
-  }
-  if (g_force_bn && a->cout % g_force_bn == 0 && (!p.gn_partial || (g_force_bn % p.gn_cpg == 0 && g_force_bn / p.gn_cpg <= NGMAX)))
-    bn = g_force_bn;
+  for (int i = 0; i < 3 && bn == 0; ++i)
+    if (legal(cands[i]) && m_tiles * zdim * (a->cout / cands[i]) >= tedm_num_sms()) bn = cands[i];
+  for (int i = 2; i >= 0 && bn == 0; --i)  // nothing fills the machine: take the narrowest legal tile
+    if (legal(cands[i])) bn = cands[i];
+  if (g_force_bn && legal(g_force_bn)) bn = g_force_bn;
   TEDM_UNSUPPORTED(bn == 0, "tedm_conv_igemm_fwd: no N tile for cout=%d with %d-channel GroupNorm groups", a->cout, p.gn_cpg);
-  TEDM_CHECK_ARG(m_tiles <= 2147483647LL, "tedm_conv_igemm_fwd: too many tiles");
+  const long long num_tiles = m_tiles * zdim * (a->cout / bn);
+  TEDM_CHECK_ARG(num_tiles <= 2147483647LL, "tedm_conv_igemm_fwd: too many tiles");
+  p.n_tiles = a->cout / bn;
+  p.zdim = zdim;
+  p.num_tiles = (int)num_tiles;
+
+  // weight-stationary row mode: 3x3, whole 128-pixel rows per tile, one N tile of 64, weights fit in smem
+  const bool ws = g_enable_ws && a->mode == 1 && p.tileH == 1 && p.tileB == 1 && p.tileW == BM && a->cout == 64 && bn == 64 &&
+                  (a->c0 + a->c1) <= 128;
 
   alignas(64) CUtensorMap mapA0, mapA1, mapW, mapOut;
+  const int boxW = ws ? ROW_PIX : p.tileW;
   int rc = encode_act_map(&mapA0, a->src0, a->batch, a->height, a->width, a->c0,
                           a->src0_image_stride ? a->src0_image_stride : (long long)a->height * a->width * a->c0, a->mode,
-                          p.tileW, p.tileH, p.tileB);
+                          boxW, p.tileH, p.tileB);
   if (rc) return rc;
   if (a->src1) {
     rc = encode_act_map(&mapA1, a->src1, a->batch, a->height, a->width, a->c1,
                         a->src1_image_stride ? a->src1_image_stride : (long long)a->height * a->width * a->c1, a->mode,
-                        p.tileW, p.tileH, p.tileB);
+                        boxW, p.tileH, p.tileB);
     if (rc) return rc;
   } else {
     mapA1 = mapA0;
@@ -453,7 +636,6 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   const long long ktot = (long long)p.taps * (a->c0 + a->c1);
   rc = encode_weight_map(&mapW, a->weight, (long long)zdim * a->cout, ktot, bn);
   if (rc) return rc;
-
   if (!p.out_f32) {
     // bf16 outputs leave through a TMA store; the upsample mode scatters each parity through the same
     // (2C, W, 2, H, B) view the stride-2 mode uses for its input
@@ -464,11 +646,11 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
     mapOut = mapA0;
   }
 
-  dim3 grid((unsigned)m_tiles, (unsigned)(a->cout / bn), (unsigned)zdim);
   cudaStream_t s = (cudaStream_t)stream;
+  if (ws) return launch_conv<64, true>(mapA0, mapA1, mapW, mapOut, p, s);
   switch (bn) {
-    case 64: return launch_conv<64, 4>(mapA0, mapA1, mapW, mapOut, p, grid, s);
-    case 128: return launch_conv<128, 3>(mapA0, mapA1, mapW, mapOut, p, grid, s);
-    default: return launch_conv<256, 4>(mapA0, mapA1, mapW, mapOut, p, grid, s);
+    case 64: return launch_conv<64, false>(mapA0, mapA1, mapW, mapOut, p, s);
+    case 128: return launch_conv<128, false>(mapA0, mapA1, mapW, mapOut, p, s);
+    default: return launch_conv<256, false>(mapA0, mapA1, mapW, mapOut, p, s);
   }
 }

@@ -44,6 +44,7 @@ SIGNATURES = {
     "tedm_conv_igemm_fwd": (_i, [C.POINTER(ConvArgs), _p]),
     "tedm_conv_gn_parts": (_i, [_i, _i]),
     "tedm_conv_set_tile_n": (_i, [_i]),
+    "tedm_conv_set_ws": (_i, [_i]),
     "tedm_weight_to_krsc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "tedm_fold_upsample_weight": (_i, [_p, _p, _i, _i, _p]),
     "tedm_gn_silu_fwd": (_i, [_p, _p, _i, _p, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _f, _p]),

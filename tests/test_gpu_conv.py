@@ -53,6 +53,14 @@ CASES = [
     (9, 8, 8, 64, 0, 64, 1, True, False, 8, 0),
     (2, 16, 16, 64, 0, 256, 1, True, False, 8, 256),
     (2, 16, 16, 64, 0, 128, 1, True, False, 8, 128),
+    # weight-stationary row path (3x3, 128-pixel rows, cout 64) incl. two sources, 256-wide rows, many tiles per CTA
+    (3, 128, 128, 64, 0, 64, 1, True, False, 8, 0),
+    (1, 128, 128, 64, 64, 64, 1, True, False, 8, 0),
+    (2, 4, 256, 64, 0, 64, 1, True, False, 8, 0),
+    (1, 128, 128, 128, 0, 64, 1, False, False, 0, 0),
+    # persistent loop with more tiles than SMs on the generic path
+    (40, 16, 16, 128, 0, 128, 1, True, False, 8, 64),
+    (6, 64, 64, 64, 0, 384, 0, False, False, 0, 0),
 ]
 
 
@@ -111,6 +119,21 @@ def test_conv_rejects_unsupported_shapes():
     w = torch.zeros(64, 3, 3, 48, dtype=torch.bfloat16, device="cuda")
     with pytest.raises(RuntimeError, match="multiples of 64"):
         N.conv_igemm(x, w, 1, 64)
+
+
+def test_conv_ws_path_matches_generic_path():
+    from tedm_b200 import native as N
+    x, w, b = _rand((2, 64, 128, 128), 1), _rand((64, 64, 3, 3), 2, 576 ** -0.5), _rand((64,), 3, 0.1)
+    xh, wk = _nhwc(x), N.weight_to_krsc(w.cuda())
+    y_ws, p_ws = N.conv_igemm(xh, wk, 1, 64, bias=b.cuda(), gn_groups=8)
+    N.load().tedm_conv_set_ws(0)
+    try:
+        y_g, p_g = N.conv_igemm(xh, wk, 1, 64, bias=b.cuda(), gn_groups=8)
+    finally:
+        N.load().tedm_conv_set_ws(1)
+    torch.cuda.synchronize()
+    assert _rel(y_ws.float(), y_g.float()) < 2e-3          # same products, different accumulation order
+    assert _rel(p_ws.sum(1), p_g.sum(1)) < 1e-4
 
 
 def test_conv_fp32_output():
