@@ -94,6 +94,9 @@ extern "C" int tedm_time_proj(const float* temb, const float* w_cat, const float
 // stem: 7x7 pad-3 conv, fp32 NCHW in -> NHWC bf16 out            models/unet_model.py:267,334
 // thread = (pixel, 8 output channels); weights transposed into smem as [tap][cout].
 // ------------------------------------------------------------------------------------------
+// thread = (strip of 4 consecutive pixels, 8 output channels): every weight vector fetched from shared
+// memory feeds 32 FMAs and every input row segment (10 values) is reused by 7 taps x 4 pixels.
+#define STEM_PX 4
 __global__ void __launch_bounds__(256) stem_conv7x7_kernel(const float* __restrict__ x, const float* __restrict__ weight,
                                                            const float* __restrict__ bias, bf16* __restrict__ out,
                                                            int batch, int cin, int H, int W, int cout) {
@@ -105,35 +108,51 @@ __global__ void __launch_bounds__(256) stem_conv7x7_kernel(const float* __restri
   }
   __syncthreads();
   const int chunks = cout >> 3;
-  const long long total = (long long)batch * H * W * chunks;
+  const int strips_w = (W + STEM_PX - 1) / STEM_PX;
+  const long long total = (long long)batch * H * strips_w * chunks;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int ch = (int)(idx % chunks);
-    const long long pix = idx / chunks;
-    const int px = (int)(pix % W), py = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
-    float acc[8];
+    long long rest = idx / chunks;
+    const int sx = (int)(rest % strips_w);
+    rest /= strips_w;
+    const int py = (int)(rest % H), b = (int)(rest / H);
+    const int px0 = sx * STEM_PX;
+    float acc[STEM_PX][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[ch * 8 + j] : 0.0f;
+    for (int p = 0; p < STEM_PX; ++p)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[p][j] = bias ? bias[ch * 8 + j] : 0.0f;
     for (int ci = 0; ci < cin; ++ci) {
       const float* xp = x + ((size_t)b * cin + ci) * H * W;
       for (int ky = 0; ky < 7; ++ky) {
         const int yy = py + ky - 3;
         if (yy < 0 || yy >= H) continue;
+        float in[STEM_PX + 6];
+#pragma unroll
+        for (int i = 0; i < STEM_PX + 6; ++i) {
+          const int xx = px0 + i - 3;
+          in[i] = (xx >= 0 && xx < W) ? __ldg(xp + (size_t)yy * W + xx) : 0.0f;
+        }
 #pragma unroll
         for (int kx = 0; kx < 7; ++kx) {
-          const int xx = px + kx - 3;
-          if (xx < 0 || xx >= W) continue;
-          const float v = __ldg(xp + (size_t)yy * W + xx);
           const float4* wp = reinterpret_cast<const float4*>(wsm + (ci * 49 + ky * 7 + kx) * cout + ch * 8);
           const float4 w0 = wp[0], w1 = wp[1];
-          acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
-          acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
-          acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
-          acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+#pragma unroll
+          for (int p = 0; p < STEM_PX; ++p) {
+            const float v = in[p + kx];
+            acc[p][0] = fmaf(v, w0.x, acc[p][0]); acc[p][1] = fmaf(v, w0.y, acc[p][1]);
+            acc[p][2] = fmaf(v, w0.z, acc[p][2]); acc[p][3] = fmaf(v, w0.w, acc[p][3]);
+            acc[p][4] = fmaf(v, w1.x, acc[p][4]); acc[p][5] = fmaf(v, w1.y, acc[p][5]);
+            acc[p][6] = fmaf(v, w1.z, acc[p][6]); acc[p][7] = fmaf(v, w1.w, acc[p][7]);
+          }
         }
       }
     }
-    *reinterpret_cast<uint4*>(out + (size_t)pix * cout + ch * 8) = pack8(acc);
+#pragma unroll
+    for (int p = 0; p < STEM_PX; ++p)
+      if (px0 + p < W)
+        *reinterpret_cast<uint4*>(out + (((size_t)b * H + py) * W + px0 + p) * cout + ch * 8) = pack8(acc[p]);
   }
 }
 
@@ -146,7 +165,7 @@ extern "C" int tedm_stem_conv7x7(const float* x, const float* weight, const floa
   TEDM_UNSUPPORTED(smem > 96 * 1024, "tedm_stem_conv7x7: cin*49*cout=%d floats do not fit in shared memory", cin * 49 * cout);
   if (smem > 48 * 1024)
     TEDM_CUDA(cudaFuncSetAttribute(stem_conv7x7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long total = (long long)batch * height * width * (cout / 8);
+  const long long total = (long long)batch * height * ((width + STEM_PX - 1) / STEM_PX) * (cout / 8);
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)tedm_num_sms() * 16;
   if (blocks > cap) blocks = cap;
