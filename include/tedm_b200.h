@@ -115,6 +115,12 @@ typedef struct {
   int64_t src0_image_stride, src1_image_stride, out_image_stride; /* elements; 0 = dense */
 } tedm_conv_args;
 TEDM_API int tedm_conv_igemm_fwd(const tedm_conv_args* args, tedm_stream_t stream);
+/* Weight gradient of the same convolution (backward of models/unet_model.py:43,49,122,157,185,188,226,227,308,324):
+ * dw[co][tap][ci] = sum over pixels of dy[pixel][co] * src[pixel + tap offset][ci], fp32, overwritten.
+ * `args` describes the forward call (src0/src1/extent/mode/cout; weight, bias, residual, out, gn_* are ignored;
+ * out_image_stride, if non-zero, is dy's image stride); dy is the NHWC bf16 output gradient.  taps = 1 (mode 0),
+ * 9 (mode 1), 16 (mode 2: ky*4+kx; mode 3: parity*4 + a*2 + b of the folded 2x2 kernels). */
+TEDM_API int tedm_conv_igemm_wgrad(const tedm_conv_args* args, const void* dy, float* dw, tedm_stream_t stream);
 /* number of partial-statistics slots per image that tedm_conv_igemm_fwd writes for this output extent */
 TEDM_API int tedm_conv_gn_parts(int out_height, int out_width);
 /* tuning/debug: force the N tile (64/128/256; 0 = automatic) of tedm_conv_igemm_fwd */

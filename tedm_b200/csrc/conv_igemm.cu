@@ -521,6 +521,187 @@ int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   return tedm_set_error(TEDM_ERR_UNSUPPORTED, "tedm_conv_igemm_fwd: %d channels per GroupNorm group with N tile %d", cpg, BN);
 }
 
+
+// ==========================================================================================
+// weight gradient:  dW[co][tap][ci] = sum_pixels dY[pixel][co] * X[pixel + tap offset][ci]
+//
+// The contraction runs over pixels, which are the ROWS of both NHWC operands, so both are fed to the
+// tensor core as MN-major operands: a TMA box [128 pixels][64 channels] (128B swizzle) is exactly the
+// canonical MN-major SW128 layout (8-row K groups 1024 B apart = SBO, 64-channel MN blocks 16 KB
+// apart = LBO).  GEMM view:  D[m][n],  m = (tap, ci) in blocks of 2 x 64 (two boxes with their own
+// tap shift), n = co tile, k = 128 pixels per pipeline slot (8 UMMAs of K = 16).  Split-K over pixel
+// tiles across CTAs; partial tiles are reduced with fp32 red.global.add into a zeroed fp32
+// [cout][taps][cin] buffer.
+// ==========================================================================================
+struct WgradParams {
+  int mode, taps, kxc;           // taps counts parities x 2x2 in mode 3 (16)
+  int c0_blocks, c1_blocks, C0, C1, ctot;
+  int tileW, tileH, tileB, tiles_x, tiles_y;
+  int B, cout;
+  int items, n_tiles, splitk, num_ptiles, stages;
+  float* dw;
+};
+
+__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr) {
+  // MN-major, 128B swizzle: LBO = 16 KB between 64-element MN blocks, SBO = 1 KB between 8-row K groups
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1024ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CUtensorMap mapX1,
+                  const __grid_constant__ CUtensorMap mapDY, const WgradParams p) {
+  constexpr int STAGE_BYTES = 2 * A_BYTES + (BN / 64) * A_BYTES;
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_acc;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int cb_total = p.c0_blocks + p.c1_blocks;
+  const int ks = blockIdx.x;
+  const int mb = blockIdx.y / p.n_tiles, nt = blockIdx.y % p.n_tiles;
+  const int n0 = nt * BN;
+  const int item0 = 2 * mb, item1 = (2 * mb + 1 < p.items) ? 2 * mb + 1 : 2 * mb;   // odd tail: duplicate, discarded below
+  const int num_kb = (p.num_ptiles - ks + p.splitk - 1) / p.splitk;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapX0);
+    if (p.c1_blocks) tma_prefetch_desc(&mapX1);
+    tma_prefetch_desc(&mapDY);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bar_acc), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(smem_u32(&tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int pt = ks + kb * p.splitk;
+        const int tiles_per_group = p.tiles_x * p.tiles_y;
+        const int bg = pt / tiles_per_group, trem = pt % tiles_per_group;
+        const int b0 = bg * p.tileB, y0 = (trem / p.tiles_x) * p.tileH, x0 = (trem % p.tiles_x) * p.tileW;
+        mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+        const uint32_t full = smem_u32(&bar_full[stage]);
+        mbar_expect_tx(full, STAGE_BYTES);
+        const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
+        int par = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int item = h ? item1 : item0;
+          const int tap = item / cb_total, cb = item % cb_total;
+          const bool second = cb >= p.c0_blocks;
+          const int cblk = second ? cb - p.c0_blocks : cb;
+          int offy = 0, offx = 0, pc = 0, chan_off = 0;
+          if (p.mode == 1) {
+            offy = tap / 3 - 1;
+            offx = tap % 3 - 1;
+          } else if (p.mode == 2) {
+            const int ky = tap >> 2, kx = tap & 3;
+            offy = ((ky + 1) >> 1) - 1;
+            offx = ((kx + 1) >> 1) - 1;
+            pc = (ky + 1) & 1;
+            chan_off = ((kx + 1) & 1) * (second ? p.C1 : p.C0);
+          } else if (p.mode == 3) {
+            par = tap >> 2;
+            offy = ((tap >> 1) & 1) - 1 + (par >> 1);
+            offx = (tap & 1) - 1 + (par & 1);
+          }
+          tma_load_5d(a_dst + h * A_BYTES, second ? &mapX1 : &mapX0, full, chan_off + cblk * BK, x0 + offx, pc, y0 + offy, b0);
+        }
+        const int dy_chan = (p.mode == 3 ? (par & 1) * p.cout : 0) + n0;
+        const int dy_pc = p.mode == 3 ? (par >> 1) : 0;
+        for (int j = 0; j < BN / 64; ++j)
+          tma_load_5d(a_dst + (2 + j) * A_BYTES, &mapDY, full, dy_chan + j * 64, x0, dy_pc, y0, b0);
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&bar_full[stage]), phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
+        const uint64_t adesc = make_sw128_mn_desc(a_addr), bdesc = make_sw128_mn_desc(a_addr + 2 * A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BM / 16; ++k)   // 16 pixel rows (2048 B) per UMMA
+          umma_bf16(tmem_base, adesc + 128ull * k, bdesc + 128ull * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+        umma_commit(smem_u32(&bar_empty[stage]));
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(smem_u32(&bar_acc));
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3, row = q * 32 + lane;
+    const int half = row >> 6;
+    const int item = half ? item1 : item0;
+    const bool live = num_kb > 0 && (half == 0 || item1 != item0);
+    const int tap = item / cb_total, cb = item % cb_total;
+    float* dst_row = p.dw + (size_t)tap * p.ctot + cb * BK + (row & 63);
+    if (num_kb > 0) {
+      mbar_wait(smem_u32(&bar_acc), 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(chunk * 32), r);
+        tmem_ld_wait();
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            atomicAdd(dst_row + (size_t)(n0 + chunk * 32 + j) * p.taps * p.ctot, __uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+}
+
+template <int BN>
+int launch_wgrad(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap& dy, WgradParams& p, int m_blocks,
+                 cudaStream_t stream) {
+  const int stage_bytes = (2 + BN / 64) * A_BYTES;
+  int stages = (DYN_SMEM_MAX - 1024) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  p.stages = stages;
+  const int smem = 1024 + stages * stage_bytes;
+  static int configured = 0;
+  if (configured < smem) {
+    TEDM_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  dim3 grid((unsigned)p.splitk, (unsigned)(m_blocks * p.n_tiles));
+  conv_wgrad_kernel<BN><<<grid, 192, smem, stream>>>(x0, x1, dy, p);
+  TEDM_LAUNCH_CHECK();
+  return TEDM_OK;
+}
+
 int g_enable_ws = 1;  // tedm_conv_set_ws
 int g_force_bn = 0;  // debug/tuning override (tedm_conv_set_tile_n)
 
@@ -652,5 +833,73 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
     case 64: return launch_conv<64, false>(mapA0, mapA1, mapW, mapOut, p, s);
     case 128: return launch_conv<128, false>(mapA0, mapA1, mapW, mapOut, p, s);
     default: return launch_conv<256, false>(mapA0, mapA1, mapW, mapOut, p, s);
+  }
+}
+
+// dw: fp32 [cout][taps][c0+c1] (taps = 1 / 9 / 16; mode 3: 16 = parity*4 + a*2 + b of the folded kernel), overwritten.
+extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, float* dw, tedm_stream_t stream) {
+  TEDM_CHECK_ARG(a && a->src0 && dy && dw, "tedm_conv_igemm_wgrad: null pointer");
+  TEDM_CHECK_ARG(a->mode >= 0 && a->mode <= 3, "tedm_conv_igemm_wgrad: mode=%d", a->mode);
+  TEDM_CHECK_ARG(a->batch > 0 && a->height > 0 && a->width > 0 && a->c0 > 0 && a->c1 >= 0 && a->cout > 0,
+                 "tedm_conv_igemm_wgrad: bad sizes");
+  TEDM_CHECK_ARG((a->c1 > 0) == (a->src1 != nullptr), "tedm_conv_igemm_wgrad: src1/c1 mismatch");
+  TEDM_UNSUPPORTED(a->c0 % BK != 0 || a->c1 % BK != 0 || a->cout % 64 != 0,
+                   "tedm_conv_igemm_wgrad: channel counts (%d, %d -> %d) must be multiples of 64", a->c0, a->c1, a->cout);
+  TEDM_UNSUPPORTED(a->mode == 2 && a->c1 != 0, "tedm_conv_igemm_wgrad: stride-2 mode takes one source");
+  WgradParams p{};
+  p.mode = a->mode;
+  p.kxc = a->mode == 0 ? 1 : a->mode == 1 ? 3 : 4;
+  p.taps = a->mode == 0 ? 1 : a->mode == 1 ? 9 : 16;
+  p.C0 = a->c0;
+  p.C1 = a->c1;
+  p.ctot = a->c0 + a->c1;
+  p.c0_blocks = a->c0 / BK;
+  p.c1_blocks = a->c1 / BK;
+  p.B = a->batch;
+  p.cout = a->cout;
+  const int Ho = a->mode == 2 ? a->height / 2 : a->height, Wo = a->mode == 2 ? a->width / 2 : a->width;  // tile space
+  TEDM_UNSUPPORTED(!is_pow2(Ho) || !is_pow2(Wo) || (a->mode == 2 && ((a->height | a->width) & 1)) || (long long)Ho * Wo < 16,
+                   "tedm_conv_igemm_wgrad: spatial extent %dx%d unsupported", a->height, a->width);
+  p.tileW = Wo < BM ? Wo : BM;
+  p.tileH = Ho < BM / p.tileW ? Ho : BM / p.tileW;
+  p.tileB = BM / (p.tileW * p.tileH);
+  p.tiles_x = Wo / p.tileW;
+  p.tiles_y = Ho / p.tileH;
+  p.num_ptiles = ceil_div(p.B, p.tileB) * p.tiles_x * p.tiles_y;
+  p.items = p.taps * (p.c0_blocks + p.c1_blocks);
+  p.dw = dw;
+  int bn = a->cout % 256 == 0 ? 256 : (a->cout % 128 == 0 ? 128 : 64);
+  if (g_force_bn && a->cout % g_force_bn == 0) bn = g_force_bn;
+  p.n_tiles = a->cout / bn;
+  const int m_blocks = (p.items + 1) / 2;
+  // split K so that ~4 CTAs per SM exist, each with at least 4 pixel tiles
+  long long want = (4LL * tedm_num_sms() + (long long)m_blocks * p.n_tiles - 1) / ((long long)m_blocks * p.n_tiles);
+  long long cap = p.num_ptiles / 4 > 0 ? p.num_ptiles / 4 : 1;
+  p.splitk = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+
+  const int dy_h = a->mode == 3 ? 2 * a->height : Ho, dy_w = a->mode == 3 ? 2 * a->width : Wo;
+  alignas(64) CUtensorMap mapX0, mapX1, mapDY;
+  int rc = encode_act_map(&mapX0, a->src0, a->batch, a->height, a->width, a->c0,
+                          a->src0_image_stride ? a->src0_image_stride : (long long)a->height * a->width * a->c0, a->mode,
+                          p.tileW, p.tileH, p.tileB);
+  if (rc) return rc;
+  if (a->src1) {
+    rc = encode_act_map(&mapX1, a->src1, a->batch, a->height, a->width, a->c1,
+                        a->src1_image_stride ? a->src1_image_stride : (long long)a->height * a->width * a->c1, a->mode,
+                        p.tileW, p.tileH, p.tileB);
+    if (rc) return rc;
+  } else {
+    mapX1 = mapX0;
+  }
+  rc = encode_act_map(&mapDY, dy, a->batch, dy_h, dy_w, a->cout,
+                      a->out_image_stride ? a->out_image_stride : (long long)dy_h * dy_w * a->cout, a->mode == 3 ? 2 : 0,
+                      p.tileW, p.tileH, p.tileB);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  TEDM_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)a->cout * p.taps * p.ctot, s));
+  switch (bn) {
+    case 64: return launch_wgrad<64>(mapX0, mapX1, mapDY, p, m_blocks, s);
+    case 128: return launch_wgrad<128>(mapX0, mapX1, mapDY, p, m_blocks, s);
+    default: return launch_wgrad<256>(mapX0, mapX1, mapDY, p, m_blocks, s);
   }
 }

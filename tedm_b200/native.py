@@ -42,6 +42,7 @@ SIGNATURES = {
     "tedm_time_proj": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "tedm_stem_conv7x7": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "tedm_conv_igemm_fwd": (_i, [C.POINTER(ConvArgs), _p]),
+    "tedm_conv_igemm_wgrad": (_i, [C.POINTER(ConvArgs), _p, _p, _p]),
     "tedm_conv_gn_parts": (_i, [_i, _i]),
     "tedm_conv_set_tile_n": (_i, [_i]),
     "tedm_conv_set_ws": (_i, [_i]),
@@ -250,6 +251,24 @@ def conv_igemm(src0: torch.Tensor, weight: torch.Tensor, mode: int, cout: int, b
     else:
         _call("tedm_conv_igemm_fwd", C.byref(a), _stream())
     return (out, gnp) if gn_groups else out
+
+
+def conv_wgrad(src0: torch.Tensor, dy: torch.Tensor, mode: int, src1=None) -> torch.Tensor:
+    """fp32 (cout, taps, c0+c1) weight gradient of conv_igemm(src0[, src1]) given the NHWC bf16 output gradient."""
+    b, h, w, c0 = src0.shape
+    c1 = src1.shape[3] if src1 is not None else 0
+    cout = dy.shape[3]
+    taps = {MODE_1X1: 1, MODE_3X3: 9, MODE_4X4S2: 16, MODE_UP3X3: 16}[mode]
+    oh, ow = (h // 2, w // 2) if mode == MODE_4X4S2 else ((2 * h, 2 * w) if mode == MODE_UP3X3 else (h, w))
+    if tuple(dy.shape) != (b, oh, ow, cout):
+        raise ValueError(f"conv_wgrad: dy has shape {tuple(dy.shape)}, expected {(b, oh, ow, cout)}")
+    dw = torch.empty(cout, taps, c0 + c1, device=src0.device, dtype=torch.float32)
+    p0, s0 = _nhwc(src0, "src0")
+    p1, s1 = _nhwc(src1, "src1")
+    pd, sd = _nhwc(dy, "dy")
+    a = ConvArgs(p0, p1, None, None, None, None, None, b, h, w, c0, c1, cout, mode, 0, 0, s0, s1, sd)
+    _call("tedm_conv_igemm_wgrad", C.byref(a), pd, _ptr(dw), _stream())
+    return dw
 
 
 def gn_silu(x, gn_partial, gamma, beta, groups: int, eps: float = 1e-5, scale_shift=None, ss_offset: int = 0,
