@@ -172,6 +172,73 @@ TEDM_API int tedm_final_conv1x1(const void* x, const float* weight, const float*
 TEDM_API int tedm_nchw_f32_to_nhwc_bf16(const float* x, void* out, int batch, int channels, int hw, tedm_stream_t stream);
 TEDM_API int tedm_nhwc_bf16_to_nchw_f32(const void* x, float* out, int batch, int channels, int hw, tedm_stream_t stream);
 
+/* ---- training step: backward of the UNet pieces -------------------------------------------
+ * The reference gets these from torch autograd over models/unet_model.py (loss.backward() in
+ * trainers/train_CXR14.py:30-40).  Activation gradients are NHWC bf16; every PARAMETER gradient is
+ * fp32 and is accumulated (+=) into its destination, like torch's .grad.
+ * The data gradient of a convolution runs on tedm_conv_igemm_fwd itself with the weights re-laid
+ * out by tedm_weight_to_dgrad (a 3x3 becomes the flipped/transposed 3x3, the stride-2 4x4 becomes a
+ * mode-3 parity conv, the folded upsample conv becomes a mode-2 stride-2 conv). */
+
+/* fp32 OIHW parameter -> bf16 operand of the data-gradient conv; `mode` is the FORWARD mode.
+ *   0/1: [Cin][kh][kw][Cout] flipped (run as mode 0/1);  2: [4][Cin][2][2][Cout] (run as mode 3);
+ *   3 (w is the 3x3 of Upsample): [Cin][4][4][Cout] (run as mode 2 on the 2x-resolution gradient). */
+TEDM_API int tedm_weight_to_dgrad(const float* w_oihw, void* w_dgrad, int cout, int cin, int mode, tedm_stream_t stream);
+/* fp32 [Cout][taps][Cin] from tedm_conv_igemm_wgrad -> grad_oihw += (mode 3 un-folds the parity kernels to 3x3). */
+TEDM_API int tedm_wgrad_to_oihw(const float* dw, float* grad_oihw, int cout, int cin, int mode, tedm_stream_t stream);
+
+/* Backward of tedm_gn_silu_fwd (Block.forward, models/unet_model.py:126-135): dx = d loss / d (conv output).
+ * dgamma/dbeta [C] +=; dbias [C] += sum of dx over batch and pixels (the conv's bias gradient; nullable);
+ * dscale_shift (nullable): same layout as scale_shift, the (b, c) entries of this block are overwritten.
+ * workspace: fp32 [3*batch*channels].  The gradient of the fused residual input is dy itself. */
+TEDM_API int tedm_gn_silu_bwd(const void* x, const void* dy, const float* gn_partial, int gn_parts, const float* gamma,
+                     const float* beta, const float* scale_shift, int ss_stride, int ss_offset, void* dx,
+                     float* workspace, float* dgamma, float* dbeta, float* dbias, float* dscale_shift,
+                     int batch, int hw, int channels, int groups, float eps, tedm_stream_t stream);
+
+/* Backward of tedm_layernorm_fwd (models/unet_model.py:52-61): dx = LN'(x)·dy (+ add, nullable: the gradient
+ * arriving over the Residual branch); dg [C] +=. */
+TEDM_API int tedm_layernorm_bwd(const void* x, const float* g, const void* dy, const void* add, void* dx, float* dg,
+                       int64_t npix, int channels, float eps, tedm_stream_t stream);
+
+/* dbias[c] += sum over pixels of dy[pixel][c] (bias gradient of a conv not followed by GroupNorm). */
+TEDM_API int tedm_bias_grad(const void* dy, float* dbias, int64_t npix, int channels, tedm_stream_t stream);
+/* out = a + b, bf16: the two gradient streams meeting at a skip connection (models/unet_model.py:339,344). */
+TEDM_API int tedm_add_bf16(const void* a, const void* b, void* out, int64_t n, tedm_stream_t stream);
+
+/* Backward of tedm_final_conv1x1 (models/unet_model.py:331,368): dh NHWC bf16; dweight [out_dim][C], dbias += . */
+TEDM_API int tedm_final_conv1x1_bwd(const void* h, const float* weight, const float* dout, void* dh, float* dweight,
+                           float* dbias, int batch, int hw, int channels, int out_dim, tedm_stream_t stream);
+/* Weight/bias gradient of the 7x7 stem (models/unet_model.py:267,334): x fp32 NCHW, dy NHWC bf16. */
+TEDM_API int tedm_stem_conv7x7_wgrad(const float* x, const void* dy, float* dweight, float* dbias, int batch, int cin,
+                            int height, int width, int cout, tedm_stream_t stream);
+
+/* tedm_time_embed that also returns what its backward needs: emb [B][dim], hidden_pre [B][tdim] (pre-GELU). */
+TEDM_API int tedm_time_embed_train(const int64_t* t, const float* freq, const float* w1, const float* b1, const float* w2,
+                          const float* b2, float* emb, float* hidden_pre, float* temb, int batch, int dim, int tdim,
+                          tedm_stream_t stream);
+/* Backward of a small fp32 Linear of the time path (models/unet_model.py:150-152,287-292):
+ *   dY = dy_raw * act'(y_pre) ; dw [n_out][n_in] += dY^T act(x) ; db += sum_b dY ; dx_raw = dY w (overwritten, nullable)
+ * act codes: 0 identity, 1 SiLU, 2 GELU(erf).  y_pre may be NULL when act_y == 0. */
+TEDM_API int tedm_linear_bwd(const float* dy_raw, const float* y_pre, int act_y, const float* x, int act_x, const float* w,
+                    float* dw, float* db, float* dx_raw, int batch, int n_out, int n_in, tedm_stream_t stream);
+
+/* Backward of tedm_linear_attention_fwd; fwd_workspace is the forward call's workspace (column maxima and
+ * per-chunk context partials).  workspace: fp32, tedm_linear_attention_bwd_workspace() elements. */
+TEDM_API int64_t tedm_linear_attention_bwd_workspace(int batch, int n, int heads, int dim_head);
+TEDM_API int tedm_linear_attention_bwd(const void* qkv, const void* dout, const float* fwd_workspace, void* dqkv,
+                              float* workspace, int batch, int n, int heads, int dim_head, float scale,
+                              tedm_stream_t stream);
+/* Backward of tedm_attention_fwd. */
+TEDM_API int tedm_attention_bwd(const void* qkv, const void* dout, void* dqkv, int batch, int n, int heads, int dim_head,
+                       float scale, tedm_stream_t stream);
+
+/* torch.optim.Adam update (trainers/train_CXR14.py:139) over a flat fp32 arena; n % 4 == 0; `step` >= 1 is
+ * the 1-based step count (bias correction computed on the host); grad is multiplied by grad_scale first. */
+TEDM_API int tedm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                   tedm_stream_t stream);
+
 /* ---- TEDM / LEDM head ---------------------------------------------------------------------- */
 
 /* Per-pixel MLP tail after the per-level layer-1 GEMMs (commuted form of the reference's

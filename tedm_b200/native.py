@@ -59,6 +59,20 @@ SIGNATURES = {
     "tedm_nhwc_bf16_to_nchw_f32": (_i, [_p, _p, _i, _i, _i, _p]),
     "tedm_head_infer": (_i, [C.POINTER(HeadArgs), _p]),
     "tedm_ensemble_mask": (_i, [_p, _p, _p, _i, _i, _i, _p]),
+    "tedm_weight_to_dgrad": (_i, [_p, _p, _i, _i, _i, _p]),
+    "tedm_wgrad_to_oihw": (_i, [_p, _p, _i, _i, _i, _p]),
+    "tedm_gn_silu_bwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
+    "tedm_layernorm_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _f, _p]),
+    "tedm_bias_grad": (_i, [_p, _p, _i64, _i, _p]),
+    "tedm_add_bf16": (_i, [_p, _p, _p, _i64, _p]),
+    "tedm_final_conv1x1_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "tedm_stem_conv7x7_wgrad": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "tedm_time_embed_train": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "tedm_linear_bwd": (_i, [_p, _p, _i, _p, _i, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "tedm_linear_attention_bwd_workspace": (_i64, [_i, _i, _i, _i]),
+    "tedm_linear_attention_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
+    "tedm_attention_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _p]),
+    "tedm_adam_step": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i, _f, _p]),
     "tedm_debug_umma_probe": (_i, [_p, _p, C.POINTER(_i), C.POINTER(_i), _i, _p, _p]),
 }
 
@@ -290,7 +304,7 @@ def layernorm(x, g, eps: float = 1e-5, residual=None):
     return out
 
 
-def linear_attention(qkv, heads: int = 4, dim_head: int = 32, scale: Optional[float] = None):
+def linear_attention(qkv, heads: int = 4, dim_head: int = 32, scale: Optional[float] = None, want_workspace: bool = False):
     b, h, w, c3 = qkv.shape
     n = h * w
     ws_n = load().tedm_linear_attention_workspace(b, n, heads, dim_head)
@@ -300,7 +314,7 @@ def linear_attention(qkv, heads: int = 4, dim_head: int = 32, scale: Optional[fl
     out = torch.empty(b, h, w, heads * dim_head, device=qkv.device, dtype=torch.bfloat16)
     _call("tedm_linear_attention_fwd", _ptr(qkv, torch.bfloat16, "qkv"), _ptr(out), _ptr(ws), b, n, heads, dim_head,
           float(dim_head ** -0.5 if scale is None else scale), _stream())
-    return out
+    return (out, ws) if want_workspace else out
 
 
 def attention(qkv, heads: int = 4, dim_head: int = 32, scale: float = 16.0):
@@ -339,6 +353,127 @@ def nhwc_to_nchw_f32(x):
     out = torch.empty(b, c, h, w, device=x.device, dtype=torch.float32)
     _call("tedm_nhwc_bf16_to_nchw_f32", _ptr(x, torch.bfloat16, "x"), _ptr(out), b, c, h * w, _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# training step: backward pieces (parameter gradients are ACCUMULATED into the fp32 tensors passed in)
+# ------------------------------------------------------------------------------------------------
+_TAPS = {MODE_1X1: 1, MODE_3X3: 9, MODE_4X4S2: 16, MODE_UP3X3: 16}
+
+
+def weight_to_dgrad(w: torch.Tensor, mode: int) -> torch.Tensor:
+    """bf16 operand of the data-gradient conv for a forward conv of `mode` with OIHW weight w."""
+    cout, cin = w.shape[0], w.shape[1]
+    out = torch.empty(cout * cin * _TAPS[mode], device=w.device, dtype=torch.bfloat16)
+    _call("tedm_weight_to_dgrad", _ptr(w.contiguous(), torch.float32, "weight"), _ptr(out), cout, cin, mode, _stream())
+    return out
+
+
+def wgrad_to_oihw(dw: torch.Tensor, grad: torch.Tensor, mode: int) -> None:
+    cout, cin = grad.shape[0], grad.shape[1]
+    _call("tedm_wgrad_to_oihw", _ptr(dw, torch.float32, "dw"), _ptr(grad, torch.float32, "grad"), cout, cin, mode, _stream())
+
+
+def gn_silu_bwd(x, dy, gn_partial, gamma, beta, groups: int, dgamma, dbeta, dbias=None, eps: float = 1e-5, scale_shift=None,
+                ss_offset: int = 0, dscale_shift=None):
+    b, h, w, c = x.shape
+    dx = torch.empty_like(x)
+    ws = torch.empty(3 * b * c, device=x.device, dtype=torch.float32)
+    _call("tedm_gn_silu_bwd", _ptr(x, torch.bfloat16, "x"), _ptr(dy, torch.bfloat16, "dy"), _ptr(gn_partial, torch.float32),
+          gn_partial.shape[1], _ptr(gamma, torch.float32), _ptr(beta, torch.float32), _ptr(scale_shift, torch.float32),
+          scale_shift.shape[1] if scale_shift is not None else 0, ss_offset, _ptr(dx), _ptr(ws), _ptr(dgamma, torch.float32),
+          _ptr(dbeta, torch.float32), _ptr(dbias, torch.float32), _ptr(dscale_shift, torch.float32), b, h * w, c, groups, eps,
+          _stream())
+    return dx
+
+
+def layernorm_bwd(x, g, dy, dg, eps: float = 1e-5, add=None):
+    c = x.shape[-1]
+    dx = torch.empty_like(x)
+    _call("tedm_layernorm_bwd", _ptr(x, torch.bfloat16, "x"), _ptr(g, torch.float32), _ptr(dy, torch.bfloat16, "dy"),
+          _ptr(add, torch.bfloat16, "add"), _ptr(dx), _ptr(dg, torch.float32, "dg"), x.numel() // c, c, eps, _stream())
+    return dx
+
+
+def bias_grad(dy, dbias) -> None:
+    c = dy.shape[-1]
+    _call("tedm_bias_grad", _ptr(dy, torch.bfloat16, "dy"), _ptr(dbias, torch.float32, "dbias"), dy.numel() // c, c, _stream())
+
+
+def add_bf16(a, b, out=None):
+    out = torch.empty_like(a) if out is None else out
+    _call("tedm_add_bf16", _ptr(a, torch.bfloat16, "a"), _ptr(b, torch.bfloat16, "b"), _ptr(out, torch.bfloat16), a.numel(),
+          _stream())
+    return out
+
+
+def final_conv1x1_bwd(h, weight, dout, dweight, dbias):
+    b, hh, ww, c = h.shape
+    od = weight.shape[0]
+    dh = torch.empty_like(h)
+    _call("tedm_final_conv1x1_bwd", _ptr(h, torch.bfloat16, "h"), _ptr(weight, torch.float32), _ptr(dout, torch.float32, "dout"),
+          _ptr(dh), _ptr(dweight, torch.float32), _ptr(dbias, torch.float32), b, hh * ww, c, od, _stream())
+    return dh
+
+
+def stem_conv7x7_wgrad(x, dy, dweight, dbias) -> None:
+    b, cin, h, w = x.shape
+    _call("tedm_stem_conv7x7_wgrad", _ptr(x, torch.float32, "x"), _ptr(dy, torch.bfloat16, "dy"), _ptr(dweight, torch.float32),
+          _ptr(dbias, torch.float32), b, cin, h, w, dy.shape[-1], _stream())
+
+
+def time_embed_train(t, freq, w1, b1, w2, b2):
+    b, dim, tdim = t.shape[0], w1.shape[1], w1.shape[0]
+    emb = torch.empty(b, dim, device=t.device, dtype=torch.float32)
+    hid = torch.empty(b, tdim, device=t.device, dtype=torch.float32)
+    out = torch.empty(b, tdim, device=t.device, dtype=torch.float32)
+    _call("tedm_time_embed_train", _ptr(t, torch.int64, "t"), _ptr(freq, torch.float32), _ptr(w1, torch.float32),
+          _ptr(b1, torch.float32), _ptr(w2, torch.float32), _ptr(b2, torch.float32), _ptr(emb), _ptr(hid), _ptr(out), b, dim,
+          tdim, _stream())
+    return emb, hid, out
+
+
+ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
+
+
+def linear_bwd(dy_raw, y_pre, act_y: int, x, act_x: int, w, dw, db, want_dx: bool = True):
+    b, n_out = dy_raw.shape
+    n_in = x.shape[1]
+    dx = torch.empty(b, n_in, device=x.device, dtype=torch.float32) if want_dx else None
+    _call("tedm_linear_bwd", _ptr(dy_raw, torch.float32, "dy_raw"), _ptr(y_pre, torch.float32), act_y, _ptr(x, torch.float32, "x"),
+          act_x, _ptr(w, torch.float32, "w"), _ptr(dw, torch.float32, "dw"), _ptr(db, torch.float32), _ptr(dx), b, n_out, n_in,
+          _stream())
+    return dx
+
+
+def linear_attention_bwd(qkv, dout, fwd_ws, heads: int = 4, dim_head: int = 32, scale: Optional[float] = None):
+    b, h, w, c3 = qkv.shape
+    n = h * w
+    ws_n = load().tedm_linear_attention_bwd_workspace(b, n, heads, dim_head)
+    if ws_n < 0:
+        raise RuntimeError("linear_attention_bwd: unsupported configuration")
+    ws = torch.empty(ws_n, device=qkv.device, dtype=torch.float32)
+    dqkv = torch.empty_like(qkv)
+    _call("tedm_linear_attention_bwd", _ptr(qkv, torch.bfloat16, "qkv"), _ptr(dout, torch.bfloat16, "dout"),
+          _ptr(fwd_ws, torch.float32, "fwd_ws"), _ptr(dqkv), _ptr(ws), b, n, heads, dim_head,
+          float(dim_head ** -0.5 if scale is None else scale), _stream())
+    return dqkv
+
+
+def attention_bwd(qkv, dout, heads: int = 4, dim_head: int = 32, scale: float = 16.0):
+    b, h, w, c3 = qkv.shape
+    dqkv = torch.empty_like(qkv)
+    _call("tedm_attention_bwd", _ptr(qkv, torch.bfloat16, "qkv"), _ptr(dout, torch.bfloat16, "dout"), _ptr(dqkv), b, h * w, heads,
+          dim_head, float(scale), _stream())
+    return dqkv
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr: float, beta1: float, beta2: float, eps: float, weight_decay: float,
+              step: int, grad_scale: float = 1.0) -> None:
+    n = param.numel()
+    _call("tedm_adam_step", _ptr(param, torch.float32, "param"), _ptr(grad, torch.float32, "grad"),
+          _ptr(exp_avg, torch.float32), _ptr(exp_avg_sq, torch.float32), n, lr, beta1, beta2, eps, weight_decay, step,
+          grad_scale, _stream())
 
 
 # ------------------------------------------------------------------------------------------------
