@@ -1,5 +1,6 @@
-"""Kernel schedule of the UNet forward on sm_100a (the body of reference `Unet.forward`,
-models/unet_model.py:333-368, restated as a sequence of fused native ops).
+"""Kernel schedule of the UNet forward AND backward on sm_100a (the body of reference `Unet.forward`,
+models/unet_model.py:333-368, restated as a sequence of fused native ops, plus the hand-scheduled
+reverse pass that torch autograd derives for the reference).
 
 Data layout in HBM: activations NHWC bf16; conv weights bf16 [Cout][kh][kw][Cin] (a derived cache
 of the fp32 OIHW parameters, rebuilt when a parameter's version counter changes); GroupNorm
@@ -7,6 +8,13 @@ statistics, time embeddings and everything scalar fp32.  Skip-connection concats
 materialised (the conv kernel's K loop walks two sources); the ResnetBlock residual add is fused
 into the second GroupNorm+SiLU pass; the mid-attention residual into the to_out conv epilogue; the
 LinearAttention residual into the output LayerNorm.
+
+Backward: the data gradient of every convolution runs on the SAME tcgen05 implicit-GEMM kernel with
+re-laid-out weights (flipped/transposed 3x3; the stride-2 4x4 becomes a parity conv and vice versa);
+the weight gradient is a second tcgen05 kernel contracting over pixels; gradient accumulation at
+residual / skip joins rides the conv epilogue's `residual` input.  Parameter gradients are written
+into one flat fp32 arena (parameter order), so a data-parallel step needs ONE all-reduce and the
+optimiser ONE kernel.
 """
 from __future__ import annotations
 
@@ -38,6 +46,30 @@ class WeightCache:
         self._store.clear()
 
 
+class Tape:
+    """What one training-mode forward keeps for its backward: saved activations by op key."""
+
+    def __init__(self):
+        self.saved: Dict[str, tuple] = {}
+
+
+class GradArena:
+    """One flat fp32 buffer holding every parameter gradient, in `module.parameters()` order."""
+
+    def __init__(self, params: List[nn.Parameter], device):
+        self.offsets: Dict[int, Tuple[int, torch.Size]] = {}
+        off = 0
+        for p in params:
+            self.offsets[id(p)] = (off, p.shape)
+            off += p.numel()
+        self.numel = off
+        self.flat = torch.zeros((off + 3) // 4 * 4, device=device, dtype=torch.float32)
+
+    def of(self, p: nn.Parameter) -> Tensor:
+        off, shape = self.offsets[id(p)]
+        return self.flat[off:off + p.numel()].view(shape)
+
+
 class UnetEngine:
     def __init__(self, unet: nn.Module, fold_upsample: bool = True, ln_eps: float = 1e-5):
         self.m = unet
@@ -59,6 +91,7 @@ class UnetEngine:
             self._ss_offset[id(rb)] = off
             off += rb.time_mlp[1].weight.shape[0]
         self._ss_total = off
+        self.last_grad_arena: Optional[GradArena] = None
 
     # -- derived weights ------------------------------------------------------------------------
     def _f32(self, p: Tensor) -> Tensor:
@@ -70,6 +103,9 @@ class UnetEngine:
     def _folded(self, key: str, w: Tensor) -> Tensor:
         return self.cache.get(key + ":fold", (w,), lambda a: N.fold_upsample_weight(a.float()))
 
+    def _dgrad_w(self, key: str, w: Tensor, mode: int) -> Tensor:
+        return self.cache.get(key + ":dgrad", (w,), lambda a: N.weight_to_dgrad(a.float(), mode))
+
     def _time_cat(self) -> Tuple[Tensor, Tensor]:
         ws = tuple(rb.time_mlp[1].weight for rb in self._resblocks)
         bs = tuple(rb.time_mlp[1].bias for rb in self._resblocks)
@@ -79,16 +115,19 @@ class UnetEngine:
 
     # -- blocks -----------------------------------------------------------------------------------
     def _block(self, key: str, blk: nn.Module, x0: Tensor, x1: Optional[Tensor], ss, ss_off: int,
-               residual: Optional[Tensor]) -> Tensor:
+               residual: Optional[Tensor], tape: Optional[Tape] = None) -> Tensor:
         cout = blk.proj.weight.shape[0]
         h, part = N.conv_igemm(x0, self._krsc(key + ".proj", blk.proj.weight), N.MODE_3X3, cout,
                                bias=self._f32(blk.proj.bias), src1=x1, gn_groups=blk.norm.num_groups)
+        if tape is not None:
+            tape.saved[key] = (x0, x1, h, part)
         return N.gn_silu(h, part, self._f32(blk.norm.weight), self._f32(blk.norm.bias), blk.norm.num_groups,
                          eps=blk.norm.eps, scale_shift=ss, ss_offset=ss_off, residual=residual)
 
-    def _resblock(self, key: str, rb: nn.Module, x0: Tensor, x1: Optional[Tensor], tproj: Optional[Tensor]) -> Tensor:
+    def _resblock(self, key: str, rb: nn.Module, x0: Tensor, x1: Optional[Tensor], tproj: Optional[Tensor],
+                  tape: Optional[Tape] = None) -> Tensor:
         ss_off = self._ss_offset[id(rb)]
-        h = self._block(key + ".block1", rb.block1, x0, x1, tproj, ss_off, None)
+        h = self._block(key + ".block1", rb.block1, x0, x1, tproj, ss_off, None, tape)
         if isinstance(rb.res_conv, nn.Conv2d):
             cout = rb.res_conv.weight.shape[0]
             res = N.conv_igemm(x0, self._krsc(key + ".res_conv", rb.res_conv.weight), N.MODE_1X1, cout,
@@ -97,29 +136,37 @@ class UnetEngine:
             if x1 is not None:
                 raise RuntimeError("identity residual with a two-source input")
             res = x0
-        return self._block(key + ".block2", rb.block2, h, None, None, 0, res)
+        return self._block(key + ".block2", rb.block2, h, None, None, 0, res, tape)
 
-    def _linear_attention(self, key: str, wrap: nn.Module, x: Tensor) -> Tensor:
+    def _linear_attention(self, key: str, wrap: nn.Module, x: Tensor, tape: Optional[Tape] = None) -> Tensor:
         pre, att = wrap.fn.norm, wrap.fn.fn
         c = x.shape[-1]
         y = N.layernorm(x, self._f32(pre.g).reshape(-1), eps=self.ln_eps)
         qkv = N.conv_igemm(y, self._krsc(key + ".to_qkv", att.to_qkv.weight), N.MODE_1X1, att.to_qkv.weight.shape[0])
-        o = N.linear_attention(qkv, att.heads, att.dim_head, att.scale)
-        o = N.conv_igemm(o, self._krsc(key + ".to_out", att.to_out[0].weight), N.MODE_1X1, c,
-                         bias=self._f32(att.to_out[0].bias))
-        return N.layernorm(o, self._f32(att.to_out[1].g).reshape(-1), eps=self.ln_eps, residual=x)
+        if tape is not None:
+            o, ws = N.linear_attention(qkv, att.heads, att.dim_head, att.scale, want_workspace=True)
+        else:
+            o = N.linear_attention(qkv, att.heads, att.dim_head, att.scale)
+        o2 = N.conv_igemm(o, self._krsc(key + ".to_out", att.to_out[0].weight), N.MODE_1X1, c,
+                          bias=self._f32(att.to_out[0].bias))
+        if tape is not None:
+            tape.saved[key] = (x, y, qkv, o, o2, ws)
+        return N.layernorm(o2, self._f32(att.to_out[1].g).reshape(-1), eps=self.ln_eps, residual=x)
 
-    def _mid_attention(self, key: str, wrap: nn.Module, x: Tensor) -> Tensor:
+    def _mid_attention(self, key: str, wrap: nn.Module, x: Tensor, tape: Optional[Tape] = None) -> Tensor:
         pre, att = wrap.fn.norm, wrap.fn.fn
         c = x.shape[-1]
         y = N.layernorm(x, self._f32(pre.g).reshape(-1), eps=self.ln_eps)
         qkv = N.conv_igemm(y, self._krsc(key + ".to_qkv", att.to_qkv.weight), N.MODE_1X1, att.to_qkv.weight.shape[0])
         o = N.attention(qkv, att.heads, att.dim_head, float(att.scale))
+        if tape is not None:
+            tape.saved[key] = (x, y, qkv, o)
         return N.conv_igemm(o, self._krsc(key + ".to_out", att.to_out.weight), N.MODE_1X1, c,
                             bias=self._f32(att.to_out.bias), residual=x)
 
     # -- whole network ----------------------------------------------------------------------------
-    def forward(self, x: Tensor, timestep: Optional[Tensor], want_features: bool = False, skip_tail: bool = False):
+    def forward(self, x: Tensor, timestep: Optional[Tensor], want_features: bool = False, skip_tail: bool = False,
+                tape: Optional[Tape] = None):
         m = self.m
         if not x.is_cuda:
             raise RuntimeError("tedm_b200.Unet runs on CUDA (sm_100a) only; there is no CPU fallback")
@@ -131,8 +178,13 @@ class UnetEngine:
             t = timestep.detach().to(device=x.device, dtype=torch.int64).contiguous()
             pe = m.time_mlp[0]
             freq = self.cache.get("freq", (m.time_mlp[1].weight,), lambda w: pe.frequencies(w.device).float().contiguous())
-            temb = N.time_embed(t, freq, self._f32(m.time_mlp[1].weight), self._f32(m.time_mlp[1].bias),
-                                self._f32(m.time_mlp[3].weight), self._f32(m.time_mlp[3].bias))
+            tw = (self._f32(m.time_mlp[1].weight), self._f32(m.time_mlp[1].bias),
+                  self._f32(m.time_mlp[3].weight), self._f32(m.time_mlp[3].bias))
+            if tape is not None:
+                emb, hid, temb = N.time_embed_train(t, freq, *tw)
+                tape.saved["time"] = (emb, hid, temb)
+            else:
+                temb = N.time_embed(t, freq, *tw)
             wcat, bcat = self._time_cat()
             tproj = N.time_proj(temb, wcat, bcat)
 
@@ -141,26 +193,30 @@ class UnetEngine:
         skips: List[Tensor] = []
         for i, (b1, b2, attn, down) in enumerate(m.downs):
             k = f"downs.{i}"
-            h = self._resblock(k + ".0", b1, h, None, tproj)
+            h = self._resblock(k + ".0", b1, h, None, tproj, tape)
             skips.append(h)
-            h = self._resblock(k + ".1", b2, h, None, tproj)
-            h = self._linear_attention(k + ".2", attn, h)
+            h = self._resblock(k + ".1", b2, h, None, tproj, tape)
+            h = self._linear_attention(k + ".2", attn, h, tape)
             skips.append(h)
             mode = N.MODE_4X4S2 if down.kernel_size[0] == 4 else N.MODE_3X3
+            if tape is not None:
+                tape.saved[k + ".3"] = (h,)
             h = N.conv_igemm(h, self._krsc(k + ".3", down.weight), mode, down.weight.shape[0], bias=self._f32(down.bias))
-        h = self._resblock("mid_block1", m.mid_block1, h, None, tproj)
-        h = self._mid_attention("mid_attn", m.mid_attn, h)
-        h = self._resblock("mid_block2", m.mid_block2, h, None, tproj)
+        h = self._resblock("mid_block1", m.mid_block1, h, None, tproj, tape)
+        h = self._mid_attention("mid_attn", m.mid_attn, h, tape)
+        h = self._resblock("mid_block2", m.mid_block2, h, None, tproj, tape)
         feats: List[Tensor] = []
         n_up = len(m.ups)
         for i, (b1, b2, attn, up) in enumerate(m.ups):
             k = f"ups.{i}"
-            h = self._resblock(k + ".0", b1, h, skips.pop(), tproj)
-            h = self._resblock(k + ".1", b2, h, skips.pop(), tproj)
-            h = self._linear_attention(k + ".2", attn, h)
+            h = self._resblock(k + ".0", b1, h, skips.pop(), tproj, tape)
+            h = self._resblock(k + ".1", b2, h, skips.pop(), tproj, tape)
+            h = self._linear_attention(k + ".2", attn, h, tape)
             feats.append(h)
             if skip_tail and i == n_up - 1:
                 return None, feats
+            if tape is not None:
+                tape.saved[k + ".3"] = (h,)
             if isinstance(up, nn.Sequential):          # Upsample: nearest x2 + 3x3 conv
                 conv = up[1]
                 if self.fold_upsample:
@@ -171,6 +227,163 @@ class UnetEngine:
                                      conv.weight.shape[0], bias=self._f32(conv.bias))
             else:
                 h = N.conv_igemm(h, self._krsc(k + ".3", up.weight), N.MODE_3X3, up.weight.shape[0], bias=self._f32(up.bias))
-        h = self._resblock("final_res_block", m.final_res_block, h, stem, tproj)
+        h = self._resblock("final_res_block", m.final_res_block, h, stem, tproj, tape)
         out = N.final_conv1x1(h, self._f32(m.final_conv.weight).reshape(m.out_dim, -1), self._f32(m.final_conv.bias))
+        if tape is not None:
+            tape.saved["io"] = (x, tproj, h)
         return (out, feats) if want_features else out
+
+    # =============================================================================================
+    # backward
+    # =============================================================================================
+    def _conv_bwd(self, key: str, conv: nn.Conv2d, mode: int, x0: Tensor, x1: Optional[Tensor], dy: Tensor, G: GradArena,
+                  add0: Optional[Tensor] = None, add1: Optional[Tensor] = None, bias_grad: bool = True,
+                  need_dx: bool = True):
+        """Weight (+bias) gradient of conv(x0[, x1]) and its data gradient(s); add0/add1 are gradients already
+        flowing into x0/x1 from elsewhere (fused through the conv epilogue's residual input)."""
+        cout = conv.weight.shape[0]
+        c0 = x0.shape[-1]
+        c1 = x1.shape[-1] if x1 is not None else 0
+        dw = N.conv_wgrad(x0, dy, mode, src1=x1)
+        N.wgrad_to_oihw(dw, G.of(conv.weight), mode)
+        if bias_grad and conv.bias is not None:
+            N.bias_grad(dy, G.of(conv.bias))
+        if not need_dx:
+            return None, None
+        wd = self._dgrad_w(key, conv.weight, mode)
+        run_mode = {N.MODE_1X1: N.MODE_1X1, N.MODE_3X3: N.MODE_3X3, N.MODE_4X4S2: N.MODE_UP3X3,
+                    N.MODE_UP3X3: N.MODE_4X4S2}[mode]
+        taps = {N.MODE_1X1: 1, N.MODE_3X3: 9, N.MODE_4X4S2: 16, N.MODE_UP3X3: 16}[mode]
+        if c1 == 0:
+            return N.conv_igemm(dy, wd, run_mode, c0, residual=add0), None
+        if mode not in (N.MODE_1X1, N.MODE_3X3):
+            raise RuntimeError("two-source convolutions are 1x1 or 3x3")
+        split = c0 * taps * cout
+        dx0 = N.conv_igemm(dy, wd[:split], run_mode, c0, residual=add0)
+        dx1 = N.conv_igemm(dy, wd[split:], run_mode, c1, residual=add1)
+        return dx0, dx1
+
+    def _block_bwd(self, key: str, blk: nn.Module, dy: Tensor, tape: Tape, G: GradArena, ss, ss_off: int, dss,
+                   add0: Optional[Tensor] = None, add1: Optional[Tensor] = None):
+        x0, x1, h, part = tape.saved[key]
+        dh = N.gn_silu_bwd(h, dy, part, self._f32(blk.norm.weight), self._f32(blk.norm.bias), blk.norm.num_groups,
+                           G.of(blk.norm.weight), G.of(blk.norm.bias), G.of(blk.proj.bias), eps=blk.norm.eps,
+                           scale_shift=ss, ss_offset=ss_off, dscale_shift=dss if ss is not None else None)
+        return self._conv_bwd(key + ".proj", blk.proj, N.MODE_3X3, x0, x1, dh, G, add0, add1, bias_grad=False)
+
+    def _resblock_bwd(self, key: str, rb: nn.Module, dout: Tensor, tape: Tape, G: GradArena, tproj, dss):
+        """out = block2(block1(x)) + res(x)  ->  (d x0, d x1)."""
+        ss_off = self._ss_offset[id(rb)]
+        da1, _ = self._block_bwd(key + ".block2", rb.block2, dout, tape, G, None, 0, None)
+        x0, x1 = tape.saved[key + ".block1"][:2]
+        if isinstance(rb.res_conv, nn.Conv2d):
+            r0, r1 = self._conv_bwd(key + ".res_conv", rb.res_conv, N.MODE_1X1, x0, x1, dout, G)
+        else:
+            r0, r1 = dout, None
+        return self._block_bwd(key + ".block1", rb.block1, da1, tape, G, tproj, ss_off, dss, add0=r0, add1=r1)
+
+    def _linear_attention_bwd(self, key: str, wrap: nn.Module, dout: Tensor, tape: Tape, G: GradArena) -> Tensor:
+        pre, att = wrap.fn.norm, wrap.fn.fn
+        x, y, qkv, o, o2, ws = tape.saved[key]
+        do2 = N.layernorm_bwd(o2, self._f32(att.to_out[1].g).reshape(-1), dout, G.of(att.to_out[1].g).view(-1), eps=self.ln_eps)
+        do, _ = self._conv_bwd(key + ".to_out", att.to_out[0], N.MODE_1X1, o, None, do2, G)
+        dqkv = N.linear_attention_bwd(qkv, do, ws, att.heads, att.dim_head, att.scale)
+        dy, _ = self._conv_bwd(key + ".to_qkv", att.to_qkv, N.MODE_1X1, y, None, dqkv, G)
+        return N.layernorm_bwd(x, self._f32(pre.g).reshape(-1), dy, G.of(pre.g).view(-1), eps=self.ln_eps, add=dout)
+
+    def _mid_attention_bwd(self, key: str, wrap: nn.Module, dout: Tensor, tape: Tape, G: GradArena) -> Tensor:
+        pre, att = wrap.fn.norm, wrap.fn.fn
+        x, y, qkv, o = tape.saved[key]
+        do, _ = self._conv_bwd(key + ".to_out", att.to_out, N.MODE_1X1, o, None, dout, G)
+        dqkv = N.attention_bwd(qkv, do, att.heads, att.dim_head, float(att.scale))
+        dy, _ = self._conv_bwd(key + ".to_qkv", att.to_qkv, N.MODE_1X1, y, None, dqkv, G)
+        return N.layernorm_bwd(x, self._f32(pre.g).reshape(-1), dy, G.of(pre.g).view(-1), eps=self.ln_eps, add=dout)
+
+    def backward(self, tape: Tape, dout: Tensor) -> GradArena:
+        """Given d loss / d output (B, out_dim, H, W) fp32, fill a fresh gradient arena (parameter order)."""
+        m = self.m
+        params = list(m.parameters())
+        G = GradArena(params, dout.device)
+        x, tproj, hfinal = tape.saved["io"]
+        dss = torch.empty_like(tproj) if tproj is not None else None
+        dout = dout.detach().float().contiguous()
+        dh = N.final_conv1x1_bwd(hfinal, self._f32(m.final_conv.weight).reshape(m.out_dim, -1), dout,
+                                 G.of(m.final_conv.weight).view(m.out_dim, -1), G.of(m.final_conv.bias))
+        dh, dstem_skip = self._resblock_bwd("final_res_block", m.final_res_block, dh, tape, G, tproj, dss)
+        dskips: List[Tensor] = []
+        n_up = len(m.ups)
+        for i in reversed(range(n_up)):
+            b1, b2, attn, up = m.ups[i]
+            k = f"ups.{i}"
+            (hin,) = tape.saved[k + ".3"]
+            if isinstance(up, nn.Sequential):
+                if not self.fold_upsample:
+                    raise RuntimeError("training runs with the folded upsample conv")
+                dh, _ = self._conv_bwd(k + ".3.1", up[1], N.MODE_UP3X3, hin, None, dh, G)
+            else:
+                dh, _ = self._conv_bwd(k + ".3", up, N.MODE_3X3, hin, None, dh, G)
+            dh = self._linear_attention_bwd(k + ".2", attn, dh, tape, G)
+            dh, ds2 = self._resblock_bwd(k + ".1", b2, dh, tape, G, tproj, dss)
+            dh, ds1 = self._resblock_bwd(k + ".0", b1, dh, tape, G, tproj, dss)
+            # forward popped the skips in the order (b1: after-attention map, b2: after-block1 map)
+            dskips.append(ds2)
+            dskips.append(ds1)
+        dh, _ = self._resblock_bwd("mid_block2", m.mid_block2, dh, tape, G, tproj, dss)
+        dh = self._mid_attention_bwd("mid_attn", m.mid_attn, dh, tape, G)
+        dh, _ = self._resblock_bwd("mid_block1", m.mid_block1, dh, tape, G, tproj, dss)
+        for i in reversed(range(len(m.downs))):
+            b1, b2, attn, down = m.downs[i]
+            k = f"downs.{i}"
+            (hin,) = tape.saved[k + ".3"]
+            d_attn_skip = dskips.pop()      # gradient of the after-attention map from the decoder
+            d_b1_skip = dskips.pop()        # gradient of the after-block1 map from the decoder
+            mode = N.MODE_4X4S2 if down.kernel_size[0] == 4 else N.MODE_3X3
+            dh, _ = self._conv_bwd(k + ".3", down, mode, hin, None, dh, G, add0=d_attn_skip)
+            dh = self._linear_attention_bwd(k + ".2", attn, dh, tape, G)
+            dh, _ = self._resblock_bwd(k + ".1", b2, dh, tape, G, tproj, dss)
+            dh = N.add_bf16(dh, d_b1_skip)
+            dh, _ = self._resblock_bwd(k + ".0", b1, dh, tape, G, tproj, dss)
+        dstem = N.add_bf16(dh, dstem_skip)
+        N.stem_conv7x7_wgrad(x, dstem, G.of(m.init_conv.weight), G.of(m.init_conv.bias))
+        if tproj is not None:
+            self._time_bwd(tape, dss, G)
+        self.last_grad_arena = G
+        return G
+
+    def _time_bwd(self, tape: Tape, dss: Tensor, G: GradArena) -> None:
+        m = self.m
+        emb, hid, temb = tape.saved["time"]
+        wcat, _ = self._time_cat()
+        total, tdim = wcat.shape
+        dwcat = torch.zeros(total, tdim, device=dss.device, dtype=torch.float32)
+        dbcat = torch.zeros(total, device=dss.device, dtype=torch.float32)
+        d3 = N.linear_bwd(dss, None, N.ACT_NONE, temb, N.ACT_SILU, wcat, dwcat, dbcat)
+        d2 = N.linear_bwd(d3, temb, N.ACT_SILU, hid, N.ACT_GELU, self._f32(m.time_mlp[3].weight),
+                          G.of(m.time_mlp[3].weight), G.of(m.time_mlp[3].bias))
+        N.linear_bwd(d2, hid, N.ACT_GELU, emb, N.ACT_NONE, self._f32(m.time_mlp[1].weight),
+                     G.of(m.time_mlp[1].weight), G.of(m.time_mlp[1].bias), want_dx=False)
+        off = 0
+        for rb in self._resblocks:      # scatter the concatenated projection gradient back to its owners
+            lin = rb.time_mlp[1]
+            n = lin.weight.shape[0]
+            G.of(lin.weight).copy_(dwcat[off:off + n])
+            G.of(lin.bias).copy_(dbcat[off:off + n])
+            off += n
+
+
+class UnetFunction(torch.autograd.Function):
+    """Autograd node for the whole UNet: forward and backward are both native kernel schedules."""
+
+    @staticmethod
+    def forward(ctx, engine: UnetEngine, x: Tensor, timestep: Optional[Tensor], *params: Tensor) -> Tensor:
+        tape = Tape()
+        out = engine.forward(x, timestep, tape=tape)
+        ctx.engine, ctx.tape, ctx.params = engine, tape, params
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: Tensor):
+        G = ctx.engine.backward(ctx.tape, dout)
+        ctx.tape = None
+        grads = tuple(G.of(p) if p.requires_grad else None for p in ctx.params)
+        return (None, None, None) + grads

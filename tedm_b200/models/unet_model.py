@@ -164,6 +164,11 @@ class Unet(nn.Module):
     def forward(self, x: Tensor, timestep: Optional[Tensor] = None, cond: Optional[Tensor] = None) -> Tensor:
         """(B, channels, H, W) fp32, (B,) int64 -> (B, out_dim, H, W) fp32.  `cond` is accepted and ignored,
         as in the reference (unet_model.py:333)."""
+        params = tuple(self.parameters())
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            # training: forward keeps a tape, backward is the native reverse schedule (tedm_b200/engine.py)
+            from ..engine import UnetFunction
+            return UnetFunction.apply(self.engine, x, timestep, *params)
         return self.engine.forward(x, timestep)
 
     def forward_features(self, x: Tensor, timestep: Optional[Tensor], skip_tail: bool = True):

@@ -159,3 +159,26 @@ def test_bf16_storage_emulation_within_tolerance(golden, ddpm_sd):
     errs = [rel(out, g["unet_out"])] + [rel(f, g[f"feat{i}"]) for i, f in enumerate(feats)]
     print("bf16 emulation rel errors (out, feat0..3):", errs)
     assert max(errs) < 2e-2
+
+
+def test_oracle_training_gradients_match_reference(golden):
+    """Autograd through the oracle's DDPM loss reproduces the gradients of the live reference's
+    train_step + backward (tests/golden/make_golden_grads.py): this pins the oracle for the training path."""
+    from tests.golden.make_golden_grads_idx import sample_idx
+    g, gs = golden["ddpm_small_grads"], golden["ddpm_small"]
+    sd = synth_state_dict(O.unet_param_shapes(prefix="model."), 0)
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    full = dict(sd)
+    full.update(O.schedule_tables())
+    x0, t, nz = (torch.from_numpy(gs[k]) for k in ("x0", "t", "noise"))
+    loss = O.ddpm_loss(full, x0, t, nz)
+    assert abs(loss.item() - float(g["loss"])) < 1e-5
+    loss.backward()
+    num = den = 0.0
+    for k, v in sd.items():
+        name = k
+        ref = torch.from_numpy(g[f"sample/{name}"]).double()
+        got = v.grad.reshape(-1).double()[torch.from_numpy(sample_idx(v.numel()))]
+        num += float((got - ref).pow(2).sum())
+        den += float(ref.pow(2).sum())
+    assert (num / den) ** 0.5 < 1e-3, (num / den) ** 0.5
