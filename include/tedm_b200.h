@@ -119,8 +119,11 @@ TEDM_API int tedm_conv_igemm_fwd(const tedm_conv_args* args, tedm_stream_t strea
  * dw[co][tap][ci] = sum over pixels of dy[pixel][co] * src[pixel + tap offset][ci], fp32, overwritten.
  * `args` describes the forward call (src0/src1/extent/mode/cout; weight, bias, residual, out, gn_* are ignored;
  * out_image_stride, if non-zero, is dy's image stride); dy is the NHWC bf16 output gradient.  taps = 1 (mode 0),
- * 9 (mode 1), 16 (mode 2: ky*4+kx; mode 3: parity*4 + a*2 + b of the folded 2x2 kernels). */
-TEDM_API int tedm_conv_igemm_wgrad(const tedm_conv_args* args, const void* dy, float* dw, tedm_stream_t stream);
+ * 9 (mode 1), 16 (mode 2: ky*4+kx; mode 3: parity*4 + a*2 + b of the folded 2x2 kernels).
+ * With oihw_accumulate != 0, dw is instead the fp32 OIHW parameter gradient [cout][c0+c1][kh][kw] and the result is
+ * ACCUMULATED into it (mode 3: the folded taps are scattered back onto the 3x3 kernel of Upsample's conv). */
+TEDM_API int tedm_conv_igemm_wgrad(const tedm_conv_args* args, const void* dy, float* dw, int oihw_accumulate,
+                          tedm_stream_t stream);
 /* number of partial-statistics slots per image that tedm_conv_igemm_fwd writes for this output extent */
 TEDM_API int tedm_conv_gn_parts(int out_height, int out_width);
 /* tuning/debug: force the N tile (64/128/256; 0 = automatic) of tedm_conv_igemm_fwd */
@@ -133,6 +136,16 @@ TEDM_API int tedm_weight_to_krsc(const float* w_oihw, void* w_krsc, int cout, in
                         tedm_stream_t stream);
 /* fp32 OIHW 3x3 -> bf16 [4 parities][Cout][2][2][Cin] for mode 3. */
 TEDM_API int tedm_fold_upsample_weight(const float* w_oihw, void* w_folded, int cout, int cin, tedm_stream_t stream);
+/* All conv weights of a net in ONE launch (a training step changes every weight): table_dev is a DEVICE array of
+ * entries; entry i covers CTAs [cta_begin, cta_begin + (cout/32)*(cin/32)); cout, cin multiples of 32.
+ * fwd: KRSC (modes 0-2) or the folded layout (mode 3); dgrad: the tedm_weight_to_dgrad layout; either may be NULL. */
+typedef struct {
+  const void* w;   /* fp32 OIHW parameter */
+  void* fwd;       /* bf16 forward operand or NULL */
+  void* dgrad;     /* bf16 data-gradient operand or NULL */
+  int cout, cin, mode, cta_begin;
+} tedm_weight_entry;
+TEDM_API int tedm_prepare_weights(const tedm_weight_entry* table_dev, int n_entries, int total_ctas, tedm_stream_t stream);
 
 /* GroupNorm finalise + affine + optional (scale+1)/shift + SiLU (+ residual), one pass.
  * Replaces Block.forward after the conv (models/unet_model.py:126-135) and the residual add of
@@ -233,11 +246,13 @@ TEDM_API int tedm_linear_attention_bwd(const void* qkv, const void* dout, const 
 TEDM_API int tedm_attention_bwd(const void* qkv, const void* dout, void* dqkv, int batch, int n, int heads, int dim_head,
                        float scale, tedm_stream_t stream);
 
-/* torch.optim.Adam update (trainers/train_CXR14.py:139) over a flat fp32 arena; n % 4 == 0; `step` >= 1 is
- * the 1-based step count (bias correction computed on the host); grad is multiplied by grad_scale first. */
+/* torch.optim.Adam update (trainers/train_CXR14.py:139) over a flat fp32 arena; n % 4 == 0; grad is multiplied by
+ * grad_scale first.  The 1-based step count for the bias correction is `step`, or, when step_counter (a DEVICE int)
+ * is given, the counter's value after this call has incremented it -- so that a step replayed from a CUDA graph
+ * still advances. */
 TEDM_API int tedm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                   float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                   tedm_stream_t stream);
+                   float beta1, float beta2, float eps, float weight_decay, int step, int* step_counter,
+                   float grad_scale, tedm_stream_t stream);
 
 /* ---- TEDM / LEDM head ---------------------------------------------------------------------- */
 

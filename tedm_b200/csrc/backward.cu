@@ -691,10 +691,16 @@ __global__ void wgrad_to_oihw_kernel(const float* __restrict__ dw, float* __rest
 // ------------------------------------------------------------------------------------------
 // Adam (torch.optim.Adam semantics, trainers/train_CXR14.py:139) over a flat fp32 parameter arena
 // ------------------------------------------------------------------------------------------
+__global__ void adam_tick_kernel(int* step) { *step += 1; }
+
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
                                                    float4* __restrict__ v, long long n4, float lr, float beta1, float beta2,
-                                                   float eps, float weight_decay, float inv_bc1, float inv_sqrt_bc2,
+                                                   float eps, float weight_decay, const int* __restrict__ step_dev, int step_host,
                                                    float grad_scale) {
+  // bias corrections from the 1-based step count (device counter when the step is replayed from a CUDA graph)
+  const double step = (double)(step_dev ? *step_dev : step_host);
+  const float inv_bc1 = (float)(1.0 / (1.0 - pow((double)beta1, step)));
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)beta2, step)));
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
     float* pa = &pp.x; float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
@@ -879,14 +885,18 @@ extern "C" int tedm_wgrad_to_oihw(const float* dw, float* grad_oihw, int cout, i
 }
 
 extern "C" int tedm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                              float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                              tedm_stream_t stream) {
-  TEDM_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && n % 4 == 0 && step >= 1,
+                              float beta1, float beta2, float eps, float weight_decay, int step, int* step_counter,
+                              float grad_scale, tedm_stream_t stream) {
+  TEDM_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && n % 4 == 0 && (step >= 1 || step_counter),
                  "tedm_adam_step: bad arguments (n must be a multiple of 4)");
-  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-  adam_kernel<<<grid_for(n / 4, 256, 16), 256, 0, (cudaStream_t)stream>>>(
-      (float4*)param, (const float4*)grad, (float4*)exp_avg, (float4*)exp_avg_sq, n / 4, lr, beta1, beta2, eps, weight_decay,
-      (float)(1.0 / bc1), (float)(1.0 / sqrt(bc2)), grad_scale);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (step_counter) {
+    adam_tick_kernel<<<1, 1, 0, s>>>(step_counter);
+    TEDM_LAUNCH_CHECK();
+  }
+  adam_kernel<<<grid_for(n / 4, 256, 16), 256, 0, s>>>((float4*)param, (const float4*)grad, (float4*)exp_avg,
+                                                       (float4*)exp_avg_sq, n / 4, lr, beta1, beta2, eps, weight_decay,
+                                                       step_counter, step, grad_scale);
   TEDM_LAUNCH_CHECK();
   return TEDM_OK;
 }

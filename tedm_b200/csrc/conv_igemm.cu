@@ -539,6 +539,7 @@ struct WgradParams {
   int tileW, tileH, tileB, tiles_x, tiles_y;
   int B, cout;
   int items, n_tiles, splitk, num_ptiles, stages;
+  int oihw;                      // 1: accumulate into an fp32 OIHW gradient (mode 3: un-folded to 3x3)
   float* dw;
 };
 
@@ -661,7 +662,24 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_consta
     const int item = half ? item1 : item0;
     const bool live = num_kb > 0 && (half == 0 || item1 != item0);
     const int tap = item / cb_total, cb = item % cb_total;
-    float* dst_row = p.dw + (size_t)tap * p.ctot + cb * BK + (row & 63);
+    const int ci = cb * BK + (row & 63);
+    // destination of output channel co:  base + co * co_stride (+ extra 3x3 taps when un-folding mode 3)
+    size_t base, co_stride;
+    int ny = 1, nx = 1;          // mode 3 + oihw: the folded tap (par, a, b) feeds ny x nx taps of the 3x3 kernel
+    if (!p.oihw) {
+      base = (size_t)tap * p.ctot + ci;
+      co_stride = (size_t)p.taps * p.ctot;
+    } else if (p.mode != 3) {
+      base = (size_t)ci * p.taps + tap;
+      co_stride = (size_t)p.ctot * p.taps;
+    } else {
+      const int par = tap >> 2, a = (tap >> 1) & 1, b = tap & 1, py = par >> 1, px = par & 1;
+      const int ky0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), kx0 = px == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2);
+      ny = (py == 0) == (a == 1) ? 2 : 1;
+      nx = (px == 0) == (b == 1) ? 2 : 1;
+      base = (size_t)ci * 9 + ky0 * 3 + kx0;
+      co_stride = (size_t)p.ctot * 9;
+    }
     if (num_kb > 0) {
       mbar_wait(smem_u32(&bar_acc), 0);
       tc_fence_after();
@@ -672,8 +690,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_consta
         tmem_ld_wait();
         if (live) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            atomicAdd(dst_row + (size_t)(n0 + chunk * 32 + j) * p.taps * p.ctot, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; ++j) {
+            float* d = p.dw + base + (size_t)(n0 + chunk * 32 + j) * co_stride;
+            const float v = __uint_as_float(r[j]);
+            for (int yy = 0; yy < ny; ++yy)
+              for (int xx = 0; xx < nx; ++xx) atomicAdd(d + yy * 3 + xx, v);
+          }
         }
       }
     }
@@ -836,8 +858,10 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   }
 }
 
-// dw: fp32 [cout][taps][c0+c1] (taps = 1 / 9 / 16; mode 3: 16 = parity*4 + a*2 + b of the folded kernel), overwritten.
-extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, float* dw, tedm_stream_t stream) {
+// dw: fp32 [cout][taps][c0+c1] (taps = 1 / 9 / 16; mode 3: 16 = parity*4 + a*2 + b of the folded kernel), overwritten;
+// or, with oihw_accumulate, the fp32 OIHW parameter gradient itself (+=; the folded taps of mode 3 are scattered to 3x3).
+extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, float* dw, int oihw_accumulate,
+                                     tedm_stream_t stream) {
   TEDM_CHECK_ARG(a && a->src0 && dy && dw, "tedm_conv_igemm_wgrad: null pointer");
   TEDM_CHECK_ARG(a->mode >= 0 && a->mode <= 3, "tedm_conv_igemm_wgrad: mode=%d", a->mode);
   TEDM_CHECK_ARG(a->batch > 0 && a->height > 0 && a->width > 0 && a->c0 > 0 && a->c1 >= 0 && a->cout > 0,
@@ -868,6 +892,7 @@ extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, fl
   p.num_ptiles = ceil_div(p.B, p.tileB) * p.tiles_x * p.tiles_y;
   p.items = p.taps * (p.c0_blocks + p.c1_blocks);
   p.dw = dw;
+  p.oihw = oihw_accumulate != 0;
   int bn = a->cout % 256 == 0 ? 256 : (a->cout % 128 == 0 ? 128 : 64);
   if (g_force_bn && a->cout % g_force_bn == 0) bn = g_force_bn;
   p.n_tiles = a->cout / bn;
@@ -896,7 +921,7 @@ extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, fl
                       p.tileW, p.tileH, p.tileB);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  TEDM_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)a->cout * p.taps * p.ctot, s));
+  if (!p.oihw) TEDM_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)a->cout * p.taps * p.ctot, s));
   switch (bn) {
     case 64: return launch_wgrad<64>(mapX0, mapX1, mapDY, p, m_blocks, s);
     case 128: return launch_wgrad<128>(mapX0, mapX1, mapDY, p, m_blocks, s);

@@ -31,11 +31,12 @@ class WeightCache:
 
     def __init__(self):
         self._store: Dict[str, Tuple[tuple, Tensor]] = {}
+        self.force = False      # True while capturing a CUDA graph: every derivation must be part of the replay
 
     def get(self, key: str, params: Tuple[Tensor, ...], make) -> Tensor:
         sig = tuple((p.data_ptr(), p._version, p.device) for p in params)
         hit = self._store.get(key)
-        if hit is not None and hit[0] == sig:
+        if hit is not None and hit[0] == sig and not self.force:
             return hit[1]
         with torch.no_grad():
             val = make(*[p.detach() for p in params])
@@ -92,6 +93,99 @@ class UnetEngine:
             off += rb.time_mlp[1].weight.shape[0]
         self._ss_total = off
         self.last_grad_arena: Optional[GradArena] = None
+        # every implicit-GEMM conv weight of the net: key -> (parameter, forward mode); re-laid out in ONE launch
+        self._wspec: Dict[str, Tuple[nn.Parameter, int]] = {}
+        self._wsig = None
+        self._wtable = None
+        self._wfwd: Optional[Tensor] = None
+        self._wdg: Optional[Tensor] = None
+        self._wviews: Dict[str, Tuple[Tensor, Optional[Tensor]]] = {}
+        self.force_refresh = False      # set while capturing a CUDA graph: the re-layout must be part of every replay
+        self._collect_conv_specs()
+
+    # -- conv weight arena ----------------------------------------------------------------------
+    def _collect_conv_specs(self) -> None:
+        m, spec = self.m, self._wspec
+
+        def resblock(key, rb):
+            spec[key + ".block1.proj"] = (rb.block1.proj.weight, N.MODE_3X3)
+            spec[key + ".block2.proj"] = (rb.block2.proj.weight, N.MODE_3X3)
+            if isinstance(rb.res_conv, nn.Conv2d):
+                spec[key + ".res_conv"] = (rb.res_conv.weight, N.MODE_1X1)
+
+        def linattn(key, wrap):
+            att = wrap.fn.fn
+            spec[key + ".to_qkv"] = (att.to_qkv.weight, N.MODE_1X1)
+            spec[key + ".to_out"] = (att.to_out[0].weight, N.MODE_1X1)
+
+        for i, (b1, b2, attn, down) in enumerate(m.downs):
+            k = f"downs.{i}"
+            resblock(k + ".0", b1)
+            resblock(k + ".1", b2)
+            linattn(k + ".2", attn)
+            spec[k + ".3"] = (down.weight, N.MODE_4X4S2 if down.kernel_size[0] == 4 else N.MODE_3X3)
+        resblock("mid_block1", m.mid_block1)
+        spec["mid_attn.to_qkv"] = (m.mid_attn.fn.fn.to_qkv.weight, N.MODE_1X1)
+        spec["mid_attn.to_out"] = (m.mid_attn.fn.fn.to_out.weight, N.MODE_1X1)
+        resblock("mid_block2", m.mid_block2)
+        for i, (b1, b2, attn, up) in enumerate(m.ups):
+            k = f"ups.{i}"
+            resblock(k + ".0", b1)
+            resblock(k + ".1", b2)
+            linattn(k + ".2", attn)
+            if isinstance(up, nn.Sequential):
+                spec[k + ".3.1"] = (up[1].weight, N.MODE_UP3X3)
+            else:
+                spec[k + ".3"] = (up.weight, N.MODE_3X3)
+        resblock("final_res_block", m.final_res_block)
+
+    def _ensure_weights(self, train: bool) -> None:
+        """bf16 operand copies of every conv weight (forward layout; + data-gradient layout when training), refreshed
+        by one kernel launch whenever any parameter changed."""
+        params = [p for p, _ in self._wspec.values()]
+        sig = tuple((p.data_ptr(), p._version) for p in params)
+        have_dg = self._wdg is not None
+        if sig == self._wsig and (have_dg or not train) and not self.force_refresh:
+            return
+        ptrs = tuple(p.data_ptr() for p in params)
+        if self._wtable is None or self._wtable[0] != ptrs or (train and not have_dg):
+            dev = params[0].device
+            taps_f = {N.MODE_1X1: 1, N.MODE_3X3: 9, N.MODE_4X4S2: 16, N.MODE_UP3X3: 16}
+            n_f = sum(p.numel() // {N.MODE_1X1: 1, N.MODE_3X3: 9, N.MODE_4X4S2: 16, N.MODE_UP3X3: 9}[md] * taps_f[md]
+                      for p, md in self._wspec.values())
+            if self._wfwd is None or self._wfwd.device != dev:
+                self._wfwd = torch.empty(n_f, device=dev, dtype=torch.bfloat16)
+                self._wdg = None
+            if train and self._wdg is None:
+                self._wdg = torch.empty(n_f, device=dev, dtype=torch.bfloat16)
+            table = (N.WeightEntry * len(self._wspec))()
+            off, cta = 0, 0
+            self._wviews = {}
+            for i, (key, (p, md)) in enumerate(self._wspec.items()):
+                if p.dtype != torch.float32 or not p.is_contiguous() or p.device != dev:
+                    raise TypeError(f"{key}: conv weights must be contiguous fp32 on one device")
+                cout, cin = p.shape[0], p.shape[1]
+                if cout % 32 or cin % 32:
+                    raise RuntimeError(f"{key}: channel counts ({cout}, {cin}) must be multiples of 32")
+                n = cout * cin * taps_f[md]
+                fwd = self._wfwd[off:off + n]
+                dg = self._wdg[off:off + n] if self._wdg is not None else None
+                self._wviews[key] = (fwd, dg)
+                table[i] = N.WeightEntry(p.data_ptr(), fwd.data_ptr(), dg.data_ptr() if dg is not None else None, cout, cin,
+                                         md, cta)
+                off += n
+                cta += (cout // 32) * (cin // 32)
+            raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).to(dev)
+            self._wtable = (ptrs, raw, len(self._wspec), cta)
+        _, raw, n_entries, total_ctas = self._wtable
+        N.prepare_weights(raw, n_entries, total_ctas)
+        self._wsig = sig
+
+    def _w(self, key: str) -> Tensor:
+        return self._wviews[key][0]
+
+    def _wd(self, key: str) -> Tensor:
+        return self._wviews[key][1]
 
     # -- derived weights ------------------------------------------------------------------------
     def _f32(self, p: Tensor) -> Tensor:
@@ -117,7 +211,7 @@ class UnetEngine:
     def _block(self, key: str, blk: nn.Module, x0: Tensor, x1: Optional[Tensor], ss, ss_off: int,
                residual: Optional[Tensor], tape: Optional[Tape] = None) -> Tensor:
         cout = blk.proj.weight.shape[0]
-        h, part = N.conv_igemm(x0, self._krsc(key + ".proj", blk.proj.weight), N.MODE_3X3, cout,
+        h, part = N.conv_igemm(x0, self._w(key + ".proj"), N.MODE_3X3, cout,
                                bias=self._f32(blk.proj.bias), src1=x1, gn_groups=blk.norm.num_groups)
         if tape is not None:
             tape.saved[key] = (x0, x1, h, part)
@@ -130,7 +224,7 @@ class UnetEngine:
         h = self._block(key + ".block1", rb.block1, x0, x1, tproj, ss_off, None, tape)
         if isinstance(rb.res_conv, nn.Conv2d):
             cout = rb.res_conv.weight.shape[0]
-            res = N.conv_igemm(x0, self._krsc(key + ".res_conv", rb.res_conv.weight), N.MODE_1X1, cout,
+            res = N.conv_igemm(x0, self._w(key + ".res_conv"), N.MODE_1X1, cout,
                                bias=self._f32(rb.res_conv.bias), src1=x1)
         else:
             if x1 is not None:
@@ -142,12 +236,12 @@ class UnetEngine:
         pre, att = wrap.fn.norm, wrap.fn.fn
         c = x.shape[-1]
         y = N.layernorm(x, self._f32(pre.g).reshape(-1), eps=self.ln_eps)
-        qkv = N.conv_igemm(y, self._krsc(key + ".to_qkv", att.to_qkv.weight), N.MODE_1X1, att.to_qkv.weight.shape[0])
+        qkv = N.conv_igemm(y, self._w(key + ".to_qkv"), N.MODE_1X1, att.to_qkv.weight.shape[0])
         if tape is not None:
             o, ws = N.linear_attention(qkv, att.heads, att.dim_head, att.scale, want_workspace=True)
         else:
             o = N.linear_attention(qkv, att.heads, att.dim_head, att.scale)
-        o2 = N.conv_igemm(o, self._krsc(key + ".to_out", att.to_out[0].weight), N.MODE_1X1, c,
+        o2 = N.conv_igemm(o, self._w(key + ".to_out"), N.MODE_1X1, c,
                           bias=self._f32(att.to_out[0].bias))
         if tape is not None:
             tape.saved[key] = (x, y, qkv, o, o2, ws)
@@ -157,11 +251,11 @@ class UnetEngine:
         pre, att = wrap.fn.norm, wrap.fn.fn
         c = x.shape[-1]
         y = N.layernorm(x, self._f32(pre.g).reshape(-1), eps=self.ln_eps)
-        qkv = N.conv_igemm(y, self._krsc(key + ".to_qkv", att.to_qkv.weight), N.MODE_1X1, att.to_qkv.weight.shape[0])
+        qkv = N.conv_igemm(y, self._w(key + ".to_qkv"), N.MODE_1X1, att.to_qkv.weight.shape[0])
         o = N.attention(qkv, att.heads, att.dim_head, float(att.scale))
         if tape is not None:
             tape.saved[key] = (x, y, qkv, o)
-        return N.conv_igemm(o, self._krsc(key + ".to_out", att.to_out.weight), N.MODE_1X1, c,
+        return N.conv_igemm(o, self._w(key + ".to_out"), N.MODE_1X1, c,
                             bias=self._f32(att.to_out.bias), residual=x)
 
     # -- whole network ----------------------------------------------------------------------------
@@ -173,6 +267,7 @@ class UnetEngine:
         if x.dim() != 4 or x.shape[1] != m.channels:
             raise ValueError(f"expected input (B, {m.channels}, H, W), got {tuple(x.shape)}")
         x = x.detach().float().contiguous()
+        self._ensure_weights(train=tape is not None)
         tproj = None
         if timestep is not None:
             t = timestep.detach().to(device=x.device, dtype=torch.int64).contiguous()
@@ -201,7 +296,7 @@ class UnetEngine:
             mode = N.MODE_4X4S2 if down.kernel_size[0] == 4 else N.MODE_3X3
             if tape is not None:
                 tape.saved[k + ".3"] = (h,)
-            h = N.conv_igemm(h, self._krsc(k + ".3", down.weight), mode, down.weight.shape[0], bias=self._f32(down.bias))
+            h = N.conv_igemm(h, self._w(k + ".3"), mode, down.weight.shape[0], bias=self._f32(down.bias))
         h = self._resblock("mid_block1", m.mid_block1, h, None, tproj, tape)
         h = self._mid_attention("mid_attn", m.mid_attn, h, tape)
         h = self._resblock("mid_block2", m.mid_block2, h, None, tproj, tape)
@@ -220,13 +315,13 @@ class UnetEngine:
             if isinstance(up, nn.Sequential):          # Upsample: nearest x2 + 3x3 conv
                 conv = up[1]
                 if self.fold_upsample:
-                    h = N.conv_igemm(h, self._folded(k + ".3.1", conv.weight), N.MODE_UP3X3, conv.weight.shape[0],
+                    h = N.conv_igemm(h, self._w(k + ".3.1"), N.MODE_UP3X3, conv.weight.shape[0],
                                      bias=self._f32(conv.bias))
                 else:
                     h = N.conv_igemm(N.upsample2x(h), self._krsc(k + ".3.1", conv.weight), N.MODE_3X3,
                                      conv.weight.shape[0], bias=self._f32(conv.bias))
             else:
-                h = N.conv_igemm(h, self._krsc(k + ".3", up.weight), N.MODE_3X3, up.weight.shape[0], bias=self._f32(up.bias))
+                h = N.conv_igemm(h, self._w(k + ".3"), N.MODE_3X3, up.weight.shape[0], bias=self._f32(up.bias))
         h = self._resblock("final_res_block", m.final_res_block, h, stem, tproj, tape)
         out = N.final_conv1x1(h, self._f32(m.final_conv.weight).reshape(m.out_dim, -1), self._f32(m.final_conv.bias))
         if tape is not None:
@@ -244,13 +339,12 @@ class UnetEngine:
         cout = conv.weight.shape[0]
         c0 = x0.shape[-1]
         c1 = x1.shape[-1] if x1 is not None else 0
-        dw = N.conv_wgrad(x0, dy, mode, src1=x1)
-        N.wgrad_to_oihw(dw, G.of(conv.weight), mode)
+        N.conv_wgrad(x0, dy, mode, src1=x1, grad_oihw=G.of(conv.weight))
         if bias_grad and conv.bias is not None:
             N.bias_grad(dy, G.of(conv.bias))
         if not need_dx:
             return None, None
-        wd = self._dgrad_w(key, conv.weight, mode)
+        wd = self._wd(key)
         run_mode = {N.MODE_1X1: N.MODE_1X1, N.MODE_3X3: N.MODE_3X3, N.MODE_4X4S2: N.MODE_UP3X3,
                     N.MODE_UP3X3: N.MODE_4X4S2}[mode]
         taps = {N.MODE_1X1: 1, N.MODE_3X3: 9, N.MODE_4X4S2: 16, N.MODE_UP3X3: 16}[mode]

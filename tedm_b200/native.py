@@ -25,6 +25,10 @@ class ConvArgs(C.Structure):  # tedm_conv_args
                 ("src1_image_stride", _i64), ("out_image_stride", _i64)]
 
 
+class WeightEntry(C.Structure):  # tedm_weight_entry
+    _fields_ = [("w", _p), ("fwd", _p), ("dgrad", _p), ("cout", _i), ("cin", _i), ("mode", _i), ("cta_begin", _i)]
+
+
 class HeadArgs(C.Structure):  # tedm_head_args
     _fields_ = [("g", _p * 4), ("g_dtype", _i), ("shift", _i * 4), ("n_levels", _i), ("n_sum", _i), ("n_img", _i), ("height", _i),
                 ("width", _i), ("c1", _i), ("c2", _i), ("b1", _p), ("bn1_a", _p), ("bn1_c", _p), ("w2", _p),
@@ -42,7 +46,8 @@ SIGNATURES = {
     "tedm_time_proj": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "tedm_stem_conv7x7": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "tedm_conv_igemm_fwd": (_i, [C.POINTER(ConvArgs), _p]),
-    "tedm_conv_igemm_wgrad": (_i, [C.POINTER(ConvArgs), _p, _p, _p]),
+    "tedm_conv_igemm_wgrad": (_i, [C.POINTER(ConvArgs), _p, _p, _i, _p]),
+    "tedm_prepare_weights": (_i, [_p, _i, _i, _p]),
     "tedm_conv_gn_parts": (_i, [_i, _i]),
     "tedm_conv_set_tile_n": (_i, [_i]),
     "tedm_conv_set_ws": (_i, [_i]),
@@ -72,7 +77,7 @@ SIGNATURES = {
     "tedm_linear_attention_bwd_workspace": (_i64, [_i, _i, _i, _i]),
     "tedm_linear_attention_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "tedm_attention_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _p]),
-    "tedm_adam_step": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i, _f, _p]),
+    "tedm_adam_step": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i, _p, _f, _p]),
     "tedm_debug_umma_probe": (_i, [_p, _p, C.POINTER(_i), C.POINTER(_i), _i, _p, _p]),
 }
 
@@ -267,8 +272,9 @@ def conv_igemm(src0: torch.Tensor, weight: torch.Tensor, mode: int, cout: int, b
     return (out, gnp) if gn_groups else out
 
 
-def conv_wgrad(src0: torch.Tensor, dy: torch.Tensor, mode: int, src1=None) -> torch.Tensor:
-    """fp32 (cout, taps, c0+c1) weight gradient of conv_igemm(src0[, src1]) given the NHWC bf16 output gradient."""
+def conv_wgrad(src0: torch.Tensor, dy: torch.Tensor, mode: int, src1=None, grad_oihw: Optional[torch.Tensor] = None):
+    """Weight gradient of conv_igemm(src0[, src1]) given the NHWC bf16 output gradient: returns fp32 (cout, taps, c0+c1),
+    or, when grad_oihw (the fp32 OIHW parameter gradient) is given, accumulates into it and returns it."""
     b, h, w, c0 = src0.shape
     c1 = src1.shape[3] if src1 is not None else 0
     cout = dy.shape[3]
@@ -276,12 +282,18 @@ def conv_wgrad(src0: torch.Tensor, dy: torch.Tensor, mode: int, src1=None) -> to
     oh, ow = (h // 2, w // 2) if mode == MODE_4X4S2 else ((2 * h, 2 * w) if mode == MODE_UP3X3 else (h, w))
     if tuple(dy.shape) != (b, oh, ow, cout):
         raise ValueError(f"conv_wgrad: dy has shape {tuple(dy.shape)}, expected {(b, oh, ow, cout)}")
-    dw = torch.empty(cout, taps, c0 + c1, device=src0.device, dtype=torch.float32)
+    if grad_oihw is None:
+        dw = torch.empty(cout, taps, c0 + c1, device=src0.device, dtype=torch.float32)
+    else:
+        dw = grad_oihw
+        khw = 9 if mode == MODE_UP3X3 else taps
+        if dw.numel() != cout * (c0 + c1) * khw:
+            raise ValueError("conv_wgrad: grad_oihw has the wrong size")
     p0, s0 = _nhwc(src0, "src0")
     p1, s1 = _nhwc(src1, "src1")
     pd, sd = _nhwc(dy, "dy")
     a = ConvArgs(p0, p1, None, None, None, None, None, b, h, w, c0, c1, cout, mode, 0, 0, s0, s1, sd)
-    _call("tedm_conv_igemm_wgrad", C.byref(a), pd, _ptr(dw), _stream())
+    _call("tedm_conv_igemm_wgrad", C.byref(a), pd, _ptr(dw, torch.float32, "dw"), 0 if grad_oihw is None else 1, _stream())
     return dw
 
 
@@ -367,6 +379,10 @@ def weight_to_dgrad(w: torch.Tensor, mode: int) -> torch.Tensor:
     out = torch.empty(cout * cin * _TAPS[mode], device=w.device, dtype=torch.bfloat16)
     _call("tedm_weight_to_dgrad", _ptr(w.contiguous(), torch.float32, "weight"), _ptr(out), cout, cin, mode, _stream())
     return out
+
+
+def prepare_weights(table_dev: torch.Tensor, n_entries: int, total_ctas: int) -> None:
+    _call("tedm_prepare_weights", _ptr(table_dev, torch.uint8, "table"), n_entries, total_ctas, _stream())
 
 
 def wgrad_to_oihw(dw: torch.Tensor, grad: torch.Tensor, mode: int) -> None:
@@ -469,11 +485,11 @@ def attention_bwd(qkv, dout, heads: int = 4, dim_head: int = 32, scale: float = 
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr: float, beta1: float, beta2: float, eps: float, weight_decay: float,
-              step: int, grad_scale: float = 1.0) -> None:
+              step: int, grad_scale: float = 1.0, step_counter: Optional[torch.Tensor] = None) -> None:
     n = param.numel()
     _call("tedm_adam_step", _ptr(param, torch.float32, "param"), _ptr(grad, torch.float32, "grad"),
           _ptr(exp_avg, torch.float32), _ptr(exp_avg_sq, torch.float32), n, lr, beta1, beta2, eps, weight_decay, step,
-          grad_scale, _stream())
+          _ptr(step_counter, torch.int32, "step_counter"), grad_scale, _stream())
 
 
 # ------------------------------------------------------------------------------------------------

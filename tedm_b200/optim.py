@@ -47,6 +47,7 @@ class FusedAdam(torch.optim.Optimizer):
                 self._offsets.append(off)
                 off += k
         self._step = 0
+        self.step_counter = torch.zeros(1, device=dev, dtype=torch.int32)   # device copy: the count a CUDA graph replays
         for p, o in zip(self._params, self._offsets):
             k = p.numel()
             self.state[p] = {"step": torch.tensor(0.0), "exp_avg": self.exp_avg[o:o + k].view(p.shape),
@@ -89,11 +90,14 @@ class FusedAdam(torch.optim.Optimizer):
         self._step += 1
         N.adam_step(self.flat_param, self.flat_grad(), self.exp_avg, self.exp_avg_sq, float(grp["lr"]),
                     float(grp["betas"][0]), float(grp["betas"][1]), float(grp["eps"]), float(grp["weight_decay"]),
-                    self._step, grad_scale)
+                    self._step, grad_scale, step_counter=self.step_counter)
         step_t = torch.tensor(float(self._step))
         for p in self._params:
             self.state[p]["step"] = step_t
-        # the update went through the flat arena, not through each parameter tensor: bump every parameter's
-        # version counter so derived-weight caches keyed on (data_ptr, _version) notice the change
-        torch._C._autograd._unsafe_set_version_counter(tuple(self._params), tuple(p._version + 1 for p in self._params))
+        self.bump_versions()
         return loss
+
+    def bump_versions(self) -> None:
+        """The update went through the flat arena, not through each parameter tensor: bump every parameter's
+        version counter so derived-weight caches keyed on (data_ptr, _version) notice the change."""
+        torch._C._autograd._unsafe_set_version_counter(tuple(self._params), tuple(p._version + 1 for p in self._params))

@@ -1,0 +1,101 @@
+"""DDPM pre-training step as the reference runs it (trainers/train_CXR14.py:28-40:
+`loss = model.train_step(x); loss.backward(); optimizer.step()`), replayed from CUDA graphs.
+
+One step is ~450 kernel launches (q_sample, UNet forward, loss, UNet backward, Adam); at the
+reference's batch size of 16 the GPU finishes them faster than Python can issue them, so the
+launch-bound sequence is captured once and replayed:
+
+    graph A: zero_grad -> weight re-layout -> q_sample -> UNet fwd -> L1/p2 loss -> UNet bwd   (gradient arena)
+    [world > 1] ONE NCCL all-reduce of the flat gradient arena (sum; the 1/world goes into Adam's grad_scale)
+    graph B: fused Adam over the flat parameter / moment arenas -> version bump
+
+Shapes are static (batch, image size); timesteps and noise are drawn inside the graph by torch's
+graph-safe Philox generator, exactly where the reference draws them (diffusion_model.py:126-129,193).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from .models.diffusion_model import DiffusionModel
+from .optim import FusedAdam
+
+
+class GraphedTrainStep:
+    def __init__(self, model: DiffusionModel, optimizer: FusedAdam, example: Tensor, warmup: int = 3,
+                 use_graph: bool = True):
+        if not example.is_cuda:
+            raise RuntimeError("GraphedTrainStep runs on CUDA (sm_100a) only; there is no CPU fallback")
+        self.model, self.opt = model, optimizer
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.x = example.detach().float().clone()
+        self.loss = torch.zeros((), device=example.device)
+        self.use_graph = use_graph
+        self._ga: Optional[torch.cuda.CUDAGraph] = None
+        self._gb: Optional[torch.cuda.CUDAGraph] = None
+        self._params = [p for p in model.parameters() if p.requires_grad]
+        if use_graph:
+            self._capture(warmup)
+
+    # -- the two halves of a step ---------------------------------------------------------------
+    def _fwd_bwd(self) -> None:
+        self.opt.zero_grad(set_to_none=True)
+        loss = self.model.train_step(self.x)
+        loss.backward()
+        self.loss.copy_(loss.detach())
+
+    def _update(self) -> None:
+        self.opt.step(grad_scale=1.0 / self.world)
+
+    def _allreduce(self) -> None:
+        if self.world > 1:
+            dist.all_reduce(self.opt.flat_grad(), op=dist.ReduceOp.SUM)
+
+    def _capture(self, warmup: int) -> None:
+        eng = self.model.model.engine
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):            # warm-up off the capture: lazy attribute setting, allocator growth
+            for _ in range(max(1, warmup)):
+                self._fwd_bwd()
+                self._allreduce()
+                self._update()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        eng.force_refresh = True
+        eng.cache.force = True
+        from . import native as N
+        l0 = N.launches
+        try:
+            self._ga = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._ga):
+                self._fwd_bwd()
+            self._gb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._gb, pool=self._ga.pool()):
+                self._update()
+        finally:
+            eng.force_refresh = False
+            eng.cache.force = False
+        self.native_calls_per_step = N.launches - l0     # native entry points inside one replayed step
+        self.opt._step -= 1                              # the capture recorded a step, it did not execute one
+
+    # -- public ---------------------------------------------------------------------------------
+    def __call__(self, x: Tensor) -> Tensor:
+        """One optimiser step on batch x (same shape as the example); returns the loss (device scalar)."""
+        if x.shape != self.x.shape:
+            raise ValueError(f"GraphedTrainStep was captured for batch shape {tuple(self.x.shape)}, got {tuple(x.shape)}")
+        self.x.copy_(x, non_blocking=True)
+        if self._ga is None:
+            self._fwd_bwd()
+            self._allreduce()
+            self._update()
+        else:
+            self._ga.replay()
+            self._allreduce()
+            self._gb.replay()
+            self.opt._step += 1
+            self.opt.bump_versions()
+        return self.loss

@@ -159,3 +159,29 @@ def test_fused_adam_step_matches_reference(golden):
     with torch.no_grad():
         l2 = m.train_step(x0, t=t, noise=nz)
     assert abs(l2.item() - float(g["loss"])) > 1e-4
+
+
+def test_graphed_train_step_trains():
+    """The CUDA-graph replayed step (tedm_b200/train.py) advances Adam's device step counter, lowers the loss on a
+    fixed batch, and leaves the derived bf16 weights consistent for a later eager forward."""
+    from tedm_b200.optim import FusedAdam
+    from tedm_b200.train import GraphedTrainStep
+    torch.manual_seed(0)
+    m = _model()
+    opt = FusedAdam(m.parameters(), lr=2e-4)
+    x = torch.rand(4, 1, 32, 32, generator=torch.Generator().manual_seed(3)).cuda()
+    step = GraphedTrainStep(m, opt, x, warmup=2)
+    assert int(opt.step_counter.item()) == 2 and opt._step == 2
+    losses = [float(step(x)) for _ in range(60)]
+    torch.cuda.synchronize()
+    assert int(opt.step_counter.item()) == 62 and opt._step == 62
+    assert all(np.isfinite(losses))
+    assert np.mean(losses[-10:]) < 0.8 * np.mean(losses[:10]), (losses[:10], losses[-10:])
+    # eager evaluation after graph training sees the trained weights (version counters were bumped)
+    t = torch.tensor([10, 300, 600, 900]).cuda()
+    nz = torch.randn(4, 1, 32, 32, generator=torch.Generator().manual_seed(4)).cuda()
+    with torch.no_grad():
+        l_eval = float(m.train_step(x, t=t, noise=nz))
+    ref_sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    l_ref = float(O.ddpm_loss(ref_sd, x.cpu(), t.cpu(), nz.cpu()))
+    assert abs(l_eval - l_ref) < 3e-2 * abs(l_ref), (l_eval, l_ref)
