@@ -113,6 +113,12 @@ typedef struct {
   int gn_groups;         /* number of GroupNorm groups (0 when gn_partial is NULL) */
   int out_dtype;         /* 0: out is bf16 (TMA store); 1: out is fp32 (head layer 1 keeps full precision) */
   int64_t src0_image_stride, src1_image_stride, out_image_stride; /* elements; 0 = dense */
+  /* split output (0 = off): output channels [0, split) go to out (+ residual), channels [split, cout) to out2
+   * (+ residual2, nullable) as a dense [B][Ho][Wo][cout - split] tensor.  This is the data gradient of a
+   * skip-concat convolution landing in its two sources (backward of models/unet_model.py:356,359,365). */
+  int split;
+  void* out2;
+  const void* residual2;
 } tedm_conv_args;
 TEDM_API int tedm_conv_igemm_fwd(const tedm_conv_args* args, tedm_stream_t stream);
 /* Weight gradient of the same convolution (backward of models/unet_model.py:43,49,122,157,185,188,226,227,308,324):

@@ -26,10 +26,10 @@ def main():
                 loss.backward()
                 opt.step()
                 return loss
-        for _ in range(3):
+        for _ in range(int(os.environ.get('WARM', '3'))):
             step()
         torch.cuda.synchronize()
-        n = 5
+        n = int(os.environ.get('STEPS', '5'))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = N.launches
         t0 = time.perf_counter()

@@ -103,22 +103,27 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const bf16* __restri
   if (v1 > nvec) v1 = nvec;
   const size_t img = (size_t)b * hw * C;
   const int c0 = (threadIdx.x % cvec) << 3;
-  float acc[3][8];
+  float acc[3][8], ca[8], cb[8], cr[8], cq[8];   // this thread always meets the same 8 channels
 #pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+  for (int j = 0; j < 8; ++j) {
+    acc[0][j] = acc[1][j] = acc[2][j] = 0.0f;
+    ca[j] = sA[c0 + j];
+    cb[j] = sB[c0 + j];
+    cr[j] = sR[c0 + j];
+    cq[j] = sQ[c0 + j];
+  }
+#pragma unroll 2
   for (long long v = v0 + threadIdx.x; v < v1; v += 256) {
     float f[8], d[8];
     unpack8(ldg_stream(x + img + v * 8), f);
     unpack8(ldg_stream(dy + img + v * 8), d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float z = fmaf(f[j], sA[c0 + j], sB[c0 + j]);
+      const float z = fmaf(f[j], ca[j], cb[j]);
       const float sg = sigmoid_f(z);
       const float dz = d[j] * sg * fmaf(z, 1.0f - sg, 1.0f);
       acc[0][j] += dz;
-      acc[1][j] = fmaf(dz, fmaf(f[j], sR[c0 + j], sQ[c0 + j]), acc[1][j]);
+      acc[1][j] = fmaf(dz, fmaf(f[j], cr[j], cq[j]), acc[1][j]);
       acc[2][j] += f[j];
     }
   }
@@ -195,16 +200,26 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const bf16* __restric
   if (v1 > nvec) v1 = nvec;
   const size_t img = (size_t)b * hw * C;
   const int c0 = (threadIdx.x % cvec) << 3;
+  float ca[8], cb[8], k1[8], k2[8], k3[8];       // this thread always meets the same 8 channels
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ca[j] = sA[c0 + j];
+    cb[j] = sB[c0 + j];
+    k1[j] = sK1[c0 + j];
+    k2[j] = sK2[c0 + j];
+    k3[j] = sK3[c0 + j];
+  }
+#pragma unroll 2
   for (long long v = v0 + threadIdx.x; v < v1; v += 256) {
     float f[8], d[8];
     unpack8(ldg_stream(x + img + v * 8), f);
     unpack8(ldg_stream(dy + img + v * 8), d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float z = fmaf(f[j], sA[c0 + j], sB[c0 + j]);
+      const float z = fmaf(f[j], ca[j], cb[j]);
       const float sg = sigmoid_f(z);
       const float dz = d[j] * sg * fmaf(z, 1.0f - sg, 1.0f);
-      d[j] = fmaf(dz, sK1[c0 + j], fmaf(f[j], sK2[c0 + j], sK3[c0 + j]));
+      d[j] = fmaf(dz, k1[j], fmaf(f[j], k2[j], k3[j]));
     }
     *reinterpret_cast<uint4*>(dx + img + v * 8) = pack8(d);
   }

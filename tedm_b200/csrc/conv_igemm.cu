@@ -58,6 +58,12 @@ struct ConvParams {
   float* gn_partial;
   int gn_cpg, gn_groups, gn_parts;
   long long out_image_stride;    // elements
+  // split output (data gradient of a skip-concat conv): channels [0, split) go to out/residual, channels
+  // [split, cout) to out2/residual2 at channel (c - split); split == 0: single output
+  int split;
+  bf16* out2;
+  const bf16* residual2;
+  long long out2_image_stride;
 };
 
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
@@ -130,7 +136,7 @@ template <int BN, bool WS, int CPG>
 __global__ void __launch_bounds__(192, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapOut,
-                  const ConvParams p) {
+                  const __grid_constant__ CUtensorMap mapOut2, const ConvParams p) {
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = WS ? A_ROW_BYTES : A_BYTES + B_BYTES;
   constexpr int OUT_BYTES = (BN / 64) * A_BYTES;
@@ -158,6 +164,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     if (p.c1_blocks) tma_prefetch_desc(&mapA1);
     tma_prefetch_desc(&mapW);
     if (!p.out_f32) tma_prefetch_desc(&mapOut);
+    if (p.split) tma_prefetch_desc(&mapOut2);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
@@ -321,6 +328,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       }
       for (int i = e; i < BN; i += 128) sbias[i] = p.bias ? __ldg(p.bias + t.n0 + i) : 0.0f;
       named_bar_sync(1, 128);
+      // the residual row of this thread is fetched BEFORE waiting for the accumulator, so its latency hides
+      // behind the main loop of this tile (N tiles up to 128 channels; wider tiles load in place below)
+      constexpr int NPRE = BN <= 128 ? BN / 8 : 1;
+      uint4 rpre[NPRE];
+      // residual row segment of 64-channel sub-tile cp (NULL: nothing to add); with a split output the sub-tile
+      // belongs to (residual, split channels per pixel) or (residual2, cout - split channels per pixel)
+      const size_t pixoff = (size_t)oy * p.OW + ox;
+      auto res_sub = [&](int cp) -> const bf16* {
+        const int c = t.n0 + cp * 64;
+        if (p.split == 0) return p.residual ? p.residual + opix + cp * 64 : nullptr;
+        if (c < p.split) return p.residual ? p.residual + (size_t)b * p.out_image_stride + pixoff * p.split + c : nullptr;
+        return p.residual2 ? p.residual2 + (size_t)b * p.out2_image_stride + pixoff * (p.cout - p.split) + (c - p.split) : nullptr;
+      };
+      if (BN <= 128 && valid) {
+#pragma unroll
+        for (int cp = 0; cp < BN / 64; ++cp) {
+          const uint4* rp = reinterpret_cast<const uint4*>(res_sub(cp));
+          if (rp) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rpre[(cp * 8 + j) % NPRE] = __ldg(rp + j);
+          }
+        }
+      }
       mbar_wait(smem_u32(&bar_acc_full[buf]), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       float gv[NV];
@@ -360,12 +390,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
               gv[2 * gl + 1] += q_;
             }
           }
-          if (p.residual && valid) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + opix + chunk * 32);
+          const bf16* rsub = valid ? res_sub(cp) : nullptr;
+          if (rsub) {
+            const uint4* rp = reinterpret_cast<const uint4*>(rsub + half * 32);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float f[8];
-              unpack8(__ldg(rp + j), f);
+              if constexpr (BN <= 128) unpack8(rpre[(chunk * 4 + j) % NPRE], f);
+              else unpack8(__ldg(rp + j), f);
 #pragma unroll
               for (int c = 0; c < 8; ++c) v[8 * j + c] += f[c];
             }
@@ -406,8 +438,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       if (e == 0 && !p.out_f32) {
         const int chan_base = (p.mode == 3 ? par_x * p.cout : 0) + t.n0;
         const int pc_out = p.mode == 3 ? par_y : 0;
-        for (int sidx = 0; sidx < BN / 64; ++sidx)
-          tma_store_5d(&mapOut, out_buf + (uint32_t)sidx * A_BYTES, chan_base + sidx * 64, t.x0, pc_out, t.y0, t.b0);
+        for (int sidx = 0; sidx < BN / 64; ++sidx) {
+          const int c = chan_base + sidx * 64;
+          if (p.split && c >= p.split)
+            tma_store_5d(&mapOut2, out_buf + (uint32_t)sidx * A_BYTES, c - p.split, t.x0, pc_out, t.y0, t.b0);
+          else
+            tma_store_5d(&mapOut, out_buf + (uint32_t)sidx * A_BYTES, c, t.x0, pc_out, t.y0, t.b0);
+        }
         tma_store_commit();
       }
       if (CPG) {
@@ -475,8 +512,8 @@ int encode_weight_map(CUtensorMap* map, const void* ptr, long long rows, long lo
 }
 
 template <int BN, bool WS, int CPG>
-int launch_conv_cpg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o, ConvParams& p,
-                    cudaStream_t stream) {
+int launch_conv_cpg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o,
+                    const CUtensorMap& o2, ConvParams& p, cudaStream_t stream) {
   const int cb_total = p.c0_blocks + p.c1_blocks;
   const int stage_bytes = WS ? A_ROW_BYTES : A_BYTES + BN * BK * 2;
   const int out_bytes = (BN / 64) * A_BYTES;
@@ -495,28 +532,28 @@ int launch_conv_cpg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensor
     configured = smem;
   }
   int grid = p.num_tiles < tedm_num_sms() ? p.num_tiles : tedm_num_sms();
-  conv_igemm_kernel<BN, WS, CPG><<<grid, 192, smem, stream>>>(a0, a1, w, o, p);
+  conv_igemm_kernel<BN, WS, CPG><<<grid, 192, smem, stream>>>(a0, a1, w, o, o2, p);
   TEDM_LAUNCH_CHECK();
   return TEDM_OK;
 }
 
 template <int BN, bool WS>
-int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o, ConvParams& p,
-                cudaStream_t stream) {
+int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o,
+                const CUtensorMap& o2, ConvParams& p, cudaStream_t stream) {
   const int cpg = p.gn_partial ? p.gn_cpg : 0;
-  if (cpg == 0) return launch_conv_cpg<BN, WS, 0>(a0, a1, w, o, p, stream);
+  if (cpg == 0) return launch_conv_cpg<BN, WS, 0>(a0, a1, w, o, o2, p, stream);
   if constexpr (BN / 8 <= 8) {
-    if (cpg == 8) return launch_conv_cpg<BN, WS, 8>(a0, a1, w, o, p, stream);
+    if (cpg == 8) return launch_conv_cpg<BN, WS, 8>(a0, a1, w, o, o2, p, stream);
   }
   if constexpr (BN / 16 <= 8) {
-    if (cpg == 16) return launch_conv_cpg<BN, WS, 16>(a0, a1, w, o, p, stream);
+    if (cpg == 16) return launch_conv_cpg<BN, WS, 16>(a0, a1, w, o, o2, p, stream);
   }
-  if (cpg == 32) return launch_conv_cpg<BN, WS, 32>(a0, a1, w, o, p, stream);
+  if (cpg == 32) return launch_conv_cpg<BN, WS, 32>(a0, a1, w, o, o2, p, stream);
   if constexpr (BN >= 64) {
-    if (cpg == 64) return launch_conv_cpg<BN, WS, 64>(a0, a1, w, o, p, stream);
+    if (cpg == 64) return launch_conv_cpg<BN, WS, 64>(a0, a1, w, o, o2, p, stream);
   }
   if constexpr (BN >= 128) {
-    if (cpg == 128) return launch_conv_cpg<BN, WS, 128>(a0, a1, w, o, p, stream);
+    if (cpg == 128) return launch_conv_cpg<BN, WS, 128>(a0, a1, w, o, o2, p, stream);
   }
   return tedm_set_error(TEDM_ERR_UNSUPPORTED, "tedm_conv_igemm_fwd: %d channels per GroupNorm group with N tile %d", cpg, BN);
 }
@@ -786,7 +823,16 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   p.out = (bf16*)a->out;
   p.out_f32 = a->out_dtype == 1;
   TEDM_CHECK_ARG(a->out_dtype == 0 || a->out_dtype == 1, "tedm_conv_igemm_fwd: out_dtype=%d", a->out_dtype);
-  p.out_image_stride = a->out_image_stride ? a->out_image_stride : (long long)p.OH * p.OW * a->cout;
+  p.split = a->split;
+  if (a->split) {
+    TEDM_CHECK_ARG(a->out2 && a->split > 0 && a->split < a->cout, "tedm_conv_igemm_fwd: split=%d needs out2 and 0 < split < cout", a->split);
+    TEDM_UNSUPPORTED(a->split % 64 != 0 || p.out_f32 || a->gn_partial || a->mode > 1 || a->out_image_stride != 0,
+                     "tedm_conv_igemm_fwd: split output needs split %% 64 == 0, bf16 dense outputs, no GroupNorm, mode 0/1");
+    p.out2 = (bf16*)a->out2;
+    p.residual2 = (const bf16*)a->residual2;
+    p.out2_image_stride = (long long)p.OH * p.OW * (a->cout - a->split);
+  }
+  p.out_image_stride = a->out_image_stride ? a->out_image_stride : (long long)p.OH * p.OW * (a->split ? a->split : a->cout);
   p.gn_partial = a->gn_partial;
   if (a->gn_partial) {
     TEDM_CHECK_ARG(a->gn_groups > 0 && a->cout % a->gn_groups == 0, "tedm_conv_igemm_fwd: gn_groups=%d", a->gn_groups);
@@ -822,7 +868,7 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   const bool ws = g_enable_ws && a->mode == 1 && p.tileH == 1 && p.tileB == 1 && p.tileW == BM && a->cout == 64 && bn == 64 &&
                   (a->c0 + a->c1) <= 128;
 
-  alignas(64) CUtensorMap mapA0, mapA1, mapW, mapOut;
+  alignas(64) CUtensorMap mapA0, mapA1, mapW, mapOut, mapOut2;
   const int boxW = ws ? ROW_PIX : p.tileW;
   int rc = encode_act_map(&mapA0, a->src0, a->batch, a->height, a->width, a->c0,
                           a->src0_image_stride ? a->src0_image_stride : (long long)a->height * a->width * a->c0, a->mode,
@@ -842,19 +888,26 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   if (!p.out_f32) {
     // bf16 outputs leave through a TMA store; the upsample mode scatters each parity through the same
     // (2C, W, 2, H, B) view the stride-2 mode uses for its input
-    rc = encode_act_map(&mapOut, a->out, a->batch, p.OH, p.OW, a->cout, p.out_image_stride, a->mode == 3 ? 2 : 0, p.tileW,
-                        p.tileH, p.tileB);
+    rc = encode_act_map(&mapOut, a->out, a->batch, p.OH, p.OW, a->split ? a->split : a->cout, p.out_image_stride,
+                        a->mode == 3 ? 2 : 0, p.tileW, p.tileH, p.tileB);
     if (rc) return rc;
   } else {
     mapOut = mapA0;
   }
+  if (a->split) {
+    rc = encode_act_map(&mapOut2, a->out2, a->batch, p.OH, p.OW, a->cout - a->split, p.out2_image_stride, 0, p.tileW, p.tileH,
+                        p.tileB);
+    if (rc) return rc;
+  } else {
+    mapOut2 = mapOut;
+  }
 
   cudaStream_t s = (cudaStream_t)stream;
-  if (ws) return launch_conv<64, true>(mapA0, mapA1, mapW, mapOut, p, s);
+  if (ws) return launch_conv<64, true>(mapA0, mapA1, mapW, mapOut, mapOut2, p, s);
   switch (bn) {
-    case 64: return launch_conv<64, false>(mapA0, mapA1, mapW, mapOut, p, s);
-    case 128: return launch_conv<128, false>(mapA0, mapA1, mapW, mapOut, p, s);
-    default: return launch_conv<256, false>(mapA0, mapA1, mapW, mapOut, p, s);
+    case 64: return launch_conv<64, false>(mapA0, mapA1, mapW, mapOut, mapOut2, p, s);
+    case 128: return launch_conv<128, false>(mapA0, mapA1, mapW, mapOut, mapOut2, p, s);
+    default: return launch_conv<256, false>(mapA0, mapA1, mapW, mapOut, mapOut2, p, s);
   }
 }
 
@@ -897,10 +950,26 @@ extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, fl
   if (g_force_bn && a->cout % g_force_bn == 0) bn = g_force_bn;
   p.n_tiles = a->cout / bn;
   const int m_blocks = (p.items + 1) / 2;
-  // split K so that ~4 CTAs per SM exist, each with at least 4 pixel tiles
-  long long want = (4LL * tedm_num_sms() + (long long)m_blocks * p.n_tiles - 1) / ((long long)m_blocks * p.n_tiles);
-  long long cap = p.num_ptiles / 4 > 0 ? p.num_ptiles / 4 : 1;
-  p.splitk = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+  // split K over pixel tiles: one CTA per SM is resident (192 KB of pipeline smem), so pick the split whose CTA count
+  // fills whole waves of the machine (up to 4 waves, each CTA at least 4 pixel tiles)
+  {
+    const long long groups = (long long)m_blocks * p.n_tiles, sms = tedm_num_sms();
+    const long long cap = p.num_ptiles / 4 > 0 ? p.num_ptiles / 4 : 1;
+    long long best_sk = 1;
+    double best_eff = -1.0;
+    for (int w = 1; w <= 4; ++w) {
+      long long sk = (w * sms) / groups;
+      if (sk < 1) sk = 1;
+      if (sk > cap) sk = cap;
+      const long long ctas = groups * sk, waves = (ctas + sms - 1) / sms;
+      const double eff = (double)ctas / (double)(waves * sms);
+      if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && sk > best_sk)) {
+        best_eff = eff;
+        best_sk = sk;
+      }
+    }
+    p.splitk = (int)best_sk;
+  }
 
   const int dy_h = a->mode == 3 ? 2 * a->height : Ho, dy_w = a->mode == 3 ? 2 * a->width : Wo;
   alignas(64) CUtensorMap mapX0, mapX1, mapDY;

@@ -291,6 +291,32 @@ __global__ void __launch_bounds__(256) gn_silu_kernel(const bf16* __restrict__ x
   long long v1 = v0 + vec_per_cta;
   if (v1 > nvec) v1 = nvec;
   const size_t img = (size_t)b * hw * C;
+  if (256 % cvec == 0) {
+    // vec_per_cta is a multiple of 256 and 256 of cvec: this thread always meets the same 8 channels,
+    // so their affine coefficients live in registers for the whole stream
+    const int c0 = (threadIdx.x % cvec) << 3;
+    float ca[8], cb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ca[j] = sA[c0 + j];
+      cb[j] = sB[c0 + j];
+    }
+#pragma unroll 2
+    for (long long v = v0 + threadIdx.x; v < v1; v += 256) {
+      float f[8];
+      unpack8(ldg_stream(x + img + v * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = silu_f(fmaf(f[j], ca[j], cb[j]));
+      if (residual) {
+        float r[8];
+        unpack8(ldg_stream(residual + img + v * 8), r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += r[j];
+      }
+      *reinterpret_cast<uint4*>(out + img + v * 8) = pack8(f);
+    }
+    return;
+  }
   for (long long v = v0 + threadIdx.x; v < v1; v += 256) {
     const int c0 = (int)(v % cvec) << 3;
     float f[8];
@@ -321,6 +347,7 @@ extern "C" int tedm_gn_silu_fwd(const void* x, const float* gn_partial, int gn_p
   if (per_img < 1) per_img = 1;
   long long vec_per_cta = (nvec + per_img - 1) / per_img;
   if (vec_per_cta < 2048) vec_per_cta = 2048;
+  vec_per_cta = (vec_per_cta + 255) / 256 * 256;
   const int gx = (int)((nvec + vec_per_cta - 1) / vec_per_cta);
   gn_silu_kernel<<<dim3(gx, batch), 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)x, gn_partial, gn_parts, gamma, beta, scale_shift, ss_stride, ss_offset, (const bf16*)residual,

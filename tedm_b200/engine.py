@@ -352,10 +352,8 @@ class UnetEngine:
             return N.conv_igemm(dy, wd, run_mode, c0, residual=add0), None
         if mode not in (N.MODE_1X1, N.MODE_3X3):
             raise RuntimeError("two-source convolutions are 1x1 or 3x3")
-        split = c0 * taps * cout
-        dx0 = N.conv_igemm(dy, wd[:split], run_mode, c0, residual=add0)
-        dx1 = N.conv_igemm(dy, wd[split:], run_mode, c1, residual=add1)
-        return dx0, dx1
+        # one launch computes both gradients: N tiles over c0 + c1 channels, 64-channel sub-tiles routed to two tensors
+        return N.conv_igemm(dy, wd, run_mode, c0 + c1, residual=add0, split=c0, residual2=add1)
 
     def _block_bwd(self, key: str, blk: nn.Module, dy: Tensor, tape: Tape, G: GradArena, ss, ss_off: int, dss,
                    add0: Optional[Tensor] = None, add1: Optional[Tensor] = None):

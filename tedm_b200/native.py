@@ -22,7 +22,7 @@ class ConvArgs(C.Structure):  # tedm_conv_args
     _fields_ = [("src0", _p), ("src1", _p), ("weight", _p), ("bias", _p), ("residual", _p), ("out", _p),
                 ("gn_partial", _p), ("batch", _i), ("height", _i), ("width", _i), ("c0", _i), ("c1", _i),
                 ("cout", _i), ("mode", _i), ("gn_groups", _i), ("out_dtype", _i), ("src0_image_stride", _i64),
-                ("src1_image_stride", _i64), ("out_image_stride", _i64)]
+                ("src1_image_stride", _i64), ("out_image_stride", _i64), ("split", _i), ("out2", _p), ("residual2", _p)]
 
 
 class WeightEntry(C.Structure):  # tedm_weight_entry
@@ -233,9 +233,11 @@ def _nhwc(t: Optional[torch.Tensor], name: str, dtype=torch.bfloat16):
 
 
 def conv_igemm(src0: torch.Tensor, weight: torch.Tensor, mode: int, cout: int, bias=None, src1=None, residual=None,
-               gn_groups: int = 0, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16):
+               gn_groups: int = 0, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16, split: int = 0,
+               residual2=None):
     """Returns out (B, Ho, Wo, cout) bf16 (or fp32) [, gn_partial (B, parts, groups, 2) fp32 if gn_groups > 0].
-    src0/src1/out may be batch-strided views (e.g. x[s::S]); residual must share out's strides."""
+    src0/src1/out may be batch-strided views (e.g. x[s::S]); residual must share out's strides.
+    split > 0: returns (out[..., :split], out2[..., split:]) as two dense tensors (+ residual / residual2)."""
     b, h, w, c0 = src0.shape
     c1 = src1.shape[3] if src1 is not None else 0
     if src1 is not None and src1.shape[:3] != src0.shape[:3]:
@@ -244,7 +246,15 @@ def conv_igemm(src0: torch.Tensor, weight: torch.Tensor, mode: int, cout: int, b
     taps = {MODE_1X1: 1, MODE_3X3: 9, MODE_4X4S2: 16, MODE_UP3X3: 16}[mode]
     if weight.numel() != cout * taps * (c0 + c1):
         raise ValueError(f"conv_igemm: weight has {weight.numel()} elements, expected {cout * taps * (c0 + c1)}")
-    if out is None:
+    out2 = None
+    if split:
+        if out is not None or gn_groups or out_dtype != torch.bfloat16:
+            raise ValueError("conv_igemm: split output is bf16, freshly allocated, without GroupNorm statistics")
+        out = torch.empty(b, oh, ow, split, device=src0.device, dtype=torch.bfloat16)
+        out2 = torch.empty(b, oh, ow, cout - split, device=src0.device, dtype=torch.bfloat16)
+        if residual2 is not None and residual2.shape != out2.shape:
+            raise ValueError("conv_igemm: residual2 must have out2's shape")
+    elif out is None:
         out = torch.empty(b, oh, ow, cout, device=src0.device, dtype=out_dtype)
     elif tuple(out.shape) != (b, oh, ow, cout):
         raise ValueError(f"conv_igemm: out has shape {tuple(out.shape)}, expected {(b, oh, ow, cout)}")
@@ -260,7 +270,8 @@ def conv_igemm(src0: torch.Tensor, weight: torch.Tensor, mode: int, cout: int, b
     if residual is not None and (sr != so or residual.shape != out.shape):
         raise ValueError("conv_igemm: residual must have out's shape and strides")
     a = ConvArgs(p0, p1, _ptr(weight, torch.bfloat16, "weight"), _ptr(bias, torch.float32, "bias"), pr, po, _ptr(gnp),
-                 b, h, w, c0, c1, cout, mode, gn_groups, 1 if out.dtype == torch.float32 else 0, s0, s1, so)
+                 b, h, w, c0, c1, cout, mode, gn_groups, 1 if out.dtype == torch.float32 else 0, s0, s1,
+                 0 if split else so, split, _ptr(out2), _ptr(residual2, torch.bfloat16, "residual2"))
     global conv_flops
     flops = 2 * b * (h * w if mode == MODE_UP3X3 else oh * ow) * cout * taps * (c0 + c1)
     conv_flops += flops
@@ -269,6 +280,8 @@ def conv_igemm(src0: torch.Tensor, weight: torch.Tensor, mode: int, cout: int, b
             _call("tedm_conv_igemm_fwd", C.byref(a), _stream())
     else:
         _call("tedm_conv_igemm_fwd", C.byref(a), _stream())
+    if split:
+        return out, out2
     return (out, gnp) if gn_groups else out
 
 
@@ -293,6 +306,11 @@ def conv_wgrad(src0: torch.Tensor, dy: torch.Tensor, mode: int, src1=None, grad_
     p1, s1 = _nhwc(src1, "src1")
     pd, sd = _nhwc(dy, "dy")
     a = ConvArgs(p0, p1, None, None, None, None, None, b, h, w, c0, c1, cout, mode, 0, 0, s0, s1, sd)
+    if conv_timer is not None:
+        flops = 2 * b * (h * w if mode == MODE_UP3X3 else oh * ow) * cout * taps * (c0 + c1)
+        with conv_timer(flops, ("wgrad", mode, b, h, w, c0, c1, cout)):
+            _call("tedm_conv_igemm_wgrad", C.byref(a), pd, _ptr(dw, torch.float32, "dw"), 0 if grad_oihw is None else 1, _stream())
+        return dw
     _call("tedm_conv_igemm_wgrad", C.byref(a), pd, _ptr(dw, torch.float32, "dw"), 0 if grad_oihw is None else 1, _stream())
     return dw
 

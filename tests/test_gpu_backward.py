@@ -133,6 +133,18 @@ def test_conv_dgrad_two_sources_and_residual():
     torch.cuda.synchronize()
     assert _rel(dx0.float().permute(0, 3, 1, 2), dx_ref[:, :c0]) < 6e-3
     assert _rel(dx1.float().permute(0, 3, 1, 2), dx_ref[:, c0:] + extra) < 6e-3
+    # one launch, split output: 64-channel sub-tiles of the N tile are routed to the two gradient tensors
+    for force_bn in (0, 64, 128):
+        N.load().tedm_conv_set_tile_n(force_bn)
+        try:
+            s0, s1 = N.conv_igemm(dyn, wd, N.MODE_3X3, c0 + c1, split=c0, residual2=_nhwc(extra.cpu()))
+            r0, r1 = N.conv_igemm(dyn, wd, N.MODE_3X3, c0 + c1, split=c0, residual=_nhwc(dx_ref[:, :c0].detach().cpu()))
+        finally:
+            N.load().tedm_conv_set_tile_n(0)
+        torch.cuda.synchronize()
+        assert torch.equal(s0, dx0) and torch.equal(s1, dx1), force_bn
+        assert _rel(r0.float().permute(0, 3, 1, 2), 2 * dx_ref[:, :c0]) < 6e-3
+        assert _rel(r1.float().permute(0, 3, 1, 2), dx_ref[:, c0:]) < 6e-3
 
 
 @pytest.mark.parametrize("mode,cout,cin", [(0, 128, 64), (1, 64, 192), (2, 128, 64), (3, 64, 128)])
