@@ -119,6 +119,25 @@ def cpu_tedm_images_per_s(n_images: int, repeats: int = 1):
     return n_images / best, best
 
 
+def cpu_train_images_per_s(n_images: int):
+    """The reference's training step (train_step + backward, trainers/train_CXR14.py:30-40) as the oracle port runs it
+    on the host cores: fp32 torch autograd through oracle.ddpm_loss."""
+    import torch
+    from oracle import tedm_oracle as O
+    from tests.golden.synth import synth_state_dict
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = {k: v.requires_grad_(True) for k, v in synth_state_dict(O.unet_param_shapes(prefix="model."), 0).items()}
+    full = dict(sd)
+    full.update(O.schedule_tables())
+    x0 = synth_batch(n_images, 98)
+    t = torch.randint(0, 1000, (n_images,), generator=torch.Generator().manual_seed(3))
+    nz = torch.randn(n_images, 1, IMG, IMG, generator=torch.Generator().manual_seed(4))
+    t0 = time.perf_counter()
+    O.ddpm_loss(full, x0, t, nz).backward()
+    dt = time.perf_counter() - t0
+    return n_images / dt, dt
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  /root/reference is pure Python
     with no packaging (no setup.py / pyproject: `pip install /root/reference` has nothing to build) and does not
@@ -280,14 +299,91 @@ def run_ours(args):
                        "executed_conv_gflop_per_image": conv_flops_step / B / 1e9,
                        "frac_of_sustained_peak_minimal_form": value * GFLOP_TEDM_MIN / 1e3 / (pk["tflops_sustained"] * world)},
             "roofline": roofline, "clocks": clocks.summary()}
+    # ---- second half of BASELINE.json's metric: the DDPM pre-training step (UNet fwd+bwd TFLOP/s vs bf16 peak) ----
+    del model, resident, noise
+    torch.cuda.empty_cache()
+    if not args.no_train:
+        line["train"] = train_leg(args, dev, world, rank, pk, barrier)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
+            if "train" in line:
+                v, dt = cpu_train_images_per_s(2)
+                line["train"]["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+                                                 "sample": f"one fwd+bwd on 2 images ({dt:.1f} s), oracle port, torch CPU fp32 autograd"}
             v, dt = cpu_tedm_images_per_s(2)
             line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"2 images x 8 timesteps, one pass ({dt:.1f} s), oracle port on torch CPU fp32"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+GFLOP_TRAIN = 176.9             # per image: 3 x 58.97
+
+
+def train_leg(args, dev, world, rank, pk, barrier):
+    """BASELINE configs[1]: DDPM backbone pre-training, data-parallel.  One step = q_sample + UNet forward + L1/p2 loss +
+    UNet backward + ONE gradient all-reduce (world > 1) + Adam, replayed from CUDA graphs (tedm_b200/train.py)."""
+    import torch
+    import torch.distributed as dist
+    from argparse import Namespace
+    from tedm_b200.models import DiffusionModel
+    from tedm_b200.optim import FusedAdam
+    from tedm_b200.train import GraphedTrainStep
+
+    out = {"workload": "ddpm_pretraining_step", "unit": "images/s", "gflop_per_image_fwd_bwd": GFLOP_TRAIN,
+           "step": "q_sample + UNet fwd + L1/p2 loss + UNet bwd + grad all-reduce (world>1) + fused Adam; CUDA-graph replay",
+           "parallelism": f"dp{world} (one flat-arena NCCL all-reduce per step)" if world > 1 else "dp1"}
+    torch.manual_seed(1234 + rank)
+    model = DiffusionModel(Namespace(normalize=True)).to(dev).train()
+    if world > 1:                       # replicas start from rank 0's weights
+        for p in model.parameters():
+            dist.broadcast(p.data, src=0)
+    opt = FusedAdam(model.parameters(), lr=1e-4)
+    for B in args.train_batches:
+        host = [synth_batch(B, 500 + rank * 100 + i).pin_memory() for i in range(4)]
+        resident = [h.to(dev) for h in host]
+        step = GraphedTrainStep(model, opt, resident[0], warmup=max(3, args.warmup))
+
+        def timed(fn, steps):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                fn(i)
+            e1.record()
+            barrier()
+            ms = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = t.item()
+            return ms
+
+        losses = []
+
+        def e2e(i):
+            x = host[i % 4].to(dev, non_blocking=True)
+            losses.append(float(step(x)))              # loss read back to the host every step
+
+        for i in range(3):
+            step(resident[i % 4])
+        ms = timed(lambda i: step(resident[i % 4]), args.steps)
+        ms_e2e = timed(e2e, args.steps)
+        ips = world * B * args.steps / (ms * 1e-3)
+        out[f"batch{B}"] = {
+            "batch_per_gpu": B, "global_batch": B * world, "ms_per_step": ms / args.steps, "images_per_s": ips,
+            "tflops_fwd_bwd": ips * GFLOP_TRAIN / 1e3, "frac_of_sustained_bf16_peak": ips * GFLOP_TRAIN / 1e3 / (pk["tflops_sustained"] * world),
+            "e2e_images_per_s": world * B * args.steps / (ms_e2e * 1e-3), "h2d_bytes_per_step": B * IMG * IMG * 4,
+            "d2h_bytes_per_step": 4, "native_calls_per_step": step.native_calls_per_step, "loss_last": losses[-1]}
+        del step
+        torch.cuda.empty_cache()
+    best = max((k for k in out if k.startswith("batch")), key=lambda k: out[k]["tflops_fwd_bwd"])
+    out["value"] = out[best]["images_per_s"]
+    out["tflops_fwd_bwd"] = out[best]["tflops_fwd_bwd"]
+    out["frac_of_sustained_bf16_peak"] = out[best]["frac_of_sustained_bf16_peak"]
+    out["batch_per_gpu"] = out[best]["batch_per_gpu"]
+    return out
 
 
 def main():
@@ -298,6 +394,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step (config.py:58 default 16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the DDPM training-step leg")
+    ap.add_argument("--train-batches", type=int, nargs="+", default=[16, 64],
+                    help="per-GPU batch sizes of the training leg (config.py:58 default is 16)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -132,8 +132,11 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, 
 //               (x0-1 .. x0+128) of one 64-channel block, and the three horizontal taps are three
 //               UMMAs on row-shifted windows of it -> activations cross L2->SM 3x instead of 9x and
 //               weights once instead of once per tile.
-template <int BN, bool WS, int CPG>
-__global__ void __launch_bounds__(192, 1)
+constexpr int EPI_THREADS = 256;   // 8 epilogue warps
+constexpr int CONV_THREADS = 64 + EPI_THREADS;
+
+template <int BN, bool WS, int CPG, bool RES>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapOut,
                   const __grid_constant__ CUtensorMap mapOut2, const ConvParams p) {
@@ -149,7 +152,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   __shared__ __align__(8) uint64_t bar_acc_empty[2];
   __shared__ __align__(8) uint64_t bar_w;
   __shared__ uint32_t tmem_slot;
-  __shared__ float red[4][2][NGMAX][2];
+  __shared__ float red[2][4][2][4][2];   // [column half][lane quarter][segment][group][sum, sumsq]
   __shared__ __align__(16) float sbias[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -171,7 +174,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bar_acc_full[i]), 1);
-      mbar_init(smem_u32(&bar_acc_empty[i]), 4);
+      mbar_init(smem_u32(&bar_acc_empty[i]), EPI_THREADS / 32);
     }
     mbar_init(smem_u32(&bar_w), 1);
     fence_barrier_init();
@@ -300,13 +303,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     }
     __syncwarp();
   } else {
-    // ===== epilogue ===========================================================================
-    constexpr int NGL = CPG ? BN / CPG : 1;   // GroupNorm groups covered by this N tile (<= 8)
-    constexpr int NV = 2 * NGL;               // (sum, sum of squares) per group
-    const int q = warp & 3;               // TMEM lane quarter this warp may read
+    // ===== epilogue: 8 warps; warp w reads TMEM lane quarter (w & 3) and half of the tile's columns ==========
+    constexpr int CH = BN / 64;                 // 32-column chunks per warp
+    constexpr int WCOLS = BN / 2;               // columns per warp
+    constexpr int NGL = CPG ? BN / CPG : 1;     // GroupNorm groups covered by this N tile (<= 8)
+    constexpr bool SPLITG = CPG > WCOLS;        // one group spans both column halves
+    constexpr int NGLW = CPG ? (SPLITG ? 1 : WCOLS / CPG) : 1;   // groups per warp
+    constexpr int NV = 2 * NGLW;                // (sum, sum of squares) per group
+    const int q = warp & 3;                     // TMEM lane quarter this warp may read
+    const int hsel = (warp - 2) >> 2;           // column half
     const int row = q * 32 + lane;
-    const int e = threadIdx.x - 64;       // 0..127
-    const int hwt = p.tileW * p.tileH;    // pixels of one image inside the tile
+    const int e = threadIdx.x - 64;             // 0..255
+    const int hwt = p.tileW * p.tileH;          // pixels of one image inside the tile
     const int tb = row / hwt, rrem = row % hwt;
     const int ty = rrem / p.tileW, tx = rrem % p.tileW;
     const int seg_size = hwt < 32 ? hwt : 32;
@@ -317,7 +325,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       const int b = t.b0 + tb, y = t.y0 + ty, x = t.x0 + tx;
       const bool valid = b < p.B;
       const int oy = y * p.osy + par_y, ox = x * p.osx + par_x;
-      const size_t opix = (size_t)b * p.out_image_stride + ((size_t)oy * p.OW + ox) * p.cout + t.n0;
+      const size_t pixoff = (size_t)oy * p.OW + ox;
+      const size_t opix = (size_t)b * p.out_image_stride + pixoff * p.cout + t.n0;
       const int buf = it & 1;
       const uint32_t out_buf = out_base + (p.out_bufs == 2 ? (uint32_t)(buf * OUT_BYTES) : 0u);
       // the TMA store that last used this staging buffer must have drained it; every thread must be done
@@ -326,28 +335,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         if (p.out_bufs == 2) tma_store_wait_read<1>();
         else tma_store_wait_read<0>();
       }
-      for (int i = e; i < BN; i += 128) sbias[i] = p.bias ? __ldg(p.bias + t.n0 + i) : 0.0f;
-      named_bar_sync(1, 128);
-      // the residual row of this thread is fetched BEFORE waiting for the accumulator, so its latency hides
-      // behind the main loop of this tile (N tiles up to 128 channels; wider tiles load in place below)
-      constexpr int NPRE = BN <= 128 ? BN / 8 : 1;
-      uint4 rpre[NPRE];
-      // residual row segment of 64-channel sub-tile cp (NULL: nothing to add); with a split output the sub-tile
-      // belongs to (residual, split channels per pixel) or (residual2, cout - split channels per pixel)
-      const size_t pixoff = (size_t)oy * p.OW + ox;
-      auto res_sub = [&](int cp) -> const bf16* {
-        const int c = t.n0 + cp * 64;
-        if (p.split == 0) return p.residual ? p.residual + opix + cp * 64 : nullptr;
-        if (c < p.split) return p.residual ? p.residual + (size_t)b * p.out_image_stride + pixoff * p.split + c : nullptr;
-        return p.residual2 ? p.residual2 + (size_t)b * p.out2_image_stride + pixoff * (p.cout - p.split) + (c - p.split) : nullptr;
-      };
-      if (BN <= 128 && valid) {
+      for (int i = e; i < BN; i += EPI_THREADS) sbias[i] = p.bias ? __ldg(p.bias + t.n0 + i) : 0.0f;
+      named_bar_sync(1, EPI_THREADS);
+      // the residual values of this thread are fetched BEFORE waiting for the accumulator: their latency hides
+      // behind the main loop of this tile.  With a split output, 64-channel sub-tile cp belongs to
+      // (residual, `split` channels per pixel) or (residual2, cout - split channels per pixel).
+      uint4 rpre[RES ? CH * 4 : 1];
+      bool has_res[RES ? CH : 1];
+      if constexpr (RES) {
 #pragma unroll
-        for (int cp = 0; cp < BN / 64; ++cp) {
-          const uint4* rp = reinterpret_cast<const uint4*>(res_sub(cp));
-          if (rp) {
+        for (int i = 0; i < CH; ++i) {
+          const int chunk = hsel * CH + i, c = t.n0 + (chunk >> 1) * 64;
+          const bf16* rsub;
+          if (p.split == 0) rsub = p.residual ? p.residual + opix + (chunk >> 1) * 64 : nullptr;
+          else if (c < p.split) rsub = p.residual ? p.residual + (size_t)b * p.out_image_stride + pixoff * p.split + c : nullptr;
+          else rsub = p.residual2 ? p.residual2 + (size_t)b * p.out2_image_stride + pixoff * (p.cout - p.split) + (c - p.split) : nullptr;
+          has_res[i] = rsub != nullptr && valid;
+          if (has_res[i]) {
+            const uint4* rp = reinterpret_cast<const uint4*>(rsub + (chunk & 1) * 32);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) rpre[(cp * 8 + j) % NPRE] = __ldg(rp + j);
+            for (int j = 0; j < 4; ++j) rpre[i * 4 + j] = __ldg(rp + j);
           }
         }
       }
@@ -357,69 +364,63 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 #pragma unroll
       for (int i = 0; i < NV; ++i) gv[i] = 0.0f;
 #pragma unroll
-      for (int cp = 0; cp < BN / 64; ++cp) {
-        uint32_t r0[32], r1[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cp * 64);
-        tmem_ld32(taddr, r0);
-        tmem_ld32(taddr + 32, r1);
+      for (int i = 0; i < CH; ++i) {
+        const int chunk = hsel * CH + i, cp = chunk >> 1, half = chunk & 1;
+        uint32_t r0[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + chunk * 32), r0);
         tmem_ld_wait();
+        float v[32];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int chunk = cp * 2 + half;
-          float v[32];
+        for (int j = 0; j < 8; ++j) {
+          const float4 bv = *reinterpret_cast<const float4*>(&sbias[chunk * 32 + 4 * j]);
+          v[4 * j] = __uint_as_float(r0[4 * j]) + bv.x;
+          v[4 * j + 1] = __uint_as_float(r0[4 * j + 1]) + bv.y;
+          v[4 * j + 2] = __uint_as_float(r0[4 * j + 2]) + bv.z;
+          v[4 * j + 3] = __uint_as_float(r0[4 * j + 3]) + bv.w;
+        }
+        if (CPG) {
+          constexpr int W = CPG < 32 ? (CPG ? CPG : 32) : 32;   // channels per partial sum inside this chunk
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bv = *reinterpret_cast<const float4*>(&sbias[chunk * 32 + 4 * j]);
-            v[4 * j] = __uint_as_float(half ? r1[4 * j] : r0[4 * j]) + bv.x;
-            v[4 * j + 1] = __uint_as_float(half ? r1[4 * j + 1] : r0[4 * j + 1]) + bv.y;
-            v[4 * j + 2] = __uint_as_float(half ? r1[4 * j + 2] : r0[4 * j + 2]) + bv.z;
-            v[4 * j + 3] = __uint_as_float(half ? r1[4 * j + 3] : r0[4 * j + 3]) + bv.w;
-          }
-          if (CPG) {
-            constexpr int W = CPG < 32 ? (CPG ? CPG : 32) : 32;   // channels per partial sum inside this chunk
+          for (int sg = 0; sg < 32 / W; ++sg) {
+            float s_ = 0.0f, q_ = 0.0f;
 #pragma unroll
-            for (int sg = 0; sg < 32 / W; ++sg) {
-              float s_ = 0.0f, q_ = 0.0f;
-#pragma unroll
-              for (int j = 0; j < W; ++j) {
-                s_ += v[sg * W + j];
-                q_ = fmaf(v[sg * W + j], v[sg * W + j], q_);
-              }
-              const int gl = (chunk * 32 + sg * W) / (CPG ? CPG : 1);
-              gv[2 * gl] += s_;
-              gv[2 * gl + 1] += q_;
+            for (int j = 0; j < W; ++j) {
+              s_ += v[sg * W + j];
+              q_ = fmaf(v[sg * W + j], v[sg * W + j], q_);
             }
+            const int gl = SPLITG ? 0 : (i * 32 + sg * W) / (CPG ? CPG : 1);   // group index local to this warp
+            gv[2 * gl] += s_;
+            gv[2 * gl + 1] += q_;
           }
-          const bf16* rsub = valid ? res_sub(cp) : nullptr;
-          if (rsub) {
-            const uint4* rp = reinterpret_cast<const uint4*>(rsub + half * 32);
+        }
+        if constexpr (RES) {
+          if (has_res[i]) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float f[8];
-              if constexpr (BN <= 128) unpack8(rpre[(chunk * 4 + j) % NPRE], f);
-              else unpack8(__ldg(rp + j), f);
+              unpack8(rpre[i * 4 + j], f);
 #pragma unroll
               for (int c = 0; c < 8; ++c) v[8 * j + c] += f[c];
             }
           }
-          if (p.out_f32) {
-            if (valid) {
-              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix + chunk * 32);
+        }
+        if (p.out_f32) {
+          if (valid) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix + chunk * 32);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-          } else {
-            // stage the bf16 tile in the 128B-swizzled layout the TMA store expects: sub-tile = 64 channels,
-            // row = pixel (128 B), 16-byte chunk index XOR (row & 7)
-            const uint32_t sub = out_buf + (uint32_t)cp * A_BYTES + (uint32_t)row * 128u;
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        } else {
+          // stage the bf16 tile in the 128B-swizzled layout the TMA store expects: sub-tile = 64 channels,
+          // row = pixel (128 B), 16-byte chunk index XOR (row & 7)
+          const uint32_t sub = out_buf + (uint32_t)cp * A_BYTES + (uint32_t)row * 128u;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t c16 = (uint32_t)(half * 4 + j);
-              const uint32_t dst = sub + ((c16 ^ (uint32_t)(row & 7)) << 4);
-              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pack_bf16x2(v[8 * j], v[8 * j + 1])),
-                           "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])), "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])),
-                           "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7])) : "memory");
-            }
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t c16 = (uint32_t)(half * 4 + j);
+            const uint32_t dst = sub + ((c16 ^ (uint32_t)(row & 7)) << 4);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pack_bf16x2(v[8 * j], v[8 * j + 1])),
+                         "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])), "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])),
+                         "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7])) : "memory");
           }
         }
       }
@@ -430,17 +431,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       if (CPG) {
         butterfly_sum<NV>(gv, lane, seg_size);
         const int ls = lane & (seg_size - 1);
-        const int keep_shift = (seg_size == 32 ? 5 : 4) - (NV == 16 ? 4 : NV == 8 ? 3 : NV == 4 ? 2 : 1);
-        if ((ls & ((1 << keep_shift) - 1)) == 0) (&red[q][lane / seg_size][0][0])[ls >> keep_shift] = gv[0];
+        const int keep_shift = (seg_size == 32 ? 5 : 4) - (NV == 8 ? 3 : NV == 4 ? 2 : 1);
+        if ((ls & ((1 << keep_shift) - 1)) == 0) (&red[hsel][q][lane / seg_size][0][0])[ls >> keep_shift] = gv[0];
       }
       if (!p.out_f32) fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-      named_bar_sync(2, 128);
+      named_bar_sync(2, EPI_THREADS);
       if (e == 0 && !p.out_f32) {
         const int chan_base = (p.mode == 3 ? par_x * p.cout : 0) + t.n0;
         const int pc_out = p.mode == 3 ? par_y : 0;
         for (int sidx = 0; sidx < BN / 64; ++sidx) {
           const int c = chan_base + sidx * 64;
-          if (p.split && c >= p.split)
+          if (RES && p.split && c >= p.split)
             tma_store_5d(&mapOut2, out_buf + (uint32_t)sidx * A_BYTES, c - p.split, t.x0, pc_out, t.y0, t.b0);
           else
             tma_store_5d(&mapOut, out_buf + (uint32_t)sidx * A_BYTES, c, t.x0, pc_out, t.y0, t.b0);
@@ -450,15 +451,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       if (CPG) {
         const int segs_per_img = hwt / seg_size;      // 4, 2 or 1
         const int part = hwt == BM ? t.trem : 0;
-        for (int o = e; o < p.tileB * NGL; o += 128) {
+        for (int o = e; o < p.tileB * NGL; o += EPI_THREADS) {
           const int img = o / NGL, gl = o % NGL;
           if (t.b0 + img >= p.B) continue;
           float s_ = 0.0f, q_ = 0.0f;
           for (int sgi = 0; sgi < segs_per_img; ++sgi) {
             const int gseg = img * segs_per_img + sgi;       // global segment index in the tile
             const int w = (gseg * seg_size) >> 5, sl = ((gseg * seg_size) & 31) / seg_size;
-            s_ += red[w][sl][gl][0];
-            q_ += red[w][sl][gl][1];
+            if (SPLITG) {
+              s_ += red[0][w][sl][0][0] + red[1][w][sl][0][0];
+              q_ += red[0][w][sl][0][1] + red[1][w][sl][0][1];
+            } else {
+              s_ += red[gl / NGLW][w][sl][gl % NGLW][0];
+              q_ += red[gl / NGLW][w][sl][gl % NGLW][1];
+            }
           }
           float* dst = p.gn_partial + (((size_t)(t.b0 + img) * p.gn_parts + part) * p.gn_groups + t.n0 / (CPG ? CPG : 1) + gl) * 2;
           dst[0] = s_;
@@ -511,8 +517,8 @@ int encode_weight_map(CUtensorMap* map, const void* ptr, long long rows, long lo
   return TEDM_OK;
 }
 
-template <int BN, bool WS, int CPG>
-int launch_conv_cpg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o,
+template <int BN, bool WS, int CPG, bool RES>
+int launch_conv_res(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o,
                     const CUtensorMap& o2, ConvParams& p, cudaStream_t stream) {
   const int cb_total = p.c0_blocks + p.c1_blocks;
   const int stage_bytes = WS ? A_ROW_BYTES : A_BYTES + BN * BK * 2;
@@ -528,13 +534,23 @@ int launch_conv_cpg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensor
   const int smem = fixed + stages * stage_bytes;
   static int configured = 0;
   if (configured < smem) {
-    TEDM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, WS, CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TEDM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, WS, CPG, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
   int grid = p.num_tiles < tedm_num_sms() ? p.num_tiles : tedm_num_sms();
-  conv_igemm_kernel<BN, WS, CPG><<<grid, 192, smem, stream>>>(a0, a1, w, o, o2, p);
+  conv_igemm_kernel<BN, WS, CPG, RES><<<grid, CONV_THREADS, smem, stream>>>(a0, a1, w, o, o2, p);
   TEDM_LAUNCH_CHECK();
   return TEDM_OK;
+}
+
+// residual / split-output epilogues exist only without GroupNorm statistics (they never co-occur in the net)
+template <int BN, bool WS, int CPG>
+int launch_conv_cpg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o,
+                    const CUtensorMap& o2, ConvParams& p, cudaStream_t stream) {
+  if constexpr (CPG == 0) {
+    if (p.residual || p.residual2 || p.split) return launch_conv_res<BN, WS, 0, true>(a0, a1, w, o, o2, p, stream);
+  }
+  return launch_conv_res<BN, WS, CPG, false>(a0, a1, w, o, o2, p, stream);
 }
 
 template <int BN, bool WS>
@@ -837,6 +853,8 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   if (a->gn_partial) {
     TEDM_CHECK_ARG(a->gn_groups > 0 && a->cout % a->gn_groups == 0, "tedm_conv_igemm_fwd: gn_groups=%d", a->gn_groups);
     TEDM_UNSUPPORTED(a->mode == 3, "tedm_conv_igemm_fwd: GroupNorm partials are not produced in upsample mode");
+    TEDM_UNSUPPORTED(a->residual != nullptr || a->split != 0,
+                     "tedm_conv_igemm_fwd: GroupNorm partials together with a residual / split output are not supported");
     p.gn_groups = a->gn_groups;
     p.gn_cpg = a->cout / a->gn_groups;
     p.gn_parts = tedm_conv_gn_parts(p.Ho, p.Wo);

@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtedm_b200.so")
+LIB_PATH = os.environ.get("TEDM_B200_LIB") or os.path.join(_HERE, "lib", "libtedm_b200.so")   # override: A/B builds
 
 _p, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
 

@@ -61,6 +61,14 @@ CASES = [
     # persistent loop with more tiles than SMs on the generic path
     (40, 16, 16, 128, 0, 128, 1, True, False, 8, 64),
     (6, 64, 64, 64, 0, 384, 0, False, False, 0, 0),
+    # residual epilogue (prefetched rows) on every N tile width and mode; one GroupNorm group spanning both column halves
+    (2, 16, 16, 64, 0, 64, 1, True, True, 0, 0),
+    (2, 16, 16, 128, 0, 256, 1, True, True, 0, 256),
+    (3, 16, 16, 128, 64, 128, 1, False, True, 0, 128),
+    (1, 128, 128, 64, 0, 64, 1, False, True, 0, 0),
+    (2, 16, 16, 128, 0, 64, 3, True, True, 0, 0),
+    (2, 32, 32, 64, 0, 128, 2, True, True, 0, 0),
+    (5, 4, 4, 512, 0, 512, 1, True, False, 8, 64),
 ]
 
 
