@@ -284,6 +284,41 @@ typedef struct {
 } tedm_head_args;
 TEDM_API int tedm_head_infer(const tedm_head_args* args, tedm_stream_t stream);
 
+/* ---- head training (BatchNorm batch statistics; gradients into the head parameters only) --------------------
+ * Replaces model(x) in training mode + loss.backward() of trainers/train_datasetDM.py:30-42,88-99 for the
+ * classifier of models/datasetDM_model.py:57-64.  The GEMMs (layer 1 per level, layer 2 on relu(z1) with BatchNorm-1
+ * folded into its weights, d h1 = W2^T d z2, every weight gradient) are tedm_conv_igemm_fwd / _wgrad calls; these entry
+ * points are the memory-bound passes between them.  Per-pixel tensors: a1 bf16 [N][H][W][128]; z2 fp32 [N][H][W][64]
+ * (channels 32..63 padding); dz2 bf16 [N][H][W][64].  Reduction buffers are fp32 and must be zeroed by the caller. */
+/* a1 = relu(b1 + sum_s sum_l g_l[...]) as bf16; sums[0][c] += sum a1, sums[1][c] += sum a1^2 (args: g, shift, n_levels,
+ * n_sum, n_img, height, width, c1, b1 are read). */
+TEDM_API int tedm_head_train_z1(const tedm_head_args* args, void* a1, float* sums, tedm_stream_t stream);
+/* BatchNorm2d training-mode statistics from (sum, sum of squares) over `count` samples: stats[0]=mean, [1]=rstd,
+ * [2]=A=gamma*rstd, [3]=C=beta-mean*A ([4][channels]); running_mean/var (nullable pair) updated like torch. */
+TEDM_API int tedm_bn_finalize(const float* sums, double count, const float* gamma, const float* beta, float eps,
+                     float momentum, float* running_mean, float* running_var, float* stats, int channels,
+                     tedm_stream_t stream);
+/* w2_folded bf16 [64][128] = W2 diag(A1) (rows >= 32 zero); b2_folded fp32 [64] = b2 + W2 C1; w2_t bf16 [128][64] = W2^T. */
+TEDM_API int tedm_head_fold_w2(const float* w2, const float* b2, const float* stats1, void* w2_folded, float* b2_folded,
+                      void* w2_t, tedm_stream_t stream);
+/* sums[0][j] += sum relu(z2_j), sums[1][j] += sum relu(z2_j)^2, j < 32. */
+TEDM_API int tedm_head_z2_stats(const float* z2, float* sums, int64_t npix, tedm_stream_t stream);
+/* mode 0: logits = w3 . BN2(relu(z2)) + b3.   mode 1: S[0][j] += sum dh2_j, S[1][j] += sum dh2_j*a2hat_j,
+ * S[2][j] += sum dlogit*h2_j, S[3][0] += sum dlogit.   mode 2: dz2 (bf16) and S[4][j] += sum dz2_j.   S is fp32 [5][32]. */
+TEDM_API int tedm_head_train_tail(int mode, const float* z2, const float* stats2, const float* w3, const float* b3,
+                         const float* dlogit, float* logits, float* S, void* dz2, double count, int64_t npix,
+                         tedm_stream_t stream);
+/* dh1: fp32 [N][H][W][128].  mode 0: T[0][k] += sum dh1_k, T[1][k] += sum dh1_k*a1hat_k.   mode 1: dz1 through BatchNorm-1 and ReLU-1; db1 += sum dz1;
+ * pooled[l] (bf16 [N][H>>s][W>>s][128], HOST array of device pointers; shifts: HOST array, 0..3) = 2^s x 2^s block sums
+ * of dz1, the output gradient of layer 1 at level l's native resolution. */
+TEDM_API int tedm_head_bn1_bwd(int mode, const void* dh1, const void* a1, const float* stats1, float* T, float* db1,
+                      void* const* pooled, const int* shifts, int n_levels, int n_img, int height, int width,
+                      double count, tedm_stream_t stream);
+/* dW2 += dW2_folded diag(A1) + db2 C1^T; db2, dgamma/dbeta of both norms, dw3, db3 += their reduction buffers. */
+TEDM_API int tedm_head_param_grads(const float* dw2_folded, const float* stats1, const float* S, const float* T, float* dw2,
+                          float* db2, float* dgamma1, float* dbeta1, float* dgamma2, float* dbeta2, float* dw3,
+                          float* db3, tedm_stream_t stream);
+
 /* prob[b] = mean_s sigmoid(logits[b*S+s]); mask = prob > 0.5
  * (auxiliary/postprocessing/testing_shared_weights.py:113,120,133-138; app.py:79). */
 TEDM_API int tedm_ensemble_mask(const float* logits, float* prob, uint8_t* mask, int batch, int n_steps, int hw,

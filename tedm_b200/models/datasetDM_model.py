@@ -104,13 +104,35 @@ class DatasetDM(nn.Module):
             raise RuntimeError("unrecognised classifier: expected Conv1x1-ReLU-BN-Conv1x1-ReLU-BN-Conv1x1")
         return convs, bns
 
-    def forward(self, x: Tensor) -> Tensor:
-        """(datasetDM_model.py:85-88) logits: (B, 1, H, W) for LEDM/LEDMe, (B*S, 1, H, W) for the TEDM head."""
+    def forward(self, x: Tensor, noise: Optional[Tensor] = None) -> Tensor:
+        """(datasetDM_model.py:85-88) logits: (B, 1, H, W) for LEDM/LEDMe, (B*S, 1, H, W) for the TEDM head.
+        BatchNorm in training mode -> batch statistics + autograd into the head parameters (tedm_b200/head_train.py)."""
         convs, bns = self._head_layers()
-        if self.classifier.training and torch.is_grad_enabled():
+        if bns[0].training or bns[1].training:
+            if not (bns[0].training and bns[1].training):
+                raise RuntimeError("both BatchNorm layers of the classifier must be in the same mode")
             from ..head_train import head_train_forward
-            return head_train_forward(self, x, convs, bns)
-        return self._head_infer(x, convs, bns)
+            return head_train_forward(self, x, convs, bns, noise)
+        return self._head_infer(x, convs, bns, noise)
+
+    def _layer1_maps(self, feats, w1: Tensor, shared: bool, b: int, s: int, chans, offs) -> List[Tensor]:
+        """Layer 1 of the head applied per level at native resolution (it commutes with the nearest upsample):
+        fp32 NHWC maps [(B*S), h_l, w_l, 128] on the tcgen05 1x1 conv."""
+        ctot = sum(chans)
+        g_maps = []
+        for l, f in enumerate(feats):
+            cl = chans[l]
+            if shared:
+                wl = self._cache.get(f"w1.l{l}", (w1,), lambda w, o=offs[l], c=cl: w[:, o:o + c, 0, 0].to(torch.bfloat16).contiguous())
+                g_maps.append(N.conv_igemm(f, wl, N.MODE_1X1, w1.shape[0], out_dtype=torch.float32))
+            else:
+                g = torch.empty(b * s, f.shape[1], f.shape[2], w1.shape[0], device=f.device, dtype=torch.float32)
+                for st in range(s):
+                    wl = self._cache.get(f"w1.s{st}.l{l}", (w1,),
+                                         lambda w, o=st * ctot + offs[l], c=cl: w[:, o:o + c, 0, 0].to(torch.bfloat16).contiguous())
+                    N.conv_igemm(f[st::s], wl, N.MODE_1X1, w1.shape[0], out=g[st::s])
+                g_maps.append(g)
+        return g_maps
 
     @torch.no_grad()
     def _head_infer(self, x: Tensor, convs: Sequence[nn.Conv2d], bns: Sequence[nn.BatchNorm2d],
@@ -126,21 +148,8 @@ class DatasetDM(nn.Module):
             raise RuntimeError("BatchNorm in training mode goes through head_train_forward")
         size = x.shape[-1]
         shifts = [(size // f.shape[1]).bit_length() - 1 for f in feats]
-        w1 = convs[0].weight
-        g_maps = []
         offs = [sum(chans[:l]) for l in range(len(chans))]
-        for l, f in enumerate(feats):
-            cl = chans[l]
-            if shared:
-                wl = self._cache.get(f"w1.l{l}", (w1,), lambda w, o=offs[l], c=cl: w[:, o:o + c, 0, 0].to(torch.bfloat16).contiguous())
-                g_maps.append(N.conv_igemm(f, wl, N.MODE_1X1, w1.shape[0], out_dtype=torch.float32))
-            else:
-                g = torch.empty(b * s, f.shape[1], f.shape[2], w1.shape[0], device=f.device, dtype=torch.float32)
-                for st in range(s):
-                    wl = self._cache.get(f"w1.s{st}.l{l}", (w1,),
-                                         lambda w, o=st * ctot + offs[l], c=cl: w[:, o:o + c, 0, 0].to(torch.bfloat16).contiguous())
-                    N.conv_igemm(f[st::s], wl, N.MODE_1X1, w1.shape[0], out=g[st::s])
-                g_maps.append(g)
+        g_maps = self._layer1_maps(feats, convs[0].weight, shared, b, s, chans, offs)
 
         def fold(bn: nn.BatchNorm2d, tag: str):
             def mk(w, bias, rm, rv):

@@ -63,6 +63,13 @@ SIGNATURES = {
     "tedm_nchw_f32_to_nhwc_bf16": (_i, [_p, _p, _i, _i, _i, _p]),
     "tedm_nhwc_bf16_to_nchw_f32": (_i, [_p, _p, _i, _i, _i, _p]),
     "tedm_head_infer": (_i, [C.POINTER(HeadArgs), _p]),
+    "tedm_head_train_z1": (_i, [C.POINTER(HeadArgs), _p, _p, _p]),
+    "tedm_bn_finalize": (_i, [_p, C.c_double, _p, _p, _f, _f, _p, _p, _p, _i, _p]),
+    "tedm_head_fold_w2": (_i, [_p, _p, _p, _p, _p, _p, _p]),
+    "tedm_head_z2_stats": (_i, [_p, _p, _i64, _p]),
+    "tedm_head_train_tail": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _p, C.c_double, _i64, _p]),
+    "tedm_head_bn1_bwd": (_i, [_i, _p, _p, _p, _p, _p, C.POINTER(_p), C.POINTER(_i), _i, _i, _i, _i, C.c_double, _p]),
+    "tedm_head_param_grads": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "tedm_ensemble_mask": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "tedm_weight_to_dgrad": (_i, [_p, _p, _i, _i, _i, _p]),
     "tedm_wgrad_to_oihw": (_i, [_p, _p, _i, _i, _i, _p]),
@@ -533,6 +540,81 @@ def head_infer(g_maps: Sequence[torch.Tensor], shifts: Sequence[int], n_sum: int
     a.logits = _ptr(logits)
     _call("tedm_head_infer", C.byref(a), _stream())
     return logits
+
+
+# ---- head training passes (see include/tedm_b200.h "head training") ----
+def head_train_z1(g_maps: Sequence[torch.Tensor], shifts: Sequence[int], n_sum: int, n_img: int, height: int, width: int, b1):
+    a = HeadArgs()
+    a.g_dtype = 1
+    for l, (g, s) in enumerate(zip(g_maps, shifts)):
+        a.g[l] = _ptr(g, torch.float32, f"g[{l}]")
+        a.shift[l] = s
+    a.n_levels, a.n_sum, a.n_img, a.height, a.width, a.c1, a.c2 = len(g_maps), n_sum, n_img, height, width, b1.numel(), 32
+    a.b1 = _ptr(b1, torch.float32, "b1")
+    a1 = torch.empty(n_img, height, width, b1.numel(), device=b1.device, dtype=torch.bfloat16)
+    sums = torch.zeros(2, b1.numel(), device=b1.device, dtype=torch.float32)
+    _call("tedm_head_train_z1", C.byref(a), _ptr(a1), _ptr(sums), _stream())
+    return a1, sums
+
+
+def bn_finalize(sums, count: int, gamma, beta, eps: float, momentum: float, running_mean=None, running_var=None):
+    c = gamma.numel()
+    stats = torch.empty(4, c, device=gamma.device, dtype=torch.float32)
+    _call("tedm_bn_finalize", _ptr(sums, torch.float32), float(count), _ptr(gamma, torch.float32), _ptr(beta, torch.float32),
+          eps, momentum, _ptr(running_mean, torch.float32), _ptr(running_var, torch.float32), _ptr(stats), c, _stream())
+    return stats
+
+
+def head_fold_w2(w2, b2, stats1):
+    dev = w2.device
+    w2f = torch.empty(64, 128, device=dev, dtype=torch.bfloat16)
+    b2f = torch.empty(64, device=dev, dtype=torch.float32)
+    w2t = torch.empty(128, 64, device=dev, dtype=torch.bfloat16)
+    _call("tedm_head_fold_w2", _ptr(w2, torch.float32, "w2"), _ptr(b2, torch.float32), _ptr(stats1, torch.float32), _ptr(w2f),
+          _ptr(b2f), _ptr(w2t), _stream())
+    return w2f, b2f, w2t
+
+
+def head_z2_stats(z2):
+    sums = torch.zeros(2, 32, device=z2.device, dtype=torch.float32)
+    _call("tedm_head_z2_stats", _ptr(z2, torch.float32, "z2"), _ptr(sums), z2.numel() // 64, _stream())
+    return sums
+
+
+def head_train_tail(mode: int, z2, stats2, w3, b3=None, dlogit=None, S=None, count: int = 1):
+    npix = z2.numel() // 64
+    logits = dz2 = None
+    if mode == 0:
+        logits = torch.empty(z2.shape[0], 1, z2.shape[1], z2.shape[2], device=z2.device, dtype=torch.float32)
+    if mode == 2:
+        dz2 = torch.empty(z2.shape, device=z2.device, dtype=torch.bfloat16)
+    _call("tedm_head_train_tail", mode, _ptr(z2, torch.float32, "z2"), _ptr(stats2, torch.float32), _ptr(w3, torch.float32),
+          _ptr(b3, torch.float32), _ptr(dlogit, torch.float32, "dlogit"), _ptr(logits), _ptr(S, torch.float32), _ptr(dz2),
+          float(count), npix, _stream())
+    return logits if mode == 0 else dz2
+
+
+def head_bn1_bwd(mode: int, dh1, a1, stats1, T, db1=None, shifts: Sequence[int] = (), count: int = 1):
+    n, h, w, c = a1.shape
+    pooled = []
+    n_levels = len(shifts) if mode == 1 else 0
+    ptrs = (_p * max(1, n_levels))()
+    shs = (_i * max(1, n_levels))()
+    for l in range(n_levels):
+        d = torch.empty(n, h >> shifts[l], w >> shifts[l], c, device=a1.device, dtype=torch.bfloat16)
+        pooled.append(d)
+        ptrs[l] = d.data_ptr()
+        shs[l] = shifts[l]
+    _call("tedm_head_bn1_bwd", mode, _ptr(dh1, torch.float32, "dh1"), _ptr(a1, torch.bfloat16, "a1"), _ptr(stats1, torch.float32),
+          _ptr(T, torch.float32), _ptr(db1, torch.float32), ptrs, shs, n_levels, n, h, w, float(count), _stream())
+    return pooled
+
+
+def head_param_grads(dw2f, stats1, S, T, dw2, db2, dg1, dbt1, dg2, dbt2, dw3, db3) -> None:
+    _call("tedm_head_param_grads", _ptr(dw2f, torch.float32), _ptr(stats1, torch.float32), _ptr(S, torch.float32),
+          _ptr(T, torch.float32), _ptr(dw2, torch.float32), _ptr(db2, torch.float32), _ptr(dg1, torch.float32),
+          _ptr(dbt1, torch.float32), _ptr(dg2, torch.float32), _ptr(dbt2, torch.float32), _ptr(dw3, torch.float32),
+          _ptr(db3, torch.float32), _stream())
 
 
 def ensemble_mask(logits: torch.Tensor, n_steps: int):
