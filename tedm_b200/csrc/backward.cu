@@ -72,8 +72,9 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const bf16* __restri
                                                             const float* __restrict__ partial, int parts,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ ss, int ss_stride, int ss_offset,
-                                                            float* __restrict__ red_out /*[B][3][C]*/, int hw, int C,
-                                                            int groups, float eps, int vec_per_cta) {
+                                                            float* __restrict__ red_out /*[B][3][C]*/,
+                                                            bf16* __restrict__ dz_out, int hw, int C, int groups, float eps,
+                                                            int vec_per_cta) {
   __shared__ float sA[GNB_MAX_C], sB[GNB_MAX_C], sR[GNB_MAX_C], sQ[GNB_MAX_C];
   __shared__ float s_mean[32], s_rstd[32];
   extern __shared__ float red[];  // [3][256][8]
@@ -112,11 +113,23 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const bf16* __restri
     cr[j] = sR[c0 + j];
     cq[j] = sQ[c0 + j];
   }
-#pragma unroll 2
-  for (long long v = v0 + threadIdx.x; v < v1; v += 256) {
+  for (long long vb = v0 + threadIdx.x; vb < v1; vb += 2 * 256) {
+   uint4 xv[2], dv[2];    // both iterations' loads are issued before either is consumed
+#pragma unroll
+   for (int u = 0; u < 2; ++u) {
+     const long long v = vb + u * 256;
+     if (v < v1) {
+       xv[u] = ldg_stream(x + img + v * 8);
+       dv[u] = ldg_stream(dy + img + v * 8);
+     }
+   }
+#pragma unroll
+   for (int u = 0; u < 2; ++u) {
+    const long long v = vb + u * 256;
+    if (v >= v1) break;
     float f[8], d[8];
-    unpack8(ldg_stream(x + img + v * 8), f);
-    unpack8(ldg_stream(dy + img + v * 8), d);
+    unpack8(xv[u], f);
+    unpack8(dv[u], d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float z = fmaf(f[j], ca[j], cb[j]);
@@ -125,12 +138,17 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const bf16* __restri
       acc[0][j] += dz;
       acc[1][j] = fmaf(dz, fmaf(f[j], cr[j], cq[j]), acc[1][j]);
       acc[2][j] += f[j];
+      d[j] = dz;
     }
+    // dz = dy * silu'(z) is parked (bf16) in the dx buffer: the apply pass reads it back instead of recomputing the
+    // sigmoid, and overwrites it in place
+    *reinterpret_cast<uint4*>(dz_out + img + v * 8) = pack8(d);
+   }
   }
   cta_channel_reduce<3>(acc, red, 256, cvec, red_out + (size_t)b * 3 * C, C);
 }
 
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const bf16* __restrict__ x,
                                                            const float* __restrict__ partial, int parts,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ ss, int ss_stride, int ss_offset,
@@ -139,7 +157,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const bf16* __restric
                                                            float* __restrict__ dbeta, float* __restrict__ dbias,
                                                            float* __restrict__ dss, int hw, int C, int groups, float eps,
                                                            int vec_per_cta) {
-  __shared__ float sA[GNB_MAX_C], sB[GNB_MAX_C], sK1[GNB_MAX_C], sK2[GNB_MAX_C], sK3[GNB_MAX_C];
+  __shared__ float sK1[GNB_MAX_C], sK2[GNB_MAX_C], sK3[GNB_MAX_C];
   __shared__ float sT1[GNB_MAX_C], sT2[GNB_MAX_C];
   __shared__ float s_mean[32], s_rstd[32], s_m1[32], s_m2[32];
   const int b = blockIdx.y, cpg = C / groups;
@@ -170,11 +188,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const bf16* __restric
     const int g = c / cpg;
     const float rstd = s_rstd[g], mean = s_mean[g];
     const float sc = ss ? ss[(size_t)b * ss_stride + ss_offset + c] + 1.0f : 1.0f;
-    const float sh = ss ? ss[(size_t)b * ss_stride + ss_offset + C + c] : 0.0f;
     const float gm = gamma[c], bt = beta[c];
-    const float a = rstd * gm;
-    sA[c] = a * sc;
-    sB[c] = (bt - mean * a) * sc + sh;
     const float k1 = gm * sc * rstd;
     const float k2 = -rstd * rstd * s_m2[g];
     sK1[c] = k1;
@@ -200,28 +214,34 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const bf16* __restric
   if (v1 > nvec) v1 = nvec;
   const size_t img = (size_t)b * hw * C;
   const int c0 = (threadIdx.x % cvec) << 3;
-  float ca[8], cb[8], k1[8], k2[8], k3[8];       // this thread always meets the same 8 channels
+  float k1[8], k2[8], k3[8];       // this thread always meets the same 8 channels
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    ca[j] = sA[c0 + j];
-    cb[j] = sB[c0 + j];
     k1[j] = sK1[c0 + j];
     k2[j] = sK2[c0 + j];
     k3[j] = sK3[c0 + j];
   }
-#pragma unroll 2
-  for (long long v = v0 + threadIdx.x; v < v1; v += 256) {
-    float f[8], d[8];
-    unpack8(ldg_stream(x + img + v * 8), f);
-    unpack8(ldg_stream(dy + img + v * 8), d);
+  for (long long vb = v0 + threadIdx.x; vb < v1; vb += 4 * 256) {
+    uint4 xv[4], zv[4];    // four iterations' loads in flight; dz was parked in dx by the reduce pass
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float z = fmaf(f[j], ca[j], cb[j]);
-      const float sg = sigmoid_f(z);
-      const float dz = d[j] * sg * fmaf(z, 1.0f - sg, 1.0f);
-      d[j] = fmaf(dz, k1[j], fmaf(f[j], k2[j], k3[j]));
+    for (int u = 0; u < 4; ++u) {
+      const long long v = vb + u * 256;
+      if (v < v1) {
+        xv[u] = ldg_stream(x + img + v * 8);
+        zv[u] = *reinterpret_cast<const uint4*>(dx + img + v * 8);
+      }
     }
-    *reinterpret_cast<uint4*>(dx + img + v * 8) = pack8(d);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long v = vb + u * 256;
+      if (v >= v1) break;
+      float f[8], d[8];
+      unpack8(xv[u], f);
+      unpack8(zv[u], d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = fmaf(d[j], k1[j], fmaf(f[j], k2[j], k3[j]));
+      *reinterpret_cast<uint4*>(dx + img + v * 8) = pack8(d);
+    }
   }
 }
 
@@ -327,7 +347,8 @@ int launch_layernorm_bwd(const void* x, const float* g, const void* dy, const vo
                          float eps, cudaStream_t stream) {
   const long long warps = (npix + (32 / L) - 1) / (32 / L);
   long long blocks = (warps + 7) / 8;
-  const long long cap = (long long)tedm_num_sms() * 4;
+  static int cap = 0;   // one resident wave
+  if (cap == 0) cap = resident_ctas(layernorm_bwd_kernel<L, NV>, 256, 0);
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   layernorm_bwd_kernel<L, NV><<<(int)blocks, 256, 0, stream>>>((const bf16*)x, g, (const bf16*)dy, (const bf16*)add,
@@ -758,7 +779,14 @@ extern "C" int tedm_gn_silu_bwd(const void* x, const void* dy, const float* gn_p
                    "tedm_gn_silu_bwd: channels=%d groups=%d unsupported", channels, groups);
   cudaStream_t s = (cudaStream_t)stream;
   const long long nvec = (long long)hw * cvec;
-  long long per_img = ((long long)tedm_num_sms() * 4 + batch - 1) / batch;
+  // one full wave of CTAs (the same grid serves both passes: size it for the pass with fewer resident CTAs)
+  static int capacity = 0;
+  if (capacity == 0) {
+    const int c1 = resident_ctas(gn_bwd_reduce_kernel, 256, 3 * 256 * 8 * sizeof(float));
+    const int c2 = resident_ctas(gn_bwd_apply_kernel, 256, 0);
+    capacity = c1 < c2 ? c1 : c2;
+  }
+  long long per_img = capacity / batch;
   if (per_img < 1) per_img = 1;
   long long vec_per_cta = (nvec + per_img - 1) / per_img;
   if (vec_per_cta < 2048) vec_per_cta = 2048;
@@ -766,10 +794,10 @@ extern "C" int tedm_gn_silu_bwd(const void* x, const void* dy, const float* gn_p
   const int gx = (int)((nvec + vec_per_cta - 1) / vec_per_cta);
   TEDM_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * 3 * (size_t)batch * channels, s));
   gn_bwd_reduce_kernel<<<dim3(gx, batch), 256, 3 * 256 * 8 * sizeof(float), s>>>(
-      (const bf16*)x, (const bf16*)dy, gn_partial, gn_parts, gamma, beta, scale_shift, ss_stride, ss_offset, workspace, hw,
-      channels, groups, eps, (int)vec_per_cta);
+      (const bf16*)x, (const bf16*)dy, gn_partial, gn_parts, gamma, beta, scale_shift, ss_stride, ss_offset, workspace,
+      (bf16*)dx, hw, channels, groups, eps, (int)vec_per_cta);
   TEDM_LAUNCH_CHECK();
-  gn_bwd_apply_kernel<<<dim3(gx, batch), 256, 0, s>>>((const bf16*)x, (const bf16*)dy, gn_partial, gn_parts, gamma, beta,
+  gn_bwd_apply_kernel<<<dim3(gx, batch), 256, 0, s>>>((const bf16*)x, gn_partial, gn_parts, gamma, beta,
                                                       scale_shift, ss_stride, ss_offset, workspace, (bf16*)dx, dgamma, dbeta,
                                                       dbias, dscale_shift, hw, channels, groups, eps, (int)vec_per_cta);
   TEDM_LAUNCH_CHECK();

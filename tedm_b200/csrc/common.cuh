@@ -46,6 +46,17 @@ int tedm_num_sms();
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+#ifdef __CUDACC__
+// CTAs of `kernel` that are resident on the whole GPU at once (one full wave); grids of streaming kernels are sized
+// to at most this so that no partial second wave trails behind.
+template <typename K>
+static inline int resident_ctas(K kernel, int threads, size_t dyn_smem) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return per_sm * tedm_num_sms();
+}
+#endif
+
 // ------------------------------------------------------------------------------------------
 // small device helpers
 // ------------------------------------------------------------------------------------------

@@ -167,7 +167,7 @@ extern "C" int tedm_stem_conv7x7(const float* x, const float* weight, const floa
     TEDM_CUDA(cudaFuncSetAttribute(stem_conv7x7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long total = (long long)batch * height * ((width + STEM_PX - 1) / STEM_PX) * (cout / 8);
   long long blocks = (total + 255) / 256;
-  const long long cap = (long long)tedm_num_sms() * 16;
+  const long long cap = resident_ctas(stem_conv7x7_kernel, 256, smem);   // one resident wave of the grid-stride loop
   if (blocks > cap) blocks = cap;
   stem_conv7x7_kernel<<<(int)blocks, 256, smem, (cudaStream_t)stream>>>(x, weight, bias, (bf16*)out, batch, cin, height,
                                                                        width, cout);
@@ -301,8 +301,33 @@ __global__ void __launch_bounds__(256) gn_silu_kernel(const bf16* __restrict__ x
       ca[j] = sA[c0 + j];
       cb[j] = sB[c0 + j];
     }
-#pragma unroll 2
-    for (long long v = v0 + threadIdx.x; v < v1; v += 256) {
+    // four independent 16-byte loads (eight with a residual) are in flight per thread before any is consumed
+    constexpr int U = 4;
+    long long v = v0 + threadIdx.x;
+    for (; v + (U - 1) * 256 < v1; v += U * 256) {
+      uint4 xv[U], rv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) xv[u] = ldg_stream(x + img + (v + u * 256) * 8);
+      if (residual) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) rv[u] = ldg_stream(residual + img + (v + u * 256) * 8);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float f[8];
+        unpack8(xv[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = silu_f(fmaf(f[j], ca[j], cb[j]));
+        if (residual) {
+          float r[8];
+          unpack8(rv[u], r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += r[j];
+        }
+        *reinterpret_cast<uint4*>(out + img + (v + u * 256) * 8) = pack8(f);
+      }
+    }
+    for (; v < v1; v += 256) {
       float f[8];
       unpack8(ldg_stream(x + img + v * 8), f);
 #pragma unroll
@@ -342,8 +367,11 @@ extern "C" int tedm_gn_silu_fwd(const void* x, const float* gn_partial, int gn_p
   TEDM_UNSUPPORTED(channels % 8 != 0 || channels > GN_MAX_C || groups <= 0 || groups > 32 || channels % groups != 0,
                    "tedm_gn_silu_fwd: channels=%d groups=%d unsupported", channels, groups);
   const long long nvec = (long long)hw * (channels / 8);
-  // ~2 waves of CTAs over the whole batch, each CTA at least 2048 vectors (32 KB) to amortise the prologue
-  long long per_img = ((long long)tedm_num_sms() * 8 + batch - 1) / batch;
+  // one full wave of CTAs over the whole batch (never a partial second wave), each CTA at least 2048 vectors (32 KB)
+  // to amortise the prologue
+  static int capacity = 0;
+  if (capacity == 0) capacity = resident_ctas(gn_silu_kernel, 256, 0);
+  long long per_img = capacity / batch;
   if (per_img < 1) per_img = 1;
   long long vec_per_cta = (nvec + per_img - 1) / per_img;
   if (vec_per_cta < 2048) vec_per_cta = 2048;
@@ -425,7 +453,8 @@ static int launch_layernorm(const void* x, const float* g, const void* residual,
                             cudaStream_t stream) {
   const long long warps = (npix + (32 / L) - 1) / (32 / L);
   long long blocks = (warps + 7) / 8;
-  const long long cap = (long long)tedm_num_sms() * 8;
+  static int cap = 0;   // one resident wave (grid-stride loop: a partial second wave would double the time)
+  if (cap == 0) cap = resident_ctas(layernorm_kernel<L, NV>, 256, 0);
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   layernorm_kernel<L, NV><<<(int)blocks, 256, 0, stream>>>((const bf16*)x, g, (const bf16*)residual, (bf16*)out, npix, eps);

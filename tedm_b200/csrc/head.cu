@@ -111,7 +111,7 @@ extern "C" int tedm_head_infer(const tedm_head_args* a, tedm_stream_t stream) {
   p.logits = a->logits;
   const long long npix = (long long)a->n_img * a->height * a->width;
   long long blocks = (npix + 127) / 128;
-  const long long cap = (long long)tedm_num_sms() * 16;
+  const long long cap = a->g_dtype == 1 ? resident_ctas(head_tail_kernel<true>, 128, 0) : resident_ctas(head_tail_kernel<false>, 128, 0);
   if (blocks > cap) blocks = cap;
   TEDM_CHECK_ARG(a->g_dtype == 0 || a->g_dtype == 1, "tedm_head_infer: g_dtype=%d", a->g_dtype);
   if (a->g_dtype == 1) head_tail_kernel<true><<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(p);
