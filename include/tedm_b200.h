@@ -129,11 +129,16 @@ TEDM_API int tedm_conv_igemm_fwd(const tedm_conv_args* args, tedm_stream_t strea
  * With oihw_accumulate != 0, dw is instead the fp32 OIHW parameter gradient [cout][c0+c1][kh][kw] and the result is
  * ACCUMULATED into it (mode 3: the folded taps are scattered back onto the 3x3 kernel of Upsample's conv). */
 TEDM_API int tedm_conv_igemm_wgrad(const tedm_conv_args* args, const void* dy, float* dw, int oihw_accumulate,
-                          tedm_stream_t stream);
+                          float* workspace, tedm_stream_t stream);
+/* fp32 elements of the optional `workspace` above (split-K partial tiles of the 3x3 halo-tile kernel, reduced by a
+ * second kernel instead of atomics; NULL = atomics). */
+TEDM_API int64_t tedm_conv_igemm_wgrad_workspace(void);
 /* number of partial-statistics slots per image that tedm_conv_igemm_fwd writes for this output extent */
 TEDM_API int tedm_conv_gn_parts(int out_height, int out_width);
 /* tuning/debug: force the N tile (64/128/256; 0 = automatic) of tedm_conv_igemm_fwd */
 TEDM_API int tedm_conv_set_tile_n(int bn);
+/* tuning/debug: halo-tile kernel of the 3x3 weight gradient: 0 off, 1 automatic (default), 2 wherever the geometry allows */
+TEDM_API int tedm_conv_set_wgrad_halo(int enable);
 /* tuning/debug: enable (default) / disable the weight-stationary row path of the 3x3 conv */
 TEDM_API int tedm_conv_set_ws(int enable);
 

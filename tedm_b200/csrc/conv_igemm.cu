@@ -213,36 +213,40 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             }
         } else {
           const int par_y = t.par >> 1, par_x = t.par & 1;
-          const int num_kb = p.taps * cb_total;
-          for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-            const uint32_t full = smem_u32(&bar_full[stage]);
-            mbar_expect_tx(full, STAGE_BYTES);
-            const int tap = kb / cb_total, cb = kb % cb_total;
-            const int ky = tap / p.kxc, kx = tap % p.kxc;
-            int offy = 0, offx = 0, pc = 0, chan_off = 0;
-            const bool second = cb >= p.c0_blocks;
-            const int cblk = second ? cb - p.c0_blocks : cb;
-            if (p.mode == 1) {
-              offy = ky - 1;
-              offx = kx - 1;
-            } else if (p.mode == 2) {
-              offy = ((ky + 1) >> 1) - 1;
-              offx = ((kx + 1) >> 1) - 1;
-              pc = (ky + 1) & 1;
-              chan_off = ((kx + 1) & 1) * (second ? p.C1 : p.C0);
-            } else if (p.mode == 3) {
-              offy = ky - 1 + par_y;
-              offx = kx - 1 + par_x;
+          // nested counters instead of kb / cb_total etc.: this single thread paces the whole pipeline, and at N = 64 a
+          // k-block is only ~150 tensor-core cycles
+          int kb = 0;
+          for (int ky = 0; ky < p.kxc; ++ky)
+            for (int kx = 0; kx < p.kxc; ++kx) {
+              int offy = 0, offx = 0, pc = 0, xsel = 0;
+              if (p.mode == 1) {
+                offy = ky - 1;
+                offx = kx - 1;
+              } else if (p.mode == 2) {
+                offy = ((ky + 1) >> 1) - 1;
+                offx = ((kx + 1) >> 1) - 1;
+                pc = (ky + 1) & 1;
+                xsel = (kx + 1) & 1;
+              } else if (p.mode == 3) {
+                offy = ky - 1 + par_y;
+                offx = kx - 1 + par_x;
+              }
+              for (int cb = 0; cb < cb_total; ++cb, ++kb) {
+                mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+                const uint32_t full = smem_u32(&bar_full[stage]);
+                mbar_expect_tx(full, STAGE_BYTES);
+                const bool second = cb >= p.c0_blocks;
+                const int cblk = second ? cb - p.c0_blocks : cb;
+                const int chan_off = xsel * (second ? p.C1 : p.C0);
+                const uint32_t a_dst = stage_base + stage * STAGE_BYTES;
+                tma_load_5d(a_dst, second ? &mapA1 : &mapA0, full, chan_off + cblk * BK, t.x0 + offx, pc, t.y0 + offy, t.b0);
+                tma_load_2d(a_dst + A_BYTES, &mapW, full, kb * BK, t.par * p.cout + t.n0);
+                if (++stage == p.stages) {
+                  stage = 0;
+                  phase ^= 1u;
+                }
+              }
             }
-            const uint32_t a_dst = stage_base + stage * STAGE_BYTES;
-            tma_load_5d(a_dst, second ? &mapA1 : &mapA0, full, chan_off + cblk * BK, t.x0 + offx, pc, t.y0 + offy, t.b0);
-            tma_load_2d(a_dst + A_BYTES, &mapW, full, kb * BK, t.par * p.cout + t.n0);
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1u;
-            }
-          }
         }
       }
     }
@@ -777,6 +781,220 @@ int launch_wgrad(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap
   return TEDM_OK;
 }
 
+// ==========================================================================================
+// weight gradient of the 3x3 convolution, halo-tile form
+//
+// The generic kernel above fetches one 128-pixel activation box per (tap, 64-channel block) and is bound by L2 -> SM
+// traffic on the thin layers (48 KB per 1 MFLOP-pair).  Here one CTA owns a (64 input channels) x (64 output channels)
+// block of dW for ALL nine taps: per pixel tile it loads the activation tile ONCE with a one-pixel halo
+// ((tileH+2) x (tileW+2) pixels, out-of-bounds = the conv's zero padding) plus the 128-pixel dy tile, and the nine taps
+// are nine row-shifted windows of the same shared-memory box (MN-major UMMA operands: a window is just a start
+// address; two taps are stacked into one M = 128 operand through the descriptor's leading-dimension byte offset).
+// Accumulators: 5 blocks of [128 = 2 taps x 64 ci][64 co] fp32 in TMEM (taps (0,1) (2,3) (4,5) (6,7) (7,8); the second
+// copy of tap 7 is discarded).  Split-K partial tiles go to a workspace with plain stores and a second kernel sums
+// them and lays dW out (OIHW accumulate, or [co][tap][ci]); without a workspace, fp32 atomics.
+// ==========================================================================================
+struct Wgrad3Params {
+  int c0_blocks, c1_blocks, ctot;
+  int tileW, tileH, tileB, tiles_x, tiles_y;
+  int B, cout, n_tiles, splitk, num_ptiles, stages;
+  int x_bytes;       // shared-memory bytes reserved for one halo box (multiple of 1024)
+  int x_tx_bytes;    // bytes the TMA writes for one halo box
+  int oihw;
+  float* dw;
+  float* part;       // split-K partial tiles [group][ks][5][128][64] fp32 (NULL: reduce with atomics into dw)
+};
+
+__device__ __forceinline__ uint64_t make_sw128_mn_desc2(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad3_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CUtensorMap mapX1,
+                   const __grid_constant__ CUtensorMap mapDY, const Wgrad3Params p) {
+  constexpr int BN = 64;
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_acc;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int stage_bytes = p.x_bytes + A_BYTES;
+  const int ks = blockIdx.x;
+  const int cb = blockIdx.y / p.n_tiles, nt = blockIdx.y % p.n_tiles;
+  const int n0 = nt * BN;
+  const int num_kb = (p.num_ptiles - ks + p.splitk - 1) / p.splitk;
+  const int hw_pitch = p.tileW + 2;   // halo box row pitch in pixels
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapX0);
+    if (p.c1_blocks) tma_prefetch_desc(&mapX1);
+    tma_prefetch_desc(&mapDY);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bar_acc), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const bool second = cb >= p.c0_blocks;
+      const int cblk = second ? cb - p.c0_blocks : cb;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int pt = ks + kb * p.splitk;
+        const int tiles_per_group = p.tiles_x * p.tiles_y;
+        const int bg = pt / tiles_per_group, trem = pt % tiles_per_group;
+        const int b0 = bg * p.tileB, y0 = (trem / p.tiles_x) * p.tileH, x0 = (trem % p.tiles_x) * p.tileW;
+        mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+        const uint32_t full = smem_u32(&bar_full[stage]);
+        mbar_expect_tx(full, (uint32_t)(p.x_tx_bytes + A_BYTES));
+        const uint32_t dst = smem_base + stage * stage_bytes;
+        tma_load_5d(dst, second ? &mapX1 : &mapX0, full, cblk * BK, x0 - 1, 0, y0 - 1, b0);
+        tma_load_5d(dst + p.x_bytes, &mapDY, full, n0, x0, 0, y0, b0);
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // one UMMA covers 16 consecutive tile pixels = two 8-pixel K groups: contiguous inside an image row when the
+      // tile is at least 16 pixels wide, one image row apart for 8-pixel-wide tiles
+      const uint32_t sbo = p.tileW >= 16 ? 1024u : (uint32_t)hw_pitch * 128u;
+      // everything address-like is hoisted out of the issue loop (one thread issues 40 UMMAs per pixel tile): byte offset
+      // of each 16-pixel K step inside the halo box, and the descriptor template (start offset, leading-dimension byte
+      // offset between the two stacked taps) of each tap pair
+      uint32_t koff[BM / 16];
+#pragma unroll
+      for (int k = 0; k < BM / 16; ++k) {
+        const int m = 16 * k;
+        const int tb = m / (p.tileW * p.tileH), rem = m % (p.tileW * p.tileH);
+        koff[k] = (uint32_t)((tb * (p.tileH + 2) + rem / p.tileW) * hw_pitch + rem % p.tileW) * 128u;
+      }
+      uint64_t ablk[5];
+#pragma unroll
+      for (int blk = 0; blk < 5; ++blk) {
+        const int t0 = blk < 4 ? 2 * blk : 7, t1 = t0 + 1;
+        const int off0 = (t0 / 3) * hw_pitch + t0 % 3, off1 = (t1 / 3) * hw_pitch + t1 % 3;
+        ablk[blk] = make_sw128_mn_desc2((uint32_t)off0 * 128u, (uint32_t)(off1 - off0) * 128u, sbo);   // + tile address per use
+      }
+      const uint64_t btmpl = make_sw128_mn_desc2(0u, 16384u, 1024u);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&bar_full[stage]), phase);
+        tc_fence_after();
+        const uint32_t xbase = smem_base + stage * stage_bytes, dybase = xbase + p.x_bytes;
+#pragma unroll
+        for (int blk = 0; blk < 5; ++blk) {
+#pragma unroll
+          for (int k = 0; k < BM / 16; ++k) {
+            const uint64_t adesc = ablk[blk] + (uint64_t)(((xbase + koff[k]) & 0x3FFFFu) >> 4);
+            const uint64_t bdesc = btmpl + (uint64_t)(((dybase + (uint32_t)k * 2048u) & 0x3FFFFu) >> 4);
+            umma_bf16(tmem_base + (uint32_t)(blk * BN), adesc, bdesc, IDESC, (kb | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(smem_u32(&bar_empty[stage]));
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(smem_u32(&bar_acc));
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3, row = q * 32 + lane;
+    const int half = row >> 6;
+    const int ci = cb * BK + (row & 63);
+    if (num_kb > 0) {
+      mbar_wait(smem_u32(&bar_acc), 0);
+      tc_fence_after();
+    }
+    float* ptile = p.part ? p.part + ((size_t)blockIdx.y * p.splitk + ks) * (5 * BM * BN) + (size_t)row * BN : nullptr;
+#pragma unroll 1
+    for (int blk = 0; blk < 5; ++blk) {
+      const int tap = (blk < 4 ? 2 * blk : 7) + half;
+      const bool live = !(blk == 4 && half == 0);
+      size_t base, co_stride;
+      if (!p.oihw) {
+        base = (size_t)tap * p.ctot + ci;
+        co_stride = (size_t)9 * p.ctot;
+      } else {
+        base = (size_t)ci * 9 + tap;
+        co_stride = (size_t)p.ctot * 9;
+      }
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        uint32_t r[32];
+        if (num_kb > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * BN + chunk * 32), r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        if (ptile) {
+          float4* dst = reinterpret_cast<float4*>(ptile + (size_t)blk * (BM * BN) + chunk * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                 __uint_as_float(r[4 * j + 3]));
+        } else if (live && num_kb > 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(p.dw + base + (size_t)(n0 + chunk * 32 + j) * co_stride, __uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// Sums the split-K partial tiles of conv_wgrad3_kernel and writes dW: thread = (input channel, output channel) of one
+// 64 x 64 block and one tap; partial reads are coalesced along the output channel.
+//   oihw: dw[co][ci][3][3] += sum      else: dw[co][tap][ci] = sum
+__global__ void __launch_bounds__(256) wgrad3_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int splitk,
+                                                            int n_tiles, int ctot, int oihw) {
+  const int g = blockIdx.y, cb = g / n_tiles, n0 = (g % n_tiles) * 64;
+  const int t = blockIdx.z;                                    // tap
+  const int co_l = threadIdx.x & 63, ci_l = blockIdx.x * 4 + (threadIdx.x >> 6);
+  const int blk = t < 8 ? t >> 1 : 4, half = t < 8 ? t & 1 : 1;
+  const float* src = part + (size_t)g * splitk * (5 * BM * 64) + ((size_t)blk * BM + half * 64 + ci_l) * 64 + co_l;
+  float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+  int ks = 0;
+  for (; ks + 3 < splitk; ks += 4) {
+    a0 += __ldg(src + (size_t)ks * (5 * BM * 64));
+    a1 += __ldg(src + (size_t)(ks + 1) * (5 * BM * 64));
+    a2 += __ldg(src + (size_t)(ks + 2) * (5 * BM * 64));
+    a3 += __ldg(src + (size_t)(ks + 3) * (5 * BM * 64));
+  }
+  for (; ks < splitk; ++ks) a0 += __ldg(src + (size_t)ks * (5 * BM * 64));
+  const float acc = (a0 + a1) + (a2 + a3);
+  const int co = n0 + co_l, ci = cb * 64 + ci_l;
+  if (oihw) dw[((size_t)co * ctot + ci) * 9 + t] += acc;
+  else dw[((size_t)co * 9 + t) * ctot + ci] = acc;
+}
+
+int g_enable_wgrad3 = 1;  // tedm_conv_set_wgrad_halo: 0 off, 1 automatic, 2 wherever the geometry allows
+
 int g_enable_ws = 1;  // tedm_conv_set_ws
 int g_force_bn = 0;  // debug/tuning override (tedm_conv_set_tile_n)
 
@@ -787,6 +1005,11 @@ bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 extern "C" int tedm_conv_set_tile_n(int bn) {
   TEDM_CHECK_ARG(bn == 0 || bn == 64 || bn == 128 || bn == 256, "tedm_conv_set_tile_n: bn=%d", bn);
   g_force_bn = bn;
+  return TEDM_OK;
+}
+
+extern "C" int tedm_conv_set_wgrad_halo(int enable) {
+  g_enable_wgrad3 = enable;
   return TEDM_OK;
 }
 
@@ -931,8 +1154,13 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
 
 // dw: fp32 [cout][taps][c0+c1] (taps = 1 / 9 / 16; mode 3: 16 = parity*4 + a*2 + b of the folded kernel), overwritten;
 // or, with oihw_accumulate, the fp32 OIHW parameter gradient itself (+=; the folded taps of mode 3 are scattered to 3x3).
+extern "C" int64_t tedm_conv_igemm_wgrad_workspace(void) {
+  // split-K partial tiles of the halo-tile 3x3 kernel: at most 3 waves of CTAs, 5 x 128 x 64 fp32 each
+  return 3LL * tedm_num_sms() * 5 * BM * 64;
+}
+
 extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, float* dw, int oihw_accumulate,
-                                     tedm_stream_t stream) {
+                                     float* workspace, tedm_stream_t stream) {
   TEDM_CHECK_ARG(a && a->src0 && dy && dw, "tedm_conv_igemm_wgrad: null pointer");
   TEDM_CHECK_ARG(a->mode >= 0 && a->mode <= 3, "tedm_conv_igemm_wgrad: mode=%d", a->mode);
   TEDM_CHECK_ARG(a->batch > 0 && a->height > 0 && a->width > 0 && a->c0 > 0 && a->c1 >= 0 && a->cout > 0,
@@ -964,6 +1192,85 @@ extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, fl
   p.items = p.taps * (p.c0_blocks + p.c1_blocks);
   p.dw = dw;
   p.oihw = oihw_accumulate != 0;
+  cudaStream_t s = (cudaStream_t)stream;
+
+  // ---- 3x3: halo-tile kernel (every tap from one shared-memory box); needs 16-pixel K runs inside image rows, or
+  //      8-pixel-wide tiles with an even number of rows.  Measured on B200 (profiles/r01_wgrad_kernels.txt): 790-960
+  //      TFLOP/s on the 64-channel layers against 400-560 for the generic kernel; only the widest layer (768 -> 512),
+  //      where the generic kernel runs N = 256 tiles, stays on the generic kernel.
+  const bool halo_geometry = a->mode == 1 && (p.tileW >= 16 || (p.tileW == 8 && p.tileH % 2 == 0));
+  const bool halo_pays = (long long)p.ctot * a->cout < 768LL * 512;
+  if (halo_geometry && (g_enable_wgrad3 == 2 || (g_enable_wgrad3 == 1 && halo_pays))) {
+    Wgrad3Params w{};
+    w.c0_blocks = p.c0_blocks;
+    w.c1_blocks = p.c1_blocks;
+    w.ctot = p.ctot;
+    w.tileW = p.tileW; w.tileH = p.tileH; w.tileB = p.tileB; w.tiles_x = p.tiles_x; w.tiles_y = p.tiles_y;
+    w.B = p.B;
+    w.cout = a->cout;
+    w.n_tiles = a->cout / 64;
+    w.num_ptiles = p.num_ptiles;
+    w.oihw = p.oihw;
+    w.dw = dw;
+    w.x_tx_bytes = p.tileB * (p.tileH + 2) * (p.tileW + 2) * BK * 2;
+    w.x_bytes = (w.x_tx_bytes + 1023) / 1024 * 1024;
+    const int stage_bytes = w.x_bytes + A_BYTES;
+    int stages = (DYN_SMEM_MAX - 1024) / stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages >= 2) {
+      w.stages = stages;
+      const long long groups = (long long)(p.c0_blocks + p.c1_blocks) * w.n_tiles, sms = tedm_num_sms();
+      const long long cap = p.num_ptiles / 4 > 0 ? p.num_ptiles / 4 : 1;
+      long long best_sk = 1;
+      double best_eff = -1.0;
+      for (int wv = 1; wv <= 3; ++wv) {        // fewest waves that fill the machine (every CTA emits a 160 KB partial)
+        long long sk = (wv * sms) / groups;
+        if (sk < 1) sk = 1;
+        if (sk > cap) sk = cap;
+        const long long ctas = groups * sk, waves = (ctas + sms - 1) / sms;
+        const double eff = (double)ctas / (double)(waves * sms);
+        if (eff > best_eff + 0.02) {
+          best_eff = eff;
+          best_sk = sk;
+        }
+      }
+      w.splitk = (int)best_sk;
+      alignas(64) CUtensorMap mX0, mX1, mDY;
+      int rc3 = encode_act_map(&mX0, a->src0, a->batch, a->height, a->width, a->c0,
+                               a->src0_image_stride ? a->src0_image_stride : (long long)a->height * a->width * a->c0, 0,
+                               p.tileW + 2, p.tileH + 2, p.tileB);
+      if (rc3) return rc3;
+      if (a->src1) {
+        rc3 = encode_act_map(&mX1, a->src1, a->batch, a->height, a->width, a->c1,
+                             a->src1_image_stride ? a->src1_image_stride : (long long)a->height * a->width * a->c1, 0,
+                             p.tileW + 2, p.tileH + 2, p.tileB);
+        if (rc3) return rc3;
+      } else {
+        mX1 = mX0;
+      }
+      rc3 = encode_act_map(&mDY, dy, a->batch, Ho, Wo, a->cout,
+                           a->out_image_stride ? a->out_image_stride : (long long)Ho * Wo * a->cout, 0, p.tileW, p.tileH, p.tileB);
+      if (rc3) return rc3;
+      w.part = workspace;     // sized by tedm_conv_igemm_wgrad_workspace(): groups * splitk <= 3 waves of CTAs
+      if (groups * w.splitk > 3 * sms) w.part = nullptr;
+      if (!w.part && !p.oihw) TEDM_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)a->cout * 9 * p.ctot, s));
+      const int smem = 1024 + stages * stage_bytes;
+      static int configured3 = 0;
+      if (configured3 < smem) {
+        TEDM_CUDA(cudaFuncSetAttribute(conv_wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured3 = smem;
+      }
+      dim3 grid((unsigned)w.splitk, (unsigned)groups);
+      conv_wgrad3_kernel<<<grid, 192, smem, s>>>(mX0, mX1, mDY, w);
+      TEDM_LAUNCH_CHECK();
+      if (w.part) {
+        wgrad3_reduce_kernel<<<dim3(16, (unsigned)groups, 9), 256, 0, s>>>(w.part, dw, w.splitk, w.n_tiles, p.ctot, p.oihw);
+        TEDM_LAUNCH_CHECK();
+      }
+      return TEDM_OK;
+    }
+  }
+
   int bn = a->cout % 256 == 0 ? 256 : (a->cout % 128 == 0 ? 128 : 64);
   if (g_force_bn && a->cout % g_force_bn == 0) bn = g_force_bn;
   p.n_tiles = a->cout / bn;
@@ -1007,7 +1314,6 @@ extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, fl
                       a->out_image_stride ? a->out_image_stride : (long long)dy_h * dy_w * a->cout, a->mode == 3 ? 2 : 0,
                       p.tileW, p.tileH, p.tileB);
   if (rc) return rc;
-  cudaStream_t s = (cudaStream_t)stream;
   if (!p.oihw) TEDM_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)a->cout * p.taps * p.ctot, s));
   switch (bn) {
     case 64: return launch_wgrad<64>(mapX0, mapX1, mapDY, p, m_blocks, s);

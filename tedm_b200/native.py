@@ -46,11 +46,13 @@ SIGNATURES = {
     "tedm_time_proj": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "tedm_stem_conv7x7": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "tedm_conv_igemm_fwd": (_i, [C.POINTER(ConvArgs), _p]),
-    "tedm_conv_igemm_wgrad": (_i, [C.POINTER(ConvArgs), _p, _p, _i, _p]),
+    "tedm_conv_igemm_wgrad": (_i, [C.POINTER(ConvArgs), _p, _p, _i, _p, _p]),
+    "tedm_conv_igemm_wgrad_workspace": (_i64, []),
     "tedm_prepare_weights": (_i, [_p, _i, _i, _p]),
     "tedm_conv_gn_parts": (_i, [_i, _i]),
     "tedm_conv_set_tile_n": (_i, [_i]),
     "tedm_conv_set_ws": (_i, [_i]),
+    "tedm_conv_set_wgrad_halo": (_i, [_i]),
     "tedm_weight_to_krsc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "tedm_fold_upsample_weight": (_i, [_p, _p, _i, _i, _p]),
     "tedm_gn_silu_fwd": (_i, [_p, _p, _i, _p, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _f, _p]),
@@ -292,6 +294,17 @@ def conv_igemm(src0: torch.Tensor, weight: torch.Tensor, mode: int, cout: int, b
     return (out, gnp) if gn_groups else out
 
 
+_wgrad_ws = {}
+
+
+def _wgrad_workspace(device) -> torch.Tensor:
+    """Per-device scratch for the split-K partial tiles of the 3x3 weight-gradient kernel (stream-ordered reuse)."""
+    key = (device.type, device.index)
+    if key not in _wgrad_ws:
+        _wgrad_ws[key] = torch.empty(load().tedm_conv_igemm_wgrad_workspace(), device=device, dtype=torch.float32)
+    return _wgrad_ws[key]
+
+
 def conv_wgrad(src0: torch.Tensor, dy: torch.Tensor, mode: int, src1=None, grad_oihw: Optional[torch.Tensor] = None):
     """Weight gradient of conv_igemm(src0[, src1]) given the NHWC bf16 output gradient: returns fp32 (cout, taps, c0+c1),
     or, when grad_oihw (the fp32 OIHW parameter gradient) is given, accumulates into it and returns it."""
@@ -313,12 +326,15 @@ def conv_wgrad(src0: torch.Tensor, dy: torch.Tensor, mode: int, src1=None, grad_
     p1, s1 = _nhwc(src1, "src1")
     pd, sd = _nhwc(dy, "dy")
     a = ConvArgs(p0, p1, None, None, None, None, None, b, h, w, c0, c1, cout, mode, 0, 0, s0, s1, sd)
+    ws = _wgrad_workspace(src0.device) if mode == MODE_3X3 else None
     if conv_timer is not None:
         flops = 2 * b * (h * w if mode == MODE_UP3X3 else oh * ow) * cout * taps * (c0 + c1)
         with conv_timer(flops, ("wgrad", mode, b, h, w, c0, c1, cout)):
-            _call("tedm_conv_igemm_wgrad", C.byref(a), pd, _ptr(dw, torch.float32, "dw"), 0 if grad_oihw is None else 1, _stream())
+            _call("tedm_conv_igemm_wgrad", C.byref(a), pd, _ptr(dw, torch.float32, "dw"), 0 if grad_oihw is None else 1,
+                  _ptr(ws), _stream())
         return dw
-    _call("tedm_conv_igemm_wgrad", C.byref(a), pd, _ptr(dw, torch.float32, "dw"), 0 if grad_oihw is None else 1, _stream())
+    _call("tedm_conv_igemm_wgrad", C.byref(a), pd, _ptr(dw, torch.float32, "dw"), 0 if grad_oihw is None else 1, _ptr(ws),
+          _stream())
     return dw
 
 

@@ -58,6 +58,12 @@ WG_CASES = [
     (2, 16, 16, 128, 0, 64, 3, 0),
     (2, 8, 8, 256, 128, 256, 1, 128),
     (9, 8, 8, 192, 0, 384, 0, 0),
+    # halo-tile 3x3 kernel: every tile geometry (128/64/32/16/8-pixel-wide tiles), ragged batch, two sources
+    (3, 64, 64, 64, 0, 128, 1, 0),
+    (5, 32, 32, 128, 64, 64, 1, 0),
+    (3, 8, 8, 64, 0, 64, 1, 0),
+    (2, 128, 128, 64, 64, 64, 1, 0),
+    (7, 16, 16, 512, 0, 64, 1, 0),
 ]
 
 
@@ -75,10 +81,16 @@ def test_conv_wgrad(case):
     xs = _nhwc(x.cpu())
     x0, x1 = (xs[..., :c0].contiguous(), xs[..., c0:].contiguous()) if c1 else (xs, None)
     N.load().tedm_conv_set_tile_n(force_bn)
+    N.load().tedm_conv_set_wgrad_halo(2)        # the halo-tile kernel wherever its geometry allows, not only where it pays
     try:
         dw = N.conv_wgrad(x0, _nhwc(dy.cpu()), mode, src1=x1)
+        if mode == 1:                           # and the generic kernel on the same inputs
+            N.load().tedm_conv_set_wgrad_halo(0)
+            dw_generic = N.conv_wgrad(x0, _nhwc(dy.cpu()), mode, src1=x1)
+            assert _rel(dw_generic, dw) < 1e-4
     finally:
         N.load().tedm_conv_set_tile_n(0)
+        N.load().tedm_conv_set_wgrad_halo(1)
     torch.cuda.synchronize()
     if mode == 3:
         got = _unfold_mode3(dw)
@@ -96,6 +108,28 @@ DG_CASES = [
     (2, 32, 32, 64, 128, 2),
     (2, 16, 16, 128, 64, 3),
 ]
+
+
+@pytest.mark.parametrize("mode,halo", [(1, 2), (1, 0), (3, 0), (2, 0), (0, 0)])
+def test_conv_wgrad_accumulates_into_oihw(mode, halo):
+    """oihw_accumulate: the kernel adds straight into the fp32 OIHW parameter gradient (mode 3 un-folds to 3x3)."""
+    from tedm_b200 import native as N
+    B, H, W, cin, cout = 3, 16, 16, 128, 64
+    kh = {0: 1, 1: 3, 2: 4, 3: 3}[mode]
+    x = _bf(_rand((B, cin, H, W), 1)).cuda()
+    w = _rand((cout, cin, kh, kh), 2, (cin * kh * kh) ** -0.5).cuda().requires_grad_(True)
+    y = _ref_fwd(x, w, mode)
+    dy = _bf(_rand(tuple(y.shape), 3)).cuda()
+    (dw_ref,) = torch.autograd.grad(y, w, dy)
+    grad = _rand((cout, cin, kh, kh), 4).cuda()
+    base = grad.clone()
+    N.load().tedm_conv_set_wgrad_halo(halo)
+    try:
+        N.conv_wgrad(_nhwc(x.cpu()), _nhwc(dy.cpu()), mode, grad_oihw=grad)
+    finally:
+        N.load().tedm_conv_set_wgrad_halo(1)
+    torch.cuda.synchronize()
+    assert _rel(grad - base, dw_ref) < 2e-3, _rel(grad - base, dw_ref)
 
 
 @pytest.mark.parametrize("case", DG_CASES, ids=[str(c) for c in DG_CASES])
