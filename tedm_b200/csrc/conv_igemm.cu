@@ -51,6 +51,7 @@ struct ConvParams {
   int OH, OW, osy, osx;          // output tensor extent and tile->output coordinate scale
   int cout;
   int n_tiles, zdim, num_tiles, stages, out_bufs;
+  int z_shift, tpg_shift, tx_shift;   // log2 of zdim, tiles_x * tiles_y, tiles_x (all powers of two)
   const float* bias;
   const bf16* residual;
   bf16* out;
@@ -108,16 +109,17 @@ struct TileCoord {
 };
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, int bn) {
   TileCoord t;
-  const int nt = tile % p.n_tiles;
-  int rest = tile / p.n_tiles;
-  t.par = rest % p.zdim;
-  const int mt = rest / p.zdim;
-  const int tiles_per_group = p.tiles_x * p.tiles_y;
-  const int bg = mt / tiles_per_group;
-  t.trem = mt % tiles_per_group;
+  // one real division (n_tiles may be 3, 6, 12); everything else is a power of two -- the producer thread decodes a
+  // tile per handful of k-blocks on the 1x1 convolutions
+  const int rest = tile / p.n_tiles;
+  const int nt = tile - rest * p.n_tiles;
+  t.par = rest & (p.zdim - 1);
+  const int mt = rest >> p.z_shift;
+  const int bg = mt >> p.tpg_shift;
+  t.trem = mt & ((1 << p.tpg_shift) - 1);
   t.b0 = bg * p.tileB;
-  t.y0 = (t.trem / p.tiles_x) * p.tileH;
-  t.x0 = (t.trem % p.tiles_x) * p.tileW;
+  t.y0 = (t.trem >> p.tx_shift) * p.tileH;
+  t.x0 = (t.trem & (p.tiles_x - 1)) * p.tileW;
   t.n0 = nt * bn;
   return t;
 }
@@ -646,43 +648,50 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_consta
 
   if (warp == 0) {
     if (elect_one()) {
+      // per-CTA constants of the two (tap, channel block) items, hoisted out of the pixel-tile loop
+      int i_offy[2], i_offx[2], i_pc[2], i_chan[2], par = 0;
+      const CUtensorMap* i_map[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int item = h ? item1 : item0;
+        const int tap = item / cb_total, cb = item % cb_total;
+        const bool second = cb >= p.c0_blocks;
+        const int cblk = second ? cb - p.c0_blocks : cb;
+        int offy = 0, offx = 0, pc = 0, chan_off = 0;
+        if (p.mode == 1) {
+          offy = tap / 3 - 1;
+          offx = tap % 3 - 1;
+        } else if (p.mode == 2) {
+          const int ky = tap >> 2, kx = tap & 3;
+          offy = ((ky + 1) >> 1) - 1;
+          offx = ((kx + 1) >> 1) - 1;
+          pc = (ky + 1) & 1;
+          chan_off = ((kx + 1) & 1) * (second ? p.C1 : p.C0);
+        } else if (p.mode == 3) {
+          par = tap >> 2;
+          offy = ((tap >> 1) & 1) - 1 + (par >> 1);
+          offx = (tap & 1) - 1 + (par & 1);
+        }
+        i_offy[h] = offy; i_offx[h] = offx; i_pc[h] = pc; i_chan[h] = chan_off + cblk * BK;
+        i_map[h] = second ? &mapX1 : &mapX0;
+      }
+      const int dy_chan = (p.mode == 3 ? (par & 1) * p.cout : 0) + n0;
+      const int dy_pc = p.mode == 3 ? (par >> 1) : 0;
+      const int tiles_per_group = p.tiles_x * p.tiles_y;
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int pt = ks + kb * p.splitk;
-        const int tiles_per_group = p.tiles_x * p.tiles_y;
-        const int bg = pt / tiles_per_group, trem = pt % tiles_per_group;
-        const int b0 = bg * p.tileB, y0 = (trem / p.tiles_x) * p.tileH, x0 = (trem % p.tiles_x) * p.tileW;
+        const int bg = pt / tiles_per_group, trem = pt - bg * tiles_per_group;
+        const int ty = trem / p.tiles_x;
+        const int b0 = bg * p.tileB, y0 = ty * p.tileH, x0 = (trem - ty * p.tiles_x) * p.tileW;
         mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
         const uint32_t full = smem_u32(&bar_full[stage]);
         mbar_expect_tx(full, STAGE_BYTES);
         const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
-        int par = 0;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int item = h ? item1 : item0;
-          const int tap = item / cb_total, cb = item % cb_total;
-          const bool second = cb >= p.c0_blocks;
-          const int cblk = second ? cb - p.c0_blocks : cb;
-          int offy = 0, offx = 0, pc = 0, chan_off = 0;
-          if (p.mode == 1) {
-            offy = tap / 3 - 1;
-            offx = tap % 3 - 1;
-          } else if (p.mode == 2) {
-            const int ky = tap >> 2, kx = tap & 3;
-            offy = ((ky + 1) >> 1) - 1;
-            offx = ((kx + 1) >> 1) - 1;
-            pc = (ky + 1) & 1;
-            chan_off = ((kx + 1) & 1) * (second ? p.C1 : p.C0);
-          } else if (p.mode == 3) {
-            par = tap >> 2;
-            offy = ((tap >> 1) & 1) - 1 + (par >> 1);
-            offx = (tap & 1) - 1 + (par & 1);
-          }
-          tma_load_5d(a_dst + h * A_BYTES, second ? &mapX1 : &mapX0, full, chan_off + cblk * BK, x0 + offx, pc, y0 + offy, b0);
-        }
-        const int dy_chan = (p.mode == 3 ? (par & 1) * p.cout : 0) + n0;
-        const int dy_pc = p.mode == 3 ? (par >> 1) : 0;
+        for (int h = 0; h < 2; ++h)
+          tma_load_5d(a_dst + h * A_BYTES, i_map[h], full, i_chan[h], x0 + i_offx[h], i_pc[h], y0 + i_offy[h], b0);
         for (int j = 0; j < BN / 64; ++j)
           tma_load_5d(a_dst + (2 + j) * A_BYTES, &mapDY, full, dy_chan + j * 64, x0, dy_pc, y0, b0);
         if (++stage == p.stages) {
@@ -1104,6 +1113,10 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   p.n_tiles = a->cout / bn;
   p.zdim = zdim;
   p.num_tiles = (int)num_tiles;
+  auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
+  p.z_shift = ilog2(zdim);
+  p.tx_shift = ilog2(p.tiles_x);
+  p.tpg_shift = p.tx_shift + ilog2(p.tiles_y);
 
   // weight-stationary row mode: 3x3, whole 128-pixel rows per tile, one N tile of 64, weights fit in smem
   const bool ws = g_enable_ws && a->mode == 1 && p.tileH == 1 && p.tileB == 1 && p.tileW == BM && a->cout == 64 && bn == 64 &&
