@@ -977,29 +977,65 @@ conv_wgrad3_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_const
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-// Sums the split-K partial tiles of conv_wgrad3_kernel and writes dW: thread = (input channel, output channel) of one
-// 64 x 64 block and one tap; partial reads are coalesced along the output channel.
+// Sums the split-K partial tiles of conv_wgrad3_kernel and writes dW.  CTA = (input channel, 64 x 64 block, tap):
+// 64 output channels x 4 split-K slices; every thread keeps 8 independent loads in flight (the sum over up to 148
+// partials is latency-bound otherwise), partial reads are coalesced along the output channel.
 //   oihw: dw[co][ci][3][3] += sum      else: dw[co][tap][ci] = sum
+template <int SLICES>   // 4: CTA = 1 input channel x 64 co x 4 split-K slices (deep splits); 1: CTA = 4 input channels x 64 co
 __global__ void __launch_bounds__(256) wgrad3_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int splitk,
                                                             int n_tiles, int ctot, int oihw) {
+  __shared__ float red[4][64];
   const int g = blockIdx.y, cb = g / n_tiles, n0 = (g % n_tiles) * 64;
   const int t = blockIdx.z;                                    // tap
-  const int co_l = threadIdx.x & 63, ci_l = blockIdx.x * 4 + (threadIdx.x >> 6);
+  const int co_l = threadIdx.x & 63, sub = threadIdx.x >> 6;
+  const int ci_l = SLICES == 4 ? blockIdx.x : blockIdx.x * 4 + sub;
+  const int slice = SLICES == 4 ? sub : 0;
   const int blk = t < 8 ? t >> 1 : 4, half = t < 8 ? t & 1 : 1;
-  const float* src = part + (size_t)g * splitk * (5 * BM * 64) + ((size_t)blk * BM + half * 64 + ci_l) * 64 + co_l;
-  float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-  int ks = 0;
-  for (; ks + 3 < splitk; ks += 4) {
-    a0 += __ldg(src + (size_t)ks * (5 * BM * 64));
-    a1 += __ldg(src + (size_t)(ks + 1) * (5 * BM * 64));
-    a2 += __ldg(src + (size_t)(ks + 2) * (5 * BM * 64));
-    a3 += __ldg(src + (size_t)(ks + 3) * (5 * BM * 64));
+  constexpr size_t TILE = 5 * BM * 64;
+  const float* src = part + (size_t)g * splitk * TILE + ((size_t)blk * BM + half * 64 + ci_l) * 64 + co_l;
+  float a[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) a[u] = 0.0f;
+  int ks = slice;
+  for (; ks + 7 * SLICES < splitk; ks += 8 * SLICES) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] += __ldg(src + (size_t)(ks + SLICES * u) * TILE);
   }
-  for (; ks < splitk; ++ks) a0 += __ldg(src + (size_t)ks * (5 * BM * 64));
-  const float acc = (a0 + a1) + (a2 + a3);
+  for (; ks < splitk; ks += SLICES) a[0] += __ldg(src + (size_t)ks * TILE);
+  float acc = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  if (SLICES == 4) {
+    red[slice][co_l] = acc;
+    __syncthreads();
+    if (slice != 0) return;
+    acc = (red[0][co_l] + red[1][co_l]) + (red[2][co_l] + red[3][co_l]);
+  }
   const int co = n0 + co_l, ci = cb * 64 + ci_l;
   if (oihw) dw[((size_t)co * ctot + ci) * 9 + t] += acc;
   else dw[((size_t)co * 9 + t) * ctot + ci] = acc;
+}
+
+// Shallow splits (many 64 x 64 blocks, few partials each), OIHW accumulate: CTA = 4 output channels x 64 input channels x
+// all nine taps, so that every thread adds 9 consecutive floats and a warp covers 288-byte runs of the OIHW gradient
+// (the per-tap variant above scatters 4-byte read-modify-writes 9 * ctot floats apart).
+__global__ void __launch_bounds__(256) wgrad3_reduce_oihw_kernel(const float* __restrict__ part, float* __restrict__ dw,
+                                                                 int splitk, int n_tiles, int ctot) {
+  const int g = blockIdx.y, cb = g / n_tiles, n0 = (g % n_tiles) * 64;
+  const int co_l = blockIdx.x * 4 + (threadIdx.x & 3), ci_l = threadIdx.x >> 2;
+  constexpr size_t TILE = 5 * BM * 64;
+  const float* src = part + (size_t)g * splitk * TILE + (size_t)ci_l * 64 + co_l;
+  float acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.0f;
+  for (int ks = 0; ks < splitk; ++ks) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int blk = t < 8 ? t >> 1 : 4, half = t < 8 ? t & 1 : 1;
+      acc[t] += __ldg(src + (size_t)ks * TILE + ((size_t)blk * BM + half * 64) * 64);
+    }
+  }
+  float* d = dw + ((size_t)(n0 + co_l) * ctot + cb * 64 + ci_l) * 9;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) d[t] += acc[t];
 }
 
 int g_enable_wgrad3 = 1;  // tedm_conv_set_wgrad_halo: 0 off, 1 automatic, 2 wherever the geometry allows
@@ -1277,7 +1313,12 @@ extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, fl
       conv_wgrad3_kernel<<<grid, 192, smem, s>>>(mX0, mX1, mDY, w);
       TEDM_LAUNCH_CHECK();
       if (w.part) {
-        wgrad3_reduce_kernel<<<dim3(16, (unsigned)groups, 9), 256, 0, s>>>(w.part, dw, w.splitk, w.n_tiles, p.ctot, p.oihw);
+        if (w.splitk <= 16 && p.oihw)
+          wgrad3_reduce_oihw_kernel<<<dim3(16, (unsigned)groups), 256, 0, s>>>(w.part, dw, w.splitk, w.n_tiles, p.ctot);
+        else if (w.splitk > 16)
+          wgrad3_reduce_kernel<4><<<dim3(64, (unsigned)groups, 9), 256, 0, s>>>(w.part, dw, w.splitk, w.n_tiles, p.ctot, p.oihw);
+        else
+          wgrad3_reduce_kernel<1><<<dim3(16, (unsigned)groups, 9), 256, 0, s>>>(w.part, dw, w.splitk, w.n_tiles, p.ctot, p.oihw);
         TEDM_LAUNCH_CHECK();
       }
       return TEDM_OK;
