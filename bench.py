@@ -280,7 +280,10 @@ def run_ours(args):
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (all conv launches of one step)", "achieved": achieved,
                 "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
-                "peak_source": pk["source"] + " (sustained cuBLAS bf16)", "traffic": None,
+                "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
+                # ncu --set full, dominant launch (3x3 64->64 @128x128, 128 images): dram read + write per launch; the
+                # algorithmic in+out of that launch is 536.9 MB (profiles/r01_h_ncu_full_conv_kernels.txt)
+                "traffic": 496.1e6, "traffic_unit": "bytes/launch (conv_igemm_kernel<64,WS,GN>, B*S=128)",
                 "conv_launches_per_step": len(records), "conv_ms_per_step": conv_ms,
                 "conv_share_of_step": conv_ms / (ms / args.steps) if ms > 0 else None,
                 "conv_gflop_per_step": conv_fl / 1e9}
