@@ -65,6 +65,14 @@ static inline int resident_ctas(K kernel, int threads, size_t dyn_smem) {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// one MUFU op instead of two (ex2 + rcp): tanh.approx has |abs err| < 2^-10.9, far below the bf16 storage rounding
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// silu(2*zh) = zh + zh * tanh(zh): callers fold the factor 1/2 into the affine that produces zh
+__device__ __forceinline__ float silu_half(float zh) { return fmaf(zh, tanh_approx(zh), zh); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

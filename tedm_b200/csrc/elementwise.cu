@@ -295,11 +295,11 @@ __global__ void __launch_bounds__(256) gn_silu_kernel(const bf16* __restrict__ x
     // vec_per_cta is a multiple of 256 and 256 of cvec: this thread always meets the same 8 channels,
     // so their affine coefficients live in registers for the whole stream
     const int c0 = (threadIdx.x % cvec) << 3;
-    float ca[8], cb[8];
+    float ca[8], cb[8];     // halved: silu(z) = zh + zh * tanh(zh), zh = z / 2
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      ca[j] = sA[c0 + j];
-      cb[j] = sB[c0 + j];
+      ca[j] = 0.5f * sA[c0 + j];
+      cb[j] = 0.5f * sB[c0 + j];
     }
     // four independent 16-byte loads (eight with a residual) are in flight per thread before any is consumed
     constexpr int U = 4;
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(256) gn_silu_kernel(const bf16* __restrict__ x
         float f[8];
         unpack8(xv[u], f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = silu_f(fmaf(f[j], ca[j], cb[j]));
+        for (int j = 0; j < 8; ++j) f[j] = silu_half(fmaf(f[j], ca[j], cb[j]));
         if (residual) {
           float r[8];
           unpack8(rv[u], r);
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256) gn_silu_kernel(const bf16* __restrict__ x
       float f[8];
       unpack8(ldg_stream(x + img + v * 8), f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = silu_f(fmaf(f[j], ca[j], cb[j]));
+      for (int j = 0; j < 8; ++j) f[j] = silu_half(fmaf(f[j], ca[j], cb[j]));
       if (residual) {
         float r[8];
         unpack8(ldg_stream(residual + img + v * 8), r);
