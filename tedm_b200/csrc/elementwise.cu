@@ -403,46 +403,59 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
   for (int v = 0; v < NV; ++v)
 #pragma unroll
     for (int j = 0; j < 8; ++j) gain[v][j] = g[(v * L + sub) * 8 + j];
-  for (long long p0 = warp_global * PIX_PER_WARP; p0 < npix; p0 += nwarps * PIX_PER_WARP) {
-    const long long p = p0 + lane / L;
-    const bool ok = p < npix;
-    float f[NV][8];
-    float s = 0.0f;
+  // U pixel groups per iteration: all their loads (input and residual) are issued before the first is consumed
+  constexpr int U = NV == 1 ? 4 : (NV == 2 ? 2 : 1);
+  const long long stride = nwarps * PIX_PER_WARP;
+  for (long long p0 = warp_global * PIX_PER_WARP; p0 < npix; p0 += U * stride) {
+    uint4 xv[U][NV], rv[U][NV];
+    bool ok[U];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      if (ok) unpack8(ldg_stream(x + (size_t)p * C + (v * L + sub) * 8), f[v]);
-      else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[v][j] = 0.0f;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s += f[v][j];
-    }
-    s = group_sum<L>(s);
-    const float mean = s * (1.0f / C);
-    float q = 0.0f;
-#pragma unroll
-    for (int v = 0; v < NV; ++v)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = f[v][j] - mean;
-        q = fmaf(d, d, q);
-      }
-    q = group_sum<L>(q);
-    const float rstd = rsqrtf(q * (1.0f / C) + eps);
-    if (ok) {
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + u * stride + lane / L;
+      ok[u] = p < npix;
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
-        float o[8];
+        xv[u][v] = ok[u] ? ldg_stream(x + (size_t)p * C + (v * L + sub) * 8) : make_uint4(0, 0, 0, 0);
+        if (residual) rv[u][v] = ok[u] ? ldg_stream(residual + (size_t)p * C + (v * L + sub) * 8) : make_uint4(0, 0, 0, 0);
+      }
+    }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (f[v][j] - mean) * rstd * gain[v][j];
-        if (residual) {
-          float r[8];
-          unpack8(ldg_stream(residual + (size_t)p * C + (v * L + sub) * 8), r);
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + u * stride + lane / L;
+      float f[NV][8];
+      float s = 0.0f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += r[j];
+      for (int v = 0; v < NV; ++v) {
+        unpack8(xv[u][v], f[v]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += f[v][j];
+      }
+      s = group_sum<L>(s);
+      const float mean = s * (1.0f / C);
+      float q = 0.0f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f[v][j] -= mean;
+          q = fmaf(f[v][j], f[v][j], q);
         }
-        *reinterpret_cast<uint4*>(out + (size_t)p * C + (v * L + sub) * 8) = pack8(o);
+      q = group_sum<L>(q);
+      const float rstd = rsqrtf(q * (1.0f / C) + eps);
+      if (ok[u]) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = f[v][j] * rstd * gain[v][j];
+          if (residual) {
+            float r[8];
+            unpack8(rv[u][v], r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += r[j];
+          }
+          *reinterpret_cast<uint4*>(out + (size_t)p * C + (v * L + sub) * 8) = pack8(o);
+        }
       }
     }
   }
