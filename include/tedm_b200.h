@@ -329,6 +329,33 @@ TEDM_API int tedm_head_param_grads(const float* dw2_folded, const float* stats1,
 TEDM_API int tedm_ensemble_mask(const float* logits, float* prob, uint8_t* mask, int batch, int n_steps, int hw,
                        tedm_stream_t stream);
 
+/* ---- supervised segmentation: loss, metrics, input transport -------------------------------- */
+
+/* Rows are the (b, c) planes of an NCHW fp32 logit tensor (n_rows = B*C, row_len = H*W); row r is compared with target
+ * row r / target_repeat, i.e. repeat(y, 'b c h w -> (b step) c h w') (trainers/train_baseline.py:30-31) is never built.
+ * row_mean[r] (nullable) = mean_i bce(logits[r][i], target[.][i]); loss[0] = mean_r row_mean[r]: replaces
+ * reduce(binary_cross_entropy_with_logits(pred, y, reduction='none'), 'b c h w -> b c', 'mean').mean()
+ * (trainers/train_baseline.py:44-45).  grad (nullable) = grad_scale * (sigmoid(x) - y) / (row_len * n_rows).
+ * workspace: tedm_bce_workspace_floats(n_rows) floats.  Summation order is fixed (deterministic). */
+TEDM_API int tedm_bce_logits(const float* logits, const float* target, float* row_mean, float* loss, float* grad,
+                    float* workspace, long long n_rows, long long row_len, int target_repeat, float grad_scale,
+                    tedm_stream_t stream);
+TEDM_API int tedm_bce_workspace_floats(long long n_rows);
+
+/* dice / precision / recall per (b, c) row (trainers/train_baseline.py:146-161).  pred: uint8 mask (nonzero = True) or,
+ * with pred_is_logits, fp32 logits thresholded as sigmoid(x) > .5 (:122).  out fp32 [n_rows][8] =
+ * {dice = 2TP/(sum pred + sum target), precision = TP/(TP+FP), recall = TP/(TP+FN), TP, FP, FN, sum pred, sum target};
+ * an empty denominator gives NaN like the reference (its callers nanmean). */
+TEDM_API int tedm_seg_metrics(const void* pred, int pred_is_logits, const float* target, float* out, long long n_rows,
+                     long long row_len, int target_repeat, tedm_stream_t stream);
+
+/* dst = src / 255 (fp32 true division: bit-exact torchvision ToTensor, dataloaders/CXR14.py:67-70, JSRT.py:62-65);
+ * images cross PCIe as uint8, a quarter of the reference's fp32 bytes. */
+TEDM_API int tedm_u8_to_unit(const uint8_t* src, float* dst, long long n, tedm_stream_t stream);
+/* src uint8 [n_img][n_masks][hw] -> dst fp32 [n_img][hw] = min(sum_k (src_k / 255 > .5), 1)  (dataloaders/JSRT.py:67-82). */
+TEDM_API int tedm_u8_masks_to_label(const uint8_t* src, float* dst, long long n_img, long long hw, int n_masks,
+                           tedm_stream_t stream);
+
 /* ---- test-only ----------------------------------------------------------------------------- */
 
 /* Hardware probe used by tests/test_umma_probe.py: runs 128x64x64 UMMAs whose A descriptor start

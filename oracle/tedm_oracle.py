@@ -417,10 +417,37 @@ def bce_with_logits_loss(logits: Tensor, y: Tensor) -> Tensor:
     return F.binary_cross_entropy_with_logits(logits, y, reduction="none").mean(dim=(2, 3)).mean()
 
 
-def seg_metrics(y_hat: Tensor, y: Tensor) -> Dict[str, Tensor]:
-    """dice / precision / recall per (b, c) (train_baseline.py:146-161)."""
-    y_hat, y = y_hat.bool(), y.bool()
-    tp = (y_hat & y).sum(dim=(2, 3)).float()
-    return {"dice": 2 * tp / (y_hat.sum(dim=(2, 3)) + y.sum(dim=(2, 3))),
-            "precision": tp / (tp + (y_hat & ~y).sum(dim=(2, 3))),
-            "recall": tp / (tp + (~y_hat & y).sum(dim=(2, 3)))}
+def bce_rows(logits: Tensor, y: Tensor, n_steps: int = 1) -> Tensor:
+    """Per-(b, c) mean BCE with the TEDM label repetition (train_baseline.py:30-31,44): (B*S, C)."""
+    if n_steps > 1:
+        y = y.repeat_interleave(n_steps, dim=0)          # repeat(y, 'b c h w -> (b step) c h w')
+    return F.binary_cross_entropy_with_logits(logits, y, reduction="none").mean(dim=(2, 3))
+
+
+def seg_metrics(y_hat: Tensor, y: Tensor, n_steps: int = 1) -> Dict[str, Tensor]:
+    """dice / precision / recall per (b, c) (train_baseline.py:146-161), on float labels exactly as written there:
+    logical_and treats any nonzero label as True, `1 - x` is the negative class, and the dice denominator adds the
+    label VALUES (not their count)."""
+    y_hat = y_hat.bool()
+    y = y.float()
+    if n_steps > 1:
+        y = y.repeat_interleave(n_steps, dim=0)
+    red = lambda a: a.sum(dim=(2, 3))
+    tp = red(torch.logical_and(y, y_hat))
+    fp = red(torch.logical_and(1 - y, y_hat))
+    fn = red(torch.logical_and(y, ~y_hat))
+    return {"dice": 2 * tp / (red(y_hat) + red(y)), "precision": tp / (tp + fp), "recall": tp / (tp + fn)}
+
+
+def to_tensor_u8(img_u8: Tensor) -> Tensor:
+    """torchvision ToTensor on an 8-bit 'L' image (dataloaders/CXR14.py:67-70, JSRT.py:62-65): u8 -> fp32 / 255."""
+    return img_u8.to(torch.float32).div(255)
+
+
+def jsrt_label(masks_u8: Tensor) -> Tensor:
+    """(dataloaders/JSRT.py:67-82) masks (K, H, W) uint8 -> (1, H, W): sum_k (ToTensor(mask_k) > .5), made binary
+    when the structures overlap."""
+    label = torch.stack([(to_tensor_u8(m)[None] > .5).float() for m in masks_u8]).sum(0)
+    if (label > 1).sum() > 0:
+        label = (label > .5).float()
+    return label

@@ -3,7 +3,7 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
-for t in probe conv ops e2e backward train head_train; do
+for t in probe conv ops e2e backward train head_train seg; do
   timeout 600 python -m pytest tests/test_gpu_$t.py -q -s --tb=short -m gpu > gpurun_out/t_$t.log 2>&1
   echo "== test_gpu_$t exit $? =="; tail -n 4 gpurun_out/t_$t.log
 done

@@ -87,6 +87,11 @@ SIGNATURES = {
     "tedm_linear_attention_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "tedm_attention_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "tedm_adam_step": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i, _p, _f, _p]),
+    "tedm_bce_logits": (_i, [_p, _p, _p, _p, _p, _p, C.c_longlong, C.c_longlong, _i, _f, _p]),
+    "tedm_bce_workspace_floats": (_i, [C.c_longlong]),
+    "tedm_seg_metrics": (_i, [_p, _i, _p, _p, C.c_longlong, C.c_longlong, _i, _p]),
+    "tedm_u8_to_unit": (_i, [_p, _p, C.c_longlong, _p]),
+    "tedm_u8_masks_to_label": (_i, [_p, _p, C.c_longlong, C.c_longlong, _i, _p]),
     "tedm_debug_umma_probe": (_i, [_p, _p, C.POINTER(_i), C.POINTER(_i), _i, _p, _p]),
 }
 
@@ -641,6 +646,63 @@ def ensemble_mask(logits: torch.Tensor, n_steps: int):
     _call("tedm_ensemble_mask", _ptr(logits, torch.float32, "logits"), _ptr(prob), _ptr(mask), b, n_steps, c * h * w,
           _stream())
     return mask.bool(), prob
+
+
+# ------------------------------------------------------------------------------------------------
+# supervised segmentation: loss, metrics, input transport
+# ------------------------------------------------------------------------------------------------
+def _rows(logits: torch.Tensor, target: torch.Tensor):
+    """(n_rows, row_len, target_repeat) of an NCHW logit tensor against its (possibly un-repeated) label tensor."""
+    if logits.dim() != 4 or target.dim() != 4 or logits.shape[1:] != target.shape[1:]:
+        raise ValueError(f"logits {tuple(logits.shape)} and target {tuple(target.shape)} must be NCHW with equal C, H, W")
+    if target.shape[0] == 0 or logits.shape[0] % target.shape[0]:
+        raise ValueError(f"logit batch {logits.shape[0]} is not a multiple of the label batch {target.shape[0]}")
+    rep = logits.shape[0] // target.shape[0]
+    if rep > 1 and logits.shape[1] != 1:
+        raise ValueError("label repetition over timesteps needs single-channel logits")
+    return logits.shape[0] * logits.shape[1], logits.shape[2] * logits.shape[3], rep
+
+
+def bce_logits(logits: torch.Tensor, target: torch.Tensor, want_grad: bool = False, grad_scale: float = 1.0):
+    """-> (loss scalar, per-(b,c) mean (B, C), grad or None).  target may hold B / S images: row r uses label r // S."""
+    n_rows, row_len, rep = _rows(logits, target)
+    dev = logits.device
+    row_mean = torch.empty(logits.shape[0], logits.shape[1], device=dev, dtype=torch.float32)
+    loss = torch.empty((), device=dev, dtype=torch.float32)
+    grad = torch.empty_like(logits) if want_grad else None
+    ws = torch.empty(load().tedm_bce_workspace_floats(n_rows), device=dev, dtype=torch.float32)
+    _call("tedm_bce_logits", _ptr(logits, torch.float32, "logits"), _ptr(target, torch.float32, "target"), _ptr(row_mean),
+          _ptr(loss), _ptr(grad), _ptr(ws), n_rows, row_len, rep, float(grad_scale), _stream())
+    return loss, row_mean, grad
+
+
+def seg_metrics(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """pred: bool / uint8 mask or fp32 logits (thresholded as sigmoid > .5), NCHW.  -> fp32 (B, C, 8):
+    dice, precision, recall, TP, FP, FN, sum(pred), sum(target)."""
+    n_rows, row_len, rep = _rows(pred, target)
+    if pred.dtype == torch.bool:
+        pred = pred.view(torch.uint8)
+    if pred.dtype not in (torch.uint8, torch.float32):
+        raise TypeError(f"pred must be bool, uint8 or float32, got {pred.dtype}")
+    out = torch.empty(pred.shape[0], pred.shape[1], 8, device=pred.device, dtype=torch.float32)
+    _call("tedm_seg_metrics", _ptr(pred, name="pred"), int(pred.dtype == torch.float32), _ptr(target, torch.float32, "target"),
+          _ptr(out), n_rows, row_len, rep, _stream())
+    return out
+
+
+def u8_to_unit(src: torch.Tensor) -> torch.Tensor:
+    """uint8 image tensor -> fp32 in [0, 1] (ToTensor), same shape."""
+    dst = torch.empty(src.shape, device=src.device, dtype=torch.float32)
+    _call("tedm_u8_to_unit", _ptr(src, torch.uint8, "src"), _ptr(dst), src.numel(), _stream())
+    return dst
+
+
+def u8_masks_to_label(src: torch.Tensor) -> torch.Tensor:
+    """uint8 (B, K, H, W) structure masks -> fp32 (B, 1, H, W) label = min(sum_k (mask_k / 255 > .5), 1)."""
+    b, k, h, w = src.shape
+    dst = torch.empty(b, 1, h, w, device=src.device, dtype=torch.float32)
+    _call("tedm_u8_masks_to_label", _ptr(src, torch.uint8, "src"), _ptr(dst), b, h * w, k, _stream())
+    return dst
 
 
 def umma_probe(A, Bm, shifts: Sequence[int], base_offsets: Sequence[int]):

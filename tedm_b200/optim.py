@@ -81,14 +81,15 @@ class FusedAdam(torch.optim.Optimizer):
         return self._grad_buf
 
     @torch.no_grad()
-    def step(self, closure=None, grad_scale: float = 1.0):
+    def step(self, closure=None, grad_scale: float = 1.0, flat_grad: Optional[torch.Tensor] = None):
+        """`flat_grad`: the buffer a caller already obtained from `flat_grad()` (and e.g. all-reduced)."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
         grp = self.param_groups[0]
         self._step += 1
-        N.adam_step(self.flat_param, self.flat_grad(), self.exp_avg, self.exp_avg_sq, float(grp["lr"]),
+        N.adam_step(self.flat_param, self.flat_grad() if flat_grad is None else flat_grad, self.exp_avg, self.exp_avg_sq, float(grp["lr"]),
                     float(grp["betas"][0]), float(grp["betas"][1]), float(grp["eps"]), float(grp["weight_decay"]),
                     self._step, grad_scale, step_counter=self.step_counter)
         step_t = torch.tensor(float(self._step))
@@ -96,6 +97,30 @@ class FusedAdam(torch.optim.Optimizer):
             self.state[p]["step"] = step_t
         self.bump_versions()
         return loss
+
+    def load_state_dict(self, state_dict) -> None:
+        """Accepts what torch.optim.Adam.state_dict() produces (the reference's checkpoints, train_CXR14.py:96-114)
+        as well as its own: the moments are copied into the flat arenas and the per-parameter views rebound."""
+        super().load_state_dict(state_dict)
+        step = 0
+        with torch.no_grad():
+            for p, o in zip(self._params, self._offsets):
+                k = p.numel()
+                st = self.state.get(p, {})
+                for name, arena in (("exp_avg", self.exp_avg), ("exp_avg_sq", self.exp_avg_sq)):
+                    view = arena[o:o + k].view(p.shape)
+                    if name in st and st[name].data_ptr() != view.data_ptr():
+                        view.copy_(st[name].to(view.dtype))
+                    elif name not in st:
+                        view.zero_()
+                    st[name] = view
+                step = max(step, int(float(st.get("step", 0.0))))
+                self.state[p] = st
+        self._step = step
+        self.step_counter.fill_(step)
+        step_t = torch.tensor(float(step))
+        for p in self._params:
+            self.state[p]["step"] = step_t
 
     def bump_versions(self) -> None:
         """The update went through the flat arena, not through each parameter tensor: bump every parameter's

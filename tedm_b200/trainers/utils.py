@@ -57,3 +57,98 @@ def sample_images(diffusion_model, T: int, img_size: int, batch: int, channels: 
         if t % stepsize == 0:
             snaps.append(unnormalize_to_zero_to_one(img))
     return unnormalize_to_zero_to_one(img), snaps
+
+
+@torch.no_grad()
+def sample_plot_image(diffusion_model, T: int, img_size: int, batch: int, channels: Optional[int] = 1,
+                      cond: Optional[Tensor] = None, **kwargs) -> Tensor:
+    """(trainers/utils.py:62-98) grids of 8 snapshots per sampled image, (batch, C, H, W) on the host.  The reference's
+    own caller passes a `normalized=` keyword the function does not take (train_CXR14.py:84); extra keywords are
+    accepted and ignored here.  The 8 D2H copies happen once at the end instead of inside the loop."""
+    _, snaps = sample_images(diffusion_model, T, img_size, batch, channels, cond, n_snapshots=8)
+    imgs = torch.stack([s.cpu() for s in snaps]).transpose(0, 1)             # n b c h w -> b n c h w
+    rows = []
+    for img_row in imgs:                                                     # make_grid(nrow=4, padding=2), 3-channel
+        n, c, h, w = img_row.shape
+        img_row = img_row.expand(n, 3, h, w) if c == 1 else img_row
+        ncol, nrow = min(4, n), (n + 3) // 4
+        grid = torch.zeros(img_row.shape[1], nrow * (h + 2) + 2, ncol * (w + 2) + 2)
+        for k in range(n):
+            r, cc = divmod(k, 4)
+            grid[:, r * (h + 2) + 2:r * (h + 2) + 2 + h, cc * (w + 2) + 2:cc * (w + 2) + 2 + w] = img_row[k]
+        rows.append(grid)
+    return torch.stack(rows)
+
+
+class TensorboardLogger:
+    """(trainers/utils.py:101-147) scalar / image logging; a no-op when disabled or when tensorboard is absent."""
+
+    def __init__(self, log_dir=None, config=None, enabled: bool = True, **kwargs):
+        self.enabled = enabled
+        self.writer = None
+        if enabled:
+            try:
+                from torch.utils.tensorboard import SummaryWriter
+                self.writer = SummaryWriter(log_dir=str(log_dir), **kwargs)
+            except Exception as e:  # tensorboard is an optional dependency
+                print(f"tensorboard unavailable ({e}); logging to stdout only")
+                self.enabled = False
+
+    def log(self, data, step: int) -> None:
+        if not self.enabled:
+            return
+        for k, v in data.items():
+            if isinstance(v, (int, float)):
+                self.writer.add_scalar(k, v, step)
+            elif isinstance(v, (np.ndarray, torch.Tensor)) and len(v.shape) == 3:
+                self.writer.add_image(k, v, step)
+            elif isinstance(v, (np.ndarray, torch.Tensor)) and len(v.shape) == 4:
+                self.writer.add_images(k, v, step)
+            else:
+                raise ValueError(f"Unsupported data type: {type(v)}")
+
+
+def compare_configs(config_old, config_new) -> None:  # trainers/utils.py:150-169
+    c_old, c_new = vars(config_old), vars(config_new)
+    for k, v in c_old.items():
+        if k in c_new and c_new[k] != v:
+            print(f"{k} differs - old: {v} new: {c_new[k]}")
+    for k, v in c_new.items():
+        if k not in c_old:
+            print(f"{k} is new - {v}")
+    for k, v in c_old.items():
+        if k not in c_new:
+            print(f"{k} is removed - {v}")
+
+
+# -- data-parallel launcher glue (one process per GPU under torchrun; a single process otherwise) -------------------
+def init_distributed(config) -> Tuple[int, int]:
+    """Join the torchrun rendezvous when there is one; pin this process to its GPU.  -> (rank, world_size)."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if str(getattr(config, "device", "cuda")).startswith("cuda") and torch.cuda.is_available():
+        torch.cuda.set_device(local)
+        config.device = f"cuda:{local}"
+    if world > 1 and not dist.is_initialized():
+        backend = "nccl" if str(config.device).startswith("cuda") else "gloo"
+        dist.init_process_group(backend=backend)
+    config.rank, config.world_size = rank, world
+    return rank, world
+
+
+def dp_optimizer_step(optimizer, world_size: int = 1) -> None:
+    """optimizer.step() of the reference loops; with world_size > 1 the gradients are summed over ranks first
+    (ONE all-reduce when the optimiser keeps a flat gradient arena) and the mean is taken inside Adam."""
+    import torch.distributed as dist
+    from ..optim import FusedAdam
+    if world_size > 1:
+        if isinstance(optimizer, FusedAdam):
+            flat = optimizer.flat_grad()
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            optimizer.step(grad_scale=1.0 / world_size, flat_grad=flat)
+            return
+        from ..parallel import allreduce_gradients
+        allreduce_gradients([p for g in optimizer.param_groups for p in g["params"]])
+    optimizer.step()

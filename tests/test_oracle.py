@@ -182,3 +182,31 @@ def test_oracle_training_gradients_match_reference(golden):
         num += float((got - ref).pow(2).sum())
         den += float(ref.pow(2).sum())
     assert (num / den) ** 0.5 < 1e-3, (num / den) ** 0.5
+
+
+# ---- supervised-segmentation edges: loss, metrics, loader arithmetic (golden: tests/golden/make_golden_seg.py) --------
+def test_oracle_seg_loss_and_metrics_match_reference(golden):
+    import numpy as np
+    import torch
+    from oracle import tedm_oracle as O
+    g = golden["seg_small"]
+    logits, y, s = torch.from_numpy(g["logits"]), torch.from_numpy(g["y"]), int(g["n_steps"])
+    rows = O.bce_rows(logits, y, s)
+    assert np.allclose(rows.numpy(), g["bce_rows"], rtol=1e-6, atol=1e-7)
+    assert abs(float(rows.mean()) - float(g["bce_loss"])) < 1e-6
+    y_hat = torch.sigmoid(logits) > .5
+    assert np.array_equal(y_hat.numpy(), g["y_hat"])
+    m = O.seg_metrics(y_hat, y, s)
+    for k in ("dice", "precision", "recall"):
+        assert np.array_equal(m[k].numpy(), g[k], equal_nan=True), k
+    assert np.isnan(g["dice"]).sum() == 4 and np.isnan(g["precision"]).sum() >= 4      # empty rows are NaN in the reference
+
+
+def test_oracle_loader_arithmetic_matches_reference(golden):
+    import numpy as np
+    import torch
+    from oracle import tedm_oracle as O
+    g = golden["seg_small"]
+    assert np.array_equal(O.to_tensor_u8(torch.from_numpy(g["u8_img"]))[None].numpy(), g["f32_img"])
+    for k in ("overlap", "disjoint"):
+        assert np.array_equal(O.jsrt_label(torch.from_numpy(g[f"u8_masks_{k}"])).numpy(), g[f"label_{k}"]), k
