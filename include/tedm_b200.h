@@ -329,6 +329,19 @@ TEDM_API int tedm_head_param_grads(const float* dw2_folded, const float* stats1,
 TEDM_API int tedm_ensemble_mask(const float* logits, float* prob, uint8_t* mask, int batch, int n_steps, int hw,
                        tedm_stream_t stream);
 
+/* Whole Residual(PreNorm(LinearAttention)) block, inference forward, in three launches (models/unet_model.py:29-36,
+ * 64-73,178-210): out = LayerNorm(W_out . linattn(W_qkv . LayerNorm(x; g_pre)) + b_out; g_out) + x.
+ * x, out: NHWC bf16 [B][n][channels]; wqkv bf16 [3*heads*dim_head][channels]; wout bf16 [channels][heads*dim_head].
+ * q, k, v and the attention output stay on chip (softmax over n is computed online).  Supported: 4 heads x 32,
+ * channels 64 or 128, n a multiple of 64 (tedm_linear_attention_fused_supported); anything else is TEDM_ERR_UNSUPPORTED
+ * and the caller runs the unfused sequence.  workspace: tedm_linear_attention_fused_workspace(batch, n) floats. */
+TEDM_API int tedm_linear_attention_fused_supported(int n, int channels, int heads, int dim_head);
+TEDM_API int64_t tedm_linear_attention_fused_workspace(int batch, int n);
+TEDM_API int tedm_linear_attention_fused_fwd(const void* x, const void* wqkv, const float* g_pre, const void* wout,
+                                    const float* b_out, const float* g_out, void* out, float* workspace, int batch,
+                                    int n, int channels, int heads, int dim_head, float scale, float eps,
+                                    tedm_stream_t stream);
+
 /* ---- supervised segmentation: loss, metrics, input transport -------------------------------- */
 
 /* Rows are the (b, c) planes of an NCHW fp32 logit tensor (n_rows = B*C, row_len = H*W); row r is compared with target

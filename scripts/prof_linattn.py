@@ -1,0 +1,28 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from tedm_b200 import native as N
+def timeit(fn, iters=10):
+    for i in range(3): fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters): fn(i)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+for (H, C) in [(128, 64), (64, 128)]:
+    nset = 3
+    xs = [torch.randn(B, H, H, C, device="cuda").to(torch.bfloat16) for _ in range(nset)]
+    wq = (torch.randn(384, C, device="cuda") / C ** 0.5).to(torch.bfloat16)
+    wo = (torch.randn(C, 128, device="cuda") * 0.1).to(torch.bfloat16)
+    g1 = torch.ones(C, device="cuda"); g2 = torch.ones(C, device="cuda"); bo = torch.zeros(C, device="cuda")
+    def unfused(i):
+        x = xs[i % nset]
+        y = N.layernorm(x, g1)
+        o = N.linear_attention(N.conv_igemm(y, wq, N.MODE_1X1, 384))
+        return N.layernorm(N.conv_igemm(o, wo, N.MODE_1X1, C, bias=bo), g2, residual=x)
+    t0 = timeit(unfused)
+    t1 = timeit(lambda i: N.linear_attention_block_fused(xs[i % nset], wq, g1, wo, bo, g2))
+    nb = B * H * H * C * 2
+    print(f"B={B} {H}x{H}x{C}: unfused {t0*1e3:.0f} us, fused {t1*1e3:.0f} us ({3*nb/t1/1e6:.0f} GB/s algorithmic)")

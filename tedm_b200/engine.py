@@ -77,6 +77,7 @@ class UnetEngine:
         self.cache = WeightCache()
         self.fold_upsample = fold_upsample
         self.ln_eps = ln_eps
+        self.fuse_linear_attention = True
         # every ResnetBlock in execution order, for the batched time projection
         m = unet
         self._resblocks: List[nn.Module] = []
@@ -235,6 +236,13 @@ class UnetEngine:
     def _linear_attention(self, key: str, wrap: nn.Module, x: Tensor, tape: Optional[Tape] = None) -> Tensor:
         pre, att = wrap.fn.norm, wrap.fn.fn
         c = x.shape[-1]
+        if (tape is None and self.fuse_linear_attention
+                and N.linear_attention_fused_supported(x.shape[1] * x.shape[2], c, att.heads, att.dim_head)):
+            # inference at the high-resolution levels: the whole block in 3 launches, q/k/v never leave the SM
+            return N.linear_attention_block_fused(x, self._w(key + ".to_qkv"), self._f32(pre.g).reshape(-1),
+                                                  self._w(key + ".to_out"), self._f32(att.to_out[0].bias),
+                                                  self._f32(att.to_out[1].g).reshape(-1), att.heads, att.dim_head,
+                                                  att.scale, self.ln_eps)
         y = N.layernorm(x, self._f32(pre.g).reshape(-1), eps=self.ln_eps)
         qkv = N.conv_igemm(y, self._w(key + ".to_qkv"), N.MODE_1X1, att.to_qkv.weight.shape[0])
         if tape is not None:

@@ -60,6 +60,9 @@ SIGNATURES = {
     "tedm_linear_attention_workspace": (_i64, [_i, _i, _i, _i]),
     "tedm_linear_attention_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "tedm_attention_fwd": (_i, [_p, _p, _i, _i, _i, _i, _f, _p]),
+    "tedm_linear_attention_fused_supported": (_i, [_i, _i, _i, _i]),
+    "tedm_linear_attention_fused_workspace": (_i64, [_i, _i]),
+    "tedm_linear_attention_fused_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _p]),
     "tedm_upsample2x": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "tedm_final_conv1x1": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "tedm_nchw_f32_to_nhwc_bf16": (_i, [_p, _p, _i, _i, _i, _p]),
@@ -373,6 +376,26 @@ def linear_attention(qkv, heads: int = 4, dim_head: int = 32, scale: Optional[fl
     _call("tedm_linear_attention_fwd", _ptr(qkv, torch.bfloat16, "qkv"), _ptr(out), _ptr(ws), b, n, heads, dim_head,
           float(dim_head ** -0.5 if scale is None else scale), _stream())
     return (out, ws) if want_workspace else out
+
+
+def linear_attention_fused_supported(n: int, channels: int, heads: int = 4, dim_head: int = 32) -> bool:
+    return bool(load().tedm_linear_attention_fused_supported(n, channels, heads, dim_head))
+
+
+def linear_attention_block_fused(x, wqkv, g_pre, wout, b_out, g_out, heads: int = 4, dim_head: int = 32,
+                                 scale: Optional[float] = None, eps: float = 1e-5):
+    """Residual(PreNorm(LinearAttention)) inference forward in 3 launches; x NHWC bf16 -> same shape."""
+    if x.dim() != 4 or not x.is_contiguous():
+        raise ValueError("x must be a contiguous NHWC tensor")
+    b, h, w, c = x.shape
+    scale = dim_head ** -0.5 if scale is None else scale
+    out = torch.empty_like(x)
+    ws = torch.empty(load().tedm_linear_attention_fused_workspace(b, h * w), device=x.device, dtype=torch.float32)
+    _call("tedm_linear_attention_fused_fwd", _ptr(x, torch.bfloat16, "x"), _ptr(wqkv, torch.bfloat16, "wqkv"),
+          _ptr(g_pre, torch.float32, "g_pre"), _ptr(wout, torch.bfloat16, "wout"), _ptr(b_out, torch.float32, "b_out"),
+          _ptr(g_out, torch.float32, "g_out"), _ptr(out), _ptr(ws), b, h * w, c, heads, dim_head, float(scale), float(eps),
+          _stream())
+    return out
 
 
 def attention(qkv, heads: int = 4, dim_head: int = 32, scale: float = 16.0):

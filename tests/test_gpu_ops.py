@@ -183,6 +183,37 @@ def test_linear_attention_core(hw, B):
     assert _rel(_nchw(got), ref) < 1e-2      # P, ctx and softmax(q) are bf16 tensor-core operands
 
 
+@pytest.mark.parametrize("C,hw,B", [(64, 8, 2), (64, 32, 3), (64, 128, 2), (128, 64, 2), (128, 16, 1)])
+def test_linear_attention_block_fused(C, hw, B):
+    """The whole Residual(PreNorm(LinearAttention)) block in three launches (inference path of the 128^2 / 64^2
+    levels) against the oracle's block on the same bf16-rounded input and weights, and against the unfused kernel
+    sequence it replaces."""
+    from tedm_b200 import native as N
+    n = hw * hw
+    x = _bf(_rand((B, C, hw, hw), 1, 1.2))
+    sd = {"a.fn.norm.g": 1 + 0.2 * _rand((1, C, 1, 1), 2), "a.fn.fn.to_qkv.weight": _bf(_rand((384, C, 1, 1), 3, 2.0 / C ** 0.5)),
+          "a.fn.fn.to_out.0.weight": _bf(_rand((C, 128, 1, 1), 4, 0.12)), "a.fn.fn.to_out.0.bias": _rand((C,), 5, 0.1),
+          "a.fn.fn.to_out.1.g": 1 + 0.2 * _rand((1, C, 1, 1), 6)}
+    ref = O._linear_attention(sd, "a.", x, 1e-5, lambda t: t)
+    assert N.linear_attention_fused_supported(n, C)
+    wq = sd["a.fn.fn.to_qkv.weight"].reshape(384, C).to(torch.bfloat16).cuda()
+    wo = sd["a.fn.fn.to_out.0.weight"].reshape(C, 128).to(torch.bfloat16).cuda()
+    g1, g2 = sd["a.fn.norm.g"].reshape(-1).cuda(), sd["a.fn.fn.to_out.1.g"].reshape(-1).cuda()
+    bo = sd["a.fn.fn.to_out.0.bias"].cuda()
+    xh = _nhwc(x)
+    got = N.linear_attention_block_fused(xh, wq, g1, wo, bo, g2)
+    # the residual branch alone (x itself dominates the output norm)
+    err = _rel(_nchw(got) - x, ref - x)
+    assert err < 1.5e-2, err
+    y = N.layernorm(xh, g1)
+    o = N.linear_attention(N.conv_igemm(y, wq, N.MODE_1X1, 384))
+    unf = N.layernorm(N.conv_igemm(o, wo, N.MODE_1X1, C, bias=bo), g2, residual=xh)
+    err_unf = _rel(_nchw(unf) - x, ref - x)
+    print(f"C={C} hw={hw}: fused branch rel err {err:.4f}, unfused {err_unf:.4f}")
+    assert err < max(1.2 * err_unf, 6e-3)           # at least as accurate as the chain it replaces
+    assert not N.linear_attention_fused_supported(n, 256) and not N.linear_attention_fused_supported(100, 64)
+
+
 @pytest.mark.parametrize("hw,B", [(4, 2), (16, 3), (8, 1)])
 def test_mid_attention_core(hw, B):
     from tedm_b200 import native as N
