@@ -286,6 +286,12 @@ typedef struct {
   const float* w3;       /* [c2] */
   float b3;
   float* logits;
+  /* optional (tedm_head_infer only): the full-resolution level given as its FEATURE map instead of a g map --
+   * f_full bf16 [n_img][H][W][c_full] and that level's layer-1 weight slice w1_full bf16 [c1][c_full]; its layer 1 then
+   * runs inside the tail kernel.  Needs fp32 g maps for the other levels, c_full == 64, n_sum == 1. */
+  const void* f_full;
+  const void* w1_full;
+  int c_full;
 } tedm_head_args;
 TEDM_API int tedm_head_infer(const tedm_head_args* args, tedm_stream_t stream);
 

@@ -115,13 +115,15 @@ class DatasetDM(nn.Module):
             return head_train_forward(self, x, convs, bns, noise)
         return self._head_infer(x, convs, bns, noise)
 
-    def _layer1_maps(self, feats, w1: Tensor, shared: bool, b: int, s: int, chans, offs) -> List[Tensor]:
+    def _layer1_maps(self, feats, w1: Tensor, shared: bool, b: int, s: int, chans, offs, skip=()) -> List[Tensor]:
         """Layer 1 of the head applied per level at native resolution (it commutes with the nearest upsample):
         fp32 NHWC maps [(B*S), h_l, w_l, 128] on the tcgen05 1x1 conv."""
         ctot = sum(chans)
         g_maps = []
         for l, f in enumerate(feats):
             cl = chans[l]
+            if l in skip:
+                continue
             if shared:
                 wl = self._cache.get(f"w1.l{l}", (w1,), lambda w, o=offs[l], c=cl: w[:, o:o + c, 0, 0].to(torch.bfloat16).contiguous())
                 g_maps.append(N.conv_igemm(f, wl, N.MODE_1X1, w1.shape[0], out_dtype=torch.float32))
@@ -149,7 +151,16 @@ class DatasetDM(nn.Module):
         size = x.shape[-1]
         shifts = [(size // f.shape[1]).bit_length() - 1 for f in feats]
         offs = [sum(chans[:l]) for l in range(len(chans))]
-        g_maps = self._layer1_maps(feats, convs[0].weight, shared, b, s, chans, offs)
+        # shared head: the full-resolution level's layer 1 (64 -> 128) runs inside the tail kernel, its fp32 map never exists
+        fuse_full = shared and shifts[-1] == 0 and chans[-1] == 64 and convs[0].out_channels == 128 and (b * s * size * size) % 16 == 0
+        last = len(feats) - 1
+        g_maps = self._layer1_maps(feats, convs[0].weight, shared, b, s, chans, offs, skip=(last,) if fuse_full else ())
+        f_full = w1_full = None
+        if fuse_full:
+            f_full = feats[last]
+            w1_full = self._cache.get(f"w1.l{last}", (convs[0].weight,),
+                                      lambda w, o=offs[last], c=chans[last]: w[:, o:o + c, 0, 0].to(torch.bfloat16).contiguous())
+            shifts = shifts[:last]
 
         def fold(bn: nn.BatchNorm2d, tag: str):
             def mk(w, bias, rm, rv):
@@ -162,7 +173,8 @@ class DatasetDM(nn.Module):
         logits = N.head_infer(g_maps, shifts, 1 if shared else s, b * s if shared else b, size, size,
                               f32(convs[0].bias), ac1[0], ac1[1], f32(convs[1].weight).reshape(convs[1].out_channels, -1),
                               f32(convs[1].bias), ac2[0], ac2[1], f32(convs[2].weight).reshape(-1),
-                              float(self._cache.get("b3", (convs[2].bias,), lambda bb: bb.float().cpu()).item()))
+                              float(self._cache.get("b3", (convs[2].bias,), lambda bb: bb.float().cpu()).item()),
+                              f_full=f_full, w1_full=w1_full)
         return logits
 
     @torch.no_grad()

@@ -32,7 +32,7 @@ class WeightEntry(C.Structure):  # tedm_weight_entry
 class HeadArgs(C.Structure):  # tedm_head_args
     _fields_ = [("g", _p * 4), ("g_dtype", _i), ("shift", _i * 4), ("n_levels", _i), ("n_sum", _i), ("n_img", _i), ("height", _i),
                 ("width", _i), ("c1", _i), ("c2", _i), ("b1", _p), ("bn1_a", _p), ("bn1_c", _p), ("w2", _p),
-                ("b2", _p), ("bn2_a", _p), ("bn2_c", _p), ("w3", _p), ("b3", _f), ("logits", _p)]
+                ("b2", _p), ("bn2_a", _p), ("bn2_c", _p), ("w3", _p), ("b3", _f), ("logits", _p), ("f_full", _p), ("w1_full", _p), ("c_full", _i)]
 
 
 # name -> (restype, argtypes); must list every symbol include/tedm_b200.h declares
@@ -565,9 +565,13 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr: float, beta1: float, beta2: 
 # head
 # ------------------------------------------------------------------------------------------------
 def head_infer(g_maps: Sequence[torch.Tensor], shifts: Sequence[int], n_sum: int, n_img: int, height: int, width: int,
-               b1, bn1_a, bn1_c, w2, b2, bn2_a, bn2_c, w3, b3: float):
+               b1, bn1_a, bn1_c, w2, b2, bn2_a, bn2_c, w3, b3: float, f_full=None, w1_full=None):
+    """g_maps: layer-1 outputs per level (fp32 / bf16 NHWC); optionally the full-resolution level as its bf16 feature map
+    `f_full` + weight slice `w1_full` (its layer 1 is then fused into the tail kernel)."""
     a = HeadArgs()
-    gdt = g_maps[0].dtype
+    gdt = g_maps[0].dtype if g_maps else torch.float32
+    a.f_full, a.w1_full = _ptr(f_full, torch.bfloat16, "f_full"), _ptr(w1_full, torch.bfloat16, "w1_full")
+    a.c_full = f_full.shape[-1] if f_full is not None else 0
     if gdt not in (torch.bfloat16, torch.float32):
         raise TypeError("head_infer: g maps must be bf16 or fp32")
     a.g_dtype = 1 if gdt == torch.float32 else 0
@@ -580,7 +584,7 @@ def head_infer(g_maps: Sequence[torch.Tensor], shifts: Sequence[int], n_sum: int
     a.w2, a.b2, a.bn2_a, a.bn2_c = (_ptr(w2, torch.float32), _ptr(b2, torch.float32), _ptr(bn2_a, torch.float32),
                                     _ptr(bn2_c, torch.float32))
     a.w3, a.b3 = _ptr(w3, torch.float32), float(b3)
-    logits = torch.empty(n_img, 1, height, width, device=g_maps[0].device, dtype=torch.float32)
+    logits = torch.empty(n_img, 1, height, width, device=b1.device, dtype=torch.float32)
     a.logits = _ptr(logits)
     _call("tedm_head_infer", C.byref(a), _stream())
     return logits

@@ -278,6 +278,14 @@ def test_head_and_ensemble(gdt):
                           sd["classifier.4.weight"].reshape(32, 128).cuda(), sd["classifier.4.bias"].cuda(), a2, c2,
                           sd["classifier.7.weight"].reshape(32).cuda(), float(sd["classifier.7.bias"]))
     assert _rel(logits, ref) < 1e-2
+    if gdt == "f32":
+        # the full-resolution level handed over as its feature map: layer 1 of that level runs inside the tail kernel
+        fused = N.head_infer(g[:3], [3, 2, 1], 1, B * S, size, size, sd["classifier.1.bias"].cuda(), a1, c1,
+                             sd["classifier.4.weight"].reshape(32, 128).cuda(), sd["classifier.4.bias"].cuda(), a2, c2,
+                             sd["classifier.7.weight"].reshape(32).cuda(), float(sd["classifier.7.bias"]),
+                             f_full=_nhwc(feats[3]), w1_full=w1[:, 896:960, 0, 0].to(torch.bfloat16).contiguous().cuda())
+        assert _rel(fused, ref) < 1e-2
+        assert _rel(fused, logits) < 1e-5, _rel(fused, logits)      # same arithmetic (bf16 operands, fp32 accumulation)
     mask, prob = N.ensemble_mask(logits, S)
     mref, pref = O.ensemble_mask(logits.cpu(), S)
     assert _rel(prob, pref) < 1e-6 and torch.equal(mask.cpu(), mref)
