@@ -54,27 +54,51 @@ extern "C" int tedm_time_embed(const int64_t* t, const float* freq, const float*
 }
 
 // out[b][j] = sum_k W[j][k] * silu(temb[b][k]) + bias[j]          models/unet_model.py:150-152,168-171
-// One warp per output row j (weights streamed once, coalesced), batch chunk of <=32 rows in smem.
+// CTA = (32 output rows j, 32 batch rows b); lane = batch row, warp = 4 consecutive j.  Weights and activations sit
+// transposed in shared memory ([k][j], [k][b]) so the inner loop is one conflict-free load of act[k][lane], one broadcast
+// float4 of W[k][4 j] and four FMAs; nothing is reduced across lanes.
 #define TP_BCHUNK 32
+#define TP_JTILE 32
+#define TP_WPITCH 36
 __global__ void __launch_bounds__(256) time_proj_kernel(const float* __restrict__ temb, const float* __restrict__ w,
                                                         const float* __restrict__ bias, float* __restrict__ out, int batch,
                                                         int tdim, int total) {
-  extern __shared__ float act[];  // [TP_BCHUNK][tdim] silu(temb)
-  const int b0 = blockIdx.y * TP_BCHUNK;
-  const int nb = min(TP_BCHUNK, batch - b0);
-  for (int i = threadIdx.x; i < nb * tdim; i += blockDim.x) {
-    const float v = temb[(size_t)b0 * tdim + i];
-    act[i] = v / (1.0f + expf(-v));
+  extern __shared__ __align__(16) float tp_smem[];
+  float* act = tp_smem;                        // [tdim][TP_BCHUNK]  silu(temb)^T
+  float* wt = tp_smem + tdim * TP_BCHUNK;      // [tdim][TP_WPITCH]  W^T tile
+  const int b0 = blockIdx.y * TP_BCHUNK, j0 = blockIdx.x * TP_JTILE;
+  const int nb = min(TP_BCHUNK, batch - b0), nj = min(TP_JTILE, total - j0);
+  for (int i = threadIdx.x; i < TP_BCHUNK * tdim; i += blockDim.x) {
+    const int bb = i / tdim, k = i - bb * tdim;
+    float v = 0.0f;
+    if (bb < nb) {
+      v = temb[(size_t)(b0 + bb) * tdim + k];
+      v = v / (1.0f + expf(-v));
+    }
+    act[k * TP_BCHUNK + bb] = v;
+  }
+  for (int i = threadIdx.x; i < TP_JTILE * tdim; i += blockDim.x) {
+    const int jj = i / tdim, k = i - jj * tdim;
+    wt[k * TP_WPITCH + jj] = jj < nj ? w[(size_t)(j0 + jj) * tdim + k] : 0.0f;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = blockIdx.x * 8 + warp;
-  if (j >= total) return;
-  for (int bb = 0; bb < nb; ++bb) {
-    float acc = 0.0f;
-    for (int k = lane; k < tdim; k += 32) acc = fmaf(w[(size_t)j * tdim + k], act[bb * tdim + k], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) out[(size_t)(b0 + bb) * total + j] = acc + bias[j];
+  float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 8
+  for (int k = 0; k < tdim; ++k) {
+    const float a = act[k * TP_BCHUNK + lane];
+    const float4 wv = *reinterpret_cast<const float4*>(wt + k * TP_WPITCH + warp * 4);
+    acc[0] = fmaf(wv.x, a, acc[0]);
+    acc[1] = fmaf(wv.y, a, acc[1]);
+    acc[2] = fmaf(wv.z, a, acc[2]);
+    acc[3] = fmaf(wv.w, a, acc[3]);
+  }
+  if (lane < nb) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = j0 + warp * 4 + i;
+      if (j < total) out[(size_t)(b0 + lane) * total + j] = acc[i] + bias[j];
+    }
   }
 }
 
@@ -83,9 +107,14 @@ extern "C" int tedm_time_proj(const float* temb, const float* w_cat, const float
   TEDM_CHECK_ARG(temb && w_cat && b_cat && out, "tedm_time_proj: null pointer");
   TEDM_CHECK_ARG(batch > 0 && tdim > 0 && total > 0 && tdim <= 384, "tedm_time_proj: bad sizes batch=%d tdim=%d total=%d",
                  batch, tdim, total);
-  dim3 grid(ceil_div(total, 8), ceil_div(batch, TP_BCHUNK));
-  time_proj_kernel<<<grid, 256, TP_BCHUNK * tdim * sizeof(float), (cudaStream_t)stream>>>(temb, w_cat, b_cat, out, batch,
-                                                                                           tdim, total);
+  const int smem = tdim * (TP_BCHUNK + TP_WPITCH) * (int)sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    TEDM_CUDA(cudaFuncSetAttribute(time_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 384 * (TP_BCHUNK + TP_WPITCH) * 4));
+    configured = true;
+  }
+  dim3 grid(ceil_div(total, TP_JTILE), ceil_div(batch, TP_BCHUNK));
+  time_proj_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(temb, w_cat, b_cat, out, batch, tdim, total);
   TEDM_LAUNCH_CHECK();
   return TEDM_OK;
 }
@@ -156,11 +185,108 @@ __global__ void __launch_bounds__(256) stem_conv7x7_kernel(const float* __restri
   }
 }
 
+// Tensor-core stem for the reference's shape (1 -> 64 channels): implicit GEMM with M = 16 pixels of an image row,
+// N = 64, K = 2 x 49 -> 112.  The fp32 input is split into bf16 (hi, lo) halves that occupy K slots [0, 49) and [49, 98)
+// against the same bf16 weights, so the input keeps ~16 mantissa bits (the weights are bf16 like every other conv's).
+// A fragments are gathered straight from a 7-row bf16 staging of the image rows through a K -> (row, tap) offset table.
+#define STEM_XP 272          // staged row pitch (elements): W + 6 <= 262
+#define STEM_K 112
+#define STEM_WPITCH 240      // bytes per weight row (112 bf16 + 16)
+__global__ void __launch_bounds__(256) stem_conv7x7_mma_kernel(const float* __restrict__ x, const float* __restrict__ weight,
+                                                               const float* __restrict__ bias, bf16* __restrict__ out,
+                                                               int batch, int H, int W) {
+  __shared__ __align__(16) uint8_t wB[64 * STEM_WPITCH];
+  __shared__ __align__(16) bf16 xs[(2 * 7 + 1) * STEM_XP];   // hi rows, lo rows, one zero row
+  __shared__ __align__(8) int koff[STEM_K];
+  __shared__ __align__(16) uint8_t stage[8][16 * 144];
+  __shared__ float sbias[64];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 64 * STEM_K; i += 256) {
+    const int co = i / STEM_K, k = i % STEM_K;
+    const float wv = k < 98 ? weight[co * 49 + (k < 49 ? k : k - 49)] : 0.0f;
+    *reinterpret_cast<bf16*>(wB + co * STEM_WPITCH + k * 2) = __float2bfloat16_rn(wv);
+  }
+  for (int k = tid; k < STEM_K; k += 256) {
+    const int kk = k < 49 ? k : k - 49;
+    koff[k] = k < 98 ? (k < 49 ? 0 : 7 * STEM_XP) + (kk / 7) * STEM_XP + kk % 7 : 14 * STEM_XP;
+  }
+  for (int i = tid; i < STEM_XP; i += 256) xs[14 * STEM_XP + i] = __float2bfloat16_rn(0.0f);
+  if (tid < 64) sbias[tid] = bias ? bias[tid] : 0.0f;
+  const int g = lane >> 2, t4 = lane & 3, j = lane >> 3, rr = lane & 7;
+  const uint32_t wB_u = smem_u32(wB);
+  const int rows = batch * H;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int b = r / H, y = r - b * H;
+    __syncthreads();                       // the previous row's gathers are done (and, first time, the tables are written)
+    for (int i = tid; i < 7 * (W + 6); i += 256) {
+      const int ky = i / (W + 6), xi = i - ky * (W + 6);
+      const int yy = y + ky - 3, xx = xi - 3;
+      const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + ((size_t)b * H + yy) * W + xx) : 0.0f;
+      const bf16 hi = __float2bfloat16_rn(v);
+      xs[ky * STEM_XP + xi] = hi;
+      xs[(7 + ky) * STEM_XP + xi] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+    __syncthreads();
+    for (int mt = warp; mt < W / 16; mt += 8) {
+      const int px0 = mt * 16;
+      float acc[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0f;
+      const unsigned short* xu = reinterpret_cast<const unsigned short*>(xs) + px0 + g;
+#pragma unroll
+      for (int ks = 0; ks < STEM_K / 16; ++ks) {
+        uint32_t a[4];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int2 o = *reinterpret_cast<const int2*>(koff + ks * 16 + half * 8 + 2 * t4);
+          a[half * 2] = (uint32_t)xu[o.x] | ((uint32_t)xu[o.y] << 16);
+          a[half * 2 + 1] = (uint32_t)xu[o.x + 8] | ((uint32_t)xu[o.y + 8] << 16);
+        }
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          uint32_t bfr[4];
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(bfr[0]), "=r"(bfr[1]), "=r"(bfr[2]), "=r"(bfr[3])
+                       : "r"(wB_u + ((2 * np + (j >> 1)) * 8 + rr) * STEM_WPITCH + (ks * 16 + (j & 1) * 8) * 2));
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(acc[2 * np + q][0]), "+f"(acc[2 * np + q][1]), "+f"(acc[2 * np + q][2]), "+f"(acc[2 * np + q][3])
+                         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(bfr[2 * q]), "r"(bfr[2 * q + 1]));
+        }
+      }
+      uint8_t* st = stage[warp];
+      __syncwarp();
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int c = nt * 8 + 2 * t4;
+        const float b0 = sbias[c], b1 = sbias[c + 1];
+        *reinterpret_cast<uint32_t*>(st + g * 144 + c * 2) = pack_bf16x2(acc[nt][0] + b0, acc[nt][1] + b1);
+        *reinterpret_cast<uint32_t*>(st + (g + 8) * 144 + c * 2) = pack_bf16x2(acc[nt][2] + b0, acc[nt][3] + b1);
+      }
+      __syncwarp();
+      bf16* dst = out + (((size_t)b * H + y) * W + px0) * 64;
+      for (int i = lane; i < 16 * 8; i += 32) {
+        const int row = i >> 3, v = i & 7;
+        *reinterpret_cast<uint4*>(dst + (size_t)row * 64 + v * 8) = *reinterpret_cast<const uint4*>(st + row * 144 + v * 16);
+      }
+    }
+  }
+}
+
 extern "C" int tedm_stem_conv7x7(const float* x, const float* weight, const float* bias, void* out, int batch, int cin,
                                  int height, int width, int cout, tedm_stream_t stream) {
   TEDM_CHECK_ARG(x && weight && out, "tedm_stem_conv7x7: null pointer");
   TEDM_CHECK_ARG(batch > 0 && cin > 0 && height > 0 && width > 0 && cout > 0, "tedm_stem_conv7x7: bad sizes");
   TEDM_UNSUPPORTED(cout % 8 != 0, "tedm_stem_conv7x7: cout=%d must be a multiple of 8", cout);
+  if (cin == 1 && cout == 64 && width % 16 == 0 && width <= 256) {   // the reference's stem: tensor-core path
+    int grid = batch * height;
+    const int cap = resident_ctas(stem_conv7x7_mma_kernel, 256, 0);
+    if (grid > cap) grid = cap;
+    stem_conv7x7_mma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, weight, bias, (bf16*)out, batch, height, width);
+    TEDM_LAUNCH_CHECK();
+    return TEDM_OK;
+  }
   const size_t smem = (size_t)cin * 49 * cout * sizeof(float);
   TEDM_UNSUPPORTED(smem > 96 * 1024, "tedm_stem_conv7x7: cin*49*cout=%d floats do not fit in shared memory", cin * 49 * cout);
   if (smem > 48 * 1024)
