@@ -119,6 +119,64 @@ def cpu_tedm_images_per_s(n_images: int, repeats: int = 1):
     return n_images / best, best
 
 
+def gpu_eager_baselines(dev, n_images: int = 8):
+    """the reference's path as plain PyTorch eager ops ON THE SAME GPU (cuDNN / cuBLAS kernels; the
+    oracle restatement, since /root/reference is not on the box), fp32 and under autocast(bf16).  A reported baseline
+    only -- never part of the product path."""
+    import torch
+    from oracle import tedm_oracle as O
+    torch.backends.cudnn.benchmark = True
+    sd = synth_state(len(STEPS_TEDM))
+    sd.update(O.schedule_tables())
+    sd = {k: v.to(dev) for k, v in sd.items()}
+    x0 = synth_batch(n_images, 99).to(dev)
+    noises = [torch.randn(n_images, 1, IMG, IMG, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + i))
+              for i in range(len(STEPS_TEDM))]
+    out = {"unit": "images/s", "sample": f"{n_images} images x 8 timesteps per pass, 3 timed passes after 2 warm-ups",
+           "kind": "port (oracle restatement as torch eager CUDA ops)"}
+    for name, ctx in (("fp32", contextlib.nullcontext()), ("autocast_bf16", torch.autocast("cuda", dtype=torch.bfloat16))):
+        try:
+            with torch.no_grad(), ctx:
+                for _ in range(2):
+                    O.tedm_segment(sd, x0, STEPS_TEDM, noises, shared=True)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    O.tedm_segment(sd, x0, STEPS_TEDM, noises, shared=True)
+                e1.record()
+                torch.cuda.synchronize()
+            out[name] = 3 * n_images / (e0.elapsed_time(e1) * 1e-3)
+        except Exception as e:  # a baseline must never take the bench down
+            out[name] = None
+            out[name + "_error"] = f"{type(e).__name__}: {e}"[:200]
+    return out
+
+
+def sampler_leg(dev, batch: int = 64, steps: int = 20):
+    """BASELINE configs[4]: DDPM ancestral sampling.  Times `steps` reverse steps (UNet forward + the one-kernel
+    posterior update with the exact dynamic-threshold quantile) of a `batch`-image chain batch; a full chain is 1000."""
+    import torch
+    from argparse import Namespace
+    from tedm_b200.models import DiffusionModel
+    torch.manual_seed(7)
+    m = DiffusionModel(Namespace(normalize=True)).to(dev).eval()
+    img = torch.randn(batch, 1, IMG, IMG, device=dev)
+    for t in range(999, 996, -1):
+        img = m.sample_timestep(img, t)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(996, 996 - steps, -1):
+        img = m.sample_timestep(img, t)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"workload": "ddpm_ancestral_sampling", "batch_per_gpu": batch, "timed_reverse_steps": steps, "ms_per_reverse_step": ms,
+            "image_steps_per_s": batch / (ms * 1e-3), "images_per_s_full_1000_step_chain": batch / ms,
+            "tflops_unet_fwd": batch * GFLOP_UNET_FWD / ms, "finite": bool(torch.isfinite(img).all())}
+
+
 def cpu_train_images_per_s(n_images: int):
     """The reference's training step (train_step + backward, trainers/train_CXR14.py:30-40) as the oracle port runs it
     on the host cores: fp32 torch autograd through oracle.ddpm_loss."""
@@ -307,15 +365,20 @@ def run_ours(args):
     torch.cuda.empty_cache()
     if not args.no_train:
         line["train"] = train_leg(args, dev, world, rank, pk, barrier)
+        if rank == 0 and world == 1:
+            line["sampler"] = sampler_leg(dev)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
+            line["gpu_eager_baseline"] = gpu_eager_baselines(dev)
+            torch.cuda.empty_cache()
             if "train" in line:
-                v, dt = cpu_train_images_per_s(2)
+                v, dt = cpu_train_images_per_s(8)
                 line["train"]["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-                                                 "sample": f"one fwd+bwd on 2 images ({dt:.1f} s), oracle port, torch CPU fp32 autograd"}
-            v, dt = cpu_tedm_images_per_s(2)
+                                                 "sample": f"one fwd+bwd on 8 images ({dt:.1f} s), oracle port, torch CPU fp32 autograd"}
+            cpu_tedm_images_per_s(1)                                   # warm-up (thread pool, allocator)
+            v, dt = cpu_tedm_images_per_s(16)
             line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"2 images x 8 timesteps, one pass ({dt:.1f} s), oracle port on torch CPU fp32"}
+                                    "sample": f"16 images x 8 timesteps, one pass ({dt:.1f} s), oracle port on torch CPU fp32"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

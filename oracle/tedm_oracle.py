@@ -183,7 +183,7 @@ def head_param_shapes(n_steps: int, shared: bool, prefix: str = "classifier.") -
 def time_embedding(sd: StateDict, p: str, t: Tensor, dim: int) -> Tensor:
     """SinusoidalPosEmb + time_mlp (unet_model.py:76-93, 287-292)."""
     half = dim // 2
-    freq = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1)))
+    freq = torch.exp(torch.arange(half, device=t.device) * -(math.log(10000) / (half - 1)))
     ang = t[:, None] * freq[None, :]
     e = torch.cat((ang.sin(), ang.cos()), dim=-1)
     e = F.linear(e, sd[p + "time_mlp.1.weight"], sd[p + "time_mlp.1.bias"])
@@ -333,11 +333,11 @@ def l1_p2_loss(pred: Tensor, target: Tensor, w_t: Tensor) -> Tensor:
 def sampler_update(tb: Dict[str, Tensor], x_t: Tensor, eps: Tensor, t: int, z: Optional[Tensor],
                    pct: float = 0.995) -> Tuple[Tensor, Tensor]:
     """Everything in sample_timestep after the UNet call.  Returns (x_{t-1}, clipped x0_hat)."""
-    tt = torch.full((x_t.shape[0],), t, dtype=torch.long)
+    tt = torch.full((x_t.shape[0],), t, dtype=torch.long, device=x_t.device)
     x0h = gather_t(tb["sqrt_recip_alphas_cumprod"], tt) * x_t - \
         gather_t(tb["sqrt_recipm1_alphas_cumprod"], tt) * eps
     s = torch.quantile(x0h.flatten(1).abs(), pct, dim=1)
-    s = torch.max(s, torch.tensor(1.0))[:, None, None, None]
+    s = torch.max(s, torch.tensor(1.0, device=s.device))[:, None, None, None]
     x0h = torch.clip(x0h, -s, s) / s
     mean = gather_t(tb["posterior_mean_coef1"], tt) * x0h + gather_t(tb["posterior_mean_coef2"], tt) * x_t
     logvar = gather_t(tb["posterior_log_variance_clipped"], tt)
@@ -347,7 +347,7 @@ def sampler_update(tb: Dict[str, Tensor], x_t: Tensor, eps: Tensor, t: int, z: O
 
 
 def sample_timestep(sd: StateDict, x_t: Tensor, t: int, z: Optional[Tensor], store=_ident, **kw) -> Tensor:
-    tt = torch.full((x_t.shape[0],), t, dtype=torch.long)
+    tt = torch.full((x_t.shape[0],), t, dtype=torch.long, device=x_t.device)
     eps = unet_forward(sd, x_t, tt, prefix="model.", store=store, **kw)
     return sampler_update(sd, x_t, eps, t, z)[0]
 
@@ -361,7 +361,7 @@ def extract_feature_maps(sd: StateDict, x0: Tensor, steps: Sequence[int], noises
     NB: x0 is *not* rescaled to [-1,1] here (datasetDM_model.py:76)."""
     maps = []
     for s, nz in zip(steps, noises):
-        t = torch.full((x0.shape[0],), int(s), dtype=torch.long)
+        t = torch.full((x0.shape[0],), int(s), dtype=torch.long, device=x0.device)
         x_t = q_sample(sd, x0, t, nz)
         _, f = unet_forward(sd, x_t, t, prefix="diffusion_model.model." if
                             any(k.startswith("diffusion_model.") for k in sd) else "model.",

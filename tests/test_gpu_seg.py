@@ -202,3 +202,53 @@ def test_train_cli_debug_step(tmp_path, experiment):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "Train loss" in r.stdout and "Validation loss" in r.stdout, r.stdout[-2000:]
+
+
+def test_evaluate_shared_weights_matches_reference_formulae():
+    """Per-timestep + ensemble report (testing_shared_weights.py:113-138) against the oracle's metrics on the same logits."""
+    from tedm_b200.dataloaders.device_loader import build_synthetic_dataloaders
+    from tedm_b200.evaluate import evaluate_shared_weights
+    from tedm_b200.models import DatasetDM, tedm_classifier
+    steps = [10, 200, 600]
+    torch.manual_seed(0)
+    m = DatasetDM(Namespace(normalize=True, saved_diffusion_model="", t_steps_to_save=steps, dim_mults=[1, 2, 4, 8]))
+    m.classifier = tedm_classifier(len(steps))
+    m = m.cuda().eval()
+    dl = build_synthetic_dataloaders(128, 2, labelled=True, n_train=2, n_val=4)["val"]
+    torch.manual_seed(5)
+    res = evaluate_shared_weights(m, dl)
+    assert res["n_images"] == 4 and sorted(res["per_timestep"]) == steps
+    # same logits again (same noise seed) through the oracle's formulae
+    torch.manual_seed(5)
+    rows, ens = [], []
+    for x, y in dl:
+        logits = m(x).cpu()
+        pr = torch.sigmoid(logits).reshape(x.shape[0], len(steps), 1, 128, 128)
+        rows.append(torch.stack([O.seg_metrics(pr[:, i] > .5, y.cpu())["dice"] for i in range(len(steps))], dim=1))
+        ens.append(O.seg_metrics(pr.mean(1) > .5, y.cpu())["dice"])
+    rows, ens = torch.cat(rows), torch.cat(ens)
+    for i, t in enumerate(steps):
+        a, b = res["per_timestep"][t]["dice"][0], rows[:, i].mean().item()
+        assert (np.isnan(a) and np.isnan(b)) or abs(a - b) < 1e-6, (t, a, b)
+    a, b = res["ensemble"]["dice"][0], ens.mean().item()
+    assert (np.isnan(a) and np.isnan(b)) or abs(a - b) < 1e-6
+
+
+def test_val_step_and_sampling_driver():
+    """val_step batches its timestep grid along the image axis (diffusion_model.py:145-156); sample_images /
+    sample_plot_image drive sample_timestep for T steps (trainers/utils.py:62-98)."""
+    from tedm_b200.models import DiffusionModel
+    from tedm_b200.trainers.utils import sample_images, sample_plot_image
+    torch.manual_seed(0)
+    m = DiffusionModel(Namespace(normalize=True, timesteps=40, dim_mults=[1, 2, 4])).cuda().eval()
+    x = synth_images(4, 64, 3).cuda()
+    torch.manual_seed(1)
+    v = m.val_step(x, t_steps=4).item()
+    torch.manual_seed(2)
+    ref = np.mean([m.train_step(x, t=torch.full((4,), t, device="cuda")).item() for t in range(0, 40, 10)])
+    assert abs(v - ref) < 0.03 * ref, (v, ref)          # same timestep grid, independent noise draws
+    final, snaps = sample_images(m, 40, 64, 2)
+    assert final.shape == (2, 1, 64, 64) and len(snaps) == 8 and torch.isfinite(final).all()
+    assert final.min() >= -1e-6 and final.max() <= 1 + 1e-6      # dynamic thresholding keeps x in [-1, 1] -> [0, 1]
+    grid = sample_plot_image(m, 40, 64, 2, normalized=True)
+    assert grid.shape == (2, 3, 2 * 66 + 2, 4 * 66 + 2)
