@@ -462,12 +462,147 @@ __global__ void __launch_bounds__(ATT_MAX_N) attention_kernel(const bf16* __rest
                        pack_bf16x2(acc[8 * j + 4] * inv, acc[8 * j + 5] * inv), pack_bf16x2(acc[8 * j + 6] * inv, acc[8 * j + 7] * inv));
 }
 
+// Tensor-core (mma.sync) flash form of the same attention, any n: CTA = (64-query tile, head, image), 4 warps x 16
+// queries.  The L2 norms over tokens are recomputed per CTA from L2-resident qkv (n x 64 values), q-hat * scale and k-hat
+// are written to shared memory as bf16 (|sim| <= scale, so bf16 operands cost ~1e-3 relative on the logits' scale), the
+// softmax over keys is online, P goes register-to-register into the P V product.
+#define FA_PITCH 80
+__global__ void __launch_bounds__(128) attention_flash_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int n,
+                                                              int heads, float scale) {
+  __shared__ __align__(16) uint8_t sq[64 * FA_PITCH], sk[64 * FA_PITCH], sv[64 * FA_PITCH];
+  __shared__ float s_inv[64], s_red[64];
+  const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C3 = 3 * heads * DH, C = heads * DH;
+  const bf16* base = qkv + (size_t)b * n * C3;
+  {  // column norms of this head's q (channels 0..31) and k (32..63) over all tokens
+    const int c = tid & 63, part = tid >> 6;
+    const int ch = c < DH ? h * DH + c : C + h * DH + (c - DH);
+    float acc = 0.0f;
+    for (int px = part; px < n; px += 2) {
+      const float v = __bfloat162float(base[(size_t)px * C3 + ch]);
+      acc = fmaf(v, v, acc);
+    }
+    if (part == 1) s_red[c] = acc;
+    __syncthreads();
+    if (part == 0) {
+      const float inv = 1.0f / fmaxf(sqrtf(acc + s_red[c]), 1e-12f);
+      s_inv[c] = c < DH ? inv * scale : inv;
+    }
+    __syncthreads();
+  }
+  auto load_scaled = [&](uint8_t* dst, int row0, int ch0, const float* inv) {   // 64 rows x 32 channels, optional scaling
+    const int row = tid >> 1, half = tid & 1;
+    const int px = row0 + row;
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (px < n) {
+        u = __ldg(reinterpret_cast<const uint4*>(base + (size_t)px * C3 + ch0 + half * 16 + v * 8));
+        if (inv) {
+          float f[8];
+          unpack8(u, f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] *= inv[half * 16 + v * 8 + e];
+          u = pack8(f);
+        }
+      }
+      *reinterpret_cast<uint4*>(dst + row * FA_PITCH + (half * 16 + v * 8) * 2) = u;
+    }
+  };
+  load_scaled(sq, q0, h * DH, s_inv);
+  const int g = lane >> 2, t4 = lane & 3, j = lane >> 3, rr = lane & 7;
+  const uint32_t sq_u = smem_u32(sq), sk_u = smem_u32(sk), sv_u = smem_u32(sv);
+  float o[4][4], mrun[2] = {-INFINITY, -INFINITY}, lrun[2] = {0.0f, 0.0f};
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.0f;
+  for (int k0 = 0; k0 < n; k0 += 64) {
+    __syncthreads();                                  // previous tile consumed (first pass: q tile visible after the next sync)
+    load_scaled(sk, k0, C + h * DH, s_inv + DH);
+    load_scaled(sv, k0, 2 * C + h * DH, nullptr);
+    __syncthreads();
+    float sc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.0f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t a[4];
+      ldsm_x4(sq_u + (warp * 16 + (j & 1) * 8 + rr) * FA_PITCH + (ks * 16 + (j >> 1) * 8) * 2, a);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t bfr[4];
+        ldsm_x4(sk_u + ((2 * np + (j >> 1)) * 8 + rr) * FA_PITCH + (ks * 16 + (j & 1) * 8) * 2, bfr);
+        mma_bf16_16816(sc[2 * np], a, bfr[0], bfr[1]);
+        mma_bf16_16816(sc[2 * np + 1], a, bfr[2], bfr[3]);
+      }
+    }
+    if (k0 + 64 > n) {                                // ragged last tile: keys beyond n do not exist
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (k0 + nt * 8 + 2 * t4 + (e & 1) >= n) sc[nt][e] = -INFINITY;
+    }
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float tm = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) tm = fmaxf(tm, fmaxf(sc[nt][2 * r], sc[nt][2 * r + 1]));
+      tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, 1));
+      tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, 2));
+      const float mn = fmaxf(mrun[r], tm);
+      const float corr = __expf(mrun[r] - mn);
+      mrun[r] = mn;
+      float ls = 0.0f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float e0 = __expf(sc[nt][2 * r] - mn), e1 = __expf(sc[nt][2 * r + 1] - mn);
+        ls += e0 + e1;
+        pa[nt >> 1][(nt & 1) * 2 + r] = pack_bf16x2(e0, e1);
+      }
+      lrun[r] = fmaf(lrun[r], corr, ls);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        o[nt][2 * r] *= corr;
+        o[nt][2 * r + 1] *= corr;
+      }
+    }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t bfr[4];
+        ldsm_x4_trans(sv_u + (ks * 16 + (j & 1) * 8 + rr) * FA_PITCH + ((2 * np + (j >> 1)) * 8) * 2, bfr);
+        mma_bf16_16816(o[2 * np], pa[ks], bfr[0], bfr[1]);
+        mma_bf16_16816(o[2 * np + 1], pa[ks], bfr[2], bfr[3]);
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float l = lrun[r];
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    const float inv = 1.0f / l;
+    const int qi = q0 + warp * 16 + g + r * 8;
+    if (qi < n) {
+      bf16* op = out + ((size_t)b * n + qi) * C + h * DH + 2 * t4;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) *reinterpret_cast<uint32_t*>(op + nt * 8) = pack_bf16x2(o[nt][2 * r] * inv, o[nt][2 * r + 1] * inv);
+    }
+  }
+}
+
 extern "C" int tedm_attention_fwd(const void* qkv, void* out, int batch, int n, int heads, int dim_head, float scale,
                                   tedm_stream_t stream) {
   TEDM_CHECK_ARG(qkv && out && batch > 0 && n > 0 && heads > 0, "tedm_attention_fwd: bad arguments");
   TEDM_UNSUPPORTED(dim_head != DH, "tedm_attention_fwd: dim_head=%d (only 32)", dim_head);
-  TEDM_UNSUPPORTED(n > ATT_MAX_N, "tedm_attention_fwd: n=%d tokens > %d", n, ATT_MAX_N);
-  TEDM_CHECK_ARG(batch <= 65535, "tedm_attention_fwd: batch too large");
+  TEDM_CHECK_ARG(batch <= 65535 && heads <= 65535, "tedm_attention_fwd: batch / heads too large");
+  if (n >= 64) {   // tensor-core flash form, any n
+    attention_flash_kernel<<<dim3((n + 63) / 64, heads, batch), 128, 0, (cudaStream_t)stream>>>((const bf16*)qkv, (bf16*)out, n,
+                                                                                            heads, scale);
+    TEDM_LAUNCH_CHECK();
+    return TEDM_OK;
+  }
   const int smem = 2 * ATT_MAX_N * DH * (int)sizeof(float);
   static bool configured = false;
   if (!configured) {

@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(256, 2) linattn_fused_ctx_kernel(const bf16* _
     gemm_rows(h * kDh, acc);
     // online softmax over pixels, per k channel (rows g / g+8 of the two m-tiles)
     uint32_t pa[2][2][4];
+    float corrs[2][2];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -206,11 +207,22 @@ __global__ void __launch_bounds__(256, 2) linattn_fused_ctx_kernel(const bf16* _
           const float e0 = ex2f(fmaf(acc[mt][nt][2 * r], kLog2e, mn2)), e1 = ex2f(fmaf(acc[mt][nt][2 * r + 1], kLog2e, mn2));
           ls += e0 + e1;
           pa[mt][nt >> 1][(nt & 1) * 2 + r] = pack_bf16x2(e0, e1);
-          ctx[mt][nt][2 * r] *= corr;
-          ctx[mt][nt][2 * r + 1] *= corr;
         }
         ssum[mt][r] = fmaf(ssum[mt][r], corr, ls);
+        corrs[mt][r] = corr;
       }
+    // the running maxima settle after the first tiles: rescale the context only when one of them moved (warp-uniform)
+    if (__any_sync(0xffffffffu, corrs[0][0] != 1.0f || corrs[0][1] != 1.0f || corrs[1][0] != 1.0f || corrs[1][1] != 1.0f)) {
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          ctx[mt][nt][0] *= corrs[mt][0];
+          ctx[mt][nt][1] *= corrs[mt][0];
+          ctx[mt][nt][2] *= corrs[mt][1];
+          ctx[mt][nt][3] *= corrs[mt][1];
+        }
+    }
     gemm_rows(kHid + h * kDh, acc);
     // ctx[d][e] += sum_px P[d][px] v[e][px]: B fragments straight from the v^T accumulators
 #pragma unroll
@@ -368,11 +380,16 @@ __global__ void __launch_bounds__(kWarpsB * 32, 1) linattn_fused_out_kernel(
       load_group(grp + kWarpsB);
       cp_commit();
     }
-    float o2[MT][NT][4];
+    float o2[MT][NT][4];          // starts from the to_out bias (fragment columns nt*8 + 2*t4, +1)
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
+    for (int nt = 0; nt < NT; ++nt) {
+      const float2 b2 = *reinterpret_cast<const float2*>(fpar + C + nt * 8 + 2 * t4);
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) o2[mt][nt][0] = o2[mt][nt][1] = o2[mt][nt][2] = o2[mt][nt][3] = 0.0f;
+      for (int mt = 0; mt < MT; ++mt) {
+        o2[mt][nt][0] = o2[mt][nt][2] = b2.x;
+        o2[mt][nt][1] = o2[mt][nt][3] = b2.y;
+      }
+    }
 #pragma unroll 1
     for (int h = 0; h < kHeads; ++h) {
       // q_h (ROWS px x 32 d) = y W_q,h^T
@@ -462,37 +479,23 @@ __global__ void __launch_bounds__(kWarpsB * 32, 1) linattn_fused_out_kernel(
       }
     }
     // + bias, LayerNorm over the C channels of each row, * g_out, + x (re-read: an L2 hit), -> bf16 staging -> store
-    const float* bo = fpar + C;
     const float* go = fpar + 2 * C;
     const bf16* xg = xb + (size_t)(p0 + grp * ROWS) * C;
     __syncwarp();                            // every lane is done reading y: the buffer becomes the output staging area
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      const float2 b2 = *reinterpret_cast<const float2*>(bo + nt * 8 + 2 * t4);
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        o2[mt][nt][0] += b2.x;
-        o2[mt][nt][1] += b2.y;
-        o2[mt][nt][2] += b2.x;
-        o2[mt][nt][3] += b2.y;
-      }
-    }
     float mean[MT][2], rstd[MT][2];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        float s = 0.0f;
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) s += o2[mt][nt][2 * r] + o2[mt][nt][2 * r + 1];
-        mean[mt][r] = quad_sum(s) * (1.0f / C);
-        float qv = 0.0f;
+        float s = 0.0f, qv = 0.0f;                 // one pass: E[x], E[x^2] (values are O(1), fp32 accumulators)
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
-          const float d0 = o2[mt][nt][2 * r] - mean[mt][r], d1 = o2[mt][nt][2 * r + 1] - mean[mt][r];
-          qv = fmaf(d0, d0, fmaf(d1, d1, qv));
+          s += o2[mt][nt][2 * r] + o2[mt][nt][2 * r + 1];
+          qv = fmaf(o2[mt][nt][2 * r], o2[mt][nt][2 * r], fmaf(o2[mt][nt][2 * r + 1], o2[mt][nt][2 * r + 1], qv));
         }
-        rstd[mt][r] = rsqrtf(quad_sum(qv) * (1.0f / C) + eps);
+        mean[mt][r] = quad_sum(s) * (1.0f / C);
+        const float var = fmaxf(quad_sum(qv) * (1.0f / C) - mean[mt][r] * mean[mt][r], 0.0f);
+        rstd[mt][r] = rsqrtf(var + eps);
       }
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {

@@ -214,7 +214,7 @@ def test_linear_attention_block_fused(C, hw, B):
     assert not N.linear_attention_fused_supported(n, 256) and not N.linear_attention_fused_supported(100, 64)
 
 
-@pytest.mark.parametrize("hw,B", [(4, 2), (16, 3), (8, 1)])
+@pytest.mark.parametrize("hw,B", [(4, 2), (16, 3), (8, 1), (32, 2), (10, 2), (24, 1)])
 def test_mid_attention_core(hw, B):
     from tedm_b200 import native as N
     qkv = _rand((B, 384, hw, hw), 1, 1.0)
