@@ -121,7 +121,12 @@ struct HeadFull {
   const bf16* w1;   // [128][64] bf16
 };
 
-template <bool FUSE>
+// STAGED (n_sum == 1, every g level has 1 <= shift <= 3, W % 16 == 0): the 14 source rows (8 + 4 + 2 pixels x 512 B) a
+// 16-pixel group gathers from are copied into shared memory with cp.async while the layer-1 product runs, instead of
+// being fetched lane by lane afterwards (the kernel was waiting on those loads for two thirds of its time).
+constexpr int kGPitch = HEAD_C1 * 4 + 16;    // bytes per staged g row
+constexpr int kGRows = 14;
+template <bool FUSE, bool STAGED>
 __global__ void __launch_bounds__(kHeadWarps * 32) head_tail_mma_kernel(const HeadParams p, const HeadFull full) {
   extern __shared__ __align__(16) uint8_t hsm[];
   uint8_t* w2h_s = hsm;                                   // [32][kW2Pitch]
@@ -129,6 +134,7 @@ __global__ void __launch_bounds__(kHeadWarps * 32) head_tail_mma_kernel(const He
   float* par = reinterpret_cast<float*>(w2l_s + HEAD_C2 * kW2Pitch);   // b1, a1, c1 [128]; b2, a2, c2, w3 [32]
   uint8_t* w1_s = reinterpret_cast<uint8_t*>(par + 3 * HEAD_C1 + 4 * HEAD_C2);  // [128][kFPitch]        (FUSE)
   uint8_t* f_s = w1_s + HEAD_C1 * kFPitch;                                       // 8 warps x [16][kFPitch] (FUSE)
+  uint8_t* g_s = FUSE ? f_s + kHeadWarps * 16 * kFPitch : w1_s;                  // 8 warps x [14][kGPitch] (STAGED)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < HEAD_C2 * HEAD_C1; i += kHeadWarps * 32) {
     const int j = i / HEAD_C1, k = i % HEAD_C1;
@@ -168,6 +174,25 @@ __global__ void __launch_bounds__(kHeadWarps * 32) head_tail_mma_kernel(const He
   for (long long grp = (long long)blockIdx.x * kHeadWarps + warp; grp < ngroups; grp += (long long)gridDim.x * kHeadWarps) {
     const long long pix0 = grp * 16;
     float z1[16][4];
+    uint8_t* my_g = g_s + warp * kGRows * kGPitch;
+    auto stage_g = [&]() {   // the group lies in one image row; level l contributes 16 >> shift consecutive source pixels
+      const long long img = pix0 / hw;
+      const int rem = (int)(pix0 - img * hw);
+      const int y = rem / p.W, x0 = rem - y * p.W;
+      int row_off = 0;
+      for (int l = 0; l < p.n_levels; ++l) {
+        const int sh = p.shift[l], npx = 16 >> sh;
+        const float* src = reinterpret_cast<const float*>(p.g[l]) +
+                           (((size_t)img * (p.H >> sh) + (y >> sh)) * (p.W >> sh) + (x0 >> sh)) * HEAD_C1;
+        for (int i = lane; i < npx * 32; i += 32) {
+          const int px = i >> 5, c16 = i & 31;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(my_g + (row_off + px) * kGPitch + c16 * 16)),
+                       "l"(src + px * HEAD_C1 + c16 * 4) : "memory");
+        }
+        row_off += npx;
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     if (FUSE) {
       const bf16* src = full.f + pix0 * 64;                // 16 px x 128 B, contiguous
       __syncwarp();
@@ -176,7 +201,12 @@ __global__ void __launch_bounds__(kHeadWarps * 32) head_tail_mma_kernel(const He
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(f_u + row * kFPitch + v * 16), "l"(src + row * 64 + v * 8) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (STAGED) {
+        stage_g();                                       // lands while the layer-1 product below runs
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
       __syncwarp();
 #pragma unroll
       for (int nt = 0; nt < 16; ++nt) z1[nt][0] = z1[nt][1] = z1[nt][2] = z1[nt][3] = 0.0f;
@@ -193,29 +223,53 @@ __global__ void __launch_bounds__(kHeadWarps * 32) head_tail_mma_kernel(const He
         }
       }
     } else {
+      if (STAGED) {
+        __syncwarp();
+        stage_g();
+      }
 #pragma unroll
       for (int nt = 0; nt < 16; ++nt) z1[nt][0] = z1[nt][1] = z1[nt][2] = z1[nt][3] = 0.0f;
     }
-    // bias + gathered maps of the other levels, at the fragment positions (rows g, g+8; columns nt*8 + 2*t4, +1)
+    // gathered maps of the other levels, at the fragment positions (rows g, g+8; columns nt*8 + 2*t4, +1)
+    if (STAGED) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      int row_off = 0;
+      for (int l = 0; l < p.n_levels; ++l) {
+        const int sh = p.shift[l];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const long long pix = pix0 + g + 8 * r;
-      const long long img = pix / hw;
-      const int rem = (int)(pix - img * hw);
-      const int y = rem / p.W, x = rem - y * p.W;
-      for (int s = 0; s < p.n_sum; ++s)
-        for (int l = 0; l < p.n_levels; ++l) {
-          const int sh = p.shift[l];
-          const int hl = p.H >> sh, wl = p.W >> sh;
-          const float* src = reinterpret_cast<const float*>(p.g[l]) +
-                             ((((size_t)img * p.n_sum + s) * hl + (y >> sh)) * wl + (x >> sh)) * HEAD_C1 + 2 * t4;
+        for (int r = 0; r < 2; ++r) {
+          const float* src = reinterpret_cast<const float*>(my_g + (row_off + ((g + 8 * r) >> sh)) * kGPitch) + 2 * t4;
 #pragma unroll
           for (int nt = 0; nt < 16; ++nt) {
-            const float2 v = __ldg(reinterpret_cast<const float2*>(src + nt * 8));
+            const float2 v = *reinterpret_cast<const float2*>(src + nt * 8);
             z1[nt][2 * r] += v.x;
             z1[nt][2 * r + 1] += v.y;
           }
         }
+        row_off += 16 >> sh;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const long long pix = pix0 + g + 8 * r;
+        const long long img = pix / hw;
+        const int rem = (int)(pix - img * hw);
+        const int y = rem / p.W, x = rem - y * p.W;
+        for (int s = 0; s < p.n_sum; ++s)
+          for (int l = 0; l < p.n_levels; ++l) {
+            const int sh = p.shift[l];
+            const int hl = p.H >> sh, wl = p.W >> sh;
+            const float* src = reinterpret_cast<const float*>(p.g[l]) +
+                               ((((size_t)img * p.n_sum + s) * hl + (y >> sh)) * wl + (x >> sh)) * HEAD_C1 + 2 * t4;
+#pragma unroll
+            for (int nt = 0; nt < 16; ++nt) {
+              const float2 v = __ldg(reinterpret_cast<const float2*>(src + nt * 8));
+              z1[nt][2 * r] += v.x;
+              z1[nt][2 * r + 1] += v.y;
+            }
+          }
+      }
     }
     // layer 2 on the fly: a1 fragments of k-step ks come from z1 tiles 2ks, 2ks+1
     float z2[4][4];
@@ -303,20 +357,33 @@ extern "C" int tedm_head_infer(const tedm_head_args* a, tedm_stream_t stream) {
     TEDM_CHECK_ARG(!fuse || (a->w1_full && a->c_full == 64 && a->n_sum == 1),
                    "tedm_head_infer: the fused full-resolution level needs its weight slice, 64 channels and n_sum == 1");
     HeadFull full{(const bf16*)a->f_full, (const bf16*)a->w1_full};
+    bool staged = a->n_sum == 1 && a->width % 16 == 0 && a->n_levels >= 1;
+    int rows = 0;
+    for (int l = 0; l < a->n_levels; ++l) {
+      staged = staged && a->shift[l] >= 1 && a->shift[l] <= 3;
+      rows += 16 >> a->shift[l];
+    }
+    staged = staged && rows <= kGRows;
     const int smem = 2 * HEAD_C2 * kW2Pitch + (3 * HEAD_C1 + 4 * HEAD_C2) * 4 +
-                     (fuse ? HEAD_C1 * kFPitch + kHeadWarps * 16 * kFPitch : 0);
+                     (fuse ? HEAD_C1 * kFPitch + kHeadWarps * 16 * kFPitch : 0) + (staged ? kHeadWarps * kGRows * kGPitch : 0);
     static bool configured = false;
     if (!configured) {
-      TEDM_CUDA(cudaFuncSetAttribute(head_tail_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      TEDM_CUDA(cudaFuncSetAttribute(head_tail_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      TEDM_CUDA(cudaFuncSetAttribute(head_tail_mma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024));
+      TEDM_CUDA(cudaFuncSetAttribute(head_tail_mma_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      TEDM_CUDA(cudaFuncSetAttribute(head_tail_mma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024));
+      TEDM_CUDA(cudaFuncSetAttribute(head_tail_mma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024));
+      TEDM_CUDA(cudaFuncSetAttribute(head_tail_mma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024));
       configured = true;
     }
     long long nb = (npix / 16 + kHeadWarps - 1) / kHeadWarps;
-    const long long capm = fuse ? resident_ctas(head_tail_mma_kernel<true>, kHeadWarps * 32, smem)
-                                : resident_ctas(head_tail_mma_kernel<false>, kHeadWarps * 32, smem);
+    const void* kfn = fuse ? (staged ? (const void*)head_tail_mma_kernel<true, true> : (const void*)head_tail_mma_kernel<true, false>)
+                           : (staged ? (const void*)head_tail_mma_kernel<false, true> : (const void*)head_tail_mma_kernel<false, false>);
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kHeadWarps * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const long long capm = (long long)per_sm * tedm_num_sms();
     if (nb > capm) nb = capm;
-    if (fuse) head_tail_mma_kernel<true><<<(int)nb, kHeadWarps * 32, smem, (cudaStream_t)stream>>>(p, full);
-    else head_tail_mma_kernel<false><<<(int)nb, kHeadWarps * 32, smem, (cudaStream_t)stream>>>(p, full);
+    void* kargs[] = {(void*)&p, (void*)&full};
+    TEDM_CUDA(cudaLaunchKernel(kfn, dim3((unsigned)nb), dim3(kHeadWarps * 32), kargs, smem, (cudaStream_t)stream));
     TEDM_LAUNCH_CHECK();
     return TEDM_OK;
   }
