@@ -78,6 +78,11 @@ class UnetEngine:
         self.fold_upsample = fold_upsample
         self.ln_eps = ln_eps
         self.fuse_linear_attention = True
+        # backward: weight gradients run on a side stream next to the data-gradient chain (they only meet in the optimiser);
+        # at the low-resolution levels neither kernel fills the 148 SMs on its own
+        self.overlap_wgrad = True
+        self._side: Optional[torch.cuda.Stream] = None
+        self._keep: list = []
         # every ResnetBlock in execution order, for the batched time projection
         m = unet
         self._resblocks: List[nn.Module] = []
@@ -347,9 +352,19 @@ class UnetEngine:
         cout = conv.weight.shape[0]
         c0 = x0.shape[-1]
         c1 = x1.shape[-1] if x1 is not None else 0
-        N.conv_wgrad(x0, dy, mode, src1=x1, grad_oihw=G.of(conv.weight))
-        if bias_grad and conv.bias is not None:
-            N.bias_grad(dy, G.of(conv.bias))
+        if self.overlap_wgrad:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=dy.device)
+            self._side.wait_stream(torch.cuda.current_stream())          # dy, x0 and the zeroed arena are ready
+            with torch.cuda.stream(self._side):
+                N.conv_wgrad(x0, dy, mode, src1=x1, grad_oihw=G.of(conv.weight))
+                if bias_grad and conv.bias is not None:
+                    N.bias_grad(dy, G.of(conv.bias))
+            self._keep.append((x0, x1, dy))       # freed only after the join: the allocator must not recycle them early
+        else:
+            N.conv_wgrad(x0, dy, mode, src1=x1, grad_oihw=G.of(conv.weight))
+            if bias_grad and conv.bias is not None:
+                N.bias_grad(dy, G.of(conv.bias))
         if not need_dx:
             return None, None
         wd = self._wd(key)
@@ -447,6 +462,9 @@ class UnetEngine:
         N.stem_conv7x7_wgrad(x, dstem, G.of(m.init_conv.weight), G.of(m.init_conv.bias))
         if tproj is not None:
             self._time_bwd(tape, dss, G)
+        if self._side is not None and self._keep:
+            torch.cuda.current_stream().wait_stream(self._side)            # join: every weight gradient has landed
+        self._keep.clear()
         self.last_grad_arena = G
         return G
 
