@@ -71,3 +71,35 @@ def test_schedule_buffers_bit_exact(golden):
         for k, v in m.state_dict().items():
             if not k.startswith("model."):
                 assert np.array_equal(v.numpy(), g[f"{kind}.{k}"]), (kind, k)
+
+
+def test_cli_options_match_reference_defaults():
+    """tedm_b200/config.py keeps the reference's option names and defaults (config.py:13-83; fixture written from the live
+    reference's parser: tests/golden/config_defaults.json), minus the SegDiff / contrastive-only options."""
+    import json
+    from tedm_b200.config import parser
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "config_defaults.json")))
+    ours = {a.dest: a for a in parser._actions}
+    out_of_scope = {"seg_out_dim", "img_out_dim", "img_inter_dim", "tau", "global_model_path", "glob_loc_model_path",
+                    "unfreeze_weights_at_step", "augment_at_finetuning"}
+    for name, spec in ref.items():
+        if name in out_of_scope:
+            continue
+        assert name in ours, f"option --{name} of the reference is missing"
+        d = ours[name].default
+        d = list(d) if isinstance(d, (list, tuple)) else d
+        assert d == spec["default"], (name, d, spec["default"])
+    cfg = parser.parse_args(["--experiment", "TEDM", "--n_labelled_images", "6"])
+    assert cfg.experiment == "TEDM" and cfg.batch_size == 16 and cfg.timesteps == 1000 and cfg.cuda_graph
+
+
+def test_trainers_import_and_refuse_cpu():
+    import torch
+    from tedm_b200.dataloaders.device_loader import DeviceLoader, SyntheticXray
+    from tedm_b200.trainers import train_baseline, train_CXR14, train_datasetDM  # noqa: F401
+    ds = SyntheticXray(4, 32, labelled=True)
+    img, masks = ds[1]
+    assert img.dtype == torch.uint8 and img.shape == (1, 32, 32) and masks.shape == (2, 32, 32)
+    assert torch.equal(ds[1][0], img)                       # deterministic per index
+    with pytest.raises(RuntimeError, match="CUDA"):
+        DeviceLoader(ds, 2, False, 0, device="cpu", labelled=True)
