@@ -119,7 +119,7 @@ def cpu_tedm_images_per_s(n_images: int, repeats: int = 1):
     return n_images / best, best
 
 
-def gpu_eager_baselines(dev, n_images: int = 8):
+def gpu_eager_baselines(dev, n_images: int = 16):
     """the reference's path as plain PyTorch eager ops ON THE SAME GPU (cuDNN / cuBLAS kernels; the
     oracle restatement, since /root/reference is not on the box), fp32 and under autocast(bf16).  A reported baseline
     only -- never part of the product path."""
@@ -132,7 +132,7 @@ def gpu_eager_baselines(dev, n_images: int = 8):
     x0 = synth_batch(n_images, 99).to(dev)
     noises = [torch.randn(n_images, 1, IMG, IMG, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + i))
               for i in range(len(STEPS_TEDM))]
-    out = {"unit": "images/s", "sample": f"{n_images} images x 8 timesteps per pass, 3 timed passes after 2 warm-ups",
+    out = {"unit": "images/s", "sample": f"{n_images} images x 8 timesteps per pass (the batch of the headline run), 3 timed passes after 2 warm-ups",
            "kind": "port (oracle restatement as torch eager CUDA ops)"}
     for name, ctx in (("fp32", contextlib.nullcontext()), ("autocast_bf16", torch.autocast("cuda", dtype=torch.bfloat16))):
         try:

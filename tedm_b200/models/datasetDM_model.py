@@ -75,7 +75,10 @@ class DatasetDM(nn.Module):
         dm = self.diffusion_model
         b, s = x_0.shape[0], len(self.steps)
         x_rep = x_0.detach().float().repeat_interleave(s, dim=0).contiguous()
-        t = torch.tensor(self.steps, device=x_0.device, dtype=torch.long).repeat(b)
+        key = (x_0.device, b, tuple(self.steps))
+        if getattr(self, "_t_key", None) != key:         # device copy of the timestep vector, built once per (device, B)
+            self._t_key, self._t_dev = key, torch.tensor(self.steps, device=x_0.device, dtype=torch.long).repeat(b)
+        t = self._t_dev
         if noise is None:
             nz = torch.randn_like(x_rep)               # a fresh draw per step, as randn_like in the loop does
         else:
