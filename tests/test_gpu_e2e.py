@@ -205,3 +205,23 @@ def test_batched_equals_per_image(ddpm):
         for i in (0, 7, 15):
             one = ddpm.model(x[i:i + 1], t[i:i + 1])
             assert _rel(one, full[i:i + 1]) < 5e-3
+
+
+@pytest.mark.parametrize("size,mults", [(256, (1, 2, 4, 8)), (64, (1, 2, 4, 8)), (128, (1, 2, 4))])
+def test_unet_forward_other_sizes_vs_oracle(size, mults):
+    """`--img_size` / `--dim_mults` other than the defaults (config.py:33,41): 256^2 puts 1024 tokens through the mid
+    attention (flash kernel) and 65536 pixels through the fused LinearAttention chunks; (1,2,4) at 128^2 gives a
+    1024-token mid attention at 512... channels 256.  Inference only (the mid-attention backward handles n <= 256)."""
+    from tedm_b200.models import Unet
+    from tests.golden.synth import synth_images, synth_state_dict, synth_timesteps
+    sd = synth_state_dict(O.unet_param_shapes(dim_mults=mults), 0)
+    m = Unet(64, dim_mults=mults).eval()
+    m.load_state_dict(sd)
+    m.cuda()
+    x, t = synth_images(1, size, 21), synth_timesteps(1, seed=3)
+    with torch.no_grad():
+        got = m(x.cuda(), t.cuda())
+    ref = O.unet_forward(sd, x, t)
+    err = _rel(got, ref)
+    print(f"unet {size}x{size} mults {mults}: rel err {err:.4f}")
+    assert err < TOL, err
