@@ -858,10 +858,112 @@ extern "C" int tedm_final_conv1x1_bwd(const void* h, const float* weight, const 
   return TEDM_OK;
 }
 
+// Tensor-core form for the reference's stem (1 -> 64 channels): D[co][tap] += sum_px dy[px][co] * x[px + tap], an mma.sync
+// GEMM with M = 64 output channels, N = 56 (49 taps, a column of ones that yields the bias gradient, padding) and
+// K = the pixels of one image row.  A = dy^T through ldmatrix.trans from the staged bf16 row; B = the input gathered from
+// a 7-row staging that holds x as bf16 (hi, lo) halves (two MMAs per tile: the fp32 input keeps ~16 mantissa bits).
+#define SWM_XP 272
+__global__ void __launch_bounds__(256) stem_wgrad_mma_kernel(const float* __restrict__ x, const bf16* __restrict__ dy,
+                                                             float* __restrict__ dw, float* __restrict__ db, int batch, int H,
+                                                             int W) {
+  __shared__ __align__(16) uint8_t sdy[256 * 144];                 // [px][64 co] bf16, pitch 144 B
+  __shared__ __align__(16) bf16 xs[(2 * 7 + 2) * SWM_XP];          // hi rows, lo rows, ones row, zero row
+  float (*red)[32][28] = reinterpret_cast<float (*)[32][28]>(sdy);   // [4][32][28], reuses the dy staging after the loop
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3, j = lane >> 3, rr = lane & 7;
+  const int mt = warp & 3, half = warp >> 2;
+  for (int i = tid; i < 2 * SWM_XP; i += 256) xs[14 * SWM_XP + i] = __float2bfloat16_rn(i < SWM_XP ? 1.0f : 0.0f);
+  int koff_hi[7], koff_lo[7];
+#pragma unroll
+  for (int nt = 0; nt < 7; ++nt) {
+    const int tap = nt * 8 + g;
+    if (tap < 49) {
+      koff_hi[nt] = (tap / 7) * SWM_XP + tap % 7;
+      koff_lo[nt] = koff_hi[nt] + 7 * SWM_XP;
+    } else {
+      koff_hi[nt] = (tap == 49 ? 14 : 15) * SWM_XP;
+      koff_lo[nt] = 15 * SWM_XP;
+    }
+  }
+  float acc[7][4];
+#pragma unroll
+  for (int nt = 0; nt < 7; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0f;
+  const uint32_t sdy_u = smem_u32(sdy);
+  const unsigned short* xu = reinterpret_cast<const unsigned short*>(xs);
+  const int ksteps = W / 16, rows = batch * H;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int b = r / H, y = r - b * H;
+    __syncthreads();
+    const bf16* dsrc = dy + (size_t)r * W * 64;
+    for (int i = tid; i < W * 8; i += 256) {
+      const int px = i >> 3, v = i & 7;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdy_u + px * 144 + v * 16), "l"(dsrc + px * 64 + v * 8) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int i = tid; i < 7 * (W + 6); i += 256) {
+      const int ky = i / (W + 6), xi = i - ky * (W + 6);
+      const int yy = y + ky - 3, xx = xi - 3;
+      const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + ((size_t)b * H + yy) * W + xx) : 0.0f;
+      const bf16 hi = __float2bfloat16_rn(v);
+      xs[ky * SWM_XP + xi] = hi;
+      xs[(7 + ky) * SWM_XP + xi] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    for (int ks = half; ks < ksteps; ks += 2) {
+      uint32_t a[4];
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
+                   : "r"(sdy_u + (ks * 16 + (j >> 1) * 8 + rr) * 144 + (mt * 16 + (j & 1) * 8) * 2));
+      const int p0 = ks * 16 + 2 * t4;
+#pragma unroll
+      for (int nt = 0; nt < 7; ++nt) {
+        const unsigned short* ph = xu + koff_hi[nt] + p0;
+        const unsigned short* pl = xu + koff_lo[nt] + p0;
+        const uint32_t h0 = (uint32_t)ph[0] | ((uint32_t)ph[1] << 16), h1 = (uint32_t)ph[8] | ((uint32_t)ph[9] << 16);
+        const uint32_t l0 = (uint32_t)pl[0] | ((uint32_t)pl[1] << 16), l1 = (uint32_t)pl[8] | ((uint32_t)pl[9] << 16);
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(h0), "r"(h1));
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(l0), "r"(l1));
+      }
+    }
+  }
+  // merge the two pixel halves, then one atomic per (co, tap) and CTA
+  __syncthreads();
+  if (half == 1) {
+#pragma unroll
+    for (int nt = 0; nt < 7; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) red[mt][lane][nt * 4 + e] = acc[nt][e];
+  }
+  __syncthreads();
+  if (half == 0) {
+#pragma unroll
+    for (int nt = 0; nt < 7; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float v = acc[nt][e] + red[mt][lane][nt * 4 + e];
+        const int co = mt * 16 + g + (e >> 1) * 8, tap = nt * 8 + 2 * t4 + (e & 1);
+        if (tap < 49) atomicAdd(dw + co * 49 + tap, v);
+        else if (tap == 49 && db) atomicAdd(db + co, v);
+      }
+  }
+}
+
 extern "C" int tedm_stem_conv7x7_wgrad(const float* x, const void* dy, float* dweight, float* dbias, int batch, int cin,
                                        int height, int width, int cout, tedm_stream_t stream) {
   TEDM_CHECK_ARG(x && dy && dweight && batch > 0 && cin > 0 && height > 0 && width > 0, "tedm_stem_conv7x7_wgrad: bad arguments");
   TEDM_UNSUPPORTED(cout % 8 != 0, "tedm_stem_conv7x7_wgrad: cout=%d must be a multiple of 8", cout);
+  if (cin == 1 && cout == 64 && width % 32 == 0 && width <= 256) {   // the reference's stem: tensor-core path
+    int g = tedm_num_sms() * 2;
+    if (g > batch * height) g = batch * height;
+    stem_wgrad_mma_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(x, (const bf16*)dy, dweight, dbias, batch, height, width);
+    TEDM_LAUNCH_CHECK();
+    return TEDM_OK;
+  }
   const long long ntiles = (long long)batch * height * ((width + STW_PX - 1) / STW_PX);
   long long grid = (long long)tedm_num_sms() * 2;
   if (grid > ntiles) grid = ntiles;

@@ -283,9 +283,10 @@ def test_final_conv_bwd():
     assert _rel(db, dout.sum(dim=(0, 2, 3))) < 1e-4
 
 
-def test_stem_wgrad():
+@pytest.mark.parametrize("H,cout", [(64, 64), (128, 64), (48, 64), (32, 32)])
+def test_stem_wgrad(H, cout):
     from tedm_b200 import native as N
-    B, H, cout = 3, 64, 64
+    B = 3
     x = torch.rand((B, 1, H, H), generator=torch.Generator().manual_seed(1)).cuda()
     w = _rand((cout, 1, 7, 7), 2, 0.1).cuda().requires_grad_(True)
     y = F.conv2d(x, w, padding=3)
