@@ -13,10 +13,10 @@
 // The two contractions are 32x32xn / nx32x32 per head: far too small in M for tcgen05 (M >= 64), so
 // they run on the warp-level bf16 tensor-core path (mma.sync m16n8k16) with fp32 accumulation, and
 // the kernels are bound by streaming qkv once from HBM:
-//   K0 colmax : per (image, 1024-pixel chunk) column max of the 128 k channels          (reads k)
-//   K1 ctx    : P = exp(k - max) built in registers from ldmatrix fragments, ctx += P^T v on
-//               tensor cores, s += sum P; one partial per chunk                          (reads k, v)
-//   K2 combine: sum partials, ctx * scale / (s * n) -> bf16 ctx^T                         (tiny)
+//   K1 ctx    : P = exp(k - m) built in registers from ldmatrix fragments with an ONLINE running column maximum m
+//               (no max pre-pass), ctx += P^T v on tensor cores, s += sum P; one partial (m, s, ctx) per chunk
+//                                                                                        (reads k, v once)
+//   K2 combine: merge the partials with exp(m_c - max_c m_c), ctx * scale / (s * n) -> bf16 ctx^T   (tiny)
 //   K3 out    : per 64-pixel tile: softmax over each head's 32 q channels in fragment layout,
 //               out = softmax(q) ctx on tensor cores, coalesced bf16 store                (reads q)
 // ------------------------------------------------------------------------------------------
@@ -49,49 +49,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// K0: partial column maxima of k.  thread = (16-byte channel vector, pixel lane)
-__global__ void __launch_bounds__(256) linattn_colmax_kernel(const bf16* __restrict__ qkv, float* __restrict__ pmax, int n,
-                                                             int nchunks) {
-  __shared__ float red[16][LA_C];
-  const int chunk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-  const int vec = tid & 15, pl = tid >> 4;
-  const int p0 = chunk * LA_CHUNK, p1 = min(n, p0 + LA_CHUNK);
-  float m[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
-  for (int px = p0 + pl; px < p1; px += 16) {
-    float f[8];
-    unpack8(ldg_stream(qkv + ((size_t)b * n + px) * (3 * LA_C) + LA_C + vec * 8), f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) red[pl][vec * 8 + j] = m[j];
-  __syncthreads();
-  if (tid < LA_C) {
-    float v = red[0][tid];
-#pragma unroll
-    for (int i = 1; i < 16; ++i) v = fmaxf(v, red[i][tid]);
-    pmax[((size_t)b * nchunks + chunk) * LA_C + tid] = v;
-  }
-}
-
 // K1: per (image, chunk): s[c] = sum_px exp(k - M), ctx[h][d][e] = sum_px exp(k[px][h,d] - M) v[px][h,e]
-__global__ void __launch_bounds__(256) linattn_ctx_kernel(const bf16* __restrict__ qkv, const float* __restrict__ pmax,
+__global__ void __launch_bounds__(256) linattn_ctx_kernel(const bf16* __restrict__ qkv, float* __restrict__ pmax,
                                                           float* __restrict__ part, int n, int nchunks) {
   extern __shared__ __align__(16) uint8_t la_smem[];
-  __shared__ float sM[LA_C];
   const int chunk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int p0 = chunk * LA_CHUNK, p1 = min(n, p0 + LA_CHUNK);
   const int nsub = (p1 - p0 + LA_SUB - 1) / LA_SUB;
   const uint32_t tile0 = smem_u32(la_smem);
   constexpr int TILE_BYTES = LA_SUB * LA_KV_PITCH;
-
-  if (tid < LA_C) {
-    float m = -INFINITY;
-    for (int c = 0; c < nchunks; ++c) m = fmaxf(m, pmax[((size_t)b * nchunks + c) * LA_C + tid]);
-    sM[tid] = m;
-  }
 
   auto load_sub = [&](int sub, int buf) {
     const int base_px = p0 + sub * LA_SUB;
@@ -123,13 +89,9 @@ __global__ void __launch_bounds__(256) linattn_ctx_kernel(const bf16* __restrict
 
   load_sub(0, 0);
   cp_async_commit();
-  __syncthreads();  // sM visible
-  float Mrow[2][2];
+  float Mrow[2][2];   // running column maxima (online softmax over the pixels): k is read ONCE, there is no max pre-pass
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
-    Mrow[mt][0] = sM[h * DH + mt * 16 + g];
-    Mrow[mt][1] = sM[h * DH + mt * 16 + g + 8];
-  }
+  for (int mt = 0; mt < 2; ++mt) Mrow[mt][0] = Mrow[mt][1] = -INFINITY;
 
   for (int sub = 0; sub < nsub; ++sub) {
     const int buf = sub & 1;
@@ -143,21 +105,59 @@ __global__ void __launch_bounds__(256) linattn_ctx_kernel(const bf16* __restrict
     __syncthreads();
     const uint32_t tile = tile0 + buf * TILE_BYTES;
     const int j = lane >> 3, rr = lane & 7;
+    // the slice's 32 pixels of k^T as A fragments, their column maxima, the rescale of what was accumulated so far
+    uint32_t a[2][2][4];
+    float tmax[2][2] = {{-INFINITY, -INFINITY}, {-INFINITY, -INFINITY}};
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int px = slice * 32 + ks * 16 + (j >> 1) * 8 + rr, dcol = h * DH + mt * 16 + (j & 1) * 8;
+        ldsm_x4_trans(tile + px * LA_KV_PITCH + dcol * 2, a[ks][mt]);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float2 kv = unpack_bf16x2(a[ks][mt][r]);
+          tmax[mt][r & 1] = fmaxf(tmax[mt][r & 1], fmaxf(kv.x, kv.y));
+        }
+      }
+    float corr[2][2];
+    bool moved = false;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float t = tmax[mt][r];
+        t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 1));
+        t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 2));
+        const float mn = fmaxf(Mrow[mt][r], t);
+        corr[mt][r] = mn == -INFINITY ? 1.0f : __expf(Mrow[mt][r] - mn);   // an all-padding slice leaves -inf in place
+        moved = moved || corr[mt][r] != 1.0f;
+        Mrow[mt][r] = mn;
+        ssum[mt][r] *= corr[mt][r];
+      }
+    if (__any_sync(0xffffffffu, moved)) {
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          acc[mt][nt][0] *= corr[mt][0];
+          acc[mt][nt][1] *= corr[mt][0];
+          acc[mt][nt][2] *= corr[mt][1];
+          acc[mt][nt][3] *= corr[mt][1];
+        }
+    }
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
       const int k0 = slice * 32 + ks * 16;
-      uint32_t a[2][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        const int px = k0 + (j >> 1) * 8 + rr, dcol = h * DH + mt * 16 + (j & 1) * 8;
-        ldsm_x4_trans(tile + px * LA_KV_PITCH + dcol * 2, a[mt]);
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          const float2 kv = unpack_bf16x2(a[mt][r]);
-          const float mm = Mrow[mt][r & 1];
+          const float2 kv = unpack_bf16x2(a[ks][mt][r]);
+          const float mm = Mrow[mt][r & 1] == -INFINITY ? 0.0f : Mrow[mt][r & 1];   // all-padding slice: exp(-inf) = 0
           const float e0 = __expf(kv.x - mm), e1 = __expf(kv.y - mm);
           ssum[mt][r & 1] += e0 + e1;
-          a[mt][r] = pack_bf16x2(e0, e1);
+          a[ks][mt][r] = pack_bf16x2(e0, e1);
         }
       }
       uint32_t bfr[2][4];
@@ -169,7 +169,8 @@ __global__ void __launch_bounds__(256) linattn_ctx_kernel(const bf16* __restrict
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[mt][nt], a[mt], bfr[nt >> 1][(nt & 1) * 2], bfr[nt >> 1][(nt & 1) * 2 + 1]);
+        for (int nt = 0; nt < 4; ++nt)
+          mma_bf16_16816(acc[mt][nt], a[ks][mt], bfr[nt >> 1][(nt & 1) * 2], bfr[nt >> 1][(nt & 1) * 2 + 1]);
     }
     __syncthreads();  // the buffer is refilled by the next iteration's prefetch
   }
@@ -181,10 +182,11 @@ __global__ void __launch_bounds__(256) linattn_ctx_kernel(const bf16* __restrict
       ssum[mt][r] += __shfl_xor_sync(0xffffffffu, ssum[mt][r], 1);
       ssum[mt][r] += __shfl_xor_sync(0xffffffffu, ssum[mt][r], 2);
     }
-  // merge the two pixel slices through shared memory, then write the chunk partial
-  float* red = reinterpret_cast<float*>(la_smem);  // [4 heads][32 lanes][36]
+  // merge the two pixel slices (their running maxima differ) through shared memory, then write the chunk partial:
+  // pmax[chunk][c] = the chunk's column maximum, part[chunk] = (s, ctx) relative to THAT maximum
+  float* red = reinterpret_cast<float*>(la_smem);  // [4 heads][32 lanes][40]
   if (slice == 1) {
-    float* r = red + (h * 32 + lane) * 36;
+    float* r = red + (h * 32 + lane) * 40;
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
@@ -193,46 +195,58 @@ __global__ void __launch_bounds__(256) linattn_ctx_kernel(const bf16* __restrict
         for (int e = 0; e < 4; ++e) r[(mt * 4 + nt) * 4 + e] = acc[mt][nt][e];
       r[32 + mt * 2] = ssum[mt][0];
       r[32 + mt * 2 + 1] = ssum[mt][1];
+      r[36 + mt * 2] = Mrow[mt][0];
+      r[36 + mt * 2 + 1] = Mrow[mt][1];
     }
   }
   __syncthreads();
   if (slice == 0) {
-    const float* r = red + (h * 32 + lane) * 36;
+    const float* r = red + (h * 32 + lane) * 40;
     float* dst = part + ((size_t)b * nchunks + chunk) * LA_PART;
+    float* mdst = pmax + ((size_t)b * nchunks + chunk) * LA_C;
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      const int d_lo = h * DH + mt * 16 + g, d_hi = d_lo + 8;
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int e = nt * 8 + 2 * t4;
-        const float* rr2 = r + (mt * 4 + nt) * 4;
-        *reinterpret_cast<float2*>(dst + LA_C + (size_t)d_lo * DH + e) = make_float2(acc[mt][nt][0] + rr2[0], acc[mt][nt][1] + rr2[1]);
-        *reinterpret_cast<float2*>(dst + LA_C + (size_t)d_hi * DH + e) = make_float2(acc[mt][nt][2] + rr2[2], acc[mt][nt][3] + rr2[3]);
+      for (int q = 0; q < 2; ++q) {
+        const float m1 = r[36 + mt * 2 + q];
+        const float M = fmaxf(Mrow[mt][q], m1);
+        const float f0 = Mrow[mt][q] == -INFINITY ? 0.0f : __expf(Mrow[mt][q] - M);
+        const float f1 = m1 == -INFINITY ? 0.0f : __expf(m1 - M);
+        const int d = h * DH + mt * 16 + g + q * 8;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const float* rr2 = r + (mt * 4 + nt) * 4 + 2 * q;
+          *reinterpret_cast<float2*>(dst + LA_C + (size_t)d * DH + nt * 8 + 2 * t4) =
+              make_float2(acc[mt][nt][2 * q] * f0 + rr2[0] * f1, acc[mt][nt][2 * q + 1] * f0 + rr2[1] * f1);
+        }
+        if (t4 == 0) {
+          mdst[d] = M;
+          dst[d] = ssum[mt][q] * f0 + r[32 + mt * 2 + q] * f1;
+        }
       }
-      if (t4 == 0) {
-        dst[d_lo] = ssum[mt][0] + r[32 + mt * 2];
-        dst[d_hi] = ssum[mt][1] + r[32 + mt * 2 + 1];
-      }
-    }
   }
 }
 
 // K2: ctxT[b][h][e][d] = bf16( scale * sum_c ctx_c[h][d][e] / (n * sum_c s_c[h][d]) )
-__global__ void __launch_bounds__(256) linattn_combine_kernel(const float* __restrict__ part, bf16* __restrict__ ctxT, int n,
-                                                              int nchunks, float scale) {
-  __shared__ float sS[LA_C];
+__global__ void __launch_bounds__(256) linattn_combine_kernel(const float* __restrict__ pmax, const float* __restrict__ part,
+                                                              bf16* __restrict__ ctxT, int n, int nchunks, float scale) {
+  __shared__ float sS[LA_C], sMx[LA_C];
   const int b = blockIdx.x, tid = threadIdx.x;
   const float* p = part + (size_t)b * nchunks * LA_PART;
+  const float* pm = pmax + (size_t)b * nchunks * LA_C;
   if (tid < LA_C) {
+    float M = -INFINITY;
+    for (int c = 0; c < nchunks; ++c) M = fmaxf(M, pm[(size_t)c * LA_C + tid]);
     float s = 0.0f;
-    for (int c = 0; c < nchunks; ++c) s += p[(size_t)c * LA_PART + tid];
+    for (int c = 0; c < nchunks; ++c) s += __expf(pm[(size_t)c * LA_C + tid] - M) * p[(size_t)c * LA_PART + tid];
+    sMx[tid] = M;
     sS[tid] = s;
   }
   __syncthreads();
   for (int idx = tid; idx < LA_C * DH; idx += 256) {
     const int hd = idx >> 5, e = idx & 31;  // hd = h*32 + d
     float acc = 0.0f;
-    for (int c = 0; c < nchunks; ++c) acc += p[(size_t)c * LA_PART + LA_C + idx];
+    for (int c = 0; c < nchunks; ++c) acc += __expf(pm[(size_t)c * LA_C + hd] - sMx[hd]) * p[(size_t)c * LA_PART + LA_C + idx];
     const int h = hd >> 5, d = hd & 31;
     ctxT[(((size_t)b * LA_HEADS + h) * DH + e) * DH + d] = __float2bfloat16_rn(acc * scale / (sS[hd] * (float)n));
   }
@@ -355,11 +369,9 @@ extern "C" int tedm_linear_attention_fwd(const void* qkv, void* out, float* work
     TEDM_CUDA(cudaFuncSetAttribute(linattn_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  linattn_colmax_kernel<<<dim3(nchunks, batch), 256, 0, s>>>((const bf16*)qkv, pmax, n, nchunks);
-  TEDM_LAUNCH_CHECK();
   linattn_ctx_kernel<<<dim3(nchunks, batch), 256, smem, s>>>((const bf16*)qkv, pmax, part, n, nchunks);
   TEDM_LAUNCH_CHECK();
-  linattn_combine_kernel<<<batch, 256, 0, s>>>(part, ctxT, n, nchunks, scale);
+  linattn_combine_kernel<<<batch, 256, 0, s>>>(pmax, part, ctxT, n, nchunks, scale);
   TEDM_LAUNCH_CHECK();
   linattn_out_kernel<<<dim3((n + LA_SUB - 1) / LA_SUB, batch), 256, 0, s>>>((const bf16*)qkv, ctxT, (bf16*)out, n);
   TEDM_LAUNCH_CHECK();

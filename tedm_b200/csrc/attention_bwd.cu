@@ -93,21 +93,22 @@ __global__ void __launch_bounds__(256) linattn_bwd_prep_kernel(const float* __re
   const float* part = fwd_ws + (size_t)batch * nchunks * LA_C + (size_t)b * nchunks * LA_PART;
   float* w = ws + (size_t)b * ws_stride;
   bf16* cbf = reinterpret_cast<bf16*>(w + LAB_BF_OFF);
-  if (tid < LA_C) {
+  __shared__ float sMx[LA_C];
+  if (tid < LA_C) {   // the forward's partials are relative to their own chunk maxima: merge with exp(m_c - M)
     float m = -INFINITY, s = 0.0f;
-    for (int c = 0; c < nchunks; ++c) {
-      m = fmaxf(m, pmax[(size_t)c * LA_C + tid]);
-      s += part[(size_t)c * LA_PART + tid];
-    }
+    for (int c = 0; c < nchunks; ++c) m = fmaxf(m, pmax[(size_t)c * LA_C + tid]);
+    for (int c = 0; c < nchunks; ++c) s += __expf(pmax[(size_t)c * LA_C + tid] - m) * part[(size_t)c * LA_PART + tid];
     w[tid] = m;
     w[LA_C + tid] = s;
     sS[tid] = s;
+    sMx[tid] = m;
   }
   __syncthreads();
   for (int idx = tid; idx < LAB_MAT; idx += 256) {
     float acc = 0.0f;
-    for (int c = 0; c < nchunks; ++c) acc += part[(size_t)c * LA_PART + LA_C + idx];
-    const float v = acc / (sS[idx >> 5] * (float)n);
+    const int hd = idx >> 5;
+    for (int c = 0; c < nchunks; ++c) acc += __expf(pmax[(size_t)c * LA_C + hd] - sMx[hd]) * part[(size_t)c * LA_PART + LA_C + idx];
+    const float v = acc / (sS[hd] * (float)n);
     w[3 * LA_C + idx] = v;
     cbf[idx] = __float2bfloat16_rn(v);
   }
