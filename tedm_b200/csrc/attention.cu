@@ -230,25 +230,25 @@ __global__ void __launch_bounds__(256) linattn_ctx_kernel(const bf16* __restrict
 // K2: ctxT[b][h][e][d] = bf16( scale * sum_c ctx_c[h][d][e] / (n * sum_c s_c[h][d]) )
 __global__ void __launch_bounds__(256) linattn_combine_kernel(const float* __restrict__ pmax, const float* __restrict__ part,
                                                               bf16* __restrict__ ctxT, int n, int nchunks, float scale) {
-  __shared__ float sS[LA_C], sMx[LA_C];
-  const int b = blockIdx.x, tid = threadIdx.x;
+  __shared__ float sS[DH], sMx[DH];
+  const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;   // one CTA per (image, head): 4x the parallelism of per-image
   const float* p = part + (size_t)b * nchunks * LA_PART;
   const float* pm = pmax + (size_t)b * nchunks * LA_C;
-  if (tid < LA_C) {
+  if (tid < DH) {
+    const int hd = h * DH + tid;
     float M = -INFINITY;
-    for (int c = 0; c < nchunks; ++c) M = fmaxf(M, pm[(size_t)c * LA_C + tid]);
+    for (int c = 0; c < nchunks; ++c) M = fmaxf(M, pm[(size_t)c * LA_C + hd]);
     float s = 0.0f;
-    for (int c = 0; c < nchunks; ++c) s += __expf(pm[(size_t)c * LA_C + tid] - M) * p[(size_t)c * LA_PART + tid];
+    for (int c = 0; c < nchunks; ++c) s += __expf(pm[(size_t)c * LA_C + hd] - M) * p[(size_t)c * LA_PART + hd];
     sMx[tid] = M;
     sS[tid] = s;
   }
   __syncthreads();
-  for (int idx = tid; idx < LA_C * DH; idx += 256) {
-    const int hd = idx >> 5, e = idx & 31;  // hd = h*32 + d
+  for (int li = tid; li < DH * DH; li += 256) {
+    const int d = li >> 5, e = li & 31, hd = h * DH + d, idx = hd * DH + e;
     float acc = 0.0f;
-    for (int c = 0; c < nchunks; ++c) acc += __expf(pm[(size_t)c * LA_C + hd] - sMx[hd]) * p[(size_t)c * LA_PART + LA_C + idx];
-    const int h = hd >> 5, d = hd & 31;
-    ctxT[(((size_t)b * LA_HEADS + h) * DH + e) * DH + d] = __float2bfloat16_rn(acc * scale / (sS[hd] * (float)n));
+    for (int c = 0; c < nchunks; ++c) acc += __expf(pm[(size_t)c * LA_C + hd] - sMx[d]) * p[(size_t)c * LA_PART + LA_C + idx];
+    ctxT[(((size_t)b * LA_HEADS + h) * DH + e) * DH + d] = __float2bfloat16_rn(acc * scale / (sS[d] * (float)n));
   }
 }
 
@@ -371,7 +371,7 @@ extern "C" int tedm_linear_attention_fwd(const void* qkv, void* out, float* work
   }
   linattn_ctx_kernel<<<dim3(nchunks, batch), 256, smem, s>>>((const bf16*)qkv, pmax, part, n, nchunks);
   TEDM_LAUNCH_CHECK();
-  linattn_combine_kernel<<<batch, 256, 0, s>>>(pmax, part, ctxT, n, nchunks, scale);
+  linattn_combine_kernel<<<dim3(batch, LA_HEADS), 256, 0, s>>>(pmax, part, ctxT, n, nchunks, scale);
   TEDM_LAUNCH_CHECK();
   linattn_out_kernel<<<dim3((n + LA_SUB - 1) / LA_SUB, batch), 256, 0, s>>>((const bf16*)qkv, ctxT, (bf16*)out, n);
   TEDM_LAUNCH_CHECK();

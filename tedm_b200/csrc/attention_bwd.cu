@@ -87,28 +87,28 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // K-prep: fold the forward's per-chunk partials into M, S and the normalised context (fp32 and bf16)
 __global__ void __launch_bounds__(256) linattn_bwd_prep_kernel(const float* __restrict__ fwd_ws, float* __restrict__ ws, int batch,
                                                                int n, int nchunks, long long ws_stride) {
-  __shared__ float sS[LA_C];
-  const int b = blockIdx.x, tid = threadIdx.x;
+  __shared__ float sS[DH], sMx[DH];
+  const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;   // one CTA per (image, head)
   const float* pmax = fwd_ws + (size_t)b * nchunks * LA_C;
   const float* part = fwd_ws + (size_t)batch * nchunks * LA_C + (size_t)b * nchunks * LA_PART;
   float* w = ws + (size_t)b * ws_stride;
   bf16* cbf = reinterpret_cast<bf16*>(w + LAB_BF_OFF);
-  __shared__ float sMx[LA_C];
-  if (tid < LA_C) {   // the forward's partials are relative to their own chunk maxima: merge with exp(m_c - M)
+  if (tid < DH) {     // the forward's partials are relative to their own chunk maxima: merge with exp(m_c - M)
+    const int hd = h * DH + tid;
     float m = -INFINITY, s = 0.0f;
-    for (int c = 0; c < nchunks; ++c) m = fmaxf(m, pmax[(size_t)c * LA_C + tid]);
-    for (int c = 0; c < nchunks; ++c) s += __expf(pmax[(size_t)c * LA_C + tid] - m) * part[(size_t)c * LA_PART + tid];
-    w[tid] = m;
-    w[LA_C + tid] = s;
+    for (int c = 0; c < nchunks; ++c) m = fmaxf(m, pmax[(size_t)c * LA_C + hd]);
+    for (int c = 0; c < nchunks; ++c) s += __expf(pmax[(size_t)c * LA_C + hd] - m) * part[(size_t)c * LA_PART + hd];
+    w[hd] = m;
+    w[LA_C + hd] = s;
     sS[tid] = s;
     sMx[tid] = m;
   }
   __syncthreads();
-  for (int idx = tid; idx < LAB_MAT; idx += 256) {
+  for (int li = tid; li < DH * DH; li += 256) {
+    const int d = li >> 5, hd = h * DH + d, idx = h * DH * DH + li;
     float acc = 0.0f;
-    const int hd = idx >> 5;
-    for (int c = 0; c < nchunks; ++c) acc += __expf(pmax[(size_t)c * LA_C + hd] - sMx[hd]) * part[(size_t)c * LA_PART + LA_C + idx];
-    const float v = acc / (sS[hd] * (float)n);
+    for (int c = 0; c < nchunks; ++c) acc += __expf(pmax[(size_t)c * LA_C + hd] - sMx[d]) * part[(size_t)c * LA_PART + LA_C + idx];
+    const float v = acc / (sS[d] * (float)n);
     w[3 * LA_C + idx] = v;
     cbf[idx] = __float2bfloat16_rn(v);
   }
@@ -239,26 +239,27 @@ __global__ void __launch_bounds__(256) linattn_bwd_dctx_kernel(const bf16* __res
 // K-C: dC = scale * sum of chunk partials (fp32, bf16, bf16 transposed) ; r[d] = sum_e dC[d][e] C[d][e]
 __global__ void __launch_bounds__(256) linattn_bwd_combine_kernel(float* __restrict__ ws, int nchunks, float scale,
                                                                   long long ws_stride) {
-  __shared__ float sprod[LAB_MAT];
+  __shared__ float sprod[DH * DH];
   float* w = ws + (size_t)blockIdx.x * ws_stride;
   bf16* dcbf = reinterpret_cast<bf16*>(w + LAB_BF_OFF) + LAB_MAT;
   bf16* dctbf = dcbf + LAB_MAT;
-  const int tid = threadIdx.x;
-  for (int idx = tid; idx < LAB_MAT; idx += 256) {
+  const int tid = threadIdx.x, hh = blockIdx.y;                  // one CTA per (image, head)
+  for (int li = tid; li < DH * DH; li += 256) {
+    const int idx = hh * DH * DH + li;
     float acc = 0.0f;
     for (int c = 0; c < nchunks; ++c) acc += w[LAB_WS_FIXED + (size_t)c * LAB_MAT + idx];
     acc *= scale;
     w[3 * LA_C + LAB_MAT + idx] = acc;
-    sprod[idx] = acc * w[3 * LA_C + idx];
-    const int hd = idx >> 5, e = idx & 31, hh = hd >> 5, d = hd & 31;
+    sprod[li] = acc * w[3 * LA_C + idx];
+    const int d = li >> 5, e = li & 31;
     dcbf[idx] = __float2bfloat16_rn(acc);
     dctbf[(hh * DH + e) * DH + d] = __float2bfloat16_rn(acc);
   }
   __syncthreads();
-  if (tid < LA_C) {
+  if (tid < DH) {
     float r = 0.0f;
     for (int e = 0; e < DH; ++e) r += sprod[tid * DH + e];
-    w[2 * LA_C + tid] = r;
+    w[2 * LA_C + hh * DH + tid] = r;
   }
 }
 
@@ -681,12 +682,12 @@ extern "C" int tedm_linear_attention_bwd(const void* qkv, const void* dout, cons
     TEDM_CUDA(cudaFuncSetAttribute(linattn_bwd_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b));
     configured = true;
   }
-  linattn_bwd_prep_kernel<<<batch, 256, 0, s>>>(fwd_workspace, workspace, batch, n, nchunks, ws_stride);
+  linattn_bwd_prep_kernel<<<dim3(batch, LA_HEADS), 256, 0, s>>>(fwd_workspace, workspace, batch, n, nchunks, ws_stride);
   TEDM_LAUNCH_CHECK();
   linattn_bwd_dctx_kernel<<<dim3(nchunks, batch), 256, smem_a, s>>>((const bf16*)qkv, (const bf16*)dout, workspace, n, nchunks,
                                                                     ws_stride);
   TEDM_LAUNCH_CHECK();
-  linattn_bwd_combine_kernel<<<batch, 256, 0, s>>>(workspace, nchunks, scale, ws_stride);
+  linattn_bwd_combine_kernel<<<dim3(batch, LA_HEADS), 256, 0, s>>>(workspace, nchunks, scale, ws_stride);
   TEDM_LAUNCH_CHECK();
   linattn_bwd_main_kernel<<<dim3((n + LAB_TILE - 1) / LAB_TILE, batch), 256, smem_b, s>>>(
       (const bf16*)qkv, (const bf16*)dout, workspace, (bf16*)dqkv, n, scale, ws_stride);

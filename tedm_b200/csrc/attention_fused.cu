@@ -287,24 +287,24 @@ __global__ void __launch_bounds__(256, 2) linattn_fused_ctx_kernel(const bf16* _
 // K-C: ctxT[b][h][e][d] = bf16( scale * sum_p w_p ctx_p[h][d][e] / (n * sum_p w_p s_p[h][d]) ),  w_p = exp(m_p - max_p m_p)
 __global__ void __launch_bounds__(256) linattn_fused_combine_kernel(const float* __restrict__ part, bf16* __restrict__ ctxT,
                                                                     int n, int nchunks, float scale) {
-  __shared__ float sM[kHid], sS[kHid];
-  const int b = blockIdx.x, tid = threadIdx.x;
+  __shared__ float sM[kDh], sS[kDh];
+  const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;   // one CTA per (image, head)
   const float* p = part + (size_t)b * nchunks * kPart;
-  if (tid < kHid) {
+  if (tid < kDh) {
+    const int hd = h * kDh + tid;
     float M = -INFINITY;
-    for (int c = 0; c < nchunks; ++c) M = fmaxf(M, p[(size_t)c * kPart + tid]);
+    for (int c = 0; c < nchunks; ++c) M = fmaxf(M, p[(size_t)c * kPart + hd]);
     float s = 0.0f;
-    for (int c = 0; c < nchunks; ++c) s += __expf(p[(size_t)c * kPart + tid] - M) * p[(size_t)c * kPart + kHid + tid];
+    for (int c = 0; c < nchunks; ++c) s += __expf(p[(size_t)c * kPart + hd] - M) * p[(size_t)c * kPart + kHid + hd];
     sM[tid] = M;
     sS[tid] = s;
   }
   __syncthreads();
-  for (int idx = tid; idx < kHid * kDh; idx += 256) {
-    const int hd = idx >> 5, e = idx & 31;
+  for (int li = tid; li < kDh * kDh; li += 256) {
+    const int d = li >> 5, e = li & 31, hd = h * kDh + d;
     float acc = 0.0f;
-    for (int c = 0; c < nchunks; ++c) acc += __expf(p[(size_t)c * kPart + hd] - sM[hd]) * p[(size_t)c * kPart + 2 * kHid + idx];
-    const int h = hd >> 5, d = hd & 31;
-    ctxT[(((size_t)b * kHeads + h) * kDh + e) * kDh + d] = __float2bfloat16_rn(acc * scale / (sS[hd] * (float)n));
+    for (int c = 0; c < nchunks; ++c) acc += __expf(p[(size_t)c * kPart + hd] - sM[d]) * p[(size_t)c * kPart + 2 * kHid + hd * kDh + e];
+    ctxT[(((size_t)b * kHeads + h) * kDh + e) * kDh + d] = __float2bfloat16_rn(acc * scale / (sS[d] * (float)n));
   }
 }
 
@@ -542,7 +542,7 @@ int launch_fused(const bf16* x, const bf16* wqkv, const float* g_pre, const bf16
   }
   linattn_fused_ctx_kernel<C><<<dim3(nchunks, batch), 256, smem_a, s>>>(x, wqkv, g_pre, part, n, nchunks, eps);
   TEDM_LAUNCH_CHECK();
-  linattn_fused_combine_kernel<<<batch, 256, 0, s>>>(part, ctxT, n, nchunks, scale);
+  linattn_fused_combine_kernel<<<dim3(batch, kHeads), 256, 0, s>>>(part, ctxT, n, nchunks, scale);
   TEDM_LAUNCH_CHECK();
   linattn_fused_out_kernel<C, MT><<<dim3((n + kChunkB - 1) / kChunkB, batch), kWarpsB * 32, smem_b, s>>>(
       x, wqkv, wout, g_pre, b_out, g_out, ctxT, out, n, eps);
