@@ -177,6 +177,54 @@ def sampler_leg(dev, batch: int = 64, steps: int = 20):
             "tflops_unet_fwd": batch * GFLOP_UNET_FWD / ms, "finite": bool(torch.isfinite(img).all())}
 
 
+def head_train_leg(dev, batch: int = 16, steps: int = 5):
+    """BASELINE configs[2]: LEDM (steps [50,150,250], 2880-input head) and TEDM (8 steps, shared 960-input head) head
+    training on JSRT-shaped synthetic pairs: frozen-UNet features + head forward / BCE / backward / Adam per step, through
+    the trainer's own loop body (tedm_b200/trainers/train_baseline.py)."""
+    import torch
+    from argparse import Namespace
+    from tedm_b200.autograd import bce_with_logits_rows
+    from tedm_b200.models import DatasetDM, tedm_classifier
+    from tedm_b200.optim import FusedAdam
+    out = {"workload": "ledm_tedm_head_training_step", "batch_per_gpu": batch, "unit": "images/s"}
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(batch, 1, IMG, IMG, generator=g).to(dev)
+    y = (torch.rand(batch, 1, IMG, IMG, generator=g) > 0.5).float().to(dev)
+    for name, t_steps, shared in (("LEDM", [50, 150, 250], False), ("TEDM", STEPS_TEDM, True)):
+        torch.manual_seed(3)
+        m = DatasetDM(Namespace(normalize=True, saved_diffusion_model="", t_steps_to_save=t_steps))
+        if shared:
+            m.classifier = tedm_classifier(len(t_steps))
+        m = m.to(dev).train()
+        m.diffusion_model.eval()
+        opt = FusedAdam(m.classifier.parameters(), lr=1e-4)
+
+        def step():
+            opt.zero_grad()
+            loss = bce_with_logits_rows(m(x), y).mean()
+            loss.backward()
+            opt.step()
+            return loss
+
+        for _ in range(5):
+            step()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(max(steps, 5))]
+        for a, b in evs:                   # per-step events, median: one-off allocator / GC hiccups do not count
+            a.record()
+            loss = step()
+            b.record()
+        torch.cuda.synchronize()
+        ms = sorted(a.elapsed_time(b) for a, b in evs)[len(evs) // 2]
+        out[name] = {"t_steps": len(t_steps), "ms_per_step": ms, "images_per_s": batch / (ms * 1e-3),
+                     "unet_forwards_per_s": batch * len(t_steps) / (ms * 1e-3), "loss_last": float(loss)}
+        del m, opt
+        import gc
+        gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
 def cpu_train_images_per_s(n_images: int):
     """The reference's training step (train_step + backward, trainers/train_CXR14.py:30-40) as the oracle port runs it
     on the host cores: fp32 torch autograd through oracle.ddpm_loss."""
@@ -367,6 +415,7 @@ def run_ours(args):
         line["train"] = train_leg(args, dev, world, rank, pk, barrier)
         if rank == 0 and world == 1:
             line["sampler"] = sampler_leg(dev)
+            line["head_train"] = head_train_leg(dev)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["gpu_eager_baseline"] = gpu_eager_baselines(dev)
