@@ -510,7 +510,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step (config.py:58 default 16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the DDPM training-step leg")
-    ap.add_argument("--train-batches", type=int, nargs="+", default=[16, 64],
+    ap.add_argument("--train-batches", type=int, nargs="+", default=[16, 64, 128],
                     help="per-GPU batch sizes of the training leg (config.py:58 default is 16)")
     args = ap.parse_args()
     if args.impl == "reference":
