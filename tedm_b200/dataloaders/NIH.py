@@ -1,0 +1,33 @@
+"""NIH chest-X-ray pairs used as an external test set (reference: dataloaders/NIH.py:14-50): one lung mask per image.
+uint8 planes until on the GPU, like JSRT."""
+from __future__ import annotations
+
+import os
+from pathlib import Path
+from typing import Tuple
+
+import numpy as np
+import torch
+from torch import Tensor
+from torch.utils.data import Dataset
+
+from .device_loader import read_csv_columns
+
+
+class NIHDataset(Dataset):
+    def __init__(self, base_path, csv_path, csv_name: str, img_size: int = 128, **kwargs) -> None:
+        cols = read_csv_columns(os.path.join(csv_path, csv_name), ("scan", "mask"))
+        self.scans, self.masks = cols["scan"], cols["mask"]
+        self.base_path = Path(base_path)
+        self.img_size = img_size
+
+    def _load_u8(self, fname) -> Tensor:
+        from PIL import Image
+        img = Image.open(self.base_path / fname).convert("L").resize((self.img_size, self.img_size))
+        return torch.from_numpy(np.asarray(img, dtype=np.uint8).copy())
+
+    def __getitem__(self, index: int) -> Tuple[Tensor, Tensor]:
+        return self._load_u8(self.scans[index])[None], self._load_u8(self.masks[index])[None]     # (1,S,S), (K=1,S,S)
+
+    def __len__(self) -> int:
+        return len(self.scans)

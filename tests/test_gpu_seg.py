@@ -252,3 +252,21 @@ def test_val_step_and_sampling_driver():
     assert final.min() >= -1e-6 and final.max() <= 1 + 1e-6      # dynamic thresholding keeps x in [-1, 1] -> [0, 1]
     grid = sample_plot_image(m, 40, 64, 2, normalized=True)
     assert grid.shape == (2, 3, 2 * 66 + 2, 4 * 66 + 2)
+
+
+def test_train_then_evaluate_cli(tmp_path):
+    """`train.py --experiment TEDM` writes a checkpoint in the reference's format; `python -m tedm_b200.evaluate -e <dir>`
+    (the reference's testing_shared_weights.py) reloads it and reports per-timestep + ensemble metrics."""
+    run = tmp_path / "run"
+    cmd = [sys.executable, os.path.join(ROOT, "train.py"), "--experiment", "TEDM", "--dataset", "synthetic", "--batch_size", "2",
+           "--log_dir", str(run), "--n_labelled_images", "6", "--max_steps", "3", "--val_freq", "3", "--log_freq", "1",
+           "--max_val_steps", "1", "--saved_diffusion_model", "/nonexistent"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    exp = tmp_path / "TEDM" / "6" / "run"
+    assert (exp / "best_model.pt").exists(), r.stdout[-2000:]
+    r = subprocess.run([sys.executable, "-m", "tedm_b200.evaluate", "-e", str(exp)], capture_output=True, text=True,
+                       timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "synthetic_val 800 metrics" in r.stdout and "synthetic_test metrics" in r.stdout, r.stdout[-2000:]
+    assert (exp / "synthetic_val_metrics.pt").exists()
