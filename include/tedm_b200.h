@@ -257,6 +257,12 @@ TEDM_API int tedm_linear_attention_bwd(const void* qkv, const void* dout, const 
 TEDM_API int tedm_attention_bwd(const void* qkv, const void* dout, void* dqkv, int batch, int n, int heads, int dim_head,
                        float scale, tedm_stream_t stream);
 
+/* The same backward for any token count, flash style on tensor cores (4 launches; nothing n x n leaves the SM).  o is the
+ * forward output [B][n][heads*dim_head] bf16 (delta_i = <dO_i, O_i>); workspace: tedm_attention_bwd_flash_workspace floats. */
+TEDM_API int64_t tedm_attention_bwd_flash_workspace(int batch, int n, int heads);
+TEDM_API int tedm_attention_bwd_flash(const void* qkv, const void* o, const void* dout, void* dqkv, float* workspace, int batch,
+                             int n, int heads, int dim_head, float scale, tedm_stream_t stream);
+
 /* torch.optim.Adam update (trainers/train_CXR14.py:139) over a flat fp32 arena; n % 4 == 0; grad is multiplied by
  * grad_scale first.  The 1-based step count for the bias correction is `step`, or, when step_counter (a DEVICE int)
  * is given, the counter's value after this call has incremented it -- so that a step replayed from a CUDA graph

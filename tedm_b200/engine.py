@@ -410,7 +410,7 @@ class UnetEngine:
         pre, att = wrap.fn.norm, wrap.fn.fn
         x, y, qkv, o = tape.saved[key]
         do, _ = self._conv_bwd(key + ".to_out", att.to_out, N.MODE_1X1, o, None, dout, G)
-        dqkv = N.attention_bwd(qkv, do, att.heads, att.dim_head, float(att.scale))
+        dqkv = N.attention_bwd(qkv, do, att.heads, att.dim_head, float(att.scale), o=o)
         dy, _ = self._conv_bwd(key + ".to_qkv", att.to_qkv, N.MODE_1X1, y, None, dqkv, G)
         return N.layernorm_bwd(x, self._f32(pre.g).reshape(-1), dy, G.of(pre.g).view(-1), eps=self.ln_eps, add=dout)
 

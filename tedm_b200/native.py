@@ -89,6 +89,8 @@ SIGNATURES = {
     "tedm_linear_attention_bwd_workspace": (_i64, [_i, _i, _i, _i]),
     "tedm_linear_attention_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "tedm_attention_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _p]),
+    "tedm_attention_bwd_flash_workspace": (_i64, [_i, _i, _i]),
+    "tedm_attention_bwd_flash": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "tedm_adam_step": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i, _p, _f, _p]),
     "tedm_bce_logits": (_i, [_p, _p, _p, _p, _p, _p, C.c_longlong, C.c_longlong, _i, _f, _p]),
     "tedm_bce_workspace_floats": (_i, [C.c_longlong]),
@@ -545,9 +547,16 @@ def linear_attention_bwd(qkv, dout, fwd_ws, heads: int = 4, dim_head: int = 32, 
     return dqkv
 
 
-def attention_bwd(qkv, dout, heads: int = 4, dim_head: int = 32, scale: float = 16.0):
+def attention_bwd(qkv, dout, heads: int = 4, dim_head: int = 32, scale: float = 16.0, o=None):
+    """Mid-attention backward.  With the forward output `o` and n >= 64 tokens: the tensor-core flash form (any n);
+    otherwise the one-CTA-per-(image, head) kernel (n <= 256)."""
     b, h, w, c3 = qkv.shape
     dqkv = torch.empty_like(qkv)
+    if o is not None and h * w >= 64:
+        ws = torch.empty(load().tedm_attention_bwd_flash_workspace(b, h * w, heads), device=qkv.device, dtype=torch.float32)
+        _call("tedm_attention_bwd_flash", _ptr(qkv, torch.bfloat16, "qkv"), _ptr(o, torch.bfloat16, "o"),
+              _ptr(dout, torch.bfloat16, "dout"), _ptr(dqkv), _ptr(ws), b, h * w, heads, dim_head, float(scale), _stream())
+        return dqkv
     _call("tedm_attention_bwd", _ptr(qkv, torch.bfloat16, "qkv"), _ptr(dout, torch.bfloat16, "dout"), _ptr(dqkv), b, h * w, heads,
           dim_head, float(scale), _stream())
     return dqkv

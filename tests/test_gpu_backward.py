@@ -350,7 +350,7 @@ def test_linear_attention_bwd(B, H):
         assert _rel(dqkv[..., sl], x.grad[..., sl]) < 1.5e-2, (name, _rel(dqkv[..., sl], x.grad[..., sl]))
 
 
-@pytest.mark.parametrize("B,H", [(2, 16), (3, 4), (1, 8)])
+@pytest.mark.parametrize("B,H", [(2, 16), (3, 4), (1, 8), (2, 32), (1, 10), (1, 24)])
 def test_attention_bwd(B, H):
     from tedm_b200 import native as N
     n, heads, dh, scale = H * H, 4, 32, 16.0
@@ -364,10 +364,13 @@ def test_attention_bwd(B, H):
     out = torch.einsum("bhij,bhdj->bhid", attn, v)                    # b h n d
     out = out.permute(0, 2, 1, 3).reshape(B, H, H, heads * dh)
     out.backward(dout.float())
-    dqkv = N.attention_bwd(qkv, dout, heads, dh, scale)
+    variants = [("flash", N.attention_bwd(qkv, dout, heads, dh, scale, o=N.attention(qkv, heads, dh, scale)))]
+    if n <= 256:
+        variants.append(("single-CTA", N.attention_bwd(qkv, dout, heads, dh, scale)))
     torch.cuda.synchronize()
-    for name, sl in (("dq", slice(0, 128)), ("dk", slice(128, 256)), ("dv", slice(256, 384))):
-        assert _rel(dqkv[..., sl], x.grad[..., sl]) < 1e-2, (name, _rel(dqkv[..., sl], x.grad[..., sl]))
+    for tag, dqkv in variants:
+        for name, sl in (("dq", slice(0, 128)), ("dk", slice(128, 256)), ("dv", slice(256, 384))):
+            assert _rel(dqkv[..., sl], x.grad[..., sl]) < 1e-2, (tag, name, _rel(dqkv[..., sl], x.grad[..., sl]))
 
 
 def test_adam_step_matches_torch():

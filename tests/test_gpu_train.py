@@ -185,3 +185,34 @@ def test_graphed_train_step_trains():
     ref_sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
     l_ref = float(O.ddpm_loss(ref_sd, x.cpu(), t.cpu(), nz.cpu()))
     assert abs(l_eval - l_ref) < 3e-2 * abs(l_ref), (l_eval, l_ref)
+
+
+def test_unet_backward_with_1024_mid_tokens():
+    """Three levels at 128^2 put 32 x 32 = 1024 tokens through the mid attention: forward and backward run on the flash
+    kernels (the single-CTA backward stops at 256 tokens); gradients against autograd through the fp32 oracle."""
+    from tedm_b200.models import Unet
+    mults = (1, 2, 4)
+    sd = synth_state_dict(O.unet_param_shapes(dim_mults=mults), 0)
+    m = Unet(64, dim_mults=mults).train()
+    m.load_state_dict(sd)
+    m = m.cuda()
+    gen = torch.Generator().manual_seed(8)
+    x = torch.randn(1, 1, 128, 128, generator=gen)
+    t = torch.tensor([400])
+    dout = torch.randn(1, 1, 128, 128, generator=gen) / 16384
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref_out = O.unet_forward(ref_sd, x, t)
+    ref_out.backward(dout)
+    out = m(x.cuda(), t.cuda())
+    assert _rel(out, ref_out) < 2e-2
+    out.backward(dout.cuda())
+    num = den = 0.0
+    for name, p in m.named_parameters():
+        r = ref_sd[name].grad.double()
+        num += float((p.grad.double().cpu() - r).pow(2).sum())
+        den += float(r.pow(2).sum())
+    mid = dict(m.named_parameters())["mid_attn.fn.fn.to_qkv.weight"].grad.double().cpu()
+    mid_ref = ref_sd["mid_attn.fn.fn.to_qkv.weight"].grad.double()
+    print("1024-token mid attention: whole-gradient rel err", (num / den) ** 0.5, "mid to_qkv", float((mid - mid_ref).norm() / mid_ref.norm()))
+    assert (num / den) ** 0.5 < 5e-2
+    assert float((mid - mid_ref).norm() / mid_ref.norm()) < 0.15
