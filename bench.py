@@ -159,16 +159,18 @@ def sampler_leg(dev, batch: int = 64, steps: int = 20):
     import torch
     from argparse import Namespace
     from tedm_b200.models import DiffusionModel
+    from tedm_b200.trainers.utils import GraphedSampler
     torch.manual_seed(7)
     m = DiffusionModel(Namespace(normalize=True)).to(dev).eval()
-    img = torch.randn(batch, 1, IMG, IMG, device=dev)
+    gs = GraphedSampler(m, batch, 1, IMG)            # what sample_images / sample_plot_image run: one graph replay per step
+    gs.x.normal_()
     for t in range(999, 996, -1):
-        img = m.sample_timestep(img, t)
+        gs.step(t)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for t in range(996, 996 - steps, -1):
-        img = m.sample_timestep(img, t)
+        img = gs.step(t)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps

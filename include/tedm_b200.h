@@ -71,6 +71,13 @@ TEDM_API int tedm_sampler_step(const float* x_t, const float* eps, const float* 
                       float sqrt_recipm1_ac, float coef1, float coef2, float sigma, int k_lo,
                       float q_weight, int batch, int chw, tedm_stream_t stream);
 
+/* The same update with the five per-step schedule values (sqrt_recip_ac, sqrt_recipm1_ac, coef1, coef2, sigma) read from
+ * DEVICE memory `coefs` and z always given (sigma = 0 at t == 0): one captured launch serves all 1000 reverse steps of
+ * sample_plot_image (trainers/utils.py:62-98) when the step is replayed from a CUDA graph. */
+TEDM_API int tedm_sampler_step_dev(const float* x_t, const float* eps, const float* z, float* x_prev,
+                          float* x0_hat /*nullable*/, float* s_out /*nullable*/, const float* coefs, int k_lo,
+                          float q_weight, int batch, int chw, tedm_stream_t stream);
+
 /* ---- UNet pieces ------------------------------------------------------------------------- */
 
 /* SinusoidalPosEmb(dim) -> Linear(dim,tdim) -> GELU(erf) -> Linear(tdim,tdim); fp32.

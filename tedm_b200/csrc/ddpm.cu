@@ -126,8 +126,16 @@ __global__ void __launch_bounds__(1024) sampler_step_kernel(const float* __restr
                                                             const float* __restrict__ z, float* __restrict__ x_prev,
                                                             float* __restrict__ x0_hat, float* __restrict__ s_out,
                                                             float cr, float crm1, float coef1, float coef2, float sigma,
-                                                            int k_lo, float q_weight, int chw) {
+                                                            int k_lo, float q_weight, int chw,
+                                                            const float* __restrict__ coefs_dev) {
   __shared__ unsigned int hist[256];
+  if (coefs_dev) {   // schedule values of this step from device memory: the launch can be replayed from a CUDA graph
+    cr = coefs_dev[0];
+    crm1 = coefs_dev[1];
+    coef1 = coefs_dev[2];
+    coef2 = coefs_dev[3];
+    sigma = coefs_dev[4];
+  }
   __shared__ unsigned int sh_prefix, sh_krem, sh_less, sh_bin_count, sh_min_gt;
   const size_t base = (size_t)blockIdx.x * chw;
   const int tid = threadIdx.x;
@@ -199,7 +207,20 @@ extern "C" int tedm_sampler_step(const float* x_t, const float* eps, const float
   TEDM_CHECK_ARG(batch > 0 && chw > 0 && k_lo >= 0 && k_lo < chw, "tedm_sampler_step: bad sizes batch=%d chw=%d k_lo=%d",
                  batch, chw, k_lo);
   sampler_step_kernel<<<batch, 1024, 0, (cudaStream_t)stream>>>(x_t, eps, z, x_prev, x0_hat, s_out, sqrt_recip_ac,
-                                                                sqrt_recipm1_ac, coef1, coef2, sigma, k_lo, q_weight, chw);
+                                                                sqrt_recipm1_ac, coef1, coef2, sigma, k_lo, q_weight, chw,
+                                                                nullptr);
+  TEDM_LAUNCH_CHECK();
+  return TEDM_OK;
+}
+
+extern "C" int tedm_sampler_step_dev(const float* x_t, const float* eps, const float* z, float* x_prev, float* x0_hat,
+                                     float* s_out, const float* coefs, int k_lo, float q_weight, int batch, int chw,
+                                     tedm_stream_t stream) {
+  TEDM_CHECK_ARG(x_t && eps && z && x_prev && coefs, "tedm_sampler_step_dev: null pointer");
+  TEDM_CHECK_ARG(batch > 0 && chw > 0 && k_lo >= 0 && k_lo < chw, "tedm_sampler_step_dev: bad sizes batch=%d chw=%d k_lo=%d",
+                 batch, chw, k_lo);
+  sampler_step_kernel<<<batch, 1024, 0, (cudaStream_t)stream>>>(x_t, eps, z, x_prev, x0_hat, s_out, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f,
+                                                                k_lo, q_weight, chw, coefs);
   TEDM_LAUNCH_CHECK();
   return TEDM_OK;
 }

@@ -188,6 +188,15 @@ class DiffusionModel(nn.Module):
             float(self._host("posterior_mean_coef2")[t]), sigma, k_lo, weight, want_x0=want_x0)
         return out, x0h, eps
 
+    def reverse_tables(self, device) -> Tensor:
+        """(T, 5) device table of the per-step scalars of a reverse step: sqrt_recip_ac, sqrt_recipm1_ac, coef1, coef2, sigma
+        (sigma = exp(0.5 logvar_t), 0 at t = 0 where no noise is added)."""
+        sig = (0.5 * self._host("posterior_log_variance_clipped")).exp()
+        sig[0] = 0.0
+        tab = torch.stack([self._host("sqrt_recip_alphas_cumprod"), self._host("sqrt_recipm1_alphas_cumprod"),
+                           self._host("posterior_mean_coef1"), self._host("posterior_mean_coef2"), sig], dim=1)
+        return tab.float().contiguous().to(device)
+
     def p_mean_variance(self, x_t: Tensor, t: Tensor, clip_denoised: bool = True, cond: Optional[Tensor] = None):
         """(:221-235) -> (model_mean, posterior_log_variance, pred_x_0).  All images must share the timestep."""
         if not clip_denoised:

@@ -42,6 +42,7 @@ SIGNATURES = {
     "tedm_q_sample": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "tedm_l1_loss": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "tedm_sampler_step": (_i, [_p, _p, _p, _p, _p, _p, _f, _f, _f, _f, _f, _i, _f, _i, _i, _p]),
+    "tedm_sampler_step_dev": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _f, _i, _i, _p]),
     "tedm_time_embed": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "tedm_time_proj": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "tedm_stem_conv7x7": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
@@ -186,6 +187,16 @@ def sampler_step(x_t, eps, z, c_recip: float, c_recipm1: float, coef1: float, co
           _ptr(z, torch.float32, "z"), _ptr(out), _ptr(x0h), _ptr(s), c_recip, c_recipm1, coef1, coef2, sigma,
           k_lo, q_weight, b, chw, _stream())
     return out, x0h, s
+
+
+def sampler_step_dev(x_t, eps, z, coefs, k_lo: int, q_weight: float, out=None):
+    """sampler_step with the step's five schedule values in the device tensor `coefs` (graph-replayable)."""
+    b, chw = x_t.shape[0], x_t[0].numel()
+    if out is None:
+        out = torch.empty_like(x_t)
+    _call("tedm_sampler_step_dev", _ptr(x_t, torch.float32, "x_t"), _ptr(eps, torch.float32, "eps"), _ptr(z, torch.float32, "z"),
+          _ptr(out), None, None, _ptr(coefs, torch.float32, "coefs"), k_lo, q_weight, b, chw, _stream())
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

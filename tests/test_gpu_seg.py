@@ -270,3 +270,24 @@ def test_train_then_evaluate_cli(tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "synthetic_val 800 metrics" in r.stdout and "synthetic_test metrics" in r.stdout, r.stdout[-2000:]
     assert (exp / "synthetic_val_metrics.pt").exists()
+
+
+def test_graphed_sampler_matches_eager_steps():
+    """One reverse step replayed from the CUDA graph (schedule values from device memory) == sample_timestep, bit for bit,
+    at several timesteps incl. t = 0 (no noise); the loop driver uses it by default."""
+    from tedm_b200.models import DiffusionModel
+    from tedm_b200.trainers.utils import GraphedSampler, sample_images
+    torch.manual_seed(0)
+    m = DiffusionModel(Namespace(normalize=True, timesteps=40, dim_mults=[1, 2, 4])).cuda().eval()
+    gs = GraphedSampler(m, 2, 1, 64)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    for t in (39, 17, 1, 0):
+        x = torch.randn(2, 1, 64, 64, device="cuda", generator=gen)
+        z = torch.randn(2, 1, 64, 64, device="cuda", generator=gen)
+        gs.x.copy_(x)
+        got = gs.step(t, noise=z).clone()
+        ref = m.sample_timestep(x, t, noise=z)
+        assert torch.equal(got, ref), (t, (got - ref).abs().max().item())
+    final, snaps = sample_images(m, 40, 64, 2)
+    assert final.shape == (2, 1, 64, 64) and len(snaps) == 8 and torch.isfinite(final).all()
+    assert final.min() >= -1e-6 and final.max() <= 1 + 1e-6
