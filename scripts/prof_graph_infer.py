@@ -5,7 +5,7 @@ from argparse import Namespace
 import torch
 import bench
 from tedm_b200.models import DatasetDM, tedm_classifier
-S = len(bench.STEPS_TEDM); B = 16
+S = len(bench.STEPS_TEDM); B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 dev = torch.device("cuda")
 m = DatasetDM(Namespace(normalize=True, saved_diffusion_model="", t_steps_to_save=bench.STEPS_TEDM))
 m.classifier = tedm_classifier(S)
@@ -22,17 +22,8 @@ def timeit(fn, n=10):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 t_eager = timeit(lambda i: m.segment(xs[i % 4], nz[i % 4]))
-sx, sn = xs[0].clone(), nz[0].clone()
-side = torch.cuda.Stream()
-side.wait_stream(torch.cuda.current_stream())
-with torch.cuda.stream(side):
-    for _ in range(2): m.segment(sx, sn)
-torch.cuda.current_stream().wait_stream(side)
-torch.cuda.synchronize()
-g = torch.cuda.CUDAGraph()
-with torch.cuda.graph(g):
-    out = m.segment(sx, sn)
-def replay(i):
-    sx.copy_(xs[i % 4]); sn.copy_(nz[i % 4]); g.replay()
-t_graph = timeit(replay)
-print(f"eager {t_eager:.3f} ms/step ({B / t_eager * 1e3:.0f} img/s), graph {t_graph:.3f} ms/step ({B / t_graph * 1e3:.0f} img/s)")
+t_graph = timeit(lambda i: m.segment(xs[i % 4], nz[i % 4], graph=True))
+ref = m.segment(xs[1], nz[1])
+got = m.segment(xs[1], nz[1], graph=True)
+assert all(torch.equal(a, b) for a, b in zip(ref, got)), "graph replay differs from the eager call"
+print(f"B={B}: eager {t_eager:.3f} ms/step ({B / t_eager * 1e3:.0f} img/s), graph {t_graph:.3f} ms/step ({B / t_graph * 1e3:.0f} img/s)")

@@ -99,6 +99,34 @@ class DatasetDM(nn.Module):
         per_step = torch.cat(ups, dim=1)                                                        # (B*S, 960, H, W)
         return per_step.reshape(b, s * per_step.shape[1], size, size)
 
+    def _segment_graphed(self, x: Tensor, noise: Optional[Tensor]):
+        if not x.is_cuda:
+            raise RuntimeError("tedm_b200.DatasetDM runs on CUDA (sm_100a) only; there is no CPU fallback")
+        sig = (tuple(x.shape), noise is not None,
+               tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers())))
+        g = getattr(self, "_seg_graph", None)
+        if g is None or g["sig"] != sig:
+            sx = x.detach().float().clone()
+            sn = noise.detach().float().clone() if noise is not None else None
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                       # warm-up off the capture: caches, allocator growth
+                for _ in range(2):
+                    self.segment(sx, sn)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            l0 = N.launches
+            with torch.cuda.graph(graph):
+                out = self.segment(sx, sn)
+            g = self._seg_graph = {"sig": sig, "graph": graph, "x": sx, "noise": sn, "out": out, "calls": N.launches - l0}
+        g["x"].copy_(x, non_blocking=True)
+        if noise is not None:
+            g["noise"].copy_(noise, non_blocking=True)
+        g["graph"].replay()
+        N.launches += g["calls"]          # native launches inside the replayed graph (bench.py's gpu_launches claim)
+        return g["out"]
+
     # -- head -------------------------------------------------------------------------------------
     def _head_layers(self):
         convs = [m for m in self.classifier if isinstance(m, nn.Conv2d)]
@@ -181,10 +209,16 @@ class DatasetDM(nn.Module):
         return logits
 
     @torch.no_grad()
-    def segment(self, x: Tensor, noise: Optional[Tensor] = None):
+    def segment(self, x: Tensor, noise: Optional[Tensor] = None, graph: bool = False):
         """TEDM/LEDM inference with the reference's ensemble semantics
         (auxiliary/postprocessing/testing_shared_weights.py:113,120,133-138; app.py:79):
-        sigmoid -> mean over steps -> > 0.5.  Returns (mask bool (B,1,H,W), prob, logits)."""
+        sigmoid -> mean over steps -> > 0.5.  Returns (mask bool (B,1,H,W), prob, logits).
+
+        graph=True replays the whole call (~600 launches) from a CUDA graph captured for this input shape and the
+        current weights: small serving batches are launch-bound from Python (B = 1: 3.4 -> 1.5 ms).  The returned
+        tensors are then the graph's static outputs, overwritten by the next call."""
+        if graph:
+            return self._segment_graphed(x, noise)
         convs, bns = self._head_layers()
         logits = self._head_infer(x, convs, bns, noise)
         n_steps = logits.shape[0] // x.shape[0]

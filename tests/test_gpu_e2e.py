@@ -225,3 +225,26 @@ def test_unet_forward_other_sizes_vs_oracle(size, mults):
     err = _rel(got, ref)
     print(f"unet {size}x{size} mults {mults}: rel err {err:.4f}")
     assert err < TOL, err
+
+
+def test_segment_graph_replay_is_bit_identical():
+    """DatasetDM.segment(graph=True) (one CUDA-graph replay per call) == the eager call, for changing inputs, and re-captures
+    when the weights change."""
+    from tedm_b200.models import DatasetDM, tedm_classifier
+    torch.manual_seed(0)
+    steps = [10, 200, 600]
+    m = DatasetDM(Namespace(normalize=True, saved_diffusion_model="", t_steps_to_save=steps))
+    m.classifier = tedm_classifier(len(steps))
+    m = m.cuda().eval()
+    for seed in (1, 2, 3):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        x = torch.rand(2, 1, 64, 64, device="cuda", generator=g)
+        nz = torch.randn(2, 1, 64, 64, device="cuda", generator=g)
+        ref = [t.clone() for t in m.segment(x, nz)]
+        got = m.segment(x, nz, graph=True)
+        assert all(torch.equal(a, b) for a, b in zip(ref, got)), seed
+    with torch.no_grad():
+        m.classifier[7].bias.add_(0.5)                       # weights changed: the graph must be rebuilt, not replayed stale
+    ref = [t.clone() for t in m.segment(x, nz)]
+    got = m.segment(x, nz, graph=True)
+    assert all(torch.equal(a, b) for a, b in zip(ref, got))
