@@ -70,17 +70,23 @@ def sample_plot_image(diffusion_model, T: int, img_size: int, batch: int, channe
     accepted and ignored here.  The 8 D2H copies happen once at the end instead of inside the loop."""
     _, snaps = sample_images(diffusion_model, T, img_size, batch, channels, cond, n_snapshots=8)
     imgs = torch.stack([s.cpu() for s in snaps]).transpose(0, 1)             # n b c h w -> b n c h w
-    rows = []
-    for img_row in imgs:                                                     # make_grid(nrow=4, padding=2), 3-channel
-        n, c, h, w = img_row.shape
-        img_row = img_row.expand(n, 3, h, w) if c == 1 else img_row
-        ncol, nrow = min(4, n), (n + 3) // 4
-        grid = torch.zeros(img_row.shape[1], nrow * (h + 2) + 2, ncol * (w + 2) + 2)
-        for k in range(n):
-            r, cc = divmod(k, 4)
-            grid[:, r * (h + 2) + 2:r * (h + 2) + 2 + h, cc * (w + 2) + 2:cc * (w + 2) + 2 + w] = img_row[k]
-        rows.append(grid)
-    return torch.stack(rows)
+    grids = torch.stack([snapshot_grid(img_row) for img_row in imgs])        # (b, 3, H, W)
+    return grids
+
+
+def snapshot_grid(images: Tensor, nrow: int = 4, padding: int = 2) -> Tensor:
+    """torchvision.utils.make_grid(images, nrow=nrow) for a (n, c, h, w) stack: single-channel images are repeated to three
+    channels, tiles sit on a zero canvas with `padding` pixels between and around them."""
+    n, c, h, w = images.shape
+    if c == 1:
+        images = images.expand(n, 3, h, w)
+    ncol, nrows = min(nrow, n), (n + nrow - 1) // nrow
+    grid = torch.zeros(images.shape[1], nrows * (h + padding) + padding, ncol * (w + padding) + padding, dtype=images.dtype)
+    for k in range(n):
+        r, cc = divmod(k, ncol)
+        grid[:, r * (h + padding) + padding:r * (h + padding) + padding + h,
+             cc * (w + padding) + padding:cc * (w + padding) + padding + w] = images[k]
+    return grid
 
 
 class TensorboardLogger:

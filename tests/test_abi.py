@@ -103,3 +103,14 @@ def test_trainers_import_and_refuse_cpu():
     assert torch.equal(ds[1][0], img)                       # deterministic per index
     with pytest.raises(RuntimeError, match="CUDA"):
         DeviceLoader(ds, 2, False, 0, device="cpu", labelled=True)
+
+
+def test_snapshot_grid_matches_torchvision_make_grid():
+    """sample_plot_image assembles its snapshot grids like torchvision.utils.make_grid(nrow=4) (trainers/utils.py:91-93)."""
+    tv = pytest.importorskip("torchvision.utils")
+    import torch
+    from tedm_b200.trainers.utils import snapshot_grid
+    g = torch.Generator().manual_seed(0)
+    for n, c, h in ((8, 1, 16), (5, 1, 12), (8, 3, 8)):
+        imgs = torch.rand(n, c, h, h, generator=g)
+        assert torch.equal(snapshot_grid(imgs), tv.make_grid(imgs, nrow=4)), (n, c, h)
