@@ -10,11 +10,10 @@ path runs at > 1000 images/s that copy and the fp32 expansion on the host are on
 from __future__ import annotations
 
 import csv
-from typing import Dict, Iterator, List, Optional, Sequence, Tuple
+from typing import Dict, Iterator, List, Optional, Sequence
 
 import numpy as np
 import torch
-from torch import Tensor
 from torch.utils.data import DataLoader, Dataset, DistributedSampler
 
 from .. import native as N

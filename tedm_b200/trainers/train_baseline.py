@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import os
 from argparse import Namespace
-from typing import Dict, Optional
+from typing import Dict
 
 import torch
 from torch import Tensor
