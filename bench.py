@@ -365,12 +365,26 @@ def run_ours(args):
         b.record()
         records.append((flops, a, b, shape))
 
+    elem_records = []
+
+    @contextlib.contextmanager
+    def elem_timer(name, nbytes):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        yield
+        b.record()
+        elem_records.append((name, nbytes, a, b))
+
     N.conv_timer = conv_timer
+    N.elem_timer = elem_timer
     try:
-        model.segment(resident[0], noise[0])          # eager: every conv launch bracketed by its own event pair
+        model.segment(resident[0], noise[0])          # eager: every conv / GroupNorm launch bracketed by its own event pair
     finally:
         N.conv_timer = None
+        N.elem_timer = None
     torch.cuda.synchronize()
+    gn_ms = sum(a.elapsed_time(b) for _, _, a, b in elem_records)
+    gn_bytes = sum(nb for _, nb, _, _ in elem_records)
     conv_ms = sum(a.elapsed_time(b) for _, a, b, _ in records)
     conv_fl = sum(f for f, _, _, _ in records)
     if os.environ.get("TEDM_BENCH_CONV_TABLE") and rank == 0:
@@ -396,6 +410,12 @@ def run_ours(args):
                 "conv_share_of_step": conv_ms / (ms / args.steps) if ms > 0 else None,
                 "conv_gflop_per_step": conv_fl / 1e9}
 
+    gn_gbs = gn_bytes / (gn_ms * 1e-3) / 1e9 if gn_ms > 0 else 0.0
+    roofline_hbm = {"bound": "hbm", "kernel": "gn_silu_kernel (all GroupNorm+SiLU launches of one step; the largest memory-bound kernel)",
+                    "achieved": gn_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gn_gbs / pk["hbm_gbs"],
+                    "peak_source": pk["source"] + " (copy bandwidth)", "algorithmic_bytes_per_step": gn_bytes,
+                    "launches_per_step": len(elem_records), "ms_per_step": gn_ms,
+                    "share_of_step": gn_ms / (ms / args.steps) if ms > 0 else None, "traffic": None}
     line = {"metric": "tedm_seg_images_per_s", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -410,7 +430,7 @@ def run_ours(args):
             "tflops": {"unet_fwd_reference_form": value * GFLOP_TEDM_REF / 1e3, "minimal_form": value * GFLOP_TEDM_MIN / 1e3,
                        "executed_conv_gflop_per_image": conv_flops_step / B / 1e9,
                        "frac_of_sustained_peak_minimal_form": value * GFLOP_TEDM_MIN / 1e3 / (pk["tflops_sustained"] * world)},
-            "roofline": roofline, "clocks": clocks.summary()}
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "clocks": clocks.summary()}
     # ---- second half of BASELINE.json's metric: the DDPM pre-training step (UNet fwd+bwd TFLOP/s vs bf16 peak) ----
     del model, resident, noise
     torch.cuda.empty_cache()

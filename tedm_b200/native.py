@@ -105,6 +105,7 @@ _lib: Optional[C.CDLL] = None
 launches = 0  # kernels-launching C calls made so far (bench.py reads this for its gpu_launches claim)
 conv_flops = 0  # executed conv MACs*2 so far (minimal form: the folded upsample conv counts 4 taps, not 9)
 conv_timer = None  # bench.py instrumentation: callable(flops) -> context manager bracketing one conv launch
+elem_timer = None  # bench.py instrumentation: callable(kernel name, algorithmic bytes) -> context manager (memory-bound kernels)
 
 
 def load() -> C.CDLL:
@@ -363,10 +364,15 @@ def gn_silu(x, gn_partial, gamma, beta, groups: int, eps: float = 1e-5, scale_sh
             residual=None):
     b, h, w, c = x.shape
     out = torch.empty_like(x)
-    _call("tedm_gn_silu_fwd", _ptr(x, torch.bfloat16, "x"), _ptr(gn_partial, torch.float32), gn_partial.shape[1],
-          _ptr(gamma, torch.float32), _ptr(beta, torch.float32), _ptr(scale_shift, torch.float32),
-          scale_shift.shape[1] if scale_shift is not None else 0, ss_offset, _ptr(residual, torch.bfloat16, "residual"),
-          _ptr(out), b, h * w, c, groups, eps, _stream())
+    args = ("tedm_gn_silu_fwd", _ptr(x, torch.bfloat16, "x"), _ptr(gn_partial, torch.float32), gn_partial.shape[1],
+            _ptr(gamma, torch.float32), _ptr(beta, torch.float32), _ptr(scale_shift, torch.float32),
+            scale_shift.shape[1] if scale_shift is not None else 0, ss_offset, _ptr(residual, torch.bfloat16, "residual"),
+            _ptr(out), b, h * w, c, groups, eps, _stream())
+    if elem_timer is not None:
+        with elem_timer("gn_silu_kernel", x.numel() * 2 * (3 if residual is not None else 2)):
+            _call(*args)
+    else:
+        _call(*args)
     return out
 
 
