@@ -273,7 +273,7 @@ class UnetEngine:
 
     # -- whole network ----------------------------------------------------------------------------
     def forward(self, x: Tensor, timestep: Optional[Tensor], want_features: bool = False, skip_tail: bool = False,
-                tape: Optional[Tape] = None):
+                tape: Optional[Tape] = None, time_key=None):
         m = self.m
         if not x.is_cuda:
             raise RuntimeError("tedm_b200.Unet runs on CUDA (sm_100a) only; there is no CPU fallback")
@@ -291,10 +291,18 @@ class UnetEngine:
             if tape is not None:
                 emb, hid, temb = N.time_embed_train(t, freq, *tw)
                 tape.saved["time"] = (emb, hid, temb)
+                wcat, bcat = self._time_cat()
+                tproj = N.time_proj(temb, wcat, bcat)
+            elif time_key is not None:
+                # the caller vouches that `timestep` holds the same values whenever it passes this key (TEDM's fixed step
+                # list): the whole time path is a function of the weights alone and is computed once per weight version
+                tparams = (m.time_mlp[1].weight, m.time_mlp[1].bias, m.time_mlp[3].weight, m.time_mlp[3].bias,
+                           *(rb.time_mlp[1].weight for rb in self._resblocks), *(rb.time_mlp[1].bias for rb in self._resblocks))
+                tproj = self.cache.get(f"tproj:{time_key}", tparams,
+                                       lambda *_: N.time_proj(N.time_embed(t, freq, *tw), *self._time_cat()))
             else:
-                temb = N.time_embed(t, freq, *tw)
-            wcat, bcat = self._time_cat()
-            tproj = N.time_proj(temb, wcat, bcat)
+                wcat, bcat = self._time_cat()
+                tproj = N.time_proj(N.time_embed(t, freq, *tw), wcat, bcat)
 
         h = N.stem_conv7x7(x, self._f32(m.init_conv.weight), self._f32(m.init_conv.bias))
         stem = h

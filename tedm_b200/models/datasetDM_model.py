@@ -85,7 +85,7 @@ class DatasetDM(nn.Module):
             nz = noise.detach().float().repeat_interleave(s, dim=0).contiguous()
         # NB: x_0 is NOT rescaled to [-1, 1] here (datasetDM_model.py:76)
         x_t = N.q_sample(x_rep, nz, t, dm.sqrt_alphas_cumprod, dm.sqrt_one_minus_alphas_cumprod, normalize=False)
-        _, feats = dm.model.forward_features(x_t, t, skip_tail=True)
+        _, feats = dm.model.forward_features(x_t, t, skip_tail=True, time_key=(b, tuple(self.steps)))
         for i, f in enumerate(feats):
             self._features[i] = f
         return feats, b, s

@@ -171,7 +171,7 @@ class Unet(nn.Module):
             return UnetFunction.apply(self.engine, x, timestep, *params)
         return self.engine.forward(x, timestep)
 
-    def forward_features(self, x: Tensor, timestep: Optional[Tensor], skip_tail: bool = True):
+    def forward_features(self, x: Tensor, timestep: Optional[Tensor], skip_tail: bool = True, time_key=None):
         """Decoder feature maps of `ups[i][2]` (what DatasetDM's hooks capture, datasetDM_model.py:50-53) as
         NHWC bf16 device tensors; with skip_tail the part of the net after the last hooked map is not run."""
-        return self.engine.forward(x, timestep, want_features=True, skip_tail=skip_tail)
+        return self.engine.forward(x, timestep, want_features=True, skip_tail=skip_tail, time_key=time_key)
