@@ -98,6 +98,15 @@ class FusedAdam(torch.optim.Optimizer):
         self.bump_versions()
         return loss
 
+    def state_dict(self):
+        """torch.optim.Adam's format.  Every parameter gets its OWN step tensor: internally they share one, and an aliased
+        tensor would be incremented once per parameter by torch's foreach Adam after `load_state_dict`."""
+        sd = super().state_dict()
+        for st in sd["state"].values():
+            if "step" in st:
+                st["step"] = torch.tensor(float(st["step"]))
+        return sd
+
     def load_state_dict(self, state_dict) -> None:
         """Accepts what torch.optim.Adam.state_dict() produces (the reference's checkpoints, train_CXR14.py:96-114)
         as well as its own: the moments are copied into the flat arenas and the per-parameter views rebound."""

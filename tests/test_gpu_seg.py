@@ -189,6 +189,22 @@ def test_fused_adam_loads_torch_adam_state():
         assert torch.allclose(p, q, rtol=1e-5, atol=1e-6)
     sd = fused.state_dict()
     assert float(sd["state"][0]["step"]) == 3.0 and sd["state"][0]["exp_avg"].shape == (33, 7)
+    # ... and the other way round: torch.optim.Adam (the reference's optimiser) resumes from a FusedAdam checkpoint
+    rs = [torch.nn.Parameter(q.detach().clone()) for q in qs]
+    back = torch.optim.Adam(rs, lr=1e-2)
+    import io
+    buf = io.BytesIO()
+    torch.save(sd, buf)                                  # through a checkpoint file, as trainers' save() / load() do
+    buf.seek(0)
+    back.load_state_dict(torch.load(buf, weights_only=False))
+    g3 = [torch.randn_like(p) for p in ps]
+    for p, q, r, g in zip(ps, qs, rs, g3):
+        p.grad, q.grad, r.grad = g.clone(), g.clone(), g.clone()
+    ref.step()
+    fused.step()
+    back.step()
+    for p, q, r in zip(ps, qs, rs):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-6) and torch.allclose(p, r, rtol=1e-5, atol=1e-6)
 
 
 @pytest.mark.parametrize("experiment", ["TEDM", "LEDM", "baseline", "img_only"])
