@@ -23,6 +23,9 @@ parser.add_argument("--dataset", type=str, default="JSRT", choices=["JSRT", "CXR
 # Data parameters
 parser.add_argument("--img_size", type=int, default=128, help="Height / width of the input image to the network")
 parser.add_argument("--data_dir", type=str, help="Path to the dataset")
+parser.add_argument("--csv_dir", type=str, default=None,
+                    help="Directory holding the split CSVs (train_split.csv, JSRT_{train,val,test}_split.csv); default <repo>/data "
+                         "as in the reference, which ships them in its own data/ directory")
 parser.add_argument("--num_workers", type=int, default=4, help="Number of subprocesses to use for data loading")
 # Model parameters
 parser.add_argument("--dim", type=int, default=64, help="Width of the U-Net")
@@ -58,3 +61,6 @@ parser.add_argument("--shared_weights_over_timesteps", default=False, action="st
 parser.add_argument("--early_stop", default=False, action="store_true")
 # additions of this implementation
 parser.add_argument("--no_cuda_graph", dest="cuda_graph", action="store_false", help="run the DDPM step eagerly")
+parser.add_argument("--sync_bn", default=False, action="store_true",
+                    help="data-parallel head training: share the head's BatchNorm batch statistics over all ranks, so N GPUs "
+                         "with B/N images each equal the single-device reference at batch B (default: per-replica statistics)")

@@ -271,6 +271,20 @@ class UnetEngine:
         return N.conv_igemm(o, self._w(key + ".to_out"), N.MODE_1X1, c,
                             bias=self._f32(att.to_out.bias), residual=x)
 
+    @staticmethod
+    def _fire(mod: nn.Module, ins, out: Tensor) -> None:
+        """Forward hooks registered on a submodule (the reference's DatasetDM hooks `ups[i][2]`, datasetDM_model.py:50-53)
+        see what they would see in the reference: NCHW fp32 input(s) and output.  The engine does not go through the
+        submodules' own forward, so it calls the hooks itself; a hook may observe, not replace, the output."""
+        if not mod._forward_hooks:
+            return
+        xin = [N.nhwc_to_nchw_f32(i) for i in ins]                 # a decoder block's input is cat(h, skip)
+        args = (torch.cat(xin, dim=1) if len(xin) > 1 else xin[0],)
+        o = N.nhwc_to_nchw_f32(out)
+        for hook in list(mod._forward_hooks.values()):
+            if hook(mod, args, o) is not None:
+                raise NotImplementedError("forward hooks that replace a submodule's output are not supported by the fused engine")
+
     # -- whole network ----------------------------------------------------------------------------
     def forward(self, x: Tensor, timestep: Optional[Tensor], want_features: bool = False, skip_tail: bool = False,
                 tape: Optional[Tape] = None, time_key=None):
@@ -282,7 +296,15 @@ class UnetEngine:
         x = x.detach().float().contiguous()
         self._ensure_weights(train=tape is not None)
         tproj = None
-        if timestep is not None:
+        if timestep is not None and getattr(m, "learned_sinusoidal_cond", False):
+            # learned-frequency embedding (unet_model.py:96-114): never enabled by a reference entry point; its (B, 17) ->
+            # (B, 256) MLP stays on the host-side torch path, everything downstream is native
+            if tape is not None:
+                raise NotImplementedError("training with learned_sinusoidal_cond=True is not part of the B200 hot path")
+            with torch.no_grad():
+                temb = m.time_mlp(timestep.detach().to(x.device))
+            tproj = N.time_proj(temb.float().contiguous(), *self._time_cat())
+        elif timestep is not None:
             t = timestep.detach().to(device=x.device, dtype=torch.int64).contiguous()
             pe = m.time_mlp[0]
             freq = self.cache.get("freq", (m.time_mlp[1].weight,), lambda w: pe.frequencies(w.device).float().contiguous())
@@ -309,25 +331,43 @@ class UnetEngine:
         skips: List[Tensor] = []
         for i, (b1, b2, attn, down) in enumerate(m.downs):
             k = f"downs.{i}"
+            hin = h
             h = self._resblock(k + ".0", b1, h, None, tproj, tape)
+            self._fire(b1, [hin], h)
             skips.append(h)
+            hin = h
             h = self._resblock(k + ".1", b2, h, None, tproj, tape)
+            self._fire(b2, [hin], h)
+            hin = h
             h = self._linear_attention(k + ".2", attn, h, tape)
+            self._fire(attn, [hin], h)
             skips.append(h)
             mode = N.MODE_4X4S2 if down.kernel_size[0] == 4 else N.MODE_3X3
             if tape is not None:
                 tape.saved[k + ".3"] = (h,)
             h = N.conv_igemm(h, self._w(k + ".3"), mode, down.weight.shape[0], bias=self._f32(down.bias))
+        hin = h
         h = self._resblock("mid_block1", m.mid_block1, h, None, tproj, tape)
+        self._fire(m.mid_block1, [hin], h)
+        hin = h
         h = self._mid_attention("mid_attn", m.mid_attn, h, tape)
+        self._fire(m.mid_attn, [hin], h)
+        hin = h
         h = self._resblock("mid_block2", m.mid_block2, h, None, tproj, tape)
+        self._fire(m.mid_block2, [hin], h)
         feats: List[Tensor] = []
         n_up = len(m.ups)
         for i, (b1, b2, attn, up) in enumerate(m.ups):
             k = f"ups.{i}"
-            h = self._resblock(k + ".0", b1, h, skips.pop(), tproj, tape)
-            h = self._resblock(k + ".1", b2, h, skips.pop(), tproj, tape)
+            hin, sk = h, skips.pop()
+            h = self._resblock(k + ".0", b1, h, sk, tproj, tape)
+            self._fire(b1, [hin, sk], h)
+            hin, sk = h, skips.pop()
+            h = self._resblock(k + ".1", b2, h, sk, tproj, tape)
+            self._fire(b2, [hin, sk], h)
+            hin = h
             h = self._linear_attention(k + ".2", attn, h, tape)
+            self._fire(attn, [hin], h)
             feats.append(h)
             if skip_tail and i == n_up - 1:
                 return None, feats

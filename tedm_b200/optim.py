@@ -89,9 +89,19 @@ class FusedAdam(torch.optim.Optimizer):
                 loss = closure()
         grp = self.param_groups[0]
         self._step += 1
+        # torch.optim.Adam skips parameters whose grad is None (no moment decay, no weight decay, no movement); the one
+        # flat launch below would treat them as zero-gradient, so their slices are put back afterwards
+        skipped = [(o, p.numel()) for p, o in zip(self._params, self._offsets) if p.grad is None]
+        if len(skipped) == len(self._params):
+            skipped = [] if flat_grad is not None else skipped
+        saved = [(o, k, [a[o:o + k].clone() for a in (self.flat_param, self.exp_avg, self.exp_avg_sq)]) for o, k in skipped]
         N.adam_step(self.flat_param, self.flat_grad() if flat_grad is None else flat_grad, self.exp_avg, self.exp_avg_sq, float(grp["lr"]),
                     float(grp["betas"][0]), float(grp["betas"][1]), float(grp["eps"]), float(grp["weight_decay"]),
                     self._step, grad_scale, step_counter=self.step_counter)
+        for o, k, (sp, sm, sv) in saved:
+            self.flat_param[o:o + k].copy_(sp)
+            self.exp_avg[o:o + k].copy_(sm)
+            self.exp_avg_sq[o:o + k].copy_(sv)
         step_t = torch.tensor(float(self._step))
         for p in self._params:
             self.state[p]["step"] = step_t

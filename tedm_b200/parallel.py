@@ -35,6 +35,16 @@ def max_over_ranks(value: float, device=None) -> float:
     return float(t.item())
 
 
+def sum_over_ranks(t: torch.Tensor) -> torch.Tensor:
+    """Sum a small tensor of validation accumulators (sums and counts) over ranks, in place.  Every rank then computes
+    the SAME metrics from the whole validation set and takes the same control-flow decisions (best-model choice, early
+    stop) -- a rank that returned early on its own shard's loss would leave the others blocked in the next all-reduce."""
+    rank, ws = world()
+    if ws > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
 def allreduce_gradients(params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64 << 20) -> int:
     """Average .grad over ranks with flat fp32 buckets (one collective per bucket; the whole UNet is
     145 MB, i.e. 3 buckets -- sized for launch latency, not link count: NVSwitch gives every pair full

@@ -37,6 +37,8 @@ class GraphedTrainStep:
         self._ga: Optional[torch.cuda.CUDAGraph] = None
         self._gb: Optional[torch.cuda.CUDAGraph] = None
         self._params = [p for p in model.parameters() if p.requires_grad]
+        self._flat: Optional[Tensor] = None      # the gradient arena graph A writes and graph B reads (fixed at capture)
+        self._hyper = None                       # optimiser hyper-parameters frozen into graph B
         if use_graph:
             self._capture(warmup)
 
@@ -47,15 +49,33 @@ class GraphedTrainStep:
         loss.backward()
         self.loss.copy_(loss.detach())
 
-    def _update(self) -> None:
-        self.opt.step(grad_scale=1.0 / self.world)
+    def _update(self, flat: Optional[Tensor] = None) -> None:
+        self.opt.step(grad_scale=1.0 / self.world, flat_grad=flat)
 
-    def _allreduce(self) -> None:
+    def _allreduce(self, flat: Optional[Tensor] = None) -> None:
         if self.world > 1:
-            dist.all_reduce(self.opt.flat_grad(), op=dist.ReduceOp.SUM)
+            dist.all_reduce(self.opt.flat_grad() if flat is None else flat, op=dist.ReduceOp.SUM)
+
+    def _hyper_sig(self):
+        g = self.opt.param_groups[0]
+        return (float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]))
+
+    def _capture_update(self) -> None:
+        """Graph B: Adam over the arena graph A fills.  lr / betas / eps / weight decay are kernel arguments frozen at
+        capture, so the graph is rebuilt whenever the param_group changes (an LR scheduler)."""
+        self._gb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._gb, pool=self._ga.pool()):
+            self._update(self._flat)
+        self.opt._step -= 1                              # the capture recorded a step, it did not execute one
+        self._hyper = self._hyper_sig()
 
     def _capture(self, warmup: int) -> None:
         eng = self.model.model.engine
+        opt = self.opt
+        # the warm-up below runs real steps (lazy initialisation, allocator growth, NCCL channels); the optimiser state it
+        # touches is restored afterwards so that constructing a GraphedTrainStep is not a training step: the reference does
+        # exactly one update per loop iteration (trainers/train_CXR14.py:28-40)
+        snap = (opt.flat_param.clone(), opt.exp_avg.clone(), opt.exp_avg_sq.clone(), opt.step_counter.clone(), opt._step)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):            # warm-up off the capture: lazy attribute setting, allocator growth
@@ -65,6 +85,14 @@ class GraphedTrainStep:
                 self._update()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        with torch.no_grad():
+            opt.flat_param.copy_(snap[0])
+            opt.exp_avg.copy_(snap[1])
+            opt.exp_avg_sq.copy_(snap[2])
+            opt.step_counter.copy_(snap[3])
+        opt._step = snap[4]
+        opt.bump_versions()
+        del snap
         eng.force_refresh = True
         eng.cache.force = True
         from . import native as N
@@ -73,14 +101,17 @@ class GraphedTrainStep:
             self._ga = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._ga):
                 self._fwd_bwd()
-            self._gb = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._gb, pool=self._ga.pool()):
-                self._update()
+            # the arena graph A writes lives at a fixed address in the graph's pool: the all-reduce and graph B must use
+            # THAT tensor, not whatever p.grad points at later (an eager odd-sized step rebinds p.grad to a fresh arena)
+            self._flat = opt.flat_grad()
+            first = self._params[0].grad
+            if first is None or self._flat.data_ptr() != first.data_ptr():
+                raise RuntimeError("GraphedTrainStep: the backward did not produce one flat gradient arena")
+            self._capture_update()
         finally:
             eng.force_refresh = False
             eng.cache.force = False
         self.native_calls_per_step = N.launches - l0     # native entry points inside one replayed step
-        self.opt._step -= 1                              # the capture recorded a step, it did not execute one
 
     # -- public ---------------------------------------------------------------------------------
     def __call__(self, x: Tensor) -> Tensor:
@@ -93,8 +124,10 @@ class GraphedTrainStep:
             self._allreduce()
             self._update()
         else:
+            if self._hyper != self._hyper_sig():
+                self._capture_update()
             self._ga.replay()
-            self._allreduce()
+            self._allreduce(self._flat)
             self._gb.replay()
             self.opt._step += 1
             self.opt.bump_versions()

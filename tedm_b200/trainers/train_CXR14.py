@@ -14,6 +14,7 @@ import torch
 
 from ..models.diffusion_model import DiffusionModel
 from ..optim import FusedAdam
+from ..parallel import sum_over_ranks
 from ..train import GraphedTrainStep
 from .train_baseline import save, write_config
 from .utils import (TensorboardLogger, compare_configs, dp_optimizer_step, init_distributed, sample_plot_image,
@@ -70,7 +71,9 @@ def validate(config, model, val_loader):
         losses.append(model.train_step(x))
         if i + 1 == config.max_val_steps or config.debug:
             break
-    avg_loss = torch.stack(losses).mean().item()
+    acc = torch.stack([torch.stack(losses).double().sum(), torch.tensor(float(len(losses)), device=losses[0].device, dtype=torch.float64)])
+    acc = sum_over_ranks(acc).cpu()                  # every rank logs / compares the loss of the whole validation set
+    avg_loss = (acc[0] / acc[1]).item()
     if getattr(config, "rank", 0) == 0:
         print(f"Validation loss: {avg_loss:.4f}")
     out = {"val/loss": avg_loss}
@@ -96,15 +99,17 @@ def load(new_config, path):
 def build_image_dataloaders(config):
     rank, world = getattr(config, "rank", 0), getattr(config, "world_size", 1)
     data_dir = getattr(config, "data_dir", None)
-    if getattr(config, "dataset", "CXR14") == "synthetic" or data_dir is None or not os.path.isdir(str(data_dir)):
+    if getattr(config, "dataset", "CXR14") != "synthetic" and (data_dir is None or not os.path.isdir(str(data_dir))):
+        raise FileNotFoundError(f"--data_dir {data_dir} does not exist; pass --dataset synthetic to train on generated images "
+                                "(real data: <data_dir>/ holds the images, the split CSVs are read from --csv_dir or <repo>/data)")
+    if getattr(config, "dataset", "CXR14") == "synthetic":
         from ..dataloaders.device_loader import build_synthetic_dataloaders
-        if getattr(config, "dataset", "CXR14") != "synthetic":
-            print(f"data_dir {data_dir} not found: using synthetic images")
         return build_synthetic_dataloaders(config.img_size, config.batch_size, 0, labelled=False, device=config.device,
                                            rank=rank, world_size=world, n_train=max(256, 16 * config.batch_size))
     from ..dataloaders.CXR14 import build_dataloaders
     return build_dataloaders(config.data_dir, config.img_size, config.batch_size, config.num_workers,
-                             device=config.device, rank=rank, world_size=world)
+                             device=config.device, rank=rank, world_size=world,
+                             **({"csv_dir": config.csv_dir} if getattr(config, "csv_dir", None) else {}))
 
 
 def main(config: Namespace) -> None:

@@ -24,6 +24,7 @@ from .. import native as N
 from ..autograd import bce_with_logits_rows
 from ..models.unet_model import Unet
 from ..optim import FusedAdam
+from ..parallel import sum_over_ranks
 from .utils import TensorboardLogger, dp_optimizer_step, init_distributed, seed_everything
 
 
@@ -104,10 +105,16 @@ def validate(config, model, val_dl) -> Dict[str, float]:
         loss_n += row_mean.numel()
         if i + 1 == config.max_val_steps or config.debug:
             break
-    m = torch.cat(rows).reshape(-1, 8)
-    out = {"val/loss": (loss_sum / loss_n).item(),              # rows are equally long: mean of row means = pixel mean
-           "val/dice": m[:, 0].nanmean().item(), "val/precision": m[:, 1].nanmean().item(),
-           "val/recall": m[:, 2].nanmean().item()}
+    m = torch.cat(rows).reshape(-1, 8)[:, :3].double()
+    ok = ~torch.isnan(m)
+    # [sum of row-mean losses, rows, nansum and non-NaN count of dice / precision / recall]: summed over ranks, so every
+    # rank reports the metrics of the WHOLE validation set and takes the same best-model / early-stop decision
+    acc = torch.cat([torch.stack([loss_sum.double(), torch.tensor(float(loss_n), device=m.device, dtype=torch.float64)]),
+                     torch.where(ok, m, torch.zeros_like(m)).sum(0), ok.double().sum(0)])
+    acc = sum_over_ranks(acc).cpu()
+    out = {"val/loss": (acc[0] / acc[1]).item(),                # rows are equally long: mean of row means = pixel mean
+           "val/dice": (acc[2] / acc[5]).item(), "val/precision": (acc[3] / acc[6]).item(),
+           "val/recall": (acc[4] / acc[7]).item()}
     if getattr(config, "rank", 0) == 0:
         print(f"Validation loss: {out['val/loss']:.4f}")
     model.train()
@@ -135,17 +142,19 @@ def build_segmentation_dataloaders(config):
     """JSRT pairs from disk when `config.data_dir` exists, otherwise the deterministic synthetic stand-in."""
     rank, world = getattr(config, "rank", 0), getattr(config, "world_size", 1)
     data_dir = getattr(config, "data_dir", None)
-    if getattr(config, "dataset", "JSRT") == "synthetic" or data_dir is None or not os.path.isdir(str(data_dir)):
+    if getattr(config, "dataset", "JSRT") != "synthetic" and (data_dir is None or not os.path.isdir(str(data_dir))):
+        raise FileNotFoundError(f"--data_dir {data_dir} does not exist; pass --dataset synthetic to train on generated pairs "
+                                "(real data: <data_dir>/ holds images and masks, the split CSVs are read from --csv_dir or <repo>/data)")
+    if getattr(config, "dataset", "JSRT") == "synthetic":
         from ..dataloaders.device_loader import build_synthetic_dataloaders
-        if getattr(config, "dataset", "JSRT") != "synthetic":
-            print(f"data_dir {data_dir} not found: using synthetic image / mask pairs")
         return build_synthetic_dataloaders(config.img_size, config.batch_size, 0, labelled=True, device=config.device,
                                            rank=rank, world_size=world, n_labelled_images=config.n_labelled_images)
     if config.dataset != "JSRT":
         raise ValueError(f"Unknown dataset: {config.dataset}")
     from ..dataloaders.JSRT import build_dataloaders
     return build_dataloaders(config.data_dir, config.img_size, config.batch_size, config.num_workers,
-                             config.n_labelled_images, device=config.device, rank=rank, world_size=world)
+                             config.n_labelled_images, device=config.device, rank=rank, world_size=world,
+                             **({"csv_dir": config.csv_dir} if getattr(config, "csv_dir", None) else {}))
 
 
 def write_config(config) -> None:

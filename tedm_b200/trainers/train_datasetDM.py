@@ -23,6 +23,7 @@ def main(config: Namespace) -> None:
     print("Experiment folder: %s" % (config.log_dir))
     seed_everything(config.seed)
     model = build_model(config).to(config.device)
+    model.sync_bn = bool(getattr(config, "sync_bn", False))          # tedm_b200/head_train.py
     model.train()
     model.diffusion_model.eval()
     optimizer = FusedAdam(model.classifier.parameters(), lr=config.lr, weight_decay=config.weight_decay)

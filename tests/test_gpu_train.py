@@ -170,11 +170,23 @@ def test_graphed_train_step_trains():
     m = _model()
     opt = FusedAdam(m.parameters(), lr=2e-4)
     x = torch.rand(4, 1, 32, 32, generator=torch.Generator().manual_seed(3)).cuda()
+    before = opt.flat_param.clone()
     step = GraphedTrainStep(m, opt, x, warmup=2)
-    assert int(opt.step_counter.item()) == 2 and opt._step == 2
-    losses = [float(step(x)) for _ in range(60)]
+    # construction (warm-up + capture) is not a training step: parameters, moments and both step counters are untouched
+    assert int(opt.step_counter.item()) == 0 and opt._step == 0
+    assert torch.equal(opt.flat_param, before) and not opt.exp_avg.any() and not opt.exp_avg_sq.any()
+    losses = [float(step(x)) for _ in range(30)]
+    # an odd-sized eager step in between (the trainer's path for the last batch of an epoch) rebinds p.grad to a fresh
+    # arena; the graphed step must keep using the arena it captured
+    opt.zero_grad()
+    m.train_step(x[:3]).backward()
+    opt.step()
+    for g in opt.param_groups:                      # an LR change must reach the replayed Adam (graph B is rebuilt)
+        g["lr"] = 1e-4
+    losses += [float(step(x)) for _ in range(29)]
     torch.cuda.synchronize()
-    assert int(opt.step_counter.item()) == 62 and opt._step == 62
+    assert step._params[0].grad.data_ptr() != step._flat.data_ptr()      # p.grad is the eager arena; the graphs own theirs
+    assert int(opt.step_counter.item()) == 60 and opt._step == 60
     assert all(np.isfinite(losses))
     assert np.mean(losses[-10:]) < 0.8 * np.mean(losses[:10]), (losses[:10], losses[-10:])
     # eager evaluation after graph training sees the trained weights (version counters were bumped)
