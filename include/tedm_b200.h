@@ -137,8 +137,9 @@ TEDM_API int tedm_conv_igemm_fwd(const tedm_conv_args* args, tedm_stream_t strea
  * ACCUMULATED into it (mode 3: the folded taps are scattered back onto the 3x3 kernel of Upsample's conv). */
 TEDM_API int tedm_conv_igemm_wgrad(const tedm_conv_args* args, const void* dy, float* dw, int oihw_accumulate,
                           float* workspace, tedm_stream_t stream);
-/* fp32 elements of the optional `workspace` above (split-K partial tiles of the 3x3 halo-tile kernel, reduced by a
- * second kernel instead of atomics; NULL = atomics). */
+/* fp32 elements of the REQUIRED `workspace` above: the split-K partial tiles of both weight-gradient kernels are stored
+ * there and summed in slice order by a second kernel -- no floating-point atomics, so the gradient is bit-reproducible
+ * from run to run.  Calls that share one workspace must be ordered on one stream. */
 TEDM_API int64_t tedm_conv_igemm_wgrad_workspace(void);
 /* number of partial-statistics slots per image that tedm_conv_igemm_fwd writes for this output extent */
 TEDM_API int tedm_conv_gn_parts(int out_height, int out_width);

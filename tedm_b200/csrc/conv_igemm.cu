@@ -600,6 +600,8 @@ struct WgradParams {
   int items, n_tiles, splitk, num_ptiles, stages;
   int oihw;                      // 1: accumulate into an fp32 OIHW gradient (mode 3: un-folded to 3x3)
   float* dw;
+  float* part;                   // split-K partial tiles [group][ks][128][BN] fp32, summed in a fixed order by wgrad_reduce_kernel
+  int group0;                    // first (m block, n tile) group of this launch (wide layers run in batches that fit `part`)
 };
 
 __device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr) {
@@ -624,9 +626,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_consta
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int cb_total = p.c0_blocks + p.c1_blocks;
   const int ks = blockIdx.x;
-  const int mb = blockIdx.y / p.n_tiles, nt = blockIdx.y % p.n_tiles;
+  const int grp = p.group0 + blockIdx.y;
+  const int mb = grp / p.n_tiles, nt = grp % p.n_tiles;
   const int n0 = nt * BN;
-  const int item0 = 2 * mb, item1 = (2 * mb + 1 < p.items) ? 2 * mb + 1 : 2 * mb;   // odd tail: duplicate, discarded below
+  const int item0 = 2 * mb, item1 = (2 * mb + 1 < p.items) ? 2 * mb + 1 : 2 * mb;   // odd tail: duplicate, discarded by the reduce
   const int num_kb = (p.num_ptiles - ks + p.splitk - 1) / p.splitk;
 
   if (warp == 0 && lane == 0) {
@@ -723,52 +726,75 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_consta
     }
     __syncwarp();
   } else {
+    // the partial tile of this CTA goes to the workspace with plain stores; wgrad_reduce_kernel sums the split-K slices in
+    // a fixed order (deterministic: no floating-point atomics) and lays dW out
     const int q = warp & 3, row = q * 32 + lane;
-    const int half = row >> 6;
-    const int item = half ? item1 : item0;
-    const bool live = num_kb > 0 && (half == 0 || item1 != item0);
-    const int tap = item / cb_total, cb = item % cb_total;
-    const int ci = cb * BK + (row & 63);
-    // destination of output channel co:  base + co * co_stride (+ extra 3x3 taps when un-folding mode 3)
-    size_t base, co_stride;
-    int ny = 1, nx = 1;          // mode 3 + oihw: the folded tap (par, a, b) feeds ny x nx taps of the 3x3 kernel
-    if (!p.oihw) {
-      base = (size_t)tap * p.ctot + ci;
-      co_stride = (size_t)p.taps * p.ctot;
-    } else if (p.mode != 3) {
-      base = (size_t)ci * p.taps + tap;
-      co_stride = (size_t)p.ctot * p.taps;
-    } else {
-      const int par = tap >> 2, a = (tap >> 1) & 1, b = tap & 1, py = par >> 1, px = par & 1;
-      const int ky0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), kx0 = px == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2);
-      ny = (py == 0) == (a == 1) ? 2 : 1;
-      nx = (px == 0) == (b == 1) ? 2 : 1;
-      base = (size_t)ci * 9 + ky0 * 3 + kx0;
-      co_stride = (size_t)p.ctot * 9;
-    }
+    float* ptile = p.part + ((size_t)blockIdx.y * p.splitk + ks) * (size_t)(BM * BN) + (size_t)row * BN;
     if (num_kb > 0) {
       mbar_wait(smem_u32(&bar_acc), 0);
       tc_fence_after();
+    }
 #pragma unroll 1
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
-        uint32_t r[32];
+    for (int chunk = 0; chunk < BN / 32; ++chunk) {
+      uint32_t r[32];
+      if (num_kb > 0) {
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(chunk * 32), r);
         tmem_ld_wait();
-        if (live) {
+      } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float* d = p.dw + base + (size_t)(n0 + chunk * 32 + j) * co_stride;
-            const float v = __uint_as_float(r[j]);
-            for (int yy = 0; yy < ny; ++yy)
-              for (int xx = 0; xx < nx; ++xx) atomicAdd(d + yy * 3 + xx, v);
-          }
-        }
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
+      float4* dst = reinterpret_cast<float4*>(ptile + chunk * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                             __uint_as_float(r[4 * j + 3]));
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<BN>(tmem_base);
+}
+
+// Sums the split-K partial tiles of conv_wgrad_kernel in slice order and writes dW.  CTA = (group, tap/channel-block item
+// of the pair, 64-column chunk): a 64 (input channel) x 64 (output channel) block; reads are coalesced along the output
+// channel, the block is transposed through shared memory so that writes run along the input channel.
+//   layout 0: dw[co][tap][ci] = sum       (raw; also the intermediate of the folded upsample conv)
+//   layout 1: dw[co][ci][tap] += sum      (OIHW accumulate)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int splitk,
+                                                           int bn, int n_tiles, int group0, int items, int cb_total, int taps,
+                                                           int ctot, int layout) {
+  __shared__ float tile[64][65];
+  const int grp = group0 + blockIdx.x, mb = grp / n_tiles, nt = grp % n_tiles;
+  const int h = blockIdx.y, cc = blockIdx.z;
+  const int item = 2 * mb + h;
+  if (item >= items) return;
+  const int tap = item / cb_total, cb = item % cb_total;
+  const float* src = part + (size_t)blockIdx.x * splitk * (size_t)(BM * bn) + (size_t)(h * 64) * bn + cc * 64;
+  {
+    const int c = threadIdx.x & 63, r0 = threadIdx.x >> 6;
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.0f;
+    for (int ks = 0; ks < splitk; ++ks) {
+      const float* s_ = src + (size_t)ks * (size_t)(BM * bn) + c;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] += __ldg(s_ + (size_t)(r0 + 4 * i) * bn);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) tile[r0 + 4 * i][c] = acc[i];
+  }
+  __syncthreads();
+  const int r = threadIdx.x & 63, c0 = threadIdx.x >> 6;
+  const int ci = cb * 64 + r;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = c0 + 4 * i;
+    const int co = nt * bn + cc * 64 + c;
+    const float v = tile[r][c];
+    if (layout == 0) dw[((size_t)co * taps + tap) * ctot + ci] = v;
+    else dw[((size_t)co * ctot + ci) * taps + tap] += v;
+  }
 }
 
 template <int BN>
@@ -784,11 +810,14 @@ int launch_wgrad(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap
     TEDM_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  dim3 grid((unsigned)p.splitk, (unsigned)(m_blocks * p.n_tiles));
+  dim3 grid((unsigned)p.splitk, (unsigned)m_blocks);     // m_blocks: the (m block, n tile) groups of this batch
   conv_wgrad_kernel<BN><<<grid, 192, smem, stream>>>(x0, x1, dy, p);
   TEDM_LAUNCH_CHECK();
   return TEDM_OK;
 }
+
+constexpr long long WGRAD_PART_FLOATS_PER_SM = 4LL * BM * 256;   // 4 waves of CTAs, each a 128 x 256 fp32 partial tile
+constexpr long long WGRAD_RAW_FLOATS = 4LL << 20;                // raw [co][16][ci] intermediate of the folded upsample conv
 
 // ==========================================================================================
 // weight gradient of the 3x3 convolution, halo-tile form
@@ -801,7 +830,7 @@ int launch_wgrad(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap
 // address; two taps are stacked into one M = 128 operand through the descriptor's leading-dimension byte offset).
 // Accumulators: 5 blocks of [128 = 2 taps x 64 ci][64 co] fp32 in TMEM (taps (0,1) (2,3) (4,5) (6,7) (7,8); the second
 // copy of tap 7 is discarded).  Split-K partial tiles go to a workspace with plain stores and a second kernel sums
-// them and lays dW out (OIHW accumulate, or [co][tap][ci]); without a workspace, fp32 atomics.
+// them in slice order and lays dW out (OIHW accumulate, or [co][tap][ci]): deterministic, no floating-point atomics.
 // ==========================================================================================
 struct Wgrad3Params {
   int c0_blocks, c1_blocks, ctot;
@@ -811,7 +840,7 @@ struct Wgrad3Params {
   int x_tx_bytes;    // bytes the TMA writes for one halo box
   int oihw;
   float* dw;
-  float* part;       // split-K partial tiles [group][ks][5][128][64] fp32 (NULL: reduce with atomics into dw)
+  float* part;       // split-K partial tiles [group][ks][5][128][64] fp32
 };
 
 __device__ __forceinline__ uint64_t make_sw128_mn_desc2(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -930,25 +959,13 @@ conv_wgrad3_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_const
     __syncwarp();
   } else {
     const int q = warp & 3, row = q * 32 + lane;
-    const int half = row >> 6;
-    const int ci = cb * BK + (row & 63);
     if (num_kb > 0) {
       mbar_wait(smem_u32(&bar_acc), 0);
       tc_fence_after();
     }
-    float* ptile = p.part ? p.part + ((size_t)blockIdx.y * p.splitk + ks) * (5 * BM * BN) + (size_t)row * BN : nullptr;
+    float* ptile = p.part + ((size_t)blockIdx.y * p.splitk + ks) * (5 * BM * BN) + (size_t)row * BN;
 #pragma unroll 1
     for (int blk = 0; blk < 5; ++blk) {
-      const int tap = (blk < 4 ? 2 * blk : 7) + half;
-      const bool live = !(blk == 4 && half == 0);
-      size_t base, co_stride;
-      if (!p.oihw) {
-        base = (size_t)tap * p.ctot + ci;
-        co_stride = (size_t)9 * p.ctot;
-      } else {
-        base = (size_t)ci * 9 + tap;
-        co_stride = (size_t)p.ctot * 9;
-      }
 #pragma unroll 1
       for (int chunk = 0; chunk < BN / 32; ++chunk) {
         uint32_t r[32];
@@ -959,16 +976,11 @@ conv_wgrad3_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = 0u;
         }
-        if (ptile) {
-          float4* dst = reinterpret_cast<float4*>(ptile + (size_t)blk * (BM * BN) + chunk * 32);
+        float4* dst = reinterpret_cast<float4*>(ptile + (size_t)blk * (BM * BN) + chunk * 32);
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                                 __uint_as_float(r[4 * j + 3]));
-        } else if (live && num_kb > 0) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(p.dw + base + (size_t)(n0 + chunk * 32 + j) * co_stride, __uint_as_float(r[j]));
-        }
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                               __uint_as_float(r[4 * j + 3]));
       }
     }
   }
@@ -1204,8 +1216,9 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
 // dw: fp32 [cout][taps][c0+c1] (taps = 1 / 9 / 16; mode 3: 16 = parity*4 + a*2 + b of the folded kernel), overwritten;
 // or, with oihw_accumulate, the fp32 OIHW parameter gradient itself (+=; the folded taps of mode 3 are scattered to 3x3).
 extern "C" int64_t tedm_conv_igemm_wgrad_workspace(void) {
-  // split-K partial tiles of the halo-tile 3x3 kernel: at most 3 waves of CTAs, 5 x 128 x 64 fp32 each
-  return 3LL * tedm_num_sms() * 5 * BM * 64;
+  // split-K partial tiles: the halo-tile 3x3 kernel needs at most 3 waves of CTAs x 5 x 128 x 64 fp32, the generic kernel
+  // at most 4 waves x 128 x 256; plus the raw intermediate of the folded upsample conv's gradient
+  return WGRAD_PART_FLOATS_PER_SM * tedm_num_sms() + WGRAD_RAW_FLOATS;
 }
 
 extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, float* dw, int oihw_accumulate,
@@ -1266,7 +1279,9 @@ extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, fl
     const int stage_bytes = w.x_bytes + A_BYTES;
     int stages = (DYN_SMEM_MAX - 1024) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
-    if (stages >= 2) {
+    const long long groups3 = (long long)(p.c0_blocks + p.c1_blocks) * (a->cout / 64);
+    // layers too wide for the partial-tile workspace even unsplit go to the generic kernel (which batches its groups)
+    if (stages >= 2 && groups3 * 5 * BM * 64 <= WGRAD_PART_FLOATS_PER_SM * tedm_num_sms()) {
       w.stages = stages;
       const long long groups = (long long)(p.c0_blocks + p.c1_blocks) * w.n_tiles, sms = tedm_num_sms();
       const long long cap = p.num_ptiles / 4 > 0 ? p.num_ptiles / 4 : 1;
@@ -1276,6 +1291,7 @@ extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, fl
         long long sk = (wv * sms) / groups;
         if (sk < 1) sk = 1;
         if (sk > cap) sk = cap;
+        while (sk > 1 && groups * sk * 5 * BM * 64 > WGRAD_PART_FLOATS_PER_SM * sms) --sk;
         const long long ctas = groups * sk, waves = (ctas + sms - 1) / sms;
         const double eff = (double)ctas / (double)(waves * sms);
         if (eff > best_eff + 0.02) {
@@ -1301,8 +1317,6 @@ extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, fl
                            a->out_image_stride ? a->out_image_stride : (long long)Ho * Wo * a->cout, 0, p.tileW, p.tileH, p.tileB);
       if (rc3) return rc3;
       w.part = workspace;     // sized by tedm_conv_igemm_wgrad_workspace(): groups * splitk <= 3 waves of CTAs
-      if (groups * w.splitk > 3 * sms) w.part = nullptr;
-      if (!w.part && !p.oihw) TEDM_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)a->cout * 9 * p.ctot, s));
       const int smem = 1024 + stages * stage_bytes;
       static int configured3 = 0;
       if (configured3 < smem) {
@@ -1312,7 +1326,7 @@ extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, fl
       dim3 grid((unsigned)w.splitk, (unsigned)groups);
       conv_wgrad3_kernel<<<grid, 192, smem, s>>>(mX0, mX1, mDY, w);
       TEDM_LAUNCH_CHECK();
-      if (w.part) {
+      {
         if (w.splitk <= 16 && p.oihw)
           wgrad3_reduce_oihw_kernel<<<dim3(16, (unsigned)groups), 256, 0, s>>>(w.part, dw, w.splitk, w.n_tiles, p.ctot);
         else if (w.splitk > 16)
@@ -1329,10 +1343,12 @@ extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, fl
   if (g_force_bn && a->cout % g_force_bn == 0) bn = g_force_bn;
   p.n_tiles = a->cout / bn;
   const int m_blocks = (p.items + 1) / 2;
+  const long long groups = (long long)m_blocks * p.n_tiles, sms = tedm_num_sms();
+  const long long part_floats = WGRAD_PART_FLOATS_PER_SM * sms, tile_floats = (long long)BM * bn;
   // split K over pixel tiles: one CTA per SM is resident (192 KB of pipeline smem), so pick the split whose CTA count
-  // fills whole waves of the machine (up to 4 waves, each CTA at least 4 pixel tiles)
+  // fills whole waves of the machine (up to 4 waves, each CTA at least 4 pixel tiles) and whose partial tiles fit the
+  // workspace; layers with more groups than the workspace holds run in batches of groups
   {
-    const long long groups = (long long)m_blocks * p.n_tiles, sms = tedm_num_sms();
     const long long cap = p.num_ptiles / 4 > 0 ? p.num_ptiles / 4 : 1;
     long long best_sk = 1;
     double best_eff = -1.0;
@@ -1340,6 +1356,7 @@ extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, fl
       long long sk = (w * sms) / groups;
       if (sk < 1) sk = 1;
       if (sk > cap) sk = cap;
+      while (sk > 1 && groups * sk * tile_floats > part_floats) --sk;
       const long long ctas = groups * sk, waves = (ctas + sms - 1) / sms;
       const double eff = (double)ctas / (double)(waves * sms);
       if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && sk > best_sk)) {
@@ -1349,6 +1366,13 @@ extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, fl
     }
     p.splitk = (int)best_sk;
   }
+  TEDM_CHECK_ARG(workspace != nullptr, "tedm_conv_igemm_wgrad: workspace (tedm_conv_igemm_wgrad_workspace() floats) is required");
+  const bool unfold = p.oihw && a->mode == 3;     // folded taps -> raw intermediate -> 3x3 OIHW accumulate
+  TEDM_UNSUPPORTED(unfold && (long long)a->cout * 16 * p.ctot > WGRAD_RAW_FLOATS,
+                   "tedm_conv_igemm_wgrad: upsample conv %d -> %d too wide for the raw-gradient workspace", p.ctot, a->cout);
+  float* raw = workspace + part_floats;
+  float* dst = unfold ? raw : dw;
+  const int layout = (p.oihw && !unfold) ? 1 : 0;
 
   const int dy_h = a->mode == 3 ? 2 * a->height : Ho, dy_w = a->mode == 3 ? 2 * a->width : Wo;
   alignas(64) CUtensorMap mapX0, mapX1, mapDY;
@@ -1368,10 +1392,23 @@ extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, fl
                       a->out_image_stride ? a->out_image_stride : (long long)dy_h * dy_w * a->cout, a->mode == 3 ? 2 : 0,
                       p.tileW, p.tileH, p.tileB);
   if (rc) return rc;
-  if (!p.oihw) TEDM_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)a->cout * p.taps * p.ctot, s));
-  switch (bn) {
-    case 64: return launch_wgrad<64>(mapX0, mapX1, mapDY, p, m_blocks, s);
-    case 128: return launch_wgrad<128>(mapX0, mapX1, mapDY, p, m_blocks, s);
-    default: return launch_wgrad<256>(mapX0, mapX1, mapDY, p, m_blocks, s);
+  p.part = workspace;
+  long long per_batch = part_floats / (p.splitk * tile_floats);
+  if (per_batch > groups) per_batch = groups;
+  for (long long g0 = 0; g0 < groups; g0 += per_batch) {
+    const int ng = (int)(groups - g0 < per_batch ? groups - g0 : per_batch);
+    p.group0 = (int)g0;
+    switch (bn) {
+      case 64: rc = launch_wgrad<64>(mapX0, mapX1, mapDY, p, ng, s); break;
+      case 128: rc = launch_wgrad<128>(mapX0, mapX1, mapDY, p, ng, s); break;
+      default: rc = launch_wgrad<256>(mapX0, mapX1, mapDY, p, ng, s); break;
+    }
+    if (rc) return rc;
+    wgrad_reduce_kernel<<<dim3((unsigned)ng, 2, (unsigned)(bn / 64)), 256, 0, s>>>(workspace, dst, p.splitk, bn, p.n_tiles, (int)g0,
+                                                                                p.items, p.c0_blocks + p.c1_blocks, p.taps,
+                                                                                p.ctot, layout);
+    TEDM_LAUNCH_CHECK();
   }
+  if (unfold) return tedm_wgrad_to_oihw(raw, dw, a->cout, p.ctot, 3, stream);
+  return TEDM_OK;
 }

@@ -320,7 +320,8 @@ _wgrad_ws = {}
 
 
 def _wgrad_workspace(device) -> torch.Tensor:
-    """Per-device scratch for the split-K partial tiles of the 3x3 weight-gradient kernel (stream-ordered reuse)."""
+    """Per-device scratch for the split-K partial tiles of the weight-gradient kernels (stream-ordered reuse: every
+    weight gradient of a backward pass is issued on ONE stream)."""
     key = (device.type, device.index)
     if key not in _wgrad_ws:
         _wgrad_ws[key] = torch.empty(load().tedm_conv_igemm_wgrad_workspace(), device=device, dtype=torch.float32)
@@ -348,7 +349,7 @@ def conv_wgrad(src0: torch.Tensor, dy: torch.Tensor, mode: int, src1=None, grad_
     p1, s1 = _nhwc(src1, "src1")
     pd, sd = _nhwc(dy, "dy")
     a = ConvArgs(p0, p1, None, None, None, None, None, b, h, w, c0, c1, cout, mode, 0, 0, s0, s1, sd)
-    ws = _wgrad_workspace(src0.device) if mode == MODE_3X3 else None
+    ws = _wgrad_workspace(src0.device)       # split-K partial tiles (summed in a fixed order: deterministic gradients)
     if conv_timer is not None:
         flops = 2 * b * (h * w if mode == MODE_UP3X3 else oh * ow) * cout * taps * (c0 + c1)
         with conv_timer(flops, ("wgrad", mode, b, h, w, c0, c1, cout)):
