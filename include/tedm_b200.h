@@ -104,12 +104,12 @@ TEDM_API int tedm_stem_conv7x7(const float* x, const float* weight, const float*
  *   mode 3: nearest-x2 upsample folded into 3x3 pad 1 (Upsample: :39-44); weight is the
  *           parity-combined [4][Cout][2][2][Cin] tensor made by tedm_fold_upsample_weight.
  * K runs over src0's channels then src1's (the skip concat of Unet.forward, :356,359,365, is
- * never materialised).  Epilogue: + bias, + residual, bf16 store, optional per-(image, group)
+ * never materialised), then over the optional extra sources.  Epilogue: + bias, + residual, bf16 store, optional per-(image, group)
  * partial sum / sum-of-squares of the fp32 accumulators for the GroupNorm that follows. */
 typedef struct {
   const void* src0;      /* [B][H][W][c0] bf16 */
   const void* src1;      /* [B][H][W][c1] bf16 or NULL */
-  const void* weight;    /* bf16 KRSC, K = taps*(c0+c1) */
+  const void* weight;    /* bf16 KRSC, K = taps*(c0+c1 [+ extra channels]) [+ centre-only extra channels] */
   const float* bias;     /* [cout] or NULL */
   const void* residual;  /* [B][Ho][Wo][cout] bf16 or NULL */
   void* out;             /* [B][Ho][Wo][cout] bf16 */
@@ -126,6 +126,16 @@ typedef struct {
   int split;
   void* out2;
   const void* residual2;
+  /* further A sources, walked after src0 / src1 inside every tap (K order: tap, then source, then channel): the same
+   * [B][H][W][c] bf16 layout.  Uses: (1) a 1x1 branch folded into a 3x3 conv as extra K at the centre tap
+   * (extra_center = 1: ResnetBlock's res_conv inside block2's conv, models/unet_model.py:157,175); (2) the fp32
+   * precision mode, where every operand is a bf16 (hi, lo) pair and the product is hi*hi + lo*hi + hi*lo, i.e. a conv
+   * over the sources [x_hi, x_lo, x_hi] against the weights [w_hi, w_hi, w_lo]. */
+  int n_extra;                      /* 0..4 */
+  const void* extra_src[4];
+  int extra_c[4];
+  int64_t extra_image_stride[4];    /* elements; 0 = dense */
+  int extra_center[4];
 } tedm_conv_args;
 TEDM_API int tedm_conv_igemm_fwd(const tedm_conv_args* args, tedm_stream_t stream);
 /* Weight gradient of the same convolution (backward of models/unet_model.py:43,49,122,157,185,188,226,227,308,324):
@@ -306,6 +316,7 @@ typedef struct {
   const void* f_full;
   const void* w1_full;
   int c_full;
+  int exact;             /* 1 (fp32 precision mode): fp32 g maps through the plain-fp32 tail kernel, no tensor-core tail */
 } tedm_head_args;
 TEDM_API int tedm_head_infer(const tedm_head_args* args, tedm_stream_t stream);
 
@@ -397,6 +408,30 @@ TEDM_API int tedm_u8_masks_to_label(const uint8_t* src, float* dst, long long n_
  * bf16 and out [nvar][128][64] fp32 are device pointers. */
 TEDM_API int tedm_debug_umma_probe(const void* A, const void* Bm, const int* shifts, const int* base_offsets,
                                    int nvar, float* out, tedm_stream_t stream);
+
+/* ---- fp32 precision mode (north star: "1e-4 in fp32 mode"; the reference's default arithmetic, config.py:15) --------
+ * Inference only.  Activations are fp32 NHWC between kernels.  Convolutions run on tedm_conv_igemm_fwd with every operand
+ * split into a bf16 (hi, lo) pair (tedm_f32_split for activations; weights likewise) and the product taken as
+ * hi*hi + lo*hi + hi*lo with fp32 accumulation: sources [x_hi, x_lo, x_hi] (tedm_conv_args.extra_src) against the
+ * channel-concatenated weights [w_hi, w_hi, w_lo], out_dtype = 1.  The functions below restate the rest of
+ * models/unet_model.py in fp32 with exact exp / division: same reference lines as their bf16 counterparts above. */
+TEDM_API int tedm_f32_split(const float* x, void* hi_bf16, void* lo_bf16, int64_t n, tedm_stream_t stream);
+TEDM_API int tedm_f32_stem_conv7x7(const float* x, const float* weight, const float* bias, float* out_nhwc, int batch, int cin,
+                          int height, int width, int cout, tedm_stream_t stream);                     /* :267,334 */
+TEDM_API int tedm_f32_gn_silu(const float* x, const float* gn_partial, int gn_parts, const float* gamma, const float* beta,
+                     const float* scale_shift, int ss_stride, int ss_offset, const float* residual, float* out, int batch,
+                     int hw, int channels, int groups, float eps, tedm_stream_t stream);              /* :126-135,175 */
+TEDM_API int tedm_f32_layernorm(const float* x, const float* g, const float* residual, float* out, int64_t npix, int channels,
+                       float eps, tedm_stream_t stream);                                               /* :52-61 */
+TEDM_API int64_t tedm_f32_linear_attention_workspace(int batch, int n, int heads);
+TEDM_API int tedm_f32_linear_attention(const float* qkv, float* out, float* workspace, int batch, int n, int heads, int dim_head,
+                              float scale, tedm_stream_t stream);                                      /* :196-210 */
+/* rnorm: scratch of batch * 2 * heads * dim_head floats (reciprocal L2 norms of q and k over the token axis) */
+TEDM_API int tedm_f32_attention(const float* qkv, float* out, float* rnorm, int batch, int n, int heads, int dim_head, float scale,
+                       tedm_stream_t stream);                                                          /* :229-241 */
+TEDM_API int tedm_f32_final_conv1x1(const float* x, const float* weight, const float* bias, float* out_nchw, int batch, int hw,
+                           int channels, int out_dim, tedm_stream_t stream);                          /* :331,368 */
+TEDM_API int tedm_f32_add(const float* a, const float* b, float* out, int64_t n, tedm_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,11 +1,30 @@
 #!/bin/bash
-# One GPU-box pass: parity tests per file (a faulting kernel poisons only its own process), smoke, short bench.
-cd "${GRAFT_REPO_ROOT:-/root/repo}"
+# One gpurun call: every GPU test file in its own process (a trapped kernel must not poison the rest), then the bench.
+#   gpurun --timeout 1500 -- 'bash scripts/gpu_check.sh [tag] [extra pytest args]'
+tag=${1:-check}
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
-for t in probe conv ops e2e backward train head_train seg; do
-  timeout 600 python -m pytest tests/test_gpu_$t.py -q -s --tb=short -m gpu > gpurun_out/t_$t.log 2>&1
-  echo "== test_gpu_$t exit $? =="; tail -n 4 gpurun_out/t_$t.log
+out=gpurun_out/${tag}_tests.log
+: > $out
+nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv >> $out 2>&1
+for f in tests/test_gpu_*.py; do
+  echo "=== $f" >> $out
+  timeout 900 python -m pytest $f -m gpu -q -x --no-header -p no:cacheprovider -s 2>&1 | grep -v "^$" | tail -60 >> $out
 done
-timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "== smoke exit $? =="; tail -n 3 gpurun_out/smoke.log
-timeout 600 python bench.py --steps 5 --warmup 3 ${BENCH_ARGS:-} > gpurun_out/bench.log 2>&1; echo "== bench exit $? =="; tail -n 2 gpurun_out/bench.log
+grep -E "^=== |passed|failed|error" $out | tail -40
+if [ "${SKIP_BENCH:-0}" != "1" ]; then
+  timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
+  tail -c 600 gpurun_out/${tag}_bench.err
+  python - <<PY
+import json
+try:
+    d = json.loads(open("gpurun_out/${tag}_bench.json").read().strip().splitlines()[-1])
+    keep = {k: d[k] for k in ("value", "ms_per_step", "e2e", "gpu_launches", "clocks") if k in d}
+    keep["roofline"] = {k: d["roofline"].get(k) for k in ("achieved", "frac", "conv_ms_per_step", "conv_share_of_step")}
+    keep["gn"] = {k: d["roofline_hbm"].get(k) for k in ("achieved", "frac", "ms_per_step")}
+    keep["train"] = {k: {kk: v.get(kk) for kk in ("ms_per_step", "images_per_s", "tflops_fwd_bwd")} for k, v in d.get("train", {}).items() if isinstance(v, dict) and k.startswith("batch")}
+    keep["cpu_baseline"] = d.get("cpu_baseline")
+    print(json.dumps(keep, indent=1))
+except Exception as e:
+    print("bench parse failed:", e)
+PY
+fi

@@ -61,6 +61,9 @@ parser.add_argument("--shared_weights_over_timesteps", default=False, action="st
 parser.add_argument("--early_stop", default=False, action="store_true")
 # additions of this implementation
 parser.add_argument("--no_cuda_graph", dest="cuda_graph", action="store_false", help="run the DDPM step eagerly")
+parser.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"],
+                    help="bf16: bf16 storage / fp32 accumulation (training and inference); fp32: the reference's default "
+                         "arithmetic to 1e-4 through split-bf16 tensor-core convolutions (inference only)")
 parser.add_argument("--sync_bn", default=False, action="store_true",
                     help="data-parallel head training: share the head's BatchNorm batch statistics over all ranks, so N GPUs "
                          "with B/N images each equal the single-device reference at batch B (default: per-replica statistics)")

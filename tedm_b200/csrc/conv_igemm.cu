@@ -43,9 +43,21 @@ constexpr int NGMAX = 32;        // max GroupNorm groups touched by one N tile
 constexpr int MAX_STAGES = 8;
 constexpr int DYN_SMEM_MAX = 221 * 1024;  // + ~3.3 KB static <= 227 KB per CTA
 
+constexpr int MAX_SRC = 6;
+
+struct ConvMaps {                // every tensor map of a launch (one __grid_constant__ parameter: its elements are addressable)
+  CUtensorMap a[MAX_SRC];
+  CUtensorMap w, out, out2;
+};
+
 struct ConvParams {
   int mode, taps, kxc;           // kxc = taps per filter row
-  int c0_blocks, c1_blocks, C0, C1;
+  int c0_blocks, c1_blocks;      // weight-stationary row mode: the (at most two) sources it walks
+  // A sources, walked in this order inside every tap (K order: tap-major, source, 64-channel block)
+  int n_src;
+  int src_blocks[MAX_SRC], src_C[MAX_SRC];
+  int src_center[MAX_SRC];       // 1: feeds only the centre tap of a 3x3 (a folded 1x1 branch)
+  int num_kb;                    // k-blocks per tile
   int tileW, tileH, tileB, tiles_x, tiles_y;
   int B, Ho, Wo;                 // tile space extent (output pixels; source pixels for mode 3)
   int OH, OW, osy, osx;          // output tensor extent and tile->output coordinate scale
@@ -139,9 +151,10 @@ constexpr int CONV_THREADS = 64 + EPI_THREADS;
 
 template <int BN, bool WS, int CPG, bool RES>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                  const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapOut,
-                  const __grid_constant__ CUtensorMap mapOut2, const ConvParams p) {
+conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
+  const CUtensorMap& mapW = maps.w;
+  const CUtensorMap& mapOut = maps.out;
+  const CUtensorMap& mapOut2 = maps.out2;
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = WS ? A_ROW_BYTES : A_BYTES + B_BYTES;
   constexpr int OUT_BYTES = (BN / 64) * A_BYTES;
@@ -165,8 +178,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   const uint32_t out_base = stage_base + (uint32_t)p.stages * STAGE_BYTES;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&mapA0);
-    if (p.c1_blocks) tma_prefetch_desc(&mapA1);
+    for (int i = 0; i < p.n_src; ++i) tma_prefetch_desc(&maps.a[i]);
     tma_prefetch_desc(&mapW);
     if (!p.out_f32) tma_prefetch_desc(&mapOut);
     if (p.split) tma_prefetch_desc(&mapOut2);
@@ -206,7 +218,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
               const uint32_t full = smem_u32(&bar_full[stage]);
               mbar_expect_tx(full, ROW_PIX * BK * 2);
               const bool second = cb >= p.c0_blocks;
-              tma_load_5d(stage_base + stage * STAGE_BYTES, second ? &mapA1 : &mapA0, full,
+              tma_load_5d(stage_base + stage * STAGE_BYTES, &maps.a[second ? 1 : 0], full,
                           (second ? cb - p.c0_blocks : cb) * BK, t.x0 - 1, 0, t.y0 + dy - 1, t.b0);
               if (++stage == p.stages) {
                 stage = 0;
@@ -233,19 +245,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 offy = ky - 1 + par_y;
                 offx = kx - 1 + par_x;
               }
-              for (int cb = 0; cb < cb_total; ++cb, ++kb) {
-                mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-                const uint32_t full = smem_u32(&bar_full[stage]);
-                mbar_expect_tx(full, STAGE_BYTES);
-                const bool second = cb >= p.c0_blocks;
-                const int cblk = second ? cb - p.c0_blocks : cb;
-                const int chan_off = xsel * (second ? p.C1 : p.C0);
-                const uint32_t a_dst = stage_base + stage * STAGE_BYTES;
-                tma_load_5d(a_dst, second ? &mapA1 : &mapA0, full, chan_off + cblk * BK, t.x0 + offx, pc, t.y0 + offy, t.b0);
-                tma_load_2d(a_dst + A_BYTES, &mapW, full, kb * BK, t.par * p.cout + t.n0);
-                if (++stage == p.stages) {
-                  stage = 0;
-                  phase ^= 1u;
+              const bool centre = p.mode == 1 && ky == 1 && kx == 1;
+              for (int si = 0; si < p.n_src; ++si) {
+                if (p.src_center[si] && !centre) continue;
+                const CUtensorMap* mapA = &maps.a[si];
+                const int chan_off = xsel * p.src_C[si];
+                for (int cblk = 0; cblk < p.src_blocks[si]; ++cblk, ++kb) {
+                  mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+                  const uint32_t full = smem_u32(&bar_full[stage]);
+                  mbar_expect_tx(full, STAGE_BYTES);
+                  const uint32_t a_dst = stage_base + stage * STAGE_BYTES;
+                  tma_load_5d(a_dst, mapA, full, chan_off + cblk * BK, t.x0 + offx, pc, t.y0 + offy, t.b0);
+                  tma_load_2d(a_dst + A_BYTES, &mapW, full, kb * BK, t.par * p.cout + t.n0);
+                  if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                  }
                 }
               }
             }
@@ -288,7 +303,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
               }
             }
         } else {
-          const int num_kb = p.taps * cb_total;
+          const int num_kb = p.num_kb;
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(smem_u32(&bar_full[stage]), phase);
             tc_fence_after();
@@ -524,8 +539,7 @@ int encode_weight_map(CUtensorMap* map, const void* ptr, long long rows, long lo
 }
 
 template <int BN, bool WS, int CPG, bool RES>
-int launch_conv_res(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o,
-                    const CUtensorMap& o2, ConvParams& p, cudaStream_t stream) {
+int launch_conv_res(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
   const int cb_total = p.c0_blocks + p.c1_blocks;
   const int stage_bytes = WS ? A_ROW_BYTES : A_BYTES + BN * BK * 2;
   const int out_bytes = (BN / 64) * A_BYTES;
@@ -544,38 +558,36 @@ int launch_conv_res(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensor
     configured = smem;
   }
   int grid = p.num_tiles < tedm_num_sms() ? p.num_tiles : tedm_num_sms();
-  conv_igemm_kernel<BN, WS, CPG, RES><<<grid, CONV_THREADS, smem, stream>>>(a0, a1, w, o, o2, p);
+  conv_igemm_kernel<BN, WS, CPG, RES><<<grid, CONV_THREADS, smem, stream>>>(maps, p);
   TEDM_LAUNCH_CHECK();
   return TEDM_OK;
 }
 
 // residual / split-output epilogues exist only without GroupNorm statistics (they never co-occur in the net)
 template <int BN, bool WS, int CPG>
-int launch_conv_cpg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o,
-                    const CUtensorMap& o2, ConvParams& p, cudaStream_t stream) {
+int launch_conv_cpg(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
   if constexpr (CPG == 0) {
-    if (p.residual || p.residual2 || p.split) return launch_conv_res<BN, WS, 0, true>(a0, a1, w, o, o2, p, stream);
+    if (p.residual || p.residual2 || p.split) return launch_conv_res<BN, WS, 0, true>(maps, p, stream);
   }
-  return launch_conv_res<BN, WS, CPG, false>(a0, a1, w, o, o2, p, stream);
+  return launch_conv_res<BN, WS, CPG, false>(maps, p, stream);
 }
 
 template <int BN, bool WS>
-int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o,
-                const CUtensorMap& o2, ConvParams& p, cudaStream_t stream) {
+int launch_conv(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
   const int cpg = p.gn_partial ? p.gn_cpg : 0;
-  if (cpg == 0) return launch_conv_cpg<BN, WS, 0>(a0, a1, w, o, o2, p, stream);
+  if (cpg == 0) return launch_conv_cpg<BN, WS, 0>(maps, p, stream);
   if constexpr (BN / 8 <= 8) {
-    if (cpg == 8) return launch_conv_cpg<BN, WS, 8>(a0, a1, w, o, o2, p, stream);
+    if (cpg == 8) return launch_conv_cpg<BN, WS, 8>(maps, p, stream);
   }
   if constexpr (BN / 16 <= 8) {
-    if (cpg == 16) return launch_conv_cpg<BN, WS, 16>(a0, a1, w, o, o2, p, stream);
+    if (cpg == 16) return launch_conv_cpg<BN, WS, 16>(maps, p, stream);
   }
-  if (cpg == 32) return launch_conv_cpg<BN, WS, 32>(a0, a1, w, o, o2, p, stream);
+  if (cpg == 32) return launch_conv_cpg<BN, WS, 32>(maps, p, stream);
   if constexpr (BN >= 64) {
-    if (cpg == 64) return launch_conv_cpg<BN, WS, 64>(a0, a1, w, o, o2, p, stream);
+    if (cpg == 64) return launch_conv_cpg<BN, WS, 64>(maps, p, stream);
   }
   if constexpr (BN >= 128) {
-    if (cpg == 128) return launch_conv_cpg<BN, WS, 128>(a0, a1, w, o, o2, p, stream);
+    if (cpg == 128) return launch_conv_cpg<BN, WS, 128>(maps, p, stream);
   }
   return tedm_set_error(TEDM_ERR_UNSUPPORTED, "tedm_conv_igemm_fwd: %d channels per GroupNorm group with N tile %d", cpg, BN);
 }
@@ -1089,16 +1101,37 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   TEDM_UNSUPPORTED(a->c0 % BK != 0 || a->c1 % BK != 0, "tedm_conv_igemm_fwd: channel counts (%d, %d) must be multiples of %d",
                    a->c0, a->c1, BK);
   TEDM_UNSUPPORTED(a->cout % 64 != 0, "tedm_conv_igemm_fwd: cout=%d must be a multiple of 64", a->cout);
-  TEDM_UNSUPPORTED(a->mode == 2 && a->c1 != 0, "tedm_conv_igemm_fwd: stride-2 mode takes one source");
+  TEDM_CHECK_ARG(a->n_extra >= 0 && a->n_extra <= MAX_SRC - 2, "tedm_conv_igemm_fwd: n_extra=%d", a->n_extra);
 
   ConvParams p{};
   p.mode = a->mode;
   p.kxc = a->mode == 0 ? 1 : a->mode == 1 ? 3 : a->mode == 2 ? 4 : 2;
   p.taps = p.kxc * p.kxc;
-  p.C0 = a->c0;
-  p.C1 = a->c1;
   p.c0_blocks = a->c0 / BK;
   p.c1_blocks = a->c1 / BK;
+  // the A sources in K order: src0, src1, then the extras
+  const void* src_ptr[MAX_SRC];
+  long long src_stride[MAX_SRC];
+  long long ktot = 0;
+  auto add_src = [&](const void* ptr, int c, long long stride, int centre) {
+    src_ptr[p.n_src] = ptr;
+    src_stride[p.n_src] = stride ? stride : (long long)a->height * a->width * c;
+    p.src_blocks[p.n_src] = c / BK;
+    p.src_C[p.n_src] = c;
+    p.src_center[p.n_src] = centre;
+    p.num_kb += (centre ? 1 : p.taps) * (c / BK);
+    ktot += (long long)(centre ? 1 : p.taps) * c;
+    ++p.n_src;
+  };
+  add_src(a->src0, a->c0, a->src0_image_stride, 0);
+  if (a->src1) add_src(a->src1, a->c1, a->src1_image_stride, 0);
+  for (int i = 0; i < a->n_extra; ++i) {
+    TEDM_CHECK_ARG(a->extra_src[i] && a->extra_c[i] > 0, "tedm_conv_igemm_fwd: extra source %d is empty", i);
+    TEDM_UNSUPPORTED(a->extra_c[i] % BK != 0, "tedm_conv_igemm_fwd: extra source %d has %d channels (multiple of %d needed)", i,
+                     a->extra_c[i], BK);
+    TEDM_UNSUPPORTED(a->extra_center[i] && a->mode != 1, "tedm_conv_igemm_fwd: centre-tap sources belong to a 3x3 conv");
+    add_src(a->extra_src[i], a->extra_c[i], a->extra_image_stride[i], a->extra_center[i] != 0);
+  }
   p.B = a->batch;
   p.Ho = a->mode == 2 ? a->height / 2 : a->height;
   p.Wo = a->mode == 2 ? a->width / 2 : a->width;
@@ -1168,23 +1201,23 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
 
   // weight-stationary row mode: 3x3, whole 128-pixel rows per tile, one N tile of 64, weights fit in smem
   const bool ws = g_enable_ws && a->mode == 1 && p.tileH == 1 && p.tileB == 1 && p.tileW == BM && a->cout == 64 && bn == 64 &&
-                  (a->c0 + a->c1) <= 128;
+                  (a->c0 + a->c1) <= 128 && a->n_extra == 0;
 
-  alignas(64) CUtensorMap mapA0, mapA1, mapW, mapOut, mapOut2;
+  alignas(64) ConvMaps maps;
+  CUtensorMap& mapW = maps.w;
+  CUtensorMap& mapOut = maps.out;
+  CUtensorMap& mapOut2 = maps.out2;
   const int boxW = ws ? ROW_PIX : p.tileW;
-  int rc = encode_act_map(&mapA0, a->src0, a->batch, a->height, a->width, a->c0,
-                          a->src0_image_stride ? a->src0_image_stride : (long long)a->height * a->width * a->c0, a->mode,
-                          boxW, p.tileH, p.tileB);
-  if (rc) return rc;
-  if (a->src1) {
-    rc = encode_act_map(&mapA1, a->src1, a->batch, a->height, a->width, a->c1,
-                        a->src1_image_stride ? a->src1_image_stride : (long long)a->height * a->width * a->c1, a->mode,
-                        boxW, p.tileH, p.tileB);
-    if (rc) return rc;
-  } else {
-    mapA1 = mapA0;
+  int rc = TEDM_OK;
+  for (int i = 0; i < MAX_SRC; ++i) {
+    if (i < p.n_src) {
+      rc = encode_act_map(&maps.a[i], src_ptr[i], a->batch, a->height, a->width, p.src_C[i], src_stride[i], a->mode, boxW,
+                          p.tileH, p.tileB);
+      if (rc) return rc;
+    } else {
+      maps.a[i] = maps.a[0];
+    }
   }
-  const long long ktot = (long long)p.taps * (a->c0 + a->c1);
   rc = encode_weight_map(&mapW, a->weight, (long long)zdim * a->cout, ktot, bn);
   if (rc) return rc;
   if (!p.out_f32) {
@@ -1194,7 +1227,7 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
                         a->mode == 3 ? 2 : 0, p.tileW, p.tileH, p.tileB);
     if (rc) return rc;
   } else {
-    mapOut = mapA0;
+    mapOut = maps.a[0];
   }
   if (a->split) {
     rc = encode_act_map(&mapOut2, a->out2, a->batch, p.OH, p.OW, a->cout - a->split, p.out2_image_stride, 0, p.tileW, p.tileH,
@@ -1205,11 +1238,11 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   }
 
   cudaStream_t s = (cudaStream_t)stream;
-  if (ws) return launch_conv<64, true>(mapA0, mapA1, mapW, mapOut, mapOut2, p, s);
+  if (ws) return launch_conv<64, true>(maps, p, s);
   switch (bn) {
-    case 64: return launch_conv<64, false>(mapA0, mapA1, mapW, mapOut, mapOut2, p, s);
-    case 128: return launch_conv<128, false>(mapA0, mapA1, mapW, mapOut, mapOut2, p, s);
-    default: return launch_conv<256, false>(mapA0, mapA1, mapW, mapOut, mapOut2, p, s);
+    case 64: return launch_conv<64, false>(maps, p, s);
+    case 128: return launch_conv<128, false>(maps, p, s);
+    default: return launch_conv<256, false>(maps, p, s);
   }
 }
 

@@ -352,7 +352,8 @@ extern "C" int tedm_head_infer(const tedm_head_args* a, tedm_stream_t stream) {
   p.logits = a->logits;
   const long long npix = (long long)a->n_img * a->height * a->width;
   TEDM_CHECK_ARG(a->g_dtype == 0 || a->g_dtype == 1, "tedm_head_infer: g_dtype=%d", a->g_dtype);
-  if (a->g_dtype == 1 && npix % 16 == 0) {   // tensor-core tail
+  TEDM_CHECK_ARG(!a->exact || (a->g_dtype == 1 && a->f_full == nullptr), "tedm_head_infer: exact mode takes fp32 g maps for every level");
+  if (a->g_dtype == 1 && npix % 16 == 0 && !a->exact) {   // tensor-core tail
     const bool fuse = a->f_full != nullptr;
     TEDM_CHECK_ARG(!fuse || (a->w1_full && a->c_full == 64 && a->n_sum == 1),
                    "tedm_head_infer: the fused full-resolution level needs its weight slice, 64 channels and n_sum == 1");

@@ -271,30 +271,10 @@ class UnetEngine:
         return N.conv_igemm(o, self._w(key + ".to_out"), N.MODE_1X1, c,
                             bias=self._f32(att.to_out.bias), residual=x)
 
-    @staticmethod
-    def _fire(mod: nn.Module, ins, out: Tensor) -> None:
-        """Forward hooks registered on a submodule (the reference's DatasetDM hooks `ups[i][2]`, datasetDM_model.py:50-53)
-        see what they would see in the reference: NCHW fp32 input(s) and output.  The engine does not go through the
-        submodules' own forward, so it calls the hooks itself; a hook may observe, not replace, the output."""
-        if not mod._forward_hooks:
-            return
-        xin = [N.nhwc_to_nchw_f32(i) for i in ins]                 # a decoder block's input is cat(h, skip)
-        args = (torch.cat(xin, dim=1) if len(xin) > 1 else xin[0],)
-        o = N.nhwc_to_nchw_f32(out)
-        for hook in list(mod._forward_hooks.values()):
-            if hook(mod, args, o) is not None:
-                raise NotImplementedError("forward hooks that replace a submodule's output are not supported by the fused engine")
-
-    # -- whole network ----------------------------------------------------------------------------
-    def forward(self, x: Tensor, timestep: Optional[Tensor], want_features: bool = False, skip_tail: bool = False,
-                tape: Optional[Tape] = None, time_key=None):
+    def _time_projection(self, x: Tensor, timestep: Optional[Tensor], tape: Optional[Tape], time_key) -> Optional[Tensor]:
+        """(B, sum of 2*Cout over the ResnetBlocks) fp32: every block's (scale, shift) from ONE batched projection of the
+        time embedding (unet_model.py:76-93, 287-292, 151, 163-166); None without a timestep."""
         m = self.m
-        if not x.is_cuda:
-            raise RuntimeError("tedm_b200.Unet runs on CUDA (sm_100a) only; there is no CPU fallback")
-        if x.dim() != 4 or x.shape[1] != m.channels:
-            raise ValueError(f"expected input (B, {m.channels}, H, W), got {tuple(x.shape)}")
-        x = x.detach().float().contiguous()
-        self._ensure_weights(train=tape is not None)
         tproj = None
         if timestep is not None and getattr(m, "learned_sinusoidal_cond", False):
             # learned-frequency embedding (unet_model.py:96-114): never enabled by a reference entry point; its (B, 17) ->
@@ -325,6 +305,34 @@ class UnetEngine:
             else:
                 wcat, bcat = self._time_cat()
                 tproj = N.time_proj(N.time_embed(t, freq, *tw), wcat, bcat)
+
+        return tproj
+
+    @staticmethod
+    def _fire(mod: nn.Module, ins, out: Tensor) -> None:
+        """Forward hooks registered on a submodule (the reference's DatasetDM hooks `ups[i][2]`, datasetDM_model.py:50-53)
+        see what they would see in the reference: NCHW fp32 input(s) and output.  The engine does not go through the
+        submodules' own forward, so it calls the hooks itself; a hook may observe, not replace, the output."""
+        if not mod._forward_hooks:
+            return
+        xin = [N.nhwc_to_nchw_f32(i) for i in ins]                 # a decoder block's input is cat(h, skip)
+        args = (torch.cat(xin, dim=1) if len(xin) > 1 else xin[0],)
+        o = N.nhwc_to_nchw_f32(out)
+        for hook in list(mod._forward_hooks.values()):
+            if hook(mod, args, o) is not None:
+                raise NotImplementedError("forward hooks that replace a submodule's output are not supported by the fused engine")
+
+    # -- whole network ----------------------------------------------------------------------------
+    def forward(self, x: Tensor, timestep: Optional[Tensor], want_features: bool = False, skip_tail: bool = False,
+                tape: Optional[Tape] = None, time_key=None):
+        m = self.m
+        if not x.is_cuda:
+            raise RuntimeError("tedm_b200.Unet runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if x.dim() != 4 or x.shape[1] != m.channels:
+            raise ValueError(f"expected input (B, {m.channels}, H, W), got {tuple(x.shape)}")
+        x = x.detach().float().contiguous()
+        self._ensure_weights(train=tape is not None)
+        tproj = self._time_projection(x, timestep, tape, time_key)
 
         h = N.stem_conv7x7(x, self._f32(m.init_conv.weight), self._f32(m.init_conv.bias))
         stem = h

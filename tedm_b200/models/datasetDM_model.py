@@ -63,6 +63,16 @@ class DatasetDM(nn.Module):
             nn.Conv2d(128, 32, 1), nn.ReLU(), nn.BatchNorm2d(32), nn.Conv2d(32, 1, 1))
         self._cache = WeightCache()
 
+    def set_precision(self, precision: str) -> "DatasetDM":
+        """'bf16' (default) | 'fp32': the UNet features AND the head then run at the reference's fp32 accuracy
+        (tedm_b200/engine_fp32.py); inference only."""
+        self.diffusion_model.set_precision(precision)
+        return self
+
+    @property
+    def precision(self) -> str:
+        return self.diffusion_model.model.precision
+
     # -- feature extraction -----------------------------------------------------------------------
     @torch.no_grad()
     def feature_maps(self, x_0: Tensor, noise: Optional[Tensor] = None) -> Tuple[List[Tensor], int, int]:
@@ -95,7 +105,8 @@ class DatasetDM(nn.Module):
         """Reference-format output (B, 960*S, H, W) fp32, channel order [step0: l0..l3, step1: ...]."""
         feats, b, s = self.feature_maps(x_0, noise)
         size = x_0.shape[-1]
-        ups = [F.interpolate(N.nhwc_to_nchw_f32(f), size=[size, size]) for f in feats]      # (B*S, C_l, H, W)
+        nchw = lambda f: f.permute(0, 3, 1, 2).contiguous() if f.dtype == torch.float32 else N.nhwc_to_nchw_f32(f)
+        ups = [F.interpolate(nchw(f), size=[size, size]) for f in feats]                        # (B*S, C_l, H, W)
         per_step = torch.cat(ups, dim=1)                                                        # (B*S, 960, H, W)
         return per_step.reshape(b, s * per_step.shape[1], size, size)
 
@@ -116,15 +127,17 @@ class DatasetDM(nn.Module):
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            l0 = N.launches
+            l0, f0 = N.launches, N.conv_flops
             with torch.cuda.graph(graph):
                 out = self.segment(sx, sn)
-            g = self._seg_graph = {"sig": sig, "graph": graph, "x": sx, "noise": sn, "out": out, "calls": N.launches - l0}
+            g = self._seg_graph = {"sig": sig, "graph": graph, "x": sx, "noise": sn, "out": out, "calls": N.launches - l0,
+                                   "conv_flops": N.conv_flops - f0}
         g["x"].copy_(x, non_blocking=True)
         if noise is not None:
             g["noise"].copy_(noise, non_blocking=True)
         g["graph"].replay()
         N.launches += g["calls"]          # native launches inside the replayed graph (bench.py's gpu_launches claim)
+        N.conv_flops += g["conv_flops"]   # ... and the conv FLOPs they execute
         return g["out"]
 
     # -- head -------------------------------------------------------------------------------------
@@ -155,6 +168,21 @@ class DatasetDM(nn.Module):
             cl = chans[l]
             if l in skip:
                 continue
+            if f.dtype == torch.float32:
+                # fp32 mode: the same per-level 1x1 conv with (hi, lo) operand pairs (hi*hi + lo*hi + hi*lo on tcgen05)
+                from ..engine_fp32 import split_weight
+                if shared:
+                    wl = self._cache.get(f"w1.l{l}:w3", (w1,), lambda w, o=offs[l], c=cl: split_weight(w[:, o:o + c], N.MODE_1X1))
+                    g_maps.append(N.f32_conv(N.f32_split(f), wl, N.MODE_1X1, w1.shape[0]))
+                else:
+                    g = torch.empty(b * s, f.shape[1], f.shape[2], w1.shape[0], device=f.device, dtype=torch.float32)
+                    hi, lo = N.f32_split(f)
+                    for st in range(s):
+                        wl = self._cache.get(f"w1.s{st}.l{l}:w3", (w1,),
+                                             lambda w, o=st * ctot + offs[l], c=cl: split_weight(w[:, o:o + c], N.MODE_1X1))
+                        N.f32_conv((hi[st::s], lo[st::s]), wl, N.MODE_1X1, w1.shape[0], out=g[st::s])
+                    g_maps.append(g)
+                continue
             if shared:
                 wl = self._cache.get(f"w1.l{l}", (w1,), lambda w, o=offs[l], c=cl: w[:, o:o + c, 0, 0].to(torch.bfloat16).contiguous())
                 g_maps.append(N.conv_igemm(f, wl, N.MODE_1X1, w1.shape[0], out_dtype=torch.float32))
@@ -183,7 +211,9 @@ class DatasetDM(nn.Module):
         shifts = [(size // f.shape[1]).bit_length() - 1 for f in feats]
         offs = [sum(chans[:l]) for l in range(len(chans))]
         # shared head: the full-resolution level's layer 1 (64 -> 128) runs inside the tail kernel, its fp32 map never exists
-        fuse_full = shared and shifts[-1] == 0 and chans[-1] == 64 and convs[0].out_channels == 128 and (b * s * size * size) % 16 == 0
+        exact = feats[0].dtype == torch.float32         # fp32 mode: every level's layer 1 as an fp32 map, pure-fp32 tail kernel
+        fuse_full = (not exact and shared and shifts[-1] == 0 and chans[-1] == 64 and convs[0].out_channels == 128
+                     and (b * s * size * size) % 16 == 0)
         last = len(feats) - 1
         g_maps = self._layer1_maps(feats, convs[0].weight, shared, b, s, chans, offs, skip=(last,) if fuse_full else ())
         f_full = w1_full = None
@@ -205,7 +235,7 @@ class DatasetDM(nn.Module):
                               f32(convs[0].bias), ac1[0], ac1[1], f32(convs[1].weight).reshape(convs[1].out_channels, -1),
                               f32(convs[1].bias), ac2[0], ac2[1], f32(convs[2].weight).reshape(-1),
                               float(self._cache.get("b3", (convs[2].bias,), lambda bb: bb.float().cpu()).item()),
-                              f_full=f_full, w1_full=w1_full)
+                              f_full=f_full, w1_full=w1_full, exact=exact)
         return logits
 
     @torch.no_grad()

@@ -74,13 +74,18 @@ class DiffusionModel(nn.Module):
         self.timesteps = timesteps
         self.objective = objective
         self.dynamic_threshold_percentile: float = self.default("dynamic_threshold_percentile", 0.995)
-        self.model = Unet(dim, dim_mults=dim_mults, channels=channels)
+        self.model = Unet(dim, dim_mults=dim_mults, channels=channels, precision=self.default("precision", "bf16"))
         for name, table in make_schedule(beta_schedule, timesteps, p2_gamma, p2_k).items():
             self.register_buffer(name, table)
         self._host_tables: Optional[Tuple[tuple, Dict[str, Tensor]]] = None
 
     def default(self, val, d):  # :117-118
         return vars(self.config)[val] if val in self.config else d
+
+    def set_precision(self, precision: str) -> "DiffusionModel":
+        """'bf16' | 'fp32' (see Unet.set_precision); the DDPM arithmetic around the UNet is fp32 in both."""
+        self.model.set_precision(precision)
+        return self
 
     # -- helpers ----------------------------------------------------------------------------------
     def _host(self, name: str) -> Tensor:

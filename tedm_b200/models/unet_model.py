@@ -292,10 +292,27 @@ class Unet(nn.Module):
         self.final_res_block = block(dim * 2, dim)
         self.final_conv = Conv2d(dim, self.out_dim, 1)
         self._engine = None
+        self._engine32 = None
+        self.precision = "bf16"
+        self.set_precision(kwargs.get("precision", "bf16"))
 
     # -- execution ------------------------------------------------------------------------------
+    def set_precision(self, precision: str) -> "Unet":
+        """"bf16" (default): bf16 storage / fp32 accumulation, forward and backward -- the throughput mode.
+        "fp32": the reference's default arithmetic (config.py:15) to 1e-4 -- fp32 storage, split-bf16 tensor-core
+        convolutions (tedm_b200/engine_fp32.py); inference only."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        self.precision = precision
+        return self
+
     @property
     def engine(self):
+        if self.precision == "fp32":
+            if self._engine32 is None:
+                from ..engine_fp32 import UnetEngineF32
+                self._engine32 = UnetEngineF32(self)
+            return self._engine32
         if self._engine is None:
             from ..engine import UnetEngine
             self._engine = UnetEngine(self)
@@ -305,6 +322,11 @@ class Unet(nn.Module):
         """(B, channels, H, W) fp32, (B,) int64 -> (B, out_dim, H, W) fp32.  `cond` is accepted and ignored,
         as in the reference (unet_model.py:333)."""
         params = tuple(self.parameters())
+        if self.precision == "fp32":
+            if torch.is_grad_enabled() and any(p.requires_grad for p in params) and self.training:
+                raise NotImplementedError("precision='fp32' is an inference mode (call under torch.no_grad() / eval()); "
+                                          "training runs in the bf16 mode")
+            return self.engine.forward(x, timestep)
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             # training: forward keeps a tape, backward is the native reverse schedule (tedm_b200/engine.py)
             from ..engine import UnetFunction

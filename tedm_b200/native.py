@@ -22,7 +22,9 @@ class ConvArgs(C.Structure):  # tedm_conv_args
     _fields_ = [("src0", _p), ("src1", _p), ("weight", _p), ("bias", _p), ("residual", _p), ("out", _p),
                 ("gn_partial", _p), ("batch", _i), ("height", _i), ("width", _i), ("c0", _i), ("c1", _i),
                 ("cout", _i), ("mode", _i), ("gn_groups", _i), ("out_dtype", _i), ("src0_image_stride", _i64),
-                ("src1_image_stride", _i64), ("out_image_stride", _i64), ("split", _i), ("out2", _p), ("residual2", _p)]
+                ("src1_image_stride", _i64), ("out_image_stride", _i64), ("split", _i), ("out2", _p), ("residual2", _p),
+                ("n_extra", _i), ("extra_src", _p * 4), ("extra_c", _i * 4), ("extra_image_stride", _i64 * 4),
+                ("extra_center", _i * 4)]
 
 
 class WeightEntry(C.Structure):  # tedm_weight_entry
@@ -32,7 +34,7 @@ class WeightEntry(C.Structure):  # tedm_weight_entry
 class HeadArgs(C.Structure):  # tedm_head_args
     _fields_ = [("g", _p * 4), ("g_dtype", _i), ("shift", _i * 4), ("n_levels", _i), ("n_sum", _i), ("n_img", _i), ("height", _i),
                 ("width", _i), ("c1", _i), ("c2", _i), ("b1", _p), ("bn1_a", _p), ("bn1_c", _p), ("w2", _p),
-                ("b2", _p), ("bn2_a", _p), ("bn2_c", _p), ("w3", _p), ("b3", _f), ("logits", _p), ("f_full", _p), ("w1_full", _p), ("c_full", _i)]
+                ("b2", _p), ("bn2_a", _p), ("bn2_c", _p), ("w3", _p), ("b3", _f), ("logits", _p), ("f_full", _p), ("w1_full", _p), ("c_full", _i), ("exact", _i)]
 
 
 # name -> (restype, argtypes); must list every symbol include/tedm_b200.h declares
@@ -99,6 +101,15 @@ SIGNATURES = {
     "tedm_u8_to_unit": (_i, [_p, _p, C.c_longlong, _p]),
     "tedm_u8_masks_to_label": (_i, [_p, _p, C.c_longlong, C.c_longlong, _i, _p]),
     "tedm_debug_umma_probe": (_i, [_p, _p, C.POINTER(_i), C.POINTER(_i), _i, _p, _p]),
+    "tedm_f32_split": (_i, [_p, _p, _p, _i64, _p]),
+    "tedm_f32_stem_conv7x7": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "tedm_f32_gn_silu": (_i, [_p, _p, _i, _p, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _f, _p]),
+    "tedm_f32_layernorm": (_i, [_p, _p, _p, _p, _i64, _i, _f, _p]),
+    "tedm_f32_linear_attention_workspace": (_i64, [_i, _i, _i]),
+    "tedm_f32_linear_attention": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _p]),
+    "tedm_f32_attention": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _p]),
+    "tedm_f32_final_conv1x1": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "tedm_f32_add": (_i, [_p, _p, _p, _i64, _p]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -265,18 +276,23 @@ def _nhwc(t: Optional[torch.Tensor], name: str, dtype=torch.bfloat16):
 
 def conv_igemm(src0: torch.Tensor, weight: torch.Tensor, mode: int, cout: int, bias=None, src1=None, residual=None,
                gn_groups: int = 0, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16, split: int = 0,
-               residual2=None):
+               residual2=None, extra: Sequence = ()):
     """Returns out (B, Ho, Wo, cout) bf16 (or fp32) [, gn_partial (B, parts, groups, 2) fp32 if gn_groups > 0].
     src0/src1/out may be batch-strided views (e.g. x[s::S]); residual must share out's strides.
-    split > 0: returns (out[..., :split], out2[..., split:]) as two dense tensors (+ residual / residual2)."""
+    split > 0: returns (out[..., :split], out2[..., split:]) as two dense tensors (+ residual / residual2).
+    extra: up to four more A sources [(tensor, centre_only)], walked after src0/src1 inside every tap (centre_only: a
+    1x1 branch folded into the centre tap of a 3x3)."""
     b, h, w, c0 = src0.shape
     c1 = src1.shape[3] if src1 is not None else 0
     if src1 is not None and src1.shape[:3] != src0.shape[:3]:
         raise ValueError("conv_igemm: src0/src1 extent mismatch")
     oh, ow = (h // 2, w // 2) if mode == MODE_4X4S2 else ((2 * h, 2 * w) if mode == MODE_UP3X3 else (h, w))
     taps = {MODE_1X1: 1, MODE_3X3: 9, MODE_4X4S2: 16, MODE_UP3X3: 16}[mode]
-    if weight.numel() != cout * taps * (c0 + c1):
-        raise ValueError(f"conv_igemm: weight has {weight.numel()} elements, expected {cout * taps * (c0 + c1)}")
+    if len(extra) > 4:
+        raise ValueError("conv_igemm: at most four extra sources")
+    k_total = taps * (c0 + c1) + sum((1 if ctr else taps) * t.shape[3] for t, ctr in extra)
+    if weight.numel() != cout * k_total:
+        raise ValueError(f"conv_igemm: weight has {weight.numel()} elements, expected {cout * k_total}")
     out2 = None
     if split:
         if out is not None or gn_groups or out_dtype != torch.bfloat16:
@@ -303,8 +319,14 @@ def conv_igemm(src0: torch.Tensor, weight: torch.Tensor, mode: int, cout: int, b
     a = ConvArgs(p0, p1, _ptr(weight, torch.bfloat16, "weight"), _ptr(bias, torch.float32, "bias"), pr, po, _ptr(gnp),
                  b, h, w, c0, c1, cout, mode, gn_groups, 1 if out.dtype == torch.float32 else 0, s0, s1,
                  0 if split else so, split, _ptr(out2), _ptr(residual2, torch.bfloat16, "residual2"))
+    a.n_extra = len(extra)
+    for i, (t, ctr) in enumerate(extra):
+        if t.shape[:3] != src0.shape[:3]:
+            raise ValueError("conv_igemm: extra source extent mismatch")
+        a.extra_src[i], a.extra_image_stride[i] = _nhwc(t, f"extra[{i}]")
+        a.extra_c[i], a.extra_center[i] = t.shape[3], int(bool(ctr))
     global conv_flops
-    flops = 2 * b * (h * w if mode == MODE_UP3X3 else oh * ow) * cout * taps * (c0 + c1)
+    flops = 2 * b * (h * w if mode == MODE_UP3X3 else oh * ow) * cout * k_total
     conv_flops += flops
     if conv_timer is not None:
         with conv_timer(flops, (mode, b, h, w, c0, c1, cout, bool(gn_groups), residual is not None)):
@@ -592,13 +614,14 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr: float, beta1: float, beta2: 
 # head
 # ------------------------------------------------------------------------------------------------
 def head_infer(g_maps: Sequence[torch.Tensor], shifts: Sequence[int], n_sum: int, n_img: int, height: int, width: int,
-               b1, bn1_a, bn1_c, w2, b2, bn2_a, bn2_c, w3, b3: float, f_full=None, w1_full=None):
+               b1, bn1_a, bn1_c, w2, b2, bn2_a, bn2_c, w3, b3: float, f_full=None, w1_full=None, exact: bool = False):
     """g_maps: layer-1 outputs per level (fp32 / bf16 NHWC); optionally the full-resolution level as its bf16 feature map
     `f_full` + weight slice `w1_full` (its layer 1 is then fused into the tail kernel)."""
     a = HeadArgs()
     gdt = g_maps[0].dtype if g_maps else torch.float32
     a.f_full, a.w1_full = _ptr(f_full, torch.bfloat16, "f_full"), _ptr(w1_full, torch.bfloat16, "w1_full")
     a.c_full = f_full.shape[-1] if f_full is not None else 0
+    a.exact = int(exact)        # fp32 precision mode: the plain-fp32 tail kernel (fp32 g maps) instead of the tensor-core one
     if gdt not in (torch.bfloat16, torch.float32):
         raise TypeError("head_infer: g maps must be bf16 or fp32")
     a.g_dtype = 1 if gdt == torch.float32 else 0
@@ -757,6 +780,90 @@ def u8_masks_to_label(src: torch.Tensor) -> torch.Tensor:
     dst = torch.empty(b, 1, h, w, device=src.device, dtype=torch.float32)
     _call("tedm_u8_masks_to_label", _ptr(src, torch.uint8, "src"), _ptr(dst), b, h * w, k, _stream())
     return dst
+
+
+# ------------------------------------------------------------------------------------------------
+# fp32 precision mode (activations: NHWC fp32 tensors of shape (B, H, W, C)); see csrc/fp32_mode.cu
+# ------------------------------------------------------------------------------------------------
+F32 = torch.float32
+
+
+def f32_split(x: torch.Tensor):
+    """fp32 -> (hi, lo) bf16 with hi + lo == x to 2^-18 relative."""
+    hi = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    lo = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _call("tedm_f32_split", _ptr(x, F32, "x"), _ptr(hi), _ptr(lo), x.numel(), _stream())
+    return hi, lo
+
+
+def f32_conv(src0, weight3, mode: int, cout: int, bias=None, src1=None, gn_groups: int = 0, out=None):
+    """fp32-grade convolution of fp32 NHWC input(s) on the tcgen05 kernel: operands as bf16 (hi, lo) pairs, product
+    hi*hi + lo*hi + hi*lo.  src0 / src1: (hi, lo) pairs from f32_split; weight3: bf16 [cout][taps][3 * (c0 + c1)] =
+    cat(w_hi, w_hi, w_lo) along the channel axis.  Returns fp32 out [, GroupNorm partials]."""
+    h0, l0 = src0
+    if src1 is None:
+        return conv_igemm(h0, weight3, mode, cout, bias=bias, gn_groups=gn_groups, out=out, out_dtype=F32,
+                          extra=[(l0, False), (h0, False)])
+    h1, l1 = src1
+    return conv_igemm(h0, weight3, mode, cout, bias=bias, src1=h1, gn_groups=gn_groups, out=out, out_dtype=F32,
+                      extra=[(l0, False), (l1, False), (h0, False), (h1, False)])
+
+
+def f32_stem_conv7x7(x, weight, bias):
+    b, cin, h, w = x.shape
+    cout = weight.shape[0]
+    out = torch.empty(b, h, w, cout, device=x.device, dtype=F32)
+    _call("tedm_f32_stem_conv7x7", _ptr(x, F32, "x"), _ptr(weight, F32), _ptr(bias, F32), _ptr(out), b, cin, h, w, cout, _stream())
+    return out
+
+
+def f32_gn_silu(x, gn_partial, gamma, beta, groups: int, eps: float = 1e-5, scale_shift=None, ss_offset: int = 0, residual=None):
+    b, h, w, c = x.shape
+    out = torch.empty_like(x)
+    _call("tedm_f32_gn_silu", _ptr(x, F32, "x"), _ptr(gn_partial, F32), gn_partial.shape[1], _ptr(gamma, F32), _ptr(beta, F32),
+          _ptr(scale_shift, F32), scale_shift.shape[1] if scale_shift is not None else 0, ss_offset, _ptr(residual, F32, "residual"),
+          _ptr(out), b, h * w, c, groups, eps, _stream())
+    return out
+
+
+def f32_layernorm(x, g, eps: float = 1e-5, residual=None):
+    c = x.shape[-1]
+    out = torch.empty_like(x)
+    _call("tedm_f32_layernorm", _ptr(x, F32, "x"), _ptr(g, F32), _ptr(residual, F32, "residual"), _ptr(out), x.numel() // c, c, eps,
+          _stream())
+    return out
+
+
+def f32_linear_attention(qkv, heads: int = 4, dim_head: int = 32, scale: Optional[float] = None):
+    b, h, w, c3 = qkv.shape
+    n = h * w
+    ws = torch.empty(load().tedm_f32_linear_attention_workspace(b, n, heads), device=qkv.device, dtype=F32)
+    out = torch.empty(b, h, w, heads * dim_head, device=qkv.device, dtype=F32)
+    _call("tedm_f32_linear_attention", _ptr(qkv, F32, "qkv"), _ptr(out), _ptr(ws), b, n, heads, dim_head,
+          float(dim_head ** -0.5 if scale is None else scale), _stream())
+    return out
+
+
+def f32_attention(qkv, heads: int = 4, dim_head: int = 32, scale: float = 16.0):
+    b, h, w, c3 = qkv.shape
+    out = torch.empty(b, h, w, heads * dim_head, device=qkv.device, dtype=F32)
+    rnorm = torch.empty(b, 2 * heads * dim_head, device=qkv.device, dtype=F32)
+    _call("tedm_f32_attention", _ptr(qkv, F32, "qkv"), _ptr(out), _ptr(rnorm), b, h * w, heads, dim_head, float(scale), _stream())
+    return out
+
+
+def f32_final_conv1x1(x, weight, bias):
+    b, h, w, c = x.shape
+    od = weight.shape[0]
+    out = torch.empty(b, od, h, w, device=x.device, dtype=F32)
+    _call("tedm_f32_final_conv1x1", _ptr(x, F32, "x"), _ptr(weight, F32), _ptr(bias, F32), _ptr(out), b, h * w, c, od, _stream())
+    return out
+
+
+def f32_add(a, b):
+    out = torch.empty_like(a)
+    _call("tedm_f32_add", _ptr(a, F32, "a"), _ptr(b, F32, "b"), _ptr(out), a.numel(), _stream())
+    return out
 
 
 def umma_probe(A, Bm, shifts: Sequence[int], base_offsets: Sequence[int]):

@@ -2,6 +2,7 @@
 include/tedm_b200.h declares (no compute calls: there is no GPU here)."""
 import os
 import re
+import sys
 
 import pytest
 
@@ -114,3 +115,26 @@ def test_snapshot_grid_matches_torchvision_make_grid():
     for n, c, h in ((8, 1, 16), (5, 1, 12), (8, 3, 8)):
         imgs = torch.rand(n, c, h, h, generator=g)
         assert torch.equal(snapshot_grid(imgs), tv.make_grid(imgs, nrow=4)), (n, c, h)
+
+
+def test_vendored_reference_is_unmodified_and_is_what_the_cpu_leg_times():
+    """oracle/_ref (git-ignored, made by oracle/make_ref.py) holds byte-identical copies of the reference's own files, and
+    bench.py's CPU leg runs THEM (cpu_baseline.kind == "reference"); without it the leg falls back to the oracle port."""
+    import hashlib
+    import json
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isfile(os.path.join(ref_dir, "MANIFEST.json")):
+        pytest.skip("oracle/_ref not built (python oracle/make_ref.py needs /root/reference)")
+    manifest = json.load(open(os.path.join(ref_dir, "MANIFEST.json")))["sha256"]
+    for rel, digest in manifest.items():
+        assert hashlib.sha256(open(os.path.join(ref_dir, rel), "rb").read()).hexdigest() == digest, rel
+        src = os.path.join("/root/reference", rel)
+        if os.path.isfile(src):
+            assert open(src, "rb").read() == open(os.path.join(ref_dir, rel), "rb").read(), rel
+    import subprocess
+    tracked = subprocess.run(["git", "ls-files", "oracle/_ref"], cwd=ROOT, capture_output=True, text=True).stdout.strip()
+    assert tracked == "", "reference sources must never be committed"
+    sys.path.insert(0, ROOT)
+    import bench
+    v, dt, kind = bench.cpu_tedm_images_per_s(1)
+    assert kind == "reference" and v > 0

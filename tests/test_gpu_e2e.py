@@ -82,13 +82,25 @@ def _tedm(n_steps, shared, steps):
     return m.eval().cuda()
 
 
-# An untrained (random-init) head puts every logit at the decision threshold: the reference's logits
-# have std 0.04 around 0.03 and ~64 % of the pixels have |prob - 0.5| < 0.01, i.e. the logits are a
-# near-cancelling residual of O(1) activations.  bf16 feature rounding (features themselves are within
-# 0.7 % of the reference) shows up as ~2 % there (the bf16-emulating oracle gives 1.8 %), so those
-# fixtures get a 3e-2 logit budget and a "disagreements only inside the rounding band" mask check;
-# the >= 99.9 % mask criterion is asserted on the fixtures whose head the reference trained.
-TOL_UNTRAINED_LOGITS = 3e-2
+# An untrained (random-init) head puts every logit at the decision threshold: the reference's logits have std 0.04
+# around 0.03 and ~64 % of the pixels have |prob - 0.5| < 0.01, i.e. the logits are a near-cancelling residual of O(1)
+# activations and amplify any rounding of the features ~4x.  What reduced-precision arithmetic can deliver there is
+# pinned by the reference itself: tests/golden/noise_floor.json holds the reference run under
+# torch.autocast(bfloat16) against the reference in fp32 on the SAME fixtures (tests/golden/make_golden_floor.py).  The
+# bf16 path must be at least that close (it is ~10x closer); the fp32 mode meets >= 99.9 % on the same fixtures
+# (tests/test_gpu_fp32.py).  The trained-head fixtures carry the north-star assertion for the bf16 path.
+import json
+import os
+
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "noise_floor.json")) as _fh:
+    FLOOR = json.load(_fh)
+
+
+def _at_least_as_close_as_reference_bf16(name, logits_rel, mask_agree):
+    fl = FLOOR[name]
+    print(f"{name}: CUDA bf16 path logits rel {logits_rel:.4g} / mask {mask_agree:.5f}  vs  reference under autocast(bf16) "
+          f"{fl['logits_rel']:.4g} / {fl['mask_agree']:.5f}")
+    assert logits_rel <= fl["logits_rel"] and mask_agree >= fl["mask_agree"], (name, logits_rel, mask_agree, fl)
 
 
 def _masks_agree_outside_threshold_band(mask, g, band=5e-3):
@@ -113,6 +125,7 @@ def test_tedm_trained_head_masks(golden, tag):
     assert lr < TOL
     if tag == "full":
         assert agree >= 0.999                      # the north-star criterion, at the BASELINE image size
+        _at_least_as_close_as_reference_bf16("tedm_full_trained", lr, agree)
     else:
         # 2 x 32 x 32 = 2048 pixels: 0.1 % is two pixels, too coarse a grid for the percentage criterion;
         # require >= 99.8 % and that every disagreement sits inside the rounding band around prob = 0.5
@@ -146,17 +159,18 @@ def test_tedm_and_ledm_small(golden):
         mask, prob, logits = ted.segment(x0)
     assert logits.shape == (x0.shape[0] * len(steps), 1, 32, 32)
     print("tedm small logits rel:", _rel(logits, g["tedm_logits"]))
-    assert _rel(logits, g["tedm_logits"]) < TOL_UNTRAINED_LOGITS
+    tol_untrained = FLOOR["tedm_full"]["logits_rel"]      # what the reference's own bf16 run achieves on an untrained head
+    assert _rel(logits, g["tedm_logits"]) < tol_untrained
     assert _rel(prob, g["tedm_prob"]) < TOL
     _masks_agree_outside_threshold_band(mask, g)
     with FixedNoise([_interleaved(noises, x0.shape[0])]):
-        assert _rel(ted(x0), g["tedm_logits"]) < TOL_UNTRAINED_LOGITS        # nn.Module.__call__ path
+        assert _rel(ted(x0), g["tedm_logits"]) < tol_untrained               # nn.Module.__call__ path
     led = _tedm(len(steps), False, steps)
     with FixedNoise([_interleaved(noises, x0.shape[0])]):
         ll = led(x0)
     assert ll.shape == (x0.shape[0], 1, 32, 32)
     print("ledm small logits rel:", _rel(ll, g["ledm_logits"]))
-    assert _rel(ll, g["ledm_logits"]) < TOL_UNTRAINED_LOGITS
+    assert _rel(ll, g["ledm_logits"]) < tol_untrained
     # reference-format feature tensor (API compatibility)
     with FixedNoise([_interleaved(noises, x0.shape[0])]):
         feats = ted.extract_features(x0)
@@ -179,7 +193,8 @@ def test_tedm_full_size(golden):
     lr = _rel(logits, g["tedm_logits"])
     agree = (mask.cpu().numpy() == g["tedm_mask"]).mean()
     print(f"tedm full (untrained head): logits rel {lr:.4g}, mask agreement {agree:.5f}")
-    assert lr < TOL_UNTRAINED_LOGITS
+    _at_least_as_close_as_reference_bf16("tedm_full", lr, agree)
+    assert agree >= 0.99                                       # measured 0.9966; the fp32 mode carries >= 0.999 here
     _masks_agree_outside_threshold_band(mask, g)
     # one full-size UNet forward with intermediate feature checks
     dm = ted.diffusion_model
@@ -193,6 +208,51 @@ def test_tedm_full_size(golden):
         assert _rel(fn[:, :8], g[f"feat{i}_t400_first8ch"]) < TOL
         assert abs(fn.norm().item() - float(g[f"feat{i}_t400_norm"])) < TOL * float(g[f"feat{i}_t400_norm"])
         assert _rel(fn.mean(dim=(0, 2, 3)), g[f"feat{i}_t400_chmean"]) < 5e-2
+
+
+class SameNoise:
+    """torch.randn_like returns ONE resident device tensor every time: usable while a CUDA graph is captured and replayed."""
+    def __init__(self, tensor):
+        self.t = tensor
+    def __enter__(self):
+        self.orig = torch.randn_like
+        torch.randn_like = lambda x, **kw: self.t
+        return self
+    def __exit__(self, *a):
+        torch.randn_like = self.orig
+
+
+def test_tedm_bench_configuration_b16_through_the_graphed_call(golden):
+    """Parity AT the bench configuration (BASELINE configs[3]: B = 16 images x S = 8 timesteps, 128 x 128 -> 262 144 mask
+    pixels), through the exact call bench.py times -- `segment(x, None, graph=True)`, one CUDA-graph replay -- against the
+    live reference's masks with a head the reference trained (tests/golden/make_golden_floor.py)."""
+    from tests.golden.synth import synth_images
+    g = golden["tedm_b16_trained"]
+    steps, b = g["steps"].tolist(), int(g["batch"])
+    x0 = synth_images(b, 128, int(g["image_seed"])).cuda()
+    noises = [synth_noise((b, 1, 128, 128), int(g["noise_seed0"]) + i, "tedm") for i in range(len(steps))]
+    ted = _tedm(len(steps), True, steps)
+    ted.load_state_dict({k: T(g[k]) for k in g.files if k.startswith("classifier.")}, strict=False)
+    ref_mask = np.unpackbits(g["tedm_mask_packed"])[:b * 128 * 128].reshape(b, 1, 128, 128).astype(bool)
+    nz = _interleaved(noises, b).cuda().float().contiguous()
+    with SameNoise(nz):
+        mask, prob, logits = ted.segment(x0, None, graph=True)      # warm-up + capture + first replay
+        mask, prob, logits = ted.segment(x0, None, graph=True)      # a pure replay
+        torch.cuda.synchronize()
+        eager = ted.segment(x0)
+    assert torch.equal(eager[0], mask) and torch.equal(eager[2], logits)      # the replay is the eager computation
+    agree = (mask.cpu().numpy() == ref_mask).mean()
+    lr = _rel(logits[:4 * len(steps)], g["tedm_logits_first4"])
+    pr = np.abs(prob.cpu().numpy().astype(np.float64) - g["tedm_prob_f16"].astype(np.float64)).max()
+    print(f"tedm B=16 x S=8 @128 (trained head, graph replay): logits rel {lr:.4g}, max |prob diff| {pr:.4g}, "
+          f"mask agreement {agree:.5f} ({int((mask.cpu().numpy() != ref_mask).sum())} of {ref_mask.size} px)")
+    assert lr < TOL
+    assert agree >= 0.999                                           # the north-star criterion at the bench configuration
+    _at_least_as_close_as_reference_bf16("tedm_b16_trained", lr, agree)
+    # no image's result depends on its batch neighbours: image 5 alone gives the same mask
+    with SameNoise(nz[5 * len(steps):6 * len(steps)].contiguous()):
+        one = ted.segment(x0[5:6])
+    assert (one[0].cpu().numpy() == mask[5:6].cpu().numpy()).mean() >= 0.9995
 
 
 def test_batched_equals_per_image(ddpm):

@@ -1,0 +1,241 @@
+"""fp32 precision mode (BASELINE north star: "UNet activations and features ... 1e-4 in fp32 mode"; the reference's default
+arithmetic, config.py:15): split-bf16 tensor-core convolutions + fp32 kernels, against the live reference's committed
+outputs (tests/golden/*.npz) and the fp32 oracle."""
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import tedm_oracle as O
+from tests.golden.synth import synth_images, synth_noise, synth_state_dict, synth_timesteps
+
+pytestmark = pytest.mark.gpu
+T = lambda a: torch.from_numpy(np.asarray(a))
+TOL32 = 1e-4          # the north star's fp32 tolerance (relative, Frobenius)
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def test_split_is_exact_to_2_pow_minus_17():
+    from tedm_b200 import native as N
+    x = torch.randn(4, 8, 8, 64, generator=torch.Generator().manual_seed(0)).cuda() * 3
+    hi, lo = N.f32_split(x)
+    back = hi.float() + lo.float()
+    assert hi.dtype == lo.dtype == torch.bfloat16
+    assert ((back - x).abs() <= x.abs() * 2.0 ** -17 + 1e-30).all()
+    assert torch.equal(hi, x.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("mode,cin,cin1,cout,size", [("1x1", 64, 0, 384, 16), ("3x3", 64, 0, 64, 32), ("3x3", 128, 64, 128, 16),
+                                                     ("4x4s2", 64, 0, 128, 32), ("up3x3", 128, 0, 64, 16), ("3x3", 512, 256, 512, 16)])
+def test_split_conv_matches_fp32_conv(mode, cin, cin1, cout, size):
+    from tedm_b200 import native as N
+    from tedm_b200.engine_fp32 import split_weight
+    g = torch.Generator().manual_seed(hash((mode, cin, cout)) % 1000)
+    b = 3
+    ctot = cin + cin1
+    k = {"1x1": 1, "3x3": 3, "4x4s2": 4, "up3x3": 3}[mode]
+    w = (torch.randn(cout, ctot, k, k, generator=g) / (ctot * k * k) ** 0.5).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    x = torch.randn(b, ctot, size, size, generator=g).cuda()
+    if mode == "1x1":
+        ref, md = F.conv2d(x, w, bias), N.MODE_1X1
+    elif mode == "3x3":
+        ref, md = F.conv2d(x, w, bias, padding=1), N.MODE_3X3
+    elif mode == "4x4s2":
+        ref, md = F.conv2d(x, w, bias, stride=2, padding=1), N.MODE_4X4S2
+    else:
+        ref, md = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, bias, padding=1), N.MODE_UP3X3
+    w3 = split_weight(w, md)
+    x0 = _nhwc(x[:, :cin])
+    s0 = N.f32_split(x0)
+    s1 = N.f32_split(_nhwc(x[:, cin:])) if cin1 else None
+    out = N.f32_conv(s0, w3, md, cout, bias=bias, src1=s1)
+    err = _rel(_nchw(out), ref)
+    print(f"split conv {mode} {cin}+{cin1}->{cout}@{size}: rel {err:.3g}")
+    assert out.dtype == torch.float32 and err < 2e-5
+    if mode == "3x3":                                   # GroupNorm partials come from the fp32 accumulators
+        out2, part = N.f32_conv(s0, w3, md, cout, bias=bias, src1=s1, gn_groups=8)
+        assert torch.equal(out2, out)
+        tot = part.double().sum(dim=1)                   # (B, groups, 2)
+        r = ref.double().reshape(b, 8, -1)
+        assert _rel(tot[..., 0], r.sum(-1)) < 1e-5 and _rel(tot[..., 1], (r * r).sum(-1)) < 1e-5
+
+
+def test_fp32_elementwise_and_attention_kernels():
+    from tedm_b200 import native as N
+    g = torch.Generator().manual_seed(2)
+    b, c, hgt = 2, 128, 16
+    x = torch.randn(b, c, hgt, hgt, generator=g)
+    gam, bet = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1
+    ss = torch.randn(b, 2 * c + 10, generator=g) * 0.2
+    res = torch.randn(b, c, hgt, hgt, generator=g)
+    # GroupNorm + scale/shift + SiLU + residual, statistics handed over as (sum, sum of squares) partials
+    xs = x.reshape(b, 8, -1)
+    part = torch.stack([xs.sum(-1), (xs * xs).sum(-1)], dim=-1).reshape(b, 1, 8, 2).contiguous()
+    y = F.group_norm(x, 8, gam, bet, eps=1e-5)
+    y = y * (ss[:, 10:10 + c, None, None] + 1) + ss[:, 10 + c:10 + 2 * c, None, None]
+    ref = F.silu(y) + res
+    got = N.f32_gn_silu(_nhwc(x).cuda(), part.cuda(), gam.cuda(), bet.cuda(), 8, 1e-5, ss.cuda(), 10, _nhwc(res).cuda())
+    assert _rel(_nchw(got), ref) < 2e-6
+    # channel LayerNorm (+ residual)
+    gl = torch.rand(c, generator=g) + 0.5
+    ref = O._chan_layernorm(x, gl.reshape(1, c, 1, 1), 1e-5) + res
+    got = N.f32_layernorm(_nhwc(x).cuda(), gl.cuda(), 1e-5, _nhwc(res).cuda())
+    assert _rel(_nchw(got), ref) < 2e-6
+    # LinearAttention core (unet_model.py:196-210)
+    for n_side in (8, 16, 48):
+        qkv = torch.randn(b, 384, n_side, n_side, generator=g) * 2
+        n = n_side * n_side
+        q, k, v = (z.reshape(b, 4, 32, n) for z in qkv.chunk(3, dim=1))
+        ctx = torch.einsum("bhdn,bhen->bhde", k.softmax(dim=-1), v / n)
+        ref = torch.einsum("bhde,bhdn->bhen", ctx, q.softmax(dim=-2) * 32 ** -0.5).reshape(b, 128, n_side, n_side)
+        got = N.f32_linear_attention(_nhwc(qkv).cuda(), 4, 32, 32 ** -0.5)
+        assert _rel(_nchw(got), ref) < 5e-6, n_side
+    # mid Attention core (unet_model.py:229-241), incl. a ragged token count
+    for n_side in (4, 16, 20):
+        qkv = torch.randn(b, 384, n_side, n_side, generator=g)
+        n = n_side * n_side
+        q, k, v = (z.reshape(b, 4, 32, n) for z in qkv.chunk(3, dim=1))
+        sim = torch.einsum("bhdi,bhdj->bhij", F.normalize(q, dim=-1), F.normalize(k, dim=-1)) * 16
+        ref = torch.einsum("bhij,bhdj->bhid", sim.softmax(dim=-1), v).permute(0, 1, 3, 2).reshape(b, 128, n_side, n_side)
+        got = N.f32_attention(_nhwc(qkv).cuda(), 4, 32, 16.0)
+        assert _rel(_nchw(got), ref) < 5e-6, n_side
+
+
+@pytest.fixture(scope="module")
+def ddpm32():
+    from tedm_b200.models import DiffusionModel
+    m = DiffusionModel(Namespace(normalize=True, precision="fp32")).eval()
+    assert m.model.precision == "fp32"
+    m.load_state_dict(synth_state_dict(O.unet_param_shapes(prefix="model."), 0), strict=False)
+    return m.cuda()
+
+
+def test_unet_fp32_small_and_full_within_1e_4(golden, ddpm32):
+    g = golden["ddpm_small"]
+    x_t, t = T(g["x_t"]).cuda(), T(g["t"]).cuda()
+    with torch.no_grad():
+        out, feats = ddpm32.model.engine.forward(x_t, t, want_features=True)
+        out_none = ddpm32.model(x_t, None)
+    errs = {"out": _rel(out, g["unet_out"]), "out_t_none": _rel(out_none, g["unet_out_t_none"]),
+            **{f"feat{i}": _rel(_nchw(f), g[f"feat{i}"]) for i, f in enumerate(feats)}}
+    print("fp32 mode, unet small rel errors:", errs)
+    assert feats[0].dtype == torch.float32 and max(errs.values()) < TOL32, errs
+    # DDPM arithmetic around it: loss and one reverse step
+    x0, nz = T(g["x0"]).cuda(), T(g["noise"]).cuda()
+    with torch.no_grad():
+        loss = ddpm32.train_step(x0, t=t, noise=nz)
+    assert abs(loss.item() - float(g["ddpm_loss"])) < TOL32 * float(g["ddpm_loss"])
+    z = synth_noise(g["x0"].shape, 1, "z").cuda()
+    for ts in (500, 0):
+        assert _rel(ddpm32.sample_timestep(x_t, ts, noise=z), g[f"sample_t{ts}"]) < 2 * TOL32, ts
+    # config.py defaults: 128 x 128
+    g = golden["tedm_full"]
+    x0 = T(g["x0"]).cuda()
+    tt = torch.tensor([400], device="cuda")
+    x_t, _ = ddpm32.forward_diffusion_model(x0, tt, synth_noise((1, 1, 128, 128), 25, "tedm").cuda())
+    with torch.no_grad():
+        out, feats = ddpm32.model.engine.forward(x_t, tt, want_features=True)
+    errs = {"out": _rel(out, g["unet_out_t400"])}
+    for i, f in enumerate(feats):
+        fn = _nchw(f)
+        errs[f"feat{i}"] = _rel(fn[:, :8], g[f"feat{i}_t400_first8ch"])
+        assert abs(fn.norm().item() - float(g[f"feat{i}_t400_norm"])) < TOL32 * float(g[f"feat{i}_t400_norm"])
+    print("fp32 mode, unet 128x128 rel errors:", errs)
+    assert max(errs.values()) < TOL32, errs
+    with pytest.raises(NotImplementedError):
+        ddpm32.train()
+        try:
+            ddpm32.train_step(x0)
+        finally:
+            ddpm32.eval()
+
+
+def _tedm32(n_steps, shared, steps, head=None):
+    from tedm_b200.models import DatasetDM, tedm_classifier
+    m = DatasetDM(Namespace(normalize=True, saved_diffusion_model="/nonexistent", t_steps_to_save=steps, precision="fp32"))
+    if shared:
+        m.classifier = tedm_classifier(n_steps)
+    shapes = {**O.unet_param_shapes(prefix="diffusion_model.model."), **O.head_param_shapes(n_steps, shared)}
+    assert not m.load_state_dict(synth_state_dict(shapes, 0), strict=False).unexpected_keys
+    if head is not None:
+        m.load_state_dict(head, strict=False)
+    assert m.precision == "fp32"
+    return m.eval().cuda()
+
+
+class FixedNoise:
+    def __init__(self, tensor):
+        self.t = tensor
+    def __enter__(self):
+        self.orig = torch.randn_like
+        torch.randn_like = lambda x, **kw: self.t.to(device=x.device, dtype=x.dtype)
+        return self
+    def __exit__(self, *a):
+        torch.randn_like = self.orig
+
+
+def _interleaved(noises, b):
+    return torch.stack(noises, dim=1).reshape(b * len(noises), *noises[0].shape[1:])
+
+
+@pytest.mark.parametrize("fixture", ["tedm_full", "tedm_full_trained", "tedm_small", "tedm_small_trained"])
+def test_tedm_fp32_mode_masks_and_logits(golden, fixture):
+    """North star in fp32 mode, on the random-init head (every logit on the decision threshold: the hard case) and on the
+    reference-trained head: masks >= 99.9 %, logits to fp32 accuracy."""
+    g = golden[fixture]
+    steps = g["steps"].tolist()
+    x0 = T(g["x0"]).cuda()
+    b, size = x0.shape[0], x0.shape[-1]
+    seed0 = 20 if "full" in fixture else 10
+    noises = [synth_noise((b, 1, size, size), seed0 + i, "tedm") for i in range(len(steps))]
+    head = {k: T(g[k]) for k in g.files if k.startswith("classifier.")} or None
+    ted = _tedm32(len(steps), True, steps, head)
+    with FixedNoise(_interleaved(noises, b).cuda()):
+        mask, prob, logits = ted.segment(x0)
+    lr, agree = _rel(logits, g["tedm_logits"]), (mask.cpu().numpy() == g["tedm_mask"]).mean()
+    n_diff = int((mask.cpu().numpy() != g["tedm_mask"]).sum())
+    print(f"fp32 mode {fixture}: logits rel {lr:.3g}, prob rel {_rel(prob, g['tedm_prob']):.3g}, mask agreement {agree:.6f} ({n_diff} px)")
+    assert lr < 10 * TOL32                      # logits of the untrained head are a near-cancelling residual of the features
+    assert agree >= 0.999
+    if fixture == "tedm_small":                 # LEDM (unshared 2880-input head) and the reference-format feature tensor
+        led = _tedm32(len(steps), False, steps)
+        with FixedNoise(_interleaved(noises, b).cuda()):
+            ll = led(x0)
+        assert _rel(ll, g["ledm_logits"]) < 10 * TOL32
+        with FixedNoise(_interleaved(noises, b).cuda()):
+            feats = ted.extract_features(x0)
+        sd = synth_state_dict({**O.unet_param_shapes(prefix="diffusion_model.model.")}, 0)
+        sd.update(O.schedule_tables())
+        with torch.no_grad():
+            ref_feats = O.concat_features(O.extract_feature_maps(sd, x0.cpu(), steps, noises), size)
+        assert _rel(feats, ref_feats) < TOL32
+
+
+def test_fp32_mode_other_sizes_vs_oracle():
+    from tedm_b200.models import Unet
+    for size, mults in ((64, (1, 2, 4, 8)), (128, (1, 2, 4))):
+        sd = synth_state_dict(O.unet_param_shapes(dim_mults=mults), 0)
+        m = Unet(64, dim_mults=mults, precision="fp32").eval()
+        m.load_state_dict(sd)
+        m.cuda()
+        x, t = synth_images(1, size, 21), synth_timesteps(1, seed=3)
+        with torch.no_grad():
+            got = m(x.cuda(), t.cuda())
+        err = _rel(got, O.unet_forward(sd, x, t))
+        print(f"fp32 mode unet {size}x{size} mults {mults}: rel err {err:.3g}")
+        assert err < TOL32, err
