@@ -147,9 +147,11 @@ TEDM_API int tedm_conv_igemm_fwd(const tedm_conv_args* args, tedm_stream_t strea
  * ACCUMULATED into it (mode 3: the folded taps are scattered back onto the 3x3 kernel of Upsample's conv). */
 TEDM_API int tedm_conv_igemm_wgrad(const tedm_conv_args* args, const void* dy, float* dw, int oihw_accumulate,
                           float* workspace, tedm_stream_t stream);
-/* fp32 elements of the REQUIRED `workspace` above: the split-K partial tiles of both weight-gradient kernels are stored
- * there and summed in slice order by a second kernel -- no floating-point atomics, so the gradient is bit-reproducible
- * from run to run.  Calls that share one workspace must be ordered on one stream. */
+/* fp32 elements of the REQUIRED `workspace` above.  Both weight-gradient kernels sum their split-K slices in a FIXED order,
+ * so the gradient is bit-reproducible from run to run: the 3x3 halo-tile kernel stores partial tiles there and a second
+ * kernel adds them in slice order; the generic kernel adds straight into dw, slice after slice, the order enforced by
+ * per-tile turn counters kept at the end of the workspace.  The workspace must be ZERO when first used (the counters reset
+ * themselves); calls that share one workspace must be ordered on one stream. */
 TEDM_API int64_t tedm_conv_igemm_wgrad_workspace(void);
 /* number of partial-statistics slots per image that tedm_conv_igemm_fwd writes for this output extent */
 TEDM_API int tedm_conv_gn_parts(int out_height, int out_width);
@@ -408,6 +410,19 @@ TEDM_API int tedm_u8_masks_to_label(const uint8_t* src, float* dst, long long n_
  * bf16 and out [nvar][128][64] fp32 are device pointers. */
 TEDM_API int tedm_debug_umma_probe(const void* A, const void* Bm, const int* shifts, const int* base_offsets,
                                    int nvar, float* out, tedm_stream_t stream);
+
+/* The same block with every GEMM on tcgen05 (csrc/attention_tc.cu): LayerNorm -> k / q projections as 128-pixel UMMA tiles
+ * -> softmaxes by the thread that owns the pixel -> context / to_out as UMMAs again; v is never materialised and the to_out
+ * conv is folded into a per-image matrix.  shift_log2[128] = log2(e) * an upper bound of k per (head, d) that depends on
+ * the weights only (||w_hd * g_pre||_2 * sqrt(C), Cauchy-Schwarz), which removes the running maximum from the softmax over
+ * pixels; the caller must route blocks whose bound exceeds ~40 to tedm_linear_attention_fused_fwd instead.
+ * n % 512 == 0, C = 64 / 128, 4 heads x 32. */
+TEDM_API int tedm_linear_attention_tc_supported(int n, int channels, int heads, int dim_head);
+TEDM_API int64_t tedm_linear_attention_tc_workspace(int batch, int n, int channels);   /* fp32 elements */
+TEDM_API int tedm_linear_attention_tc_fwd(const void* x, const void* wqkv, const float* g_pre, const float* shift_log2,
+                                 const void* wout, const float* b_out, const float* g_out, void* out, float* workspace,
+                                 int batch, int n, int channels, int heads, int dim_head, float scale, float eps,
+                                 tedm_stream_t stream);
 
 /* ---- fp32 precision mode (north star: "1e-4 in fp32 mode"; the reference's default arithmetic, config.py:15) --------
  * Inference only.  Activations are fp32 NHWC between kernels.  Convolutions run on tedm_conv_igemm_fwd with every operand

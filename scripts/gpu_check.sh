@@ -8,7 +8,7 @@ out=gpurun_out/${tag}_tests.log
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv >> $out 2>&1
 for f in tests/test_gpu_*.py; do
   echo "=== $f" >> $out
-  timeout 900 python -m pytest $f -m gpu -q -x --no-header -p no:cacheprovider -s 2>&1 | grep -v "^$" | tail -60 >> $out
+  timeout 900 python -m pytest $f -m gpu -q --no-header -p no:cacheprovider -s 2>&1 | grep -v "^$" | tail -60 >> $out
 done
 grep -E "^=== |passed|failed|error" $out | tail -40
 if [ "${SKIP_BENCH:-0}" != "1" ]; then

@@ -1,0 +1,664 @@
+// Residual(PreNorm(LinearAttention)) inference forward with every GEMM on tcgen05   models/unet_model.py:29-36,64-73,178-210
+//
+//   out = LayerNorm_out( W_o . linattn( W_qkv . LayerNorm_pre(x) ) + b_o ) + x            (C = 64 at 128^2, C = 128 at 64^2)
+//
+// The mma.sync version of this block (attention_fused.cu) is bound by instruction issue: 10 non-MMA instructions per
+// m16n8k16.  Here a 128-pixel tile is one UMMA row block, one thread owns one pixel end to end (LayerNorm and both
+// softmaxes need no cross-thread traffic), and the algebra is rearranged so that nothing but the two softmax operands
+// ever makes the TMEM -> registers -> shared memory round trip:
+//
+//   K-A ctx :  y = LN(x) (bf16, in place in the TMA-landed tile)                                      compute warps
+//              k = y Wk^T                        M = 128 px, N = 128, K = C          (tile -> TMEM)   tcgen05
+//              P = exp(k - shift)                shift[hd] >= max_n k[hd, n] is a WEIGHT-ONLY bound (Cauchy-Schwarz:
+//                                                |k| <= ||w_hd * g||_2 sqrt(C)), so the softmax over n needs no running
+//                                                maximum, no rescaling and no second pass
+//              G += P^T [y | 1]                  M = 128 (h,d), N = C + 16, K = 128 px, both operands MN-major: the SAME
+//                                                shared-memory y tile is the B operand; the ones block yields S = sum_n P
+//                 v is never computed per pixel:  ctx[d][e] = sum_n P[n,d] v[n,e] = sum_c G[d][c] Wv[e][c]
+//   K-C comb:  per image: ctx = G Wv^T / (S n);  M[c'][hd] = scale * sum_e ctx[h][d][e] W_o[c'][h,e]   (to_out folded in)
+//   K-B out :  y = LN(x);  q = y Wq^T (tcgen05);  Q = softmax_d(q) per head (in registers) -> bf16 tile
+//              o = Q M^T                         M = 128 px, N = C, K = 128 (tcgen05)  = to_out(attention output)
+//              out = LN_out(o + b_o) * g_o + x   -> bf16 tile -> TMA store
+//
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 UMMA issuer, warps 2-5 / 6-9 two compute groups that alternate
+// tiles (a thread's TMEM lane quarter is warp % 4, its pixel = quarter * 32 + lane).  HBM traffic: x once per kernel plus
+// the output: 3 x 2C bytes per pixel.  Per pixel and kernel the cost is ~128 MUFU ex2 and ~1 k issued instructions.
+#include "common.cuh"
+
+namespace {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+// bf16 [rows][cols] row-major -> 2-D map with a (64 cols, box_rows) box, 128B swizzle
+int encode_2d(CUtensorMap* map, const void* ptr, long long rows, long long cols, int box_rows) {
+  PFN_encodeTiled enc = encode_fn();
+  if (!enc) return tedm_set_error(TEDM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2ull};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return tedm_set_error(TEDM_ERR_CUDA, "cuTensorMapEncodeTiled(%lld x %lld) failed: %d", rows, cols, (int)r);
+  return TEDM_OK;
+}
+
+constexpr int TM = 128;                 // pixels per tile = UMMA M
+constexpr int HID = 128;                // heads * dim_head
+constexpr int BLK = TM * 128;           // bytes of one [128 rows][64 bf16] swizzled block
+constexpr int TC_THREADS = 320;
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint64_t desc_k(uint32_t addr) {      // K-major SW128 (rows of 128 B, 8-row atoms 1 KB apart)
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint64_t desc_mn(uint32_t addr) {     // MN-major SW128: 64-element MN blocks 16 KB apart, K groups 1 KB
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1024ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tma_store_2d(const void* desc, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(desc), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ uint32_t sw_addr(uint32_t blk_base, int row, int c16) {   // 16-byte chunk c16 of a block's row
+  return blk_base + (uint32_t)row * 128u + (uint32_t)((c16 ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// LayerNorm of one pixel row held as C/64 swizzled blocks at `src` (block stride BLK): y = (x - mean) rstd g -> bf16 at `dst`
+// (dst may equal src).  Two passes over registers.  Optionally keeps the fp32 input row in `keep` (C values).
+template <int C>
+__device__ __forceinline__ void ln_row(uint32_t src, uint32_t dst, int row, const float* g_s, float eps) {
+  float v[C];
+#pragma unroll
+  for (int b = 0; b < C / 64; ++b)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float f[8];
+      unpack8(lds128(sw_addr(src + b * BLK, row, c)), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[b * 64 + c * 8 + j] = f[j];
+    }
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < C; ++i) s += v[i];
+  const float mean = s * (1.0f / C);
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < C; ++i) {
+    v[i] -= mean;
+    q = fmaf(v[i], v[i], q);
+  }
+  const float rstd = rsqrtf(q * (1.0f / C) + eps);
+#pragma unroll
+  for (int b = 0; b < C / 64; ++b)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = v[b * 64 + c * 8 + j] * rstd * g_s[b * 64 + c * 8 + j];
+      sts128(sw_addr(dst + b * BLK, row, c), pack8(f));
+    }
+}
+
+struct TcMaps {
+  CUtensorMap x, w, m, out;
+};
+
+struct TcParams {
+  int n;                 // pixels per image
+  int tiles_per_image;   // n / 128
+  int chunk_tiles;       // K-A: tiles per work item
+  int items;             // K-A: work items = batch * (tiles_per_image / chunk_tiles)
+  int total_tiles;       // K-B
+  float eps;
+  const float* g_pre;    // [C]
+  const float* shift;    // [128] log2(e) * upper bound of k per (head, d)   (K-A)
+  float* part;           // [items][128][C + 16] fp32                          (K-A)
+  const float* b_out;    // [C]                                                (K-B)
+  const float* g_out;    // [C]                                                (K-B)
+};
+
+// ==========================================================================================================
+// K-A: per (image, chunk of tiles):  G[hd][c] = sum_px P[px][hd] y[px][c],  S[hd] = sum_px P[px][hd]
+// ==========================================================================================================
+template <int C>
+__global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_ctx_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+  constexpr int KB = C / 64;                       // 64-channel blocks of a pixel row
+  constexpr int N2 = C + 16;                       // G columns + the ones block's 16
+  constexpr int YBUF = (KB + 1) * BLK;             // y blocks + ones block (contiguous: the MN-major B operand of GEMM 2)
+  constexpr uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+  constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N2 >> 3) << 17) |
+                              ((uint32_t)(HID >> 4) << 24);
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_w, x_full[2], x_empty[2], y_ready[2], d1_full[2], p_ready[2], d2_full, d2_empty;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float g_s[C], sh_s[HID];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_s = base;                                  // Wk: KB blocks of [128 hd][64 c]
+  const uint32_t y_s = w_s + KB * BLK;                        // [2] x (y | ones)
+  const uint32_t p_s = y_s + 2 * YBUF;                        // [2] x P: two MN blocks [128 px][64 hd]
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&maps.x);
+    tma_prefetch_desc(&maps.w);
+    mbar_init(smem_u32(&bar_w), 1);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(smem_u32(&x_full[g]), 1);
+      mbar_init(smem_u32(&x_empty[g]), 1);
+      mbar_init(smem_u32(&y_ready[g]), 128);
+      mbar_init(smem_u32(&d1_full[g]), 1);
+      mbar_init(smem_u32(&p_ready[g]), 128);
+    }
+    mbar_init(smem_u32(&d2_full), 1);
+    mbar_init(smem_u32(&d2_empty), 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
+  for (int i = threadIdx.x; i < C; i += TC_THREADS) g_s[i] = p.g_pre[i];
+  for (int i = threadIdx.x; i < HID; i += TC_THREADS) sh_s[i] = p.shift[i];
+  // the two ones blocks (bf16 1.0 everywhere: whichever 16 columns GEMM 2 reads are ones)
+  for (int i = threadIdx.x; i < 2 * (BLK / 16); i += TC_THREADS) {
+    const int g = i / (BLK / 16), o = i % (BLK / 16);
+    sts128(y_s + g * YBUF + KB * BLK + o * 16, make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u));
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t d2_col = 256;                                // D1[g] at columns g * 128, D2 at 256 .. 256 + N2
+
+  // tiles of this CTA: items blockIdx.x, + gridDim.x, ...; local tile index i counts across items
+  const int my_items = p.items > (int)blockIdx.x ? (p.items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int my_tiles = my_items * p.chunk_tiles;
+  const int chunks_per_image = p.tiles_per_image / p.chunk_tiles;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t bw = smem_u32(&bar_w);
+      mbar_expect_tx(bw, KB * BLK);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(w_s + kb * BLK, &maps.w, bw, kb * 64, HID);   // rows 128..255 of wqkv = Wk
+      for (int i = 0; i < my_tiles; ++i) {
+        const int g = i & 1, it = i / p.chunk_tiles, tl = i - it * p.chunk_tiles;
+        const int item = blockIdx.x + it * gridDim.x;
+        const int img = item / chunks_per_image, ch = item - img * chunks_per_image;
+        const long long row0 = (long long)img * p.n + (long long)(ch * p.chunk_tiles + tl) * TM;
+        mbar_wait(smem_u32(&x_empty[g]), (uint32_t)(((i >> 1) & 1) ^ 1));
+        const uint32_t full = smem_u32(&x_full[g]);
+        mbar_expect_tx(full, KB * BLK);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(y_s + g * YBUF + kb * BLK, &maps.x, full, kb * 64, (int)row0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      mbar_wait(smem_u32(&bar_w), 0);
+      tc_fence_after();
+      auto gemm2 = [&](int j) {                     // G (+)= P_j^T [y_j | 1]
+        const int g = j & 1, tl = j % p.chunk_tiles;
+        if (tl == 0 && j > 0) {                     // a new item: the previous item's accumulator must have been drained
+          mbar_wait(smem_u32(&d2_empty), (uint32_t)(((j / p.chunk_tiles - 1) & 1)));
+          tc_fence_after();
+        }
+        mbar_wait(smem_u32(&p_ready[g]), (uint32_t)((j >> 1) & 1));
+        tc_fence_after();
+        const uint64_t adesc = desc_mn(p_s + g * 2 * BLK), bdesc = desc_mn(y_s + g * YBUF);
+#pragma unroll
+        for (int k = 0; k < TM / 16; ++k)
+          umma_bf16(tmem + d2_col, adesc + 128ull * k, bdesc + 128ull * k, IDESC2, (tl | k) != 0 ? 1u : 0u);
+        umma_commit(smem_u32(&x_empty[g]));         // y_j and P_j are free once these complete
+        if (tl == p.chunk_tiles - 1) umma_commit(smem_u32(&d2_full));
+      };
+      for (int i = 0; i < my_tiles; ++i) {
+        const int g = i & 1;
+        mbar_wait(smem_u32(&y_ready[g]), (uint32_t)((i >> 1) & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint64_t adesc = desc_k(y_s + g * YBUF + kb * BLK), bdesc = desc_k(w_s + kb * BLK);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem + g * HID, adesc + 2ull * k, bdesc + 2ull * k, IDESC1, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&d1_full[g]));
+        if (i > 0) gemm2(i - 1);
+      }
+      if (my_tiles > 0) gemm2(my_tiles - 1);
+    }
+    __syncwarp();
+  } else {
+    const int grp = (warp - 2) >> 2, q = warp & 3, row = q * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    for (int i = grp; i < my_tiles; i += 2) {
+      const uint32_t ph = (uint32_t)((i >> 1) & 1);
+      const uint32_t yb = y_s + grp * YBUF;
+      mbar_wait(smem_u32(&x_full[grp]), ph);
+      ln_row<C>(yb, yb, row, g_s, p.eps);
+      fence_proxy_async_smem();
+      mbar_arrive(smem_u32(&y_ready[grp]));
+      mbar_wait(smem_u32(&d1_full[grp]), ph);
+      tc_fence_after();
+      const uint32_t pb = p_s + grp * 2 * BLK;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {                     // 32 columns (= one head) at a time
+        uint32_t r[32];
+        tmem_ld32(lane_addr + (uint32_t)(grp * HID + ch * 32), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = ex2f(fmaf(__uint_as_float(r[c * 8 + j]), kLog2e, -sh_s[ch * 32 + c * 8 + j]));
+          sts128(sw_addr(pb + (ch >> 1) * BLK, row, (ch & 1) * 4 + c), pack8(f));
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(smem_u32(&p_ready[grp]));
+      if (i % p.chunk_tiles == p.chunk_tiles - 1) {        // last tile of an item: this group drains the accumulator
+        const int it = i / p.chunk_tiles;
+        mbar_wait(smem_u32(&d2_full), (uint32_t)(it & 1));
+        tc_fence_after();
+        const int item = blockIdx.x + it * gridDim.x;
+        float* dst = p.part + ((size_t)item * HID + row) * N2;
+#pragma unroll 1
+        for (int c0 = 0; c0 < N2; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(lane_addr + d2_col + (uint32_t)c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(dst + c0 + 4 * j) = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                                       __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&d2_empty));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// ==========================================================================================================
+// K-C: per image   ctx[h][d][e] = sum_c G[hd][c] Wv[he][c] / (S[hd] n);   M[c'][hd] = scale sum_e ctx[h][d][e] Wo[c'][he]
+// ==========================================================================================================
+template <int C>
+__global__ void __launch_bounds__(256) linattn_tc_combine_kernel(const float* __restrict__ part, const bf16* __restrict__ wqkv,
+                                                                 const bf16* __restrict__ wout, bf16* __restrict__ mimg,
+                                                                 int chunks, int n, float scale) {
+  constexpr int N2 = C + 16;
+  extern __shared__ float cs[];              // G [128][C + 1] | ctx [128][33]
+  float* G = cs;
+  float* ctx = cs + HID * (C + 1);
+  __shared__ float S[HID];
+  const int b = blockIdx.x;
+  const float* src = part + (size_t)b * chunks * HID * N2;
+  for (int i = threadIdx.x; i < HID * N2; i += 256) {
+    const int hd = i / N2, c = i % N2;
+    if (c > C) continue;
+    float acc = 0.0f;
+    for (int k = 0; k < chunks; ++k) acc += src[(size_t)k * HID * N2 + i];
+    if (c < C) G[hd * (C + 1) + c] = acc;
+    else S[hd] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < HID * 32; i += 256) {
+    const int hd = i >> 5, e = i & 31, h = hd >> 5;
+    const bf16* wv = wqkv + (size_t)(2 * HID + h * 32 + e) * C;
+    float acc = 0.0f;
+    for (int c = 0; c < C; ++c) acc = fmaf(G[hd * (C + 1) + c], __bfloat162float(wv[c]), acc);
+    ctx[hd * 33 + e] = acc / (S[hd] * (float)n);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * HID; i += 256) {
+    const int c = i / HID, hd = i % HID, h = hd >> 5;
+    const bf16* wo = wout + (size_t)c * HID + h * 32;
+    float acc = 0.0f;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) acc = fmaf(ctx[hd * 33 + e], __bfloat162float(wo[e]), acc);
+    mimg[((size_t)b * C + c) * HID + hd] = __float2bfloat16_rn(acc * scale);
+  }
+}
+
+// ==========================================================================================================
+// K-B: out = LN_out( softmax_d(LN(x) Wq^T) M^T + b_o ) g_o + x
+// ==========================================================================================================
+template <int C>
+__global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_out_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+  constexpr int KB = C / 64;
+  constexpr int XBUF = KB * BLK;                   // the x tile (kept for the residual)
+  constexpr int WBUF = 2 * BLK;                    // y (KB blocks) -> Q (2 blocks) -> output staging (KB blocks), in turn
+  constexpr int MBLK = C * 128;                    // bytes of one [C rows][64 hd] block of M
+  constexpr uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+  constexpr uint32_t IDESC3 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_w, x_full[2], x_empty[2], y_ready[2], d1_full[2], q_ready[2], d3_full[2], m_full, m_empty;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float g_s[C], bo_s[C], go_s[C];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_s = base;                                  // Wq: KB blocks of [128 hd][64 c]
+  const uint32_t m_s = w_s + KB * BLK;                        // M of the current image: 2 blocks of [C][64 hd]
+  const uint32_t x_s = m_s + 2 * MBLK;                        // [2] x tiles
+  const uint32_t b_s = x_s + 2 * XBUF;                        // [2] work buffers
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&maps.x);
+    tma_prefetch_desc(&maps.w);
+    tma_prefetch_desc(&maps.m);
+    tma_prefetch_desc(&maps.out);
+    mbar_init(smem_u32(&bar_w), 1);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(smem_u32(&x_full[g]), 1);
+      mbar_init(smem_u32(&x_empty[g]), 128);
+      mbar_init(smem_u32(&y_ready[g]), 128);
+      mbar_init(smem_u32(&d1_full[g]), 1);
+      mbar_init(smem_u32(&q_ready[g]), 128);
+      mbar_init(smem_u32(&d3_full[g]), 1);
+    }
+    mbar_init(smem_u32(&m_full), 1);
+    mbar_init(smem_u32(&m_empty), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
+  for (int i = threadIdx.x; i < C; i += TC_THREADS) {
+    g_s[i] = p.g_pre[i];
+    bo_s[i] = p.b_out[i];
+    go_s[i] = p.g_out[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;                            // group g: q at columns g * 256, o at g * 256 + 128
+
+  // a contiguous range of tiles per CTA (consecutive tiles share an image, so M is reloaded rarely)
+  const long long T = p.total_tiles;
+  const int t0 = (int)(T * blockIdx.x / gridDim.x), t1 = (int)(T * (blockIdx.x + 1) / gridDim.x);
+  const int my_tiles = t1 - t0;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t bw = smem_u32(&bar_w);
+      mbar_expect_tx(bw, KB * BLK);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(w_s + kb * BLK, &maps.w, bw, kb * 64, 0);      // rows 0..127 of wqkv = Wq
+      int cur_img = -1, n_img = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int g = i & 1, tile = t0 + i, img = tile / p.tiles_per_image;
+        // the x tile FIRST: the issuer runs GEMM 1 of tile i before GEMM 2 of tile i - 1, and only the latter releases M
+        mbar_wait(smem_u32(&x_empty[g]), (uint32_t)(((i >> 1) & 1) ^ 1));
+        const uint32_t full = smem_u32(&x_full[g]);
+        mbar_expect_tx(full, KB * BLK);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(x_s + g * XBUF + kb * BLK, &maps.x, full, kb * 64, tile * TM);
+        if (img != cur_img) {
+          mbar_wait(smem_u32(&m_empty), (uint32_t)((n_img & 1) ^ 1));
+          const uint32_t mf = smem_u32(&m_full);
+          mbar_expect_tx(mf, 2 * MBLK);
+          for (int kb = 0; kb < 2; ++kb) tma_load_2d(m_s + kb * MBLK, &maps.m, mf, kb * 64, img * C);
+          cur_img = img;
+          ++n_img;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      mbar_wait(smem_u32(&bar_w), 0);
+      tc_fence_after();
+      int n_img = 0;
+      auto gemm2 = [&](int j) {                     // o_j = Q_j M^T
+        const int g = j & 1, tile = t0 + j, img = tile / p.tiles_per_image;
+        if (j == 0 || (tile - 1) / p.tiles_per_image != img) {        // first tile of an image: its M must have landed
+          mbar_wait(smem_u32(&m_full), (uint32_t)(n_img & 1));
+          ++n_img;
+        }
+        mbar_wait(smem_u32(&q_ready[g]), (uint32_t)((j >> 1) & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t adesc = desc_k(b_s + g * WBUF + kb * BLK), bdesc = desc_k(m_s + kb * MBLK);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + g * 256 + HID, adesc + 2ull * k, bdesc + 2ull * k, IDESC3, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&d3_full[g]));
+        if (j == my_tiles - 1 || (tile + 1) / p.tiles_per_image != img) umma_commit(smem_u32(&m_empty));   // last tile of the image here
+      };
+      for (int i = 0; i < my_tiles; ++i) {
+        const int g = i & 1;
+        mbar_wait(smem_u32(&y_ready[g]), (uint32_t)((i >> 1) & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint64_t adesc = desc_k(b_s + g * WBUF + kb * BLK), bdesc = desc_k(w_s + kb * BLK);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem + g * 256, adesc + 2ull * k, bdesc + 2ull * k, IDESC1, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&d1_full[g]));
+        if (i > 0) gemm2(i - 1);
+      }
+      if (my_tiles > 0) gemm2(my_tiles - 1);
+    }
+    __syncwarp();
+  } else {
+    const int grp = (warp - 2) >> 2, q = warp & 3, row = q * 32 + lane;
+    const int gtid = threadIdx.x - 64 - grp * 128;            // 0..127 inside the group
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * 256);
+    const uint32_t xb = x_s + grp * XBUF, wb = b_s + grp * WBUF;
+    for (int i = grp; i < my_tiles; i += 2) {
+      const uint32_t ph = (uint32_t)((i >> 1) & 1);
+      // the TMA store of this group's previous tile must have drained the work buffer before LayerNorm rewrites it
+      if (gtid == 0) tma_store_wait_read<0>();
+      named_bar_sync(1 + grp, 128);
+      mbar_wait(smem_u32(&x_full[grp]), ph);
+      ln_row<C>(xb, wb, row, g_s, p.eps);
+      fence_proxy_async_smem();
+      mbar_arrive(smem_u32(&y_ready[grp]));
+      // ---- q -> softmax over the 32 channels of each head -> Q tile (K-major, 2 blocks of 64 (h,d))
+      mbar_wait(smem_u32(&d1_full[grp]), ph);
+      tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        uint32_t r[32];
+        tmem_ld32(lane_addr + (uint32_t)(h * 32), r);
+        tmem_ld_wait();
+        float m = __uint_as_float(r[0]);
+#pragma unroll
+        for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+        const float ml = m * kLog2e;
+        float e[32], s = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          e[j] = ex2f(fmaf(__uint_as_float(r[j]), kLog2e, -ml));
+          s += e[j];
+        }
+        const float inv = __fdividef(1.0f, s);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = e[c * 8 + j] * inv;
+          sts128(sw_addr(wb + (h >> 1) * BLK, row, (h & 1) * 4 + c), pack8(f));
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(smem_u32(&q_ready[grp]));
+      // ---- o -> + bias -> LayerNorm over C -> * g_out + x -> bf16 staging tile -> TMA store
+      mbar_wait(smem_u32(&d3_full[grp]), ph);
+      tc_fence_after();
+      float o[C];
+#pragma unroll
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(lane_addr + (uint32_t)(HID + c0), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[c0 + j] = __uint_as_float(r[j]) + bo_s[c0 + j];
+      }
+      tc_fence_before();
+      float s = 0.0f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) s += o[c];
+      const float mean = s * (1.0f / C);
+      float qv = 0.0f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        o[c] -= mean;
+        qv = fmaf(o[c], o[c], qv);
+      }
+      const float rstd = rsqrtf(qv * (1.0f / C) + p.eps);
+#pragma unroll
+      for (int b = 0; b < KB; ++b)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float res[8], f[8];
+          unpack8(lds128(sw_addr(xb + b * BLK, row, c)), res);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = fmaf(o[b * 64 + c * 8 + j] * rstd, go_s[b * 64 + c * 8 + j], res[j]);
+          sts128(sw_addr(wb + b * BLK, row, c), pack8(f));
+        }
+      fence_proxy_async_smem();
+      mbar_arrive(smem_u32(&x_empty[grp]));                  // the residual has been read: the x buffer may be refilled
+      named_bar_sync(1 + grp, 128);
+      if (gtid == 0) {
+        for (int kb = 0; kb < KB; ++kb) tma_store_2d(&maps.out, wb + kb * BLK, kb * 64, (t0 + i) * TM);
+        tma_store_commit();
+      }
+    }
+    if (gtid == 0) tma_store_wait_all<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+template <int C>
+int launch_tc(const bf16* x, const bf16* wqkv, const float* g_pre, const float* shift, const bf16* wout, const float* b_out,
+              const float* g_out, bf16* out, float* workspace, int batch, int n, float scale, float eps, cudaStream_t s) {
+  constexpr int KB = C / 64, N2 = C + 16;
+  const int tpi = n / TM, sms = tedm_num_sms();
+  // K-A work items: chunks of consecutive tiles of one image; the chunk length that wastes the least of the last wave
+  int chunk = tpi, best_waste = 1 << 30;
+  for (int c = tpi < 32 ? tpi : 32; c >= 4 && c >= tpi / 64; c >>= 1) {
+    if (tpi % c) continue;
+    const long long items = (long long)batch * (tpi / c), waves = (items + sms - 1) / sms;
+    const int waste = (int)((waves * sms - items) * c + waves * 2);          // idle tile slots + a per-item drain cost
+    if (waste < best_waste) {
+      best_waste = waste;
+      chunk = c;
+    }
+  }
+  const int chunks = tpi / chunk;
+  const long long items = (long long)batch * chunks;
+  bf16* mimg = reinterpret_cast<bf16*>(workspace);                    // [batch][C][128] bf16 first (tests read it back) ...
+  float* part = workspace + (size_t)batch * C * HID / 2;              // ... then the K-A partials [items][128][C + 16] fp32
+
+  alignas(64) TcMaps maps;
+  int rc = encode_2d(&maps.x, x, (long long)batch * n, C, TM);
+  if (rc) return rc;
+  rc = encode_2d(&maps.w, wqkv, 3 * HID, C, HID);
+  if (rc) return rc;
+  rc = encode_2d(&maps.m, mimg, (long long)batch * C, HID, C);
+  if (rc) return rc;
+  rc = encode_2d(&maps.out, out, (long long)batch * n, C, TM);
+  if (rc) return rc;
+
+  TcParams p{};
+  p.n = n;
+  p.tiles_per_image = tpi;
+  p.chunk_tiles = chunk;
+  p.items = (int)items;
+  p.total_tiles = batch * tpi;
+  p.eps = eps;
+  p.g_pre = g_pre;
+  p.shift = shift;
+  p.part = part;
+  p.b_out = b_out;
+  p.g_out = g_out;
+
+  const int smem_a = 1024 + KB * BLK + 2 * (KB + 1) * BLK + 2 * 2 * BLK;
+  const int smem_b = 1024 + KB * BLK + 2 * C * 128 + 2 * KB * BLK + 2 * 2 * BLK;
+  const int smem_c = (HID * (C + 1) + HID * 33) * (int)sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    TEDM_CUDA(cudaFuncSetAttribute(linattn_tc_ctx_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a));
+    TEDM_CUDA(cudaFuncSetAttribute(linattn_tc_out_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b));
+    TEDM_CUDA(cudaFuncSetAttribute(linattn_tc_combine_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c));
+    configured = true;
+  }
+  const int grid_a = items < sms ? (int)items : sms;
+  linattn_tc_ctx_kernel<C><<<grid_a, TC_THREADS, smem_a, s>>>(maps, p);
+  TEDM_LAUNCH_CHECK();
+  linattn_tc_combine_kernel<C><<<batch, 256, smem_c, s>>>(part, wqkv, wout, mimg, chunks, n, scale);
+  TEDM_LAUNCH_CHECK();
+  const int grid_b = p.total_tiles < sms ? p.total_tiles : sms;
+  linattn_tc_out_kernel<C><<<grid_b, TC_THREADS, smem_b, s>>>(maps, p);
+  TEDM_LAUNCH_CHECK();
+  return TEDM_OK;
+}
+
+}  // namespace
+
+extern "C" int tedm_linear_attention_tc_supported(int n, int channels, int heads, int dim_head) {
+  return heads == 4 && dim_head == 32 && (channels == 64 || channels == 128) && n >= 512 && n % 512 == 0;
+}
+
+extern "C" int64_t tedm_linear_attention_tc_workspace(int batch, int n, int channels) {
+  if (batch <= 0 || n <= 0 || n % TM) return -1;
+  // partials: at most one per 4 tiles; + the per-image folded matrices M (bf16, counted in floats)
+  const int64_t items = (int64_t)batch * ((n / TM + 3) / 4);
+  return items * HID * (channels + 16) + (int64_t)batch * channels * HID / 2 + 64;
+}
+
+extern "C" int tedm_linear_attention_tc_fwd(const void* x, const void* wqkv, const float* g_pre, const float* shift_log2,
+                                            const void* wout, const float* b_out, const float* g_out, void* out, float* workspace,
+                                            int batch, int n, int channels, int heads, int dim_head, float scale, float eps,
+                                            tedm_stream_t stream) {
+  TEDM_CHECK_ARG(x && wqkv && g_pre && shift_log2 && wout && b_out && g_out && out && workspace && batch > 0,
+                 "tedm_linear_attention_tc_fwd: bad arguments");
+  TEDM_UNSUPPORTED(!tedm_linear_attention_tc_supported(n, channels, heads, dim_head),
+                   "tedm_linear_attention_tc_fwd: n=%d channels=%d heads=%d dim_head=%d (needs 4 x 32 heads, 64 or 128 channels, "
+                   "n a multiple of 512)", n, channels, heads, dim_head);
+  TEDM_CHECK_ARG((long long)batch * n < 2147483647LL, "tedm_linear_attention_tc_fwd: too many pixels");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (channels == 64)
+    return launch_tc<64>((const bf16*)x, (const bf16*)wqkv, g_pre, shift_log2, (const bf16*)wout, b_out, g_out, (bf16*)out, workspace,
+                         batch, n, scale, eps, s);
+  return launch_tc<128>((const bf16*)x, (const bf16*)wqkv, g_pre, shift_log2, (const bf16*)wout, b_out, g_out, (bf16*)out, workspace,
+                        batch, n, scale, eps, s);
+}

@@ -612,8 +612,7 @@ struct WgradParams {
   int items, n_tiles, splitk, num_ptiles, stages;
   int oihw;                      // 1: accumulate into an fp32 OIHW gradient (mode 3: un-folded to 3x3)
   float* dw;
-  float* part;                   // split-K partial tiles [group][ks][128][BN] fp32, summed in a fixed order by wgrad_reduce_kernel
-  int group0;                    // first (m block, n tile) group of this launch (wide layers run in batches that fit `part`)
+  int* turn;                     // one counter per (m block, n tile) group: whose split-K slice adds next (self-resetting)
 };
 
 __device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr) {
@@ -638,7 +637,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_consta
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int cb_total = p.c0_blocks + p.c1_blocks;
   const int ks = blockIdx.x;
-  const int grp = p.group0 + blockIdx.y;
+  const int grp = blockIdx.y;
   const int mb = grp / p.n_tiles, nt = grp % p.n_tiles;
   const int n0 = nt * BN;
   const int item0 = 2 * mb, item1 = (2 * mb + 1 < p.items) ? 2 * mb + 1 : 2 * mb;   // odd tail: duplicate, discarded by the reduce
@@ -738,75 +737,63 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_consta
     }
     __syncwarp();
   } else {
-    // the partial tile of this CTA goes to the workspace with plain stores; wgrad_reduce_kernel sums the split-K slices in
-    // a fixed order (deterministic: no floating-point atomics) and lays dW out
     const int q = warp & 3, row = q * 32 + lane;
-    float* ptile = p.part + ((size_t)blockIdx.y * p.splitk + ks) * (size_t)(BM * BN) + (size_t)row * BN;
+    const int half = row >> 6;
+    const int item = half ? item1 : item0;
+    const bool live = num_kb > 0 && (half == 0 || item1 != item0);
+    const int tap = item / cb_total, cb = item % cb_total;
+    const int ci = cb * BK + (row & 63);
+    // destination of output channel co:  base + co * co_stride
+    size_t base, co_stride;
+    if (!p.oihw) {
+      base = (size_t)tap * p.ctot + ci;
+      co_stride = (size_t)p.taps * p.ctot;
+    } else {
+      base = (size_t)ci * p.taps + tap;
+      co_stride = (size_t)p.ctot * p.taps;
+    }
     if (num_kb > 0) {
       mbar_wait(smem_u32(&bar_acc), 0);
       tc_fence_after();
     }
+    // Split-K slices of one (m block, n tile) group add into dW with fire-and-forget fp32 reductions, but IN SLICE ORDER:
+    // slice ks waits for turn[group] == ks, adds, fences, passes the turn on (the last slice resets it to 0).  Every
+    // address therefore receives its addends in a fixed order and the gradient is bit-reproducible.  Slices of a group
+    // have consecutive linear block ids (blockIdx.x = ks), so a waiting CTA's predecessors are resident or finished.
+    int* turn = p.turn + grp;
+    if (p.splitk > 1) {
+      if (threadIdx.x == 64) {
+        int v;
+        do {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(turn) : "memory");
+        } while (v != ks);
+      }
+      named_bar_sync(1, 128);
+    }
+    if (num_kb > 0) {
 #pragma unroll 1
-    for (int chunk = 0; chunk < BN / 32; ++chunk) {
-      uint32_t r[32];
-      if (num_kb > 0) {
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(chunk * 32), r);
         tmem_ld_wait();
-      } else {
+        if (live) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0u;
+          for (int j = 0; j < 32; ++j) atomicAdd(p.dw + base + (size_t)(n0 + chunk * 32 + j) * co_stride, __uint_as_float(r[j]));
+        }
       }
-      float4* dst = reinterpret_cast<float4*>(ptile + chunk * 32);
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                             __uint_as_float(r[4 * j + 3]));
+    }
+    if (p.splitk > 1) {
+      __threadfence();
+      named_bar_sync(1, 128);
+      if (threadIdx.x == 64) {
+        const int next = ks == p.splitk - 1 ? 0 : ks + 1;
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(turn), "r"(next) : "memory");
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<BN>(tmem_base);
-}
-
-// Sums the split-K partial tiles of conv_wgrad_kernel in slice order and writes dW.  CTA = (group, tap/channel-block item
-// of the pair, 64-column chunk): a 64 (input channel) x 64 (output channel) block; reads are coalesced along the output
-// channel, the block is transposed through shared memory so that writes run along the input channel.
-//   layout 0: dw[co][tap][ci] = sum       (raw; also the intermediate of the folded upsample conv)
-//   layout 1: dw[co][ci][tap] += sum      (OIHW accumulate)
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int splitk,
-                                                           int bn, int n_tiles, int group0, int items, int cb_total, int taps,
-                                                           int ctot, int layout) {
-  __shared__ float tile[64][65];
-  const int grp = group0 + blockIdx.x, mb = grp / n_tiles, nt = grp % n_tiles;
-  const int h = blockIdx.y, cc = blockIdx.z;
-  const int item = 2 * mb + h;
-  if (item >= items) return;
-  const int tap = item / cb_total, cb = item % cb_total;
-  const float* src = part + (size_t)blockIdx.x * splitk * (size_t)(BM * bn) + (size_t)(h * 64) * bn + cc * 64;
-  {
-    const int c = threadIdx.x & 63, r0 = threadIdx.x >> 6;
-    float acc[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0.0f;
-    for (int ks = 0; ks < splitk; ++ks) {
-      const float* s_ = src + (size_t)ks * (size_t)(BM * bn) + c;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] += __ldg(s_ + (size_t)(r0 + 4 * i) * bn);
-    }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) tile[r0 + 4 * i][c] = acc[i];
-  }
-  __syncthreads();
-  const int r = threadIdx.x & 63, c0 = threadIdx.x >> 6;
-  const int ci = cb * 64 + r;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int c = c0 + 4 * i;
-    const int co = nt * bn + cc * 64 + c;
-    const float v = tile[r][c];
-    if (layout == 0) dw[((size_t)co * taps + tap) * ctot + ci] = v;
-    else dw[((size_t)co * ctot + ci) * taps + tap] += v;
-  }
 }
 
 template <int BN>
@@ -822,14 +809,15 @@ int launch_wgrad(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap
     TEDM_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  dim3 grid((unsigned)p.splitk, (unsigned)m_blocks);     // m_blocks: the (m block, n tile) groups of this batch
+  dim3 grid((unsigned)p.splitk, (unsigned)(m_blocks * p.n_tiles));
   conv_wgrad_kernel<BN><<<grid, 192, smem, stream>>>(x0, x1, dy, p);
   TEDM_LAUNCH_CHECK();
   return TEDM_OK;
 }
 
-constexpr long long WGRAD_PART_FLOATS_PER_SM = 4LL * BM * 256;   // 4 waves of CTAs, each a 128 x 256 fp32 partial tile
-constexpr long long WGRAD_RAW_FLOATS = 4LL << 20;                // raw [co][16][ci] intermediate of the folded upsample conv
+constexpr long long WGRAD_PART_FLOATS_PER_SM = 3LL * 5 * BM * 64;   // halo-tile kernel: 3 waves of CTAs x 5 x 128 x 64 fp32 partials
+constexpr long long WGRAD_RAW_FLOATS = 4LL << 20;                   // raw [co][16][ci] intermediate of the folded upsample conv
+constexpr long long WGRAD_TURN_INTS = 1LL << 16;                    // split-K turn counters of the generic kernel
 
 // ==========================================================================================
 // weight gradient of the 3x3 convolution, halo-tile form
@@ -1249,9 +1237,9 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
 // dw: fp32 [cout][taps][c0+c1] (taps = 1 / 9 / 16; mode 3: 16 = parity*4 + a*2 + b of the folded kernel), overwritten;
 // or, with oihw_accumulate, the fp32 OIHW parameter gradient itself (+=; the folded taps of mode 3 are scattered to 3x3).
 extern "C" int64_t tedm_conv_igemm_wgrad_workspace(void) {
-  // split-K partial tiles: the halo-tile 3x3 kernel needs at most 3 waves of CTAs x 5 x 128 x 64 fp32, the generic kernel
-  // at most 4 waves x 128 x 256; plus the raw intermediate of the folded upsample conv's gradient
-  return WGRAD_PART_FLOATS_PER_SM * tedm_num_sms() + WGRAD_RAW_FLOATS;
+  // split-K partial tiles of the halo-tile 3x3 kernel, the raw intermediate of the folded upsample conv's gradient, and
+  // the generic kernel's turn counters (which must be ZERO when the workspace is first used; they reset themselves)
+  return WGRAD_PART_FLOATS_PER_SM * tedm_num_sms() + WGRAD_RAW_FLOATS + WGRAD_TURN_INTS;
 }
 
 extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, float* dw, int oihw_accumulate,
@@ -1377,10 +1365,9 @@ extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, fl
   p.n_tiles = a->cout / bn;
   const int m_blocks = (p.items + 1) / 2;
   const long long groups = (long long)m_blocks * p.n_tiles, sms = tedm_num_sms();
-  const long long part_floats = WGRAD_PART_FLOATS_PER_SM * sms, tile_floats = (long long)BM * bn;
+  const long long part_floats = WGRAD_PART_FLOATS_PER_SM * sms;
   // split K over pixel tiles: one CTA per SM is resident (192 KB of pipeline smem), so pick the split whose CTA count
-  // fills whole waves of the machine (up to 4 waves, each CTA at least 4 pixel tiles) and whose partial tiles fit the
-  // workspace; layers with more groups than the workspace holds run in batches of groups
+  // fills whole waves of the machine (up to 4 waves, each CTA at least 4 pixel tiles)
   {
     const long long cap = p.num_ptiles / 4 > 0 ? p.num_ptiles / 4 : 1;
     long long best_sk = 1;
@@ -1389,7 +1376,6 @@ extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, fl
       long long sk = (w * sms) / groups;
       if (sk < 1) sk = 1;
       if (sk > cap) sk = cap;
-      while (sk > 1 && groups * sk * tile_floats > part_floats) --sk;
       const long long ctas = groups * sk, waves = (ctas + sms - 1) / sms;
       const double eff = (double)ctas / (double)(waves * sms);
       if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && sk > best_sk)) {
@@ -1400,12 +1386,16 @@ extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, fl
     p.splitk = (int)best_sk;
   }
   TEDM_CHECK_ARG(workspace != nullptr, "tedm_conv_igemm_wgrad: workspace (tedm_conv_igemm_wgrad_workspace() floats) is required");
-  const bool unfold = p.oihw && a->mode == 3;     // folded taps -> raw intermediate -> 3x3 OIHW accumulate
+  const bool unfold = p.oihw && a->mode == 3;     // folded taps -> raw [co][16][ci] intermediate -> 3x3 OIHW accumulate
   TEDM_UNSUPPORTED(unfold && (long long)a->cout * 16 * p.ctot > WGRAD_RAW_FLOATS,
                    "tedm_conv_igemm_wgrad: upsample conv %d -> %d too wide for the raw-gradient workspace", p.ctot, a->cout);
+  TEDM_UNSUPPORTED(groups > WGRAD_TURN_INTS, "tedm_conv_igemm_wgrad: %lld output tiles exceed the turn-counter workspace", groups);
   float* raw = workspace + part_floats;
-  float* dst = unfold ? raw : dw;
-  const int layout = (p.oihw && !unfold) ? 1 : 0;
+  p.turn = reinterpret_cast<int*>(workspace + part_floats + WGRAD_RAW_FLOATS);   // zero at allocation, self-resetting
+  if (unfold) {
+    p.dw = raw;
+    p.oihw = 0;
+  }
 
   const int dy_h = a->mode == 3 ? 2 * a->height : Ho, dy_w = a->mode == 3 ? 2 * a->width : Wo;
   alignas(64) CUtensorMap mapX0, mapX1, mapDY;
@@ -1425,23 +1415,13 @@ extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, fl
                       a->out_image_stride ? a->out_image_stride : (long long)dy_h * dy_w * a->cout, a->mode == 3 ? 2 : 0,
                       p.tileW, p.tileH, p.tileB);
   if (rc) return rc;
-  p.part = workspace;
-  long long per_batch = part_floats / (p.splitk * tile_floats);
-  if (per_batch > groups) per_batch = groups;
-  for (long long g0 = 0; g0 < groups; g0 += per_batch) {
-    const int ng = (int)(groups - g0 < per_batch ? groups - g0 : per_batch);
-    p.group0 = (int)g0;
-    switch (bn) {
-      case 64: rc = launch_wgrad<64>(mapX0, mapX1, mapDY, p, ng, s); break;
-      case 128: rc = launch_wgrad<128>(mapX0, mapX1, mapDY, p, ng, s); break;
-      default: rc = launch_wgrad<256>(mapX0, mapX1, mapDY, p, ng, s); break;
-    }
-    if (rc) return rc;
-    wgrad_reduce_kernel<<<dim3((unsigned)ng, 2, (unsigned)(bn / 64)), 256, 0, s>>>(workspace, dst, p.splitk, bn, p.n_tiles, (int)g0,
-                                                                                p.items, p.c0_blocks + p.c1_blocks, p.taps,
-                                                                                p.ctot, layout);
-    TEDM_LAUNCH_CHECK();
+  if (!p.oihw) TEDM_CUDA(cudaMemsetAsync(p.dw, 0, sizeof(float) * (size_t)a->cout * p.taps * p.ctot, s));
+  switch (bn) {
+    case 64: rc = launch_wgrad<64>(mapX0, mapX1, mapDY, p, m_blocks, s); break;
+    case 128: rc = launch_wgrad<128>(mapX0, mapX1, mapDY, p, m_blocks, s); break;
+    default: rc = launch_wgrad<256>(mapX0, mapX1, mapDY, p, m_blocks, s); break;
   }
+  if (rc) return rc;
   if (unfold) return tedm_wgrad_to_oihw(raw, dw, a->cout, p.ctot, 3, stream);
   return TEDM_OK;
 }

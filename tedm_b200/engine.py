@@ -78,6 +78,7 @@ class UnetEngine:
         self.fold_upsample = fold_upsample
         self.ln_eps = ln_eps
         self.fuse_linear_attention = True
+        self.linear_attention_tc = True       # tcgen05 form of the fused block (csrc/attention_tc.cu) where it applies
         # backward: weight gradients run on a side stream next to the data-gradient chain (they only meet in the optimiser);
         # at the low-resolution levels neither kernel fills the 148 SMs on its own
         self.overlap_wgrad = True
@@ -241,8 +242,20 @@ class UnetEngine:
     def _linear_attention(self, key: str, wrap: nn.Module, x: Tensor, tape: Optional[Tape] = None) -> Tensor:
         pre, att = wrap.fn.norm, wrap.fn.fn
         c = x.shape[-1]
+        n_pix = x.shape[1] * x.shape[2]
+        if tape is None and self.fuse_linear_attention and self.linear_attention_tc and N.linear_attention_tc_supported(
+                n_pix, c, att.heads, att.dim_head):
+            # the same block with every GEMM on tcgen05; its softmax over pixels uses a weight-only bound of the k logits
+            # instead of a running maximum, so blocks with extreme projection weights stay on the mma.sync kernels below
+            shift, bound = self.cache.get(key + ":kshift", (att.to_qkv.weight, pre.g),
+                                          lambda w, g: N.linear_attention_tc_shift(w.to(torch.bfloat16), g, att.heads, att.dim_head))
+            if bound <= N.LINATTN_TC_MAX_SHIFT:
+                return N.linear_attention_block_tc(x, self._w(key + ".to_qkv"), self._f32(pre.g).reshape(-1), shift,
+                                                   self._w(key + ".to_out"), self._f32(att.to_out[0].bias),
+                                                   self._f32(att.to_out[1].g).reshape(-1), att.heads, att.dim_head, att.scale,
+                                                   self.ln_eps)
         if (tape is None and self.fuse_linear_attention
-                and N.linear_attention_fused_supported(x.shape[1] * x.shape[2], c, att.heads, att.dim_head)):
+                and N.linear_attention_fused_supported(n_pix, c, att.heads, att.dim_head)):
             # inference at the high-resolution levels: the whole block in 3 launches, q/k/v never leave the SM
             return N.linear_attention_block_fused(x, self._w(key + ".to_qkv"), self._f32(pre.g).reshape(-1),
                                                   self._w(key + ".to_out"), self._f32(att.to_out[0].bias),

@@ -66,6 +66,9 @@ SIGNATURES = {
     "tedm_linear_attention_fused_supported": (_i, [_i, _i, _i, _i]),
     "tedm_linear_attention_fused_workspace": (_i64, [_i, _i]),
     "tedm_linear_attention_fused_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _p]),
+    "tedm_linear_attention_tc_supported": (_i, [_i, _i, _i, _i]),
+    "tedm_linear_attention_tc_workspace": (_i64, [_i, _i, _i]),
+    "tedm_linear_attention_tc_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _p]),
     "tedm_upsample2x": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "tedm_final_conv1x1": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "tedm_nchw_f32_to_nhwc_bf16": (_i, [_p, _p, _i, _i, _i, _p]),
@@ -346,7 +349,8 @@ def _wgrad_workspace(device) -> torch.Tensor:
     weight gradient of a backward pass is issued on ONE stream)."""
     key = (device.type, device.index)
     if key not in _wgrad_ws:
-        _wgrad_ws[key] = torch.empty(load().tedm_conv_igemm_wgrad_workspace(), device=device, dtype=torch.float32)
+        # zeros: the tail of the workspace holds the generic kernel's split-K turn counters (zero at first use, self-resetting)
+        _wgrad_ws[key] = torch.zeros(load().tedm_conv_igemm_wgrad_workspace(), device=device, dtype=torch.float32)
     return _wgrad_ws[key]
 
 
@@ -371,7 +375,7 @@ def conv_wgrad(src0: torch.Tensor, dy: torch.Tensor, mode: int, src1=None, grad_
     p1, s1 = _nhwc(src1, "src1")
     pd, sd = _nhwc(dy, "dy")
     a = ConvArgs(p0, p1, None, None, None, None, None, b, h, w, c0, c1, cout, mode, 0, 0, s0, s1, sd)
-    ws = _wgrad_workspace(src0.device)       # split-K partial tiles (summed in a fixed order: deterministic gradients)
+    ws = _wgrad_workspace(src0.device)       # split-K partials / turn counters: slices are summed in a fixed order (deterministic)
     if conv_timer is not None:
         flops = 2 * b * (h * w if mode == MODE_UP3X3 else oh * ow) * cout * taps * (c0 + c1)
         with conv_timer(flops, ("wgrad", mode, b, h, w, c0, c1, cout)):
@@ -438,6 +442,40 @@ def linear_attention_block_fused(x, wqkv, g_pre, wout, b_out, g_out, heads: int 
           _ptr(g_out, torch.float32, "g_out"), _ptr(out), _ptr(ws), b, h * w, c, heads, dim_head, float(scale), float(eps),
           _stream())
     return out
+
+
+LINATTN_TC_MAX_SHIFT = 40.0      # exp(-2 * 40) is still a normal fp32 / bf16 number
+
+
+def linear_attention_tc_supported(n: int, channels: int, heads: int = 4, dim_head: int = 32) -> bool:
+    return bool(load().tedm_linear_attention_tc_supported(n, channels, heads, dim_head))
+
+
+def linear_attention_tc_shift(wqkv: torch.Tensor, g_pre: torch.Tensor, heads: int = 4, dim_head: int = 32):
+    """Weight-only upper bound of the k logits of a LinearAttention block: k = w . y with y = LN(x) * g, ||LN(x)||_2 <=
+    sqrt(C), hence |k_hd| <= ||w_hd * g||_2 sqrt(C) (+ 2 % for the bf16 rounding of y).  -> (log2(e) * bound [128] fp32,
+    largest bound as a float)."""
+    hid = heads * dim_head
+    c = wqkv.numel() // (3 * hid)
+    wk = wqkv.reshape(3 * hid, c)[hid:2 * hid].float()
+    bound = (wk * g_pre.reshape(1, c).float()).norm(dim=1) * (c ** 0.5) * 1.02 + 1e-3
+    return (bound * 1.4426950408889634).contiguous(), float(bound.max().item())
+
+
+def linear_attention_block_tc(x, wqkv, g_pre, shift_log2, wout, b_out, g_out, heads: int = 4, dim_head: int = 32,
+                              scale: Optional[float] = None, eps: float = 1e-5, want_workspace: bool = False):
+    """Residual(PreNorm(LinearAttention)) inference forward on tcgen05 (csrc/attention_tc.cu); x NHWC bf16 -> same shape."""
+    if x.dim() != 4 or not x.is_contiguous():
+        raise ValueError("x must be a contiguous NHWC tensor")
+    b, h, w, c = x.shape
+    scale = dim_head ** -0.5 if scale is None else scale
+    out = torch.empty_like(x)
+    ws = torch.empty(load().tedm_linear_attention_tc_workspace(b, h * w, c), device=x.device, dtype=torch.float32)
+    _call("tedm_linear_attention_tc_fwd", _ptr(x, torch.bfloat16, "x"), _ptr(wqkv, torch.bfloat16, "wqkv"),
+          _ptr(g_pre, torch.float32, "g_pre"), _ptr(shift_log2, torch.float32, "shift"), _ptr(wout, torch.bfloat16, "wout"),
+          _ptr(b_out, torch.float32, "b_out"), _ptr(g_out, torch.float32, "g_out"), _ptr(out), _ptr(ws), b, h * w, c, heads,
+          dim_head, float(scale), float(eps), _stream())
+    return (out, ws) if want_workspace else out
 
 
 def attention(qkv, heads: int = 4, dim_head: int = 32, scale: float = 16.0):

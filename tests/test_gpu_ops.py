@@ -214,6 +214,49 @@ def test_linear_attention_block_fused(C, hw, B):
     assert not N.linear_attention_fused_supported(n, 256) and not N.linear_attention_fused_supported(100, 64)
 
 
+@pytest.mark.parametrize("C,hw,B", [(64, 32, 2), (64, 128, 1), (128, 64, 2), (64, 32, 40), (128, 32, 21), (64, 64, 16)])
+def test_linear_attention_block_tc(C, hw, B):
+    """The same block with every GEMM on tcgen05 (csrc/attention_tc.cu: fixed weight-only softmax shift, v never
+    materialised, to_out folded into a per-image matrix) against the oracle's block and the mma.sync kernels it replaces;
+    the per-image folded matrix is checked on its own so that a failure localises."""
+    from tedm_b200 import native as N
+    n = hw * hw
+    x = _bf(_rand((B, C, hw, hw), 21, 1.2))
+    sd = {"a.fn.norm.g": 1 + 0.2 * _rand((1, C, 1, 1), 22), "a.fn.fn.to_qkv.weight": _bf(_rand((384, C, 1, 1), 23, 2.0 / C ** 0.5)),
+          "a.fn.fn.to_out.0.weight": _bf(_rand((C, 128, 1, 1), 24, 0.12)), "a.fn.fn.to_out.0.bias": _rand((C,), 25, 0.1),
+          "a.fn.fn.to_out.1.g": 1 + 0.2 * _rand((1, C, 1, 1), 26)}
+    ref = O._linear_attention(sd, "a.", x, 1e-5, lambda t: t)
+    assert N.linear_attention_tc_supported(n, C) and not N.linear_attention_tc_supported(n, 256) and not N.linear_attention_tc_supported(192, C)
+    wq = sd["a.fn.fn.to_qkv.weight"].reshape(384, C).to(torch.bfloat16).cuda()
+    wo = sd["a.fn.fn.to_out.0.weight"].reshape(C, 128).to(torch.bfloat16).cuda()
+    g1, g2 = sd["a.fn.norm.g"].reshape(-1).cuda(), sd["a.fn.fn.to_out.1.g"].reshape(-1).cuda()
+    bo = sd["a.fn.fn.to_out.0.bias"].cuda()
+    shift, bound = N.linear_attention_tc_shift(wq, g1)
+    assert bound < N.LINATTN_TC_MAX_SHIFT
+    xh = _nhwc(x)
+    got, ws = N.linear_attention_block_tc(xh, wq, g1, shift, wo, bo, g2, want_workspace=True)
+    torch.cuda.synchronize()
+    # (1) the folded per-image matrix M[c][hd] = scale * sum_e ctx[h][d][e] Wo[c][h*32+e], recomputed in fp32 torch
+    y = O._chan_layernorm(x, sd["a.fn.norm.g"], 1e-5)
+    qkv = F.conv2d(_bf(y), sd["a.fn.fn.to_qkv.weight"])
+    k, v = (z.reshape(B, 4, 32, n) for z in qkv.chunk(3, dim=1)[1:])
+    ctx = torch.einsum("bhdn,bhen->bhde", k.softmax(dim=-1), v / n)
+    m_ref = torch.einsum("bhde,che->bchd", ctx, sd["a.fn.fn.to_out.0.weight"].reshape(C, 4, 32)).reshape(B, C, 128) * 32 ** -0.5
+    m_got = ws[:B * C * 64].view(torch.bfloat16).float().reshape(B, C, 128).cpu()      # the workspace starts with M (bf16)
+    err_m = _rel(m_got, m_ref)
+    print(f"tc block C={C} hw={hw} B={B}: folded matrix rel err {err_m:.4f}")
+    assert err_m < 1.5e-2, err_m
+    # (2) the block output
+    err = _rel(_nchw(got) - x, ref - x)
+    yk = N.layernorm(xh, g1)
+    o = N.linear_attention(N.conv_igemm(yk, wq, N.MODE_1X1, 384))
+    unf = N.layernorm(N.conv_igemm(o, wo, N.MODE_1X1, C, bias=bo), g2, residual=xh)
+    err_unf = _rel(_nchw(unf) - x, ref - x)
+    print(f"tc block C={C} hw={hw} B={B}: branch rel err {err:.4f}, unfused chain {err_unf:.4f}")
+    assert torch.isfinite(got.float()).all()
+    assert err < max(1.5 * err_unf, 8e-3), (err, err_unf)
+
+
 def test_linear_attention_block_fused_large_logits():
     """Projection weights 8x the usual scale: k reaches +-60, so exp(k - m) spans the whole fp32 range and the running
     column maxima move for many tiles -- the online softmax must neither overflow nor lose the dominant terms."""

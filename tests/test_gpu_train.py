@@ -1,9 +1,10 @@
 """Training step (UNet forward + backward + Adam) of the CUDA path against the gradients the LIVE reference
 produced (tests/golden/ddpm_small_grads.npz, made by tests/golden/make_golden_grads.py) and against the oracle.
 
-Tolerance: the forward runs with bf16 activations (north star: 2e-2 relative on activations); gradients are held
-to 5e-2 relative on the whole-gradient vector and per-parameter to 0.15 on every tensor whose gradient carries
-more than 1e-4 of the total norm (bf16 rounding noise of activations dominates the tiny ones)."""
+Tolerance: the forward runs with bf16 activations (north star: 2e-2 relative on activations); gradients are held to
+about twice what is measured on B200, so that a regression trips: 1.5e-2 relative on the whole-gradient vector (measured
+0.7e-2) and 9e-2 on every tensor whose gradient carries more than 1e-4 of the total norm (measured 4.3e-2 on the
+mid-attention qkv weight; bf16 rounding noise of activations dominates the tiny ones)."""
 from argparse import Namespace
 
 import numpy as np
@@ -48,9 +49,9 @@ def _compare_grads(named_grads, g, tag):
     worst.sort(reverse=True)
     overall = (num / den) ** 0.5
     print(f"[{tag}] whole-gradient rel err (sampled) {overall:.4f}; worst tensors:", [(round(a, 4), round(b, 4), n) for a, b, n in worst[:6]])
-    assert overall < 5e-2, overall
-    assert worst[0][0] < 0.15, worst[:5]
-    assert max(w[1] for w in worst) < 0.1, sorted(worst, key=lambda w: -w[1])[:5]
+    assert overall < 1.5e-2, overall
+    assert worst[0][0] < 9e-2, worst[:5]
+    assert max(w[1] for w in worst) < 2e-2, sorted(worst, key=lambda w: -w[1])[:5]
 
 
 def test_train_step_gradients_match_reference(golden):
@@ -102,8 +103,8 @@ def test_unet_backward_smooth_loss_vs_oracle():
             worst.append((float(d.norm() / r.norm()), name))
     worst.sort(reverse=True)
     print("smooth-loss whole-gradient rel err", (num / den) ** 0.5, worst[:6])
-    assert (num / den) ** 0.5 < 5e-2
-    assert worst[0][0] < 0.15, worst[:5]
+    assert (num / den) ** 0.5 < 2.5e-2                   # measured 1.2e-2
+    assert worst[0][0] < 0.13, worst[:5]                  # measured 6.3e-2 (mid-attention qkv)
 
 
 def test_unet_backward_without_time_embedding():
@@ -154,7 +155,7 @@ def test_fused_adam_step_matches_reference(golden):
         agree += int((torch.sign(delta[big]) == torch.sign(delta_ref[big])).sum())
         total += int(big.sum())
     print("Adam step sign agreement", agree / total, total)
-    assert agree / total > 0.97
+    assert agree / total > 0.99                      # measured 0.9953
     # a second forward must see the updated weights (derived bf16 weight caches invalidated by the step)
     with torch.no_grad():
         l2 = m.train_step(x0, t=t, noise=nz)
@@ -226,5 +227,26 @@ def test_unet_backward_with_1024_mid_tokens():
     mid = dict(m.named_parameters())["mid_attn.fn.fn.to_qkv.weight"].grad.double().cpu()
     mid_ref = ref_sd["mid_attn.fn.fn.to_qkv.weight"].grad.double()
     print("1024-token mid attention: whole-gradient rel err", (num / den) ** 0.5, "mid to_qkv", float((mid - mid_ref).norm() / mid_ref.norm()))
-    assert (num / den) ** 0.5 < 5e-2
-    assert float((mid - mid_ref).norm() / mid_ref.norm()) < 0.15
+    assert (num / den) ** 0.5 < 2.5e-2                                  # measured 1.0e-2
+    assert float((mid - mid_ref).norm() / mid_ref.norm()) < 5e-2       # measured 2.2e-2
+
+
+def test_conv_weight_gradients_are_bit_reproducible():
+    """Both tcgen05 weight-gradient kernels add their split-K slices in a fixed order (csrc/conv_igemm.cu): the same step
+    run twice gives bit-identical gradients for every convolution weight (99.9 % of the 36 M parameters)."""
+    m = _model()
+    x = torch.rand(8, 1, 64, 64, generator=torch.Generator().manual_seed(9)).cuda()
+    t = torch.randint(0, 1000, (8,), generator=torch.Generator().manual_seed(10)).cuda()
+    nz = torch.randn(8, 1, 64, 64, generator=torch.Generator().manual_seed(11)).cuda()
+    runs = []
+    for _ in range(3):
+        for p in m.parameters():
+            p.grad = None
+        m.train_step(x, t=t, noise=nz).backward()
+        torch.cuda.synchronize()
+        runs.append({n: p.grad.clone() for n, p in m.named_parameters() if p.dim() == 4 and p.shape[1] > 1})
+    n_el = sum(g.numel() for g in runs[0].values())
+    assert n_el > 35_000_000
+    for name, g in runs[0].items():
+        assert torch.isfinite(g).all() and g.abs().sum() > 0, name
+        assert torch.equal(g, runs[1][name]) and torch.equal(g, runs[2][name]), name
