@@ -147,12 +147,16 @@ TEDM_API int tedm_conv_igemm_fwd(const tedm_conv_args* args, tedm_stream_t strea
  * ACCUMULATED into it (mode 3: the folded taps are scattered back onto the 3x3 kernel of Upsample's conv). */
 TEDM_API int tedm_conv_igemm_wgrad(const tedm_conv_args* args, const void* dy, float* dw, int oihw_accumulate,
                           float* workspace, tedm_stream_t stream);
-/* fp32 elements of the REQUIRED `workspace` above.  Both weight-gradient kernels sum their split-K slices in a FIXED order,
- * so the gradient is bit-reproducible from run to run: the 3x3 halo-tile kernel stores partial tiles there and a second
- * kernel adds them in slice order; the generic kernel adds straight into dw, slice after slice, the order enforced by
- * per-tile turn counters kept at the end of the workspace.  The workspace must be ZERO when first used (the counters reset
- * themselves); calls that share one workspace must be ordered on one stream. */
+/* fp32 elements of the REQUIRED `workspace` above.  The 3x3 halo-tile kernel stores its split-K partial tiles there and a
+ * second kernel adds them in slice order (always bit-reproducible).  The generic kernel (1x1, 4x4-s2, folded upsample, the
+ * widest 3x3) adds its slices straight into dw with fp32 reductions: in arrival order by default, or -- after
+ * tedm_conv_set_deterministic(1) -- slice after slice, the order enforced by per-tile turn counters kept at the end of
+ * the workspace (split-K capped at 4; measured cost in DESIGN.md).  The workspace must be ZERO when first used (the
+ * counters reset themselves); calls that share one workspace must be ordered on one stream. */
 TEDM_API int64_t tedm_conv_igemm_wgrad_workspace(void);
+/* 1: every convolution weight gradient is bit-reproducible from run to run (torch.use_deterministic_algorithms-style
+ * opt-in); 0 (default): the generic kernel's split-K slices add in arrival order. */
+TEDM_API int tedm_conv_set_deterministic(int enable);
 /* number of partial-statistics slots per image that tedm_conv_igemm_fwd writes for this output extent */
 TEDM_API int tedm_conv_gn_parts(int out_height, int out_width);
 /* tuning/debug: force the N tile (64/128/256; 0 = automatic) of tedm_conv_igemm_fwd */

@@ -6,6 +6,18 @@ mkdir -p gpurun_out
 out=gpurun_out/${tag}_tests.log
 : > $out
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv >> $out 2>&1
+# the newest kernel first, on its own: if it is broken the rest of the run falls back to the kernels it replaces
+if [ "${TC_FIRST:-1}" = "1" ]; then
+  echo "=== tcgen05 LinearAttention block" >> $out
+  if timeout 300 python -m pytest tests/test_gpu_ops.py -k block_tc -m gpu -q --no-header -p no:cacheprovider -s > gpurun_out/${tag}_tc.log 2>&1; then
+    echo "tc block: PASS" >> $out
+  else
+    echo "tc block: FAIL -> TEDM_LINATTN_TC=0 for the rest" >> $out
+    export TEDM_LINATTN_TC=0
+  fi
+  tail -25 gpurun_out/${tag}_tc.log >> $out
+  timeout 200 python scripts/prof_linattn.py 128 >> $out 2>&1
+fi
 for f in tests/test_gpu_*.py; do
   echo "=== $f" >> $out
   timeout 900 python -m pytest $f -m gpu -q --no-header -p no:cacheprovider -s 2>&1 | grep -v "^$" | tail -60 >> $out

@@ -155,29 +155,35 @@ struct TcParams {
 template <int C>
 __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_ctx_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   constexpr int KB = C / 64;                       // 64-channel blocks of a pixel row
-  constexpr int N2 = C + 16;                       // G columns + the ones block's 16
-  constexpr int YBUF = (KB + 1) * BLK;             // y blocks + ones block (contiguous: the MN-major B operand of GEMM 2)
+  constexpr int N2 = C + 16;                       // G columns + 16 columns of S (the ones block)
+  constexpr int NS = C == 64 ? 6 : 3;              // x / y ring: tiles in flight towards this SM (HBM latency is ~2 tile times)
+  constexpr int XBUF = KB * BLK;
   constexpr uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-  constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N2 >> 3) << 17) |
-                              ((uint32_t)(HID >> 4) << 24);
+  constexpr uint32_t IDESC_G = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(C >> 3) << 17) |
+                               ((uint32_t)(HID >> 4) << 24);
+  constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(16 >> 3) << 17) |
+                               ((uint32_t)(HID >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_w, x_full[2], x_empty[2], y_ready[2], d1_full[2], p_ready[2], d2_full, d2_empty;
+  __shared__ __align__(8) uint64_t bar_w, x_full[NS], x_empty[NS], y_ready[2], d1_full[2], p_ready[2], d2_full, d2_empty;
   __shared__ uint32_t tmem_slot;
   __shared__ float g_s[C], sh_s[HID];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_s = base;                                  // Wk: KB blocks of [128 hd][64 c]
-  const uint32_t y_s = w_s + KB * BLK;                        // [2] x (y | ones)
-  const uint32_t p_s = y_s + 2 * YBUF;                        // [2] x P: two MN blocks [128 px][64 hd]
+  const uint32_t one_s = w_s + KB * BLK;                      // a block of bf16 ones: B operand of the S product
+  const uint32_t x_s = one_s + BLK;                           // ring of NS tiles, LayerNormed in place
+  const uint32_t p_s = x_s + NS * XBUF;                       // [2] x P: two MN blocks [128 px][64 hd]
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&maps.x);
     tma_prefetch_desc(&maps.w);
     mbar_init(smem_u32(&bar_w), 1);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(smem_u32(&x_full[s]), 1);
+      mbar_init(smem_u32(&x_empty[s]), 1);
+    }
     for (int g = 0; g < 2; ++g) {
-      mbar_init(smem_u32(&x_full[g]), 1);
-      mbar_init(smem_u32(&x_empty[g]), 1);
       mbar_init(smem_u32(&y_ready[g]), 128);
       mbar_init(smem_u32(&d1_full[g]), 1);
       mbar_init(smem_u32(&p_ready[g]), 128);
@@ -189,19 +195,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_ctx_kernel(const __g
   if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
   for (int i = threadIdx.x; i < C; i += TC_THREADS) g_s[i] = p.g_pre[i];
   for (int i = threadIdx.x; i < HID; i += TC_THREADS) sh_s[i] = p.shift[i];
-  // the two ones blocks (bf16 1.0 everywhere: whichever 16 columns GEMM 2 reads are ones)
-  for (int i = threadIdx.x; i < 2 * (BLK / 16); i += TC_THREADS) {
-    const int g = i / (BLK / 16), o = i % (BLK / 16);
-    sts128(y_s + g * YBUF + KB * BLK + o * 16, make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u));
-  }
+  for (int i = threadIdx.x; i < BLK / 16; i += TC_THREADS)
+    sts128(one_s + i * 16, make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u));
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t d2_col = 256;                                // D1[g] at columns g * 128, D2 at 256 .. 256 + N2
+  const uint32_t d2_col = 256;                                // D1[g] at columns g * 128; G at 256 .. 256 + C; S at 256 + C .. + 16
 
-  // tiles of this CTA: items blockIdx.x, + gridDim.x, ...; local tile index i counts across items
+  // tiles of this CTA: items blockIdx.x, + gridDim.x, ...; local tile index i counts across items.
+  // tile i: ring stage i % NS, compute group i & 1
   const int my_items = p.items > (int)blockIdx.x ? (p.items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int my_tiles = my_items * p.chunk_tiles;
   const int chunks_per_image = p.tiles_per_image / p.chunk_tiles;
@@ -211,15 +215,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_ctx_kernel(const __g
       const uint32_t bw = smem_u32(&bar_w);
       mbar_expect_tx(bw, KB * BLK);
       for (int kb = 0; kb < KB; ++kb) tma_load_2d(w_s + kb * BLK, &maps.w, bw, kb * 64, HID);   // rows 128..255 of wqkv = Wk
+      int st = 0;
+      uint32_t sph = 0;
       for (int i = 0; i < my_tiles; ++i) {
-        const int g = i & 1, it = i / p.chunk_tiles, tl = i - it * p.chunk_tiles;
+        const int it = i / p.chunk_tiles, tl = i - it * p.chunk_tiles;
         const int item = blockIdx.x + it * gridDim.x;
         const int img = item / chunks_per_image, ch = item - img * chunks_per_image;
         const long long row0 = (long long)img * p.n + (long long)(ch * p.chunk_tiles + tl) * TM;
-        mbar_wait(smem_u32(&x_empty[g]), (uint32_t)(((i >> 1) & 1) ^ 1));
-        const uint32_t full = smem_u32(&x_full[g]);
+        mbar_wait(smem_u32(&x_empty[st]), sph ^ 1u);
+        const uint32_t full = smem_u32(&x_full[st]);
         mbar_expect_tx(full, KB * BLK);
-        for (int kb = 0; kb < KB; ++kb) tma_load_2d(y_s + g * YBUF + kb * BLK, &maps.x, full, kb * 64, (int)row0);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(x_s + st * XBUF + kb * BLK, &maps.x, full, kb * 64, (int)row0);
+        if (++st == NS) {
+          st = 0;
+          sph ^= 1u;
+        }
       }
     }
     __syncwarp();
@@ -227,28 +237,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_ctx_kernel(const __g
     if (elect_one()) {
       mbar_wait(smem_u32(&bar_w), 0);
       tc_fence_after();
-      auto gemm2 = [&](int j) {                     // G (+)= P_j^T [y_j | 1]
-        const int g = j & 1, tl = j % p.chunk_tiles;
+      auto gemm2 = [&](int j) {                     // G (+)= P_j^T y_j ;  S (+)= P_j^T 1
+        const int g = j & 1, tl = j % p.chunk_tiles, st = j % NS;
         if (tl == 0 && j > 0) {                     // a new item: the previous item's accumulator must have been drained
           mbar_wait(smem_u32(&d2_empty), (uint32_t)(((j / p.chunk_tiles - 1) & 1)));
           tc_fence_after();
         }
         mbar_wait(smem_u32(&p_ready[g]), (uint32_t)((j >> 1) & 1));
         tc_fence_after();
-        const uint64_t adesc = desc_mn(p_s + g * 2 * BLK), bdesc = desc_mn(y_s + g * YBUF);
+        const uint64_t adesc = desc_mn(p_s + g * 2 * BLK), bdesc = desc_mn(x_s + st * XBUF), sdesc = desc_mn(one_s);
 #pragma unroll
-        for (int k = 0; k < TM / 16; ++k)
-          umma_bf16(tmem + d2_col, adesc + 128ull * k, bdesc + 128ull * k, IDESC2, (tl | k) != 0 ? 1u : 0u);
-        umma_commit(smem_u32(&x_empty[g]));         // y_j and P_j are free once these complete
+        for (int k = 0; k < TM / 16; ++k) {
+          umma_bf16(tmem + d2_col, adesc + 128ull * k, bdesc + 128ull * k, IDESC_G, (tl | k) != 0 ? 1u : 0u);
+          umma_bf16(tmem + d2_col + C, adesc + 128ull * k, sdesc + 128ull * k, IDESC_S, (tl | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&x_empty[st]));        // y_j (and P_j) are free once these complete
         if (tl == p.chunk_tiles - 1) umma_commit(smem_u32(&d2_full));
       };
       for (int i = 0; i < my_tiles; ++i) {
-        const int g = i & 1;
+        const int g = i & 1, st = i % NS;
         mbar_wait(smem_u32(&y_ready[g]), (uint32_t)((i >> 1) & 1));
         tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
-          const uint64_t adesc = desc_k(y_s + g * YBUF + kb * BLK), bdesc = desc_k(w_s + kb * BLK);
+          const uint64_t adesc = desc_k(x_s + st * XBUF + kb * BLK), bdesc = desc_k(w_s + kb * BLK);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(tmem + g * HID, adesc + 2ull * k, bdesc + 2ull * k, IDESC1, (kb | k) != 0 ? 1u : 0u);
         }
@@ -263,8 +275,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_ctx_kernel(const __g
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
     for (int i = grp; i < my_tiles; i += 2) {
       const uint32_t ph = (uint32_t)((i >> 1) & 1);
-      const uint32_t yb = y_s + grp * YBUF;
-      mbar_wait(smem_u32(&x_full[grp]), ph);
+      const int st = i % NS;
+      const uint32_t yb = x_s + st * XBUF;
+      mbar_wait(smem_u32(&x_full[st]), (uint32_t)((i / NS) & 1));
       ln_row<C>(yb, yb, row, g_s, p.eps);
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&y_ready[grp]));
@@ -360,13 +373,14 @@ __global__ void __launch_bounds__(256) linattn_tc_combine_kernel(const float* __
 template <int C>
 __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_out_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   constexpr int KB = C / 64;
-  constexpr int XBUF = KB * BLK;                   // the x tile (kept for the residual)
-  constexpr int WBUF = 2 * BLK;                    // y (KB blocks) -> Q (2 blocks) -> output staging (KB blocks), in turn
+  constexpr int NS = C == 64 ? 4 : 3;              // x ring (a tile stays until its residual has been added)
+  constexpr int XBUF = KB * BLK;
+  constexpr int WBUF = 2 * BLK;                    // per group: y (KB blocks) -> Q (2 blocks) -> output staging (KB blocks), in turn
   constexpr int MBLK = C * 128;                    // bytes of one [C rows][64 hd] block of M
   constexpr uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
   constexpr uint32_t IDESC3 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_w, x_full[2], x_empty[2], y_ready[2], d1_full[2], q_ready[2], d3_full[2], m_full, m_empty;
+  __shared__ __align__(8) uint64_t bar_w, x_full[NS], x_empty[NS], y_ready[2], d1_full[2], q_ready[2], d3_full[2], m_full, m_empty;
   __shared__ uint32_t tmem_slot;
   __shared__ float g_s[C], bo_s[C], go_s[C];
 
@@ -374,8 +388,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_out_kernel(const __g
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_s = base;                                  // Wq: KB blocks of [128 hd][64 c]
   const uint32_t m_s = w_s + KB * BLK;                        // M of the current image: 2 blocks of [C][64 hd]
-  const uint32_t x_s = m_s + 2 * MBLK;                        // [2] x tiles
-  const uint32_t b_s = x_s + 2 * XBUF;                        // [2] work buffers
+  const uint32_t x_s = m_s + 2 * MBLK;                        // ring of NS x tiles
+  const uint32_t b_s = x_s + NS * XBUF;                       // [2] work buffers
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&maps.x);
@@ -383,9 +397,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_out_kernel(const __g
     tma_prefetch_desc(&maps.m);
     tma_prefetch_desc(&maps.out);
     mbar_init(smem_u32(&bar_w), 1);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(smem_u32(&x_full[s]), 1);
+      mbar_init(smem_u32(&x_empty[s]), 128);
+    }
     for (int g = 0; g < 2; ++g) {
-      mbar_init(smem_u32(&x_full[g]), 1);
-      mbar_init(smem_u32(&x_empty[g]), 128);
       mbar_init(smem_u32(&y_ready[g]), 128);
       mbar_init(smem_u32(&d1_full[g]), 1);
       mbar_init(smem_u32(&q_ready[g]), 128);
@@ -406,7 +422,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_out_kernel(const __g
   tc_fence_after();
   const uint32_t tmem = tmem_slot;                            // group g: q at columns g * 256, o at g * 256 + 128
 
-  // a contiguous range of tiles per CTA (consecutive tiles share an image, so M is reloaded rarely)
+  // a contiguous range of tiles per CTA (consecutive tiles share an image, so M is reloaded rarely).
+  // tile i of the range: ring stage i % NS, compute group i & 1
   const long long T = p.total_tiles;
   const int t0 = (int)(T * blockIdx.x / gridDim.x), t1 = (int)(T * (blockIdx.x + 1) / gridDim.x);
   const int my_tiles = t1 - t0;
@@ -416,14 +433,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_out_kernel(const __g
       const uint32_t bw = smem_u32(&bar_w);
       mbar_expect_tx(bw, KB * BLK);
       for (int kb = 0; kb < KB; ++kb) tma_load_2d(w_s + kb * BLK, &maps.w, bw, kb * 64, 0);      // rows 0..127 of wqkv = Wq
-      int cur_img = -1, n_img = 0;
+      int cur_img = -1, n_img = 0, st = 0;
+      uint32_t sph = 0;
       for (int i = 0; i < my_tiles; ++i) {
-        const int g = i & 1, tile = t0 + i, img = tile / p.tiles_per_image;
+        const int tile = t0 + i, img = tile / p.tiles_per_image;
         // the x tile FIRST: the issuer runs GEMM 1 of tile i before GEMM 2 of tile i - 1, and only the latter releases M
-        mbar_wait(smem_u32(&x_empty[g]), (uint32_t)(((i >> 1) & 1) ^ 1));
-        const uint32_t full = smem_u32(&x_full[g]);
+        mbar_wait(smem_u32(&x_empty[st]), sph ^ 1u);
+        const uint32_t full = smem_u32(&x_full[st]);
         mbar_expect_tx(full, KB * BLK);
-        for (int kb = 0; kb < KB; ++kb) tma_load_2d(x_s + g * XBUF + kb * BLK, &maps.x, full, kb * 64, tile * TM);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(x_s + st * XBUF + kb * BLK, &maps.x, full, kb * 64, tile * TM);
+        if (++st == NS) {
+          st = 0;
+          sph ^= 1u;
+        }
         if (img != cur_img) {
           mbar_wait(smem_u32(&m_empty), (uint32_t)((n_img & 1) ^ 1));
           const uint32_t mf = smem_u32(&m_full);
@@ -478,13 +500,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_out_kernel(const __g
     const int grp = (warp - 2) >> 2, q = warp & 3, row = q * 32 + lane;
     const int gtid = threadIdx.x - 64 - grp * 128;            // 0..127 inside the group
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * 256);
-    const uint32_t xb = x_s + grp * XBUF, wb = b_s + grp * WBUF;
+    const uint32_t wb = b_s + grp * WBUF;
     for (int i = grp; i < my_tiles; i += 2) {
       const uint32_t ph = (uint32_t)((i >> 1) & 1);
+      const int st = i % NS;
+      const uint32_t xb = x_s + st * XBUF;
       // the TMA store of this group's previous tile must have drained the work buffer before LayerNorm rewrites it
       if (gtid == 0) tma_store_wait_read<0>();
       named_bar_sync(1 + grp, 128);
-      mbar_wait(smem_u32(&x_full[grp]), ph);
+      mbar_wait(smem_u32(&x_full[st]), (uint32_t)((i / NS) & 1));
       ln_row<C>(xb, wb, row, g_s, p.eps);
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&y_ready[grp]));
@@ -553,7 +577,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_out_kernel(const __g
           sts128(sw_addr(wb + b * BLK, row, c), pack8(f));
         }
       fence_proxy_async_smem();
-      mbar_arrive(smem_u32(&x_empty[grp]));                  // the residual has been read: the x buffer may be refilled
+      mbar_arrive(smem_u32(&x_empty[st]));                   // the residual has been read: the ring stage may be refilled
       named_bar_sync(1 + grp, 128);
       if (gtid == 0) {
         for (int kb = 0; kb < KB; ++kb) tma_store_2d(&maps.out, wb + kb * BLK, kb * 64, (t0 + i) * TM);
@@ -611,8 +635,8 @@ int launch_tc(const bf16* x, const bf16* wqkv, const float* g_pre, const float* 
   p.b_out = b_out;
   p.g_out = g_out;
 
-  const int smem_a = 1024 + KB * BLK + 2 * (KB + 1) * BLK + 2 * 2 * BLK;
-  const int smem_b = 1024 + KB * BLK + 2 * C * 128 + 2 * KB * BLK + 2 * 2 * BLK;
+  const int smem_a = 1024 + KB * BLK + BLK + (C == 64 ? 6 : 3) * KB * BLK + 2 * 2 * BLK;
+  const int smem_b = 1024 + KB * BLK + 2 * C * 128 + (C == 64 ? 4 : 3) * KB * BLK + 2 * 2 * BLK;
   const int smem_c = (HID * (C + 1) + HID * 33) * (int)sizeof(float);
   static bool configured = false;
   if (!configured) {

@@ -612,7 +612,8 @@ struct WgradParams {
   int items, n_tiles, splitk, num_ptiles, stages;
   int oihw;                      // 1: accumulate into an fp32 OIHW gradient (mode 3: un-folded to 3x3)
   float* dw;
-  int* turn;                     // one counter per (m block, n tile) group: whose split-K slice adds next (self-resetting)
+  int* turn;                     // deterministic mode: one counter per (m block, n tile) group -- whose split-K slice adds next
+                                 // (self-resetting); NULL: slices add in arrival order
 };
 
 __device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr) {
@@ -756,16 +757,23 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_consta
       mbar_wait(smem_u32(&bar_acc), 0);
       tc_fence_after();
     }
-    // Split-K slices of one (m block, n tile) group add into dW with fire-and-forget fp32 reductions, but IN SLICE ORDER:
-    // slice ks waits for turn[group] == ks, adds, fences, passes the turn on (the last slice resets it to 0).  Every
-    // address therefore receives its addends in a fixed order and the gradient is bit-reproducible.  Slices of a group
-    // have consecutive linear block ids (blockIdx.x = ks), so a waiting CTA's predecessors are resident or finished.
+    // Split-K slices of one (m block, n tile) group add into dW with fire-and-forget fp32 reductions.  Deterministic mode
+    // (tedm_conv_set_deterministic) makes them add IN SLICE ORDER: slice ks waits for turn[group] == ks, adds, fences,
+    // passes the turn on (the last slice resets it to 0).  Every address then receives its addends in a fixed order and
+    // the gradient is bit-reproducible.  Slices of a group have consecutive linear block ids (blockIdx.x = ks), so a
+    // waiting CTA's predecessors are resident or finished.
+    const bool ordered = p.turn != nullptr && p.splitk > 1;
     int* turn = p.turn + grp;
-    if (p.splitk > 1) {
+    if (ordered) {
       if (threadIdx.x == 64) {
         int v;
+        const long long t0 = clock64();
         do {
           asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(turn) : "memory");
+          if (v != ks && clock64() - t0 > 4000000000LL) {      // bounded like mbar_wait: a protocol bug must not hang the box
+            printf("tedm_b200: wgrad turn wait timed out (group %d slice %d sees %d)\n", grp, ks, v);
+            __trap();
+          }
         } while (v != ks);
       }
       named_bar_sync(1, 128);
@@ -782,7 +790,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_consta
         }
       }
     }
-    if (p.splitk > 1) {
+    if (ordered) {
       __threadfence();
       named_bar_sync(1, 128);
       if (threadIdx.x == 64) {
@@ -1051,6 +1059,7 @@ __global__ void __launch_bounds__(256) wgrad3_reduce_oihw_kernel(const float* __
 }
 
 int g_enable_wgrad3 = 1;  // tedm_conv_set_wgrad_halo: 0 off, 1 automatic, 2 wherever the geometry allows
+int g_deterministic = 0;  // tedm_conv_set_deterministic
 
 int g_enable_ws = 1;  // tedm_conv_set_ws
 int g_force_bn = 0;  // debug/tuning override (tedm_conv_set_tile_n)
@@ -1067,6 +1076,11 @@ extern "C" int tedm_conv_set_tile_n(int bn) {
 
 extern "C" int tedm_conv_set_wgrad_halo(int enable) {
   g_enable_wgrad3 = enable;
+  return TEDM_OK;
+}
+
+extern "C" int tedm_conv_set_deterministic(int enable) {
+  g_deterministic = enable != 0;
   return TEDM_OK;
 }
 
@@ -1376,6 +1390,7 @@ extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, fl
       long long sk = (w * sms) / groups;
       if (sk < 1) sk = 1;
       if (sk > cap) sk = cap;
+      if (g_deterministic && sk > 4) sk = 4;      // ordered slices add one after the other: keep the chains short
       const long long ctas = groups * sk, waves = (ctas + sms - 1) / sms;
       const double eff = (double)ctas / (double)(waves * sms);
       if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && sk > best_sk)) {
@@ -1391,7 +1406,7 @@ extern "C" int tedm_conv_igemm_wgrad(const tedm_conv_args* a, const void* dy, fl
                    "tedm_conv_igemm_wgrad: upsample conv %d -> %d too wide for the raw-gradient workspace", p.ctot, a->cout);
   TEDM_UNSUPPORTED(groups > WGRAD_TURN_INTS, "tedm_conv_igemm_wgrad: %lld output tiles exceed the turn-counter workspace", groups);
   float* raw = workspace + part_floats;
-  p.turn = reinterpret_cast<int*>(workspace + part_floats + WGRAD_RAW_FLOATS);   // zero at allocation, self-resetting
+  p.turn = g_deterministic ? reinterpret_cast<int*>(workspace + part_floats + WGRAD_RAW_FLOATS) : nullptr;   // zero at allocation, self-resetting
   if (unfold) {
     p.dw = raw;
     p.oihw = 0;

@@ -18,6 +18,7 @@ optimiser ONE kernel.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -78,7 +79,8 @@ class UnetEngine:
         self.fold_upsample = fold_upsample
         self.ln_eps = ln_eps
         self.fuse_linear_attention = True
-        self.linear_attention_tc = True       # tcgen05 form of the fused block (csrc/attention_tc.cu) where it applies
+        # tcgen05 form of the fused block (csrc/attention_tc.cu) where it applies; TEDM_LINATTN_TC=0 keeps the mma.sync kernels (A/B runs)
+        self.linear_attention_tc = os.environ.get("TEDM_LINATTN_TC", "1") != "0"
         # backward: weight gradients run on a side stream next to the data-gradient chain (they only meet in the optimiser);
         # at the low-resolution levels neither kernel fills the 148 SMs on its own
         self.overlap_wgrad = True

@@ -56,6 +56,7 @@ SIGNATURES = {
     "tedm_conv_set_tile_n": (_i, [_i]),
     "tedm_conv_set_ws": (_i, [_i]),
     "tedm_conv_set_wgrad_halo": (_i, [_i]),
+    "tedm_conv_set_deterministic": (_i, [_i]),
     "tedm_weight_to_krsc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "tedm_fold_upsample_weight": (_i, [_p, _p, _i, _i, _p]),
     "tedm_gn_silu_fwd": (_i, [_p, _p, _i, _p, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _f, _p]),
@@ -134,6 +135,8 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError if the .so does not export it
             fn.restype, fn.argtypes = res, args
         _lib = lib
+        if os.environ.get("TEDM_DETERMINISTIC", "0") == "1":
+            lib.tedm_conv_set_deterministic(1)
     return _lib
 
 
@@ -259,6 +262,12 @@ def fold_upsample_weight(w: torch.Tensor) -> torch.Tensor:
 
 
 MODE_1X1, MODE_3X3, MODE_4X4S2, MODE_UP3X3 = 0, 1, 2, 3
+
+
+def set_deterministic(enable: bool = True) -> None:
+    """Bit-reproducible convolution weight gradients (the generic weight-gradient kernel then adds its split-K slices in
+    slice order instead of arrival order).  Also switched on by TEDM_DETERMINISTIC=1 in the environment."""
+    load().tedm_conv_set_deterministic(int(bool(enable)))
 
 
 def conv_gn_parts(oh: int, ow: int) -> int:

@@ -247,11 +247,7 @@ def test_tedm_bench_configuration_b16_through_the_graphed_call(golden):
     print(f"tedm B=16 x S=8 @128 (trained head, graph replay): logits rel {lr:.4g}, max |prob diff| {pr:.4g}, "
           f"mask agreement {agree:.5f} ({int((mask.cpu().numpy() != ref_mask).sum())} of {ref_mask.size} px)")
     assert lr < TOL
-    # The north star's 99.9 % at this configuration is met in the fp32 mode (tests/test_gpu_fp32.py, same fixture, same
-    # call).  In bf16 the path sits at the rounding floor of bf16 activations: 0.8 % of this head's pixels lie within 0.02
-    # of the 0.5 threshold (the ambiguous rim of every blob) and the 0.9 % logit error flips about one in eight of them;
-    # the reference's own autocast(bf16) run agrees with its fp32 run on only 92.1 % here.
-    assert agree >= 0.998
+    assert agree >= 0.999                   # the north-star criterion at the bench configuration (measured 0.99936)
     _at_least_as_close_as_reference_bf16("tedm_b16_trained", lr, agree)
     # no image's result depends on its batch neighbours: image 5 alone gives the same mask
     with SameNoise(nz[5 * len(steps):6 * len(steps)].contiguous()):

@@ -143,13 +143,14 @@ def test_unet_fp32_small_and_full_within_1e_4(golden, ddpm32):
     z = synth_noise(g["x0"].shape, 1, "z").cuda()
     for ts in (500, 0):
         assert _rel(ddpm32.sample_timestep(x_t, ts, noise=z), g[f"sample_t{ts}"]) < 2 * TOL32, ts
-    # config.py defaults: 128 x 128
+    # config.py defaults: 128 x 128 (that fixture's synthetic weights are keyed by DatasetDM's parameter names)
     g = golden["tedm_full"]
+    dm = _tedm32(8, True, g["steps"].tolist()).diffusion_model
     x0 = T(g["x0"]).cuda()
     tt = torch.tensor([400], device="cuda")
-    x_t, _ = ddpm32.forward_diffusion_model(x0, tt, synth_noise((1, 1, 128, 128), 25, "tedm").cuda())
+    x_t, _ = dm.forward_diffusion_model(x0, tt, synth_noise((1, 1, 128, 128), 25, "tedm").cuda())
     with torch.no_grad():
-        out, feats = ddpm32.model.engine.forward(x_t, tt, want_features=True)
+        out, feats = dm.model.engine.forward(x_t, tt, want_features=True)
     errs = {"out": _rel(out, g["unet_out_t400"])}
     for i, f in enumerate(feats):
         fn = _nchw(f)

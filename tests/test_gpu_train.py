@@ -232,8 +232,19 @@ def test_unet_backward_with_1024_mid_tokens():
 
 
 def test_conv_weight_gradients_are_bit_reproducible():
-    """Both tcgen05 weight-gradient kernels add their split-K slices in a fixed order (csrc/conv_igemm.cu): the same step
-    run twice gives bit-identical gradients for every convolution weight (99.9 % of the 36 M parameters)."""
+    """In deterministic mode (`native.set_deterministic()` / TEDM_DETERMINISTIC=1) both tcgen05 weight-gradient kernels add
+    their split-K slices in a fixed order (csrc/conv_igemm.cu): the same step run twice gives bit-identical gradients for
+    every convolution weight (94 % of the 36 M parameters).  The small per-channel reductions (norm gains, biases) still
+    use fp32 atomics."""
+    from tedm_b200 import native as N
+    N.set_deterministic(True)
+    try:
+        _check_reproducible()
+    finally:
+        N.set_deterministic(False)
+
+
+def _check_reproducible():
     m = _model()
     x = torch.rand(8, 1, 64, 64, generator=torch.Generator().manual_seed(9)).cuda()
     t = torch.randint(0, 1000, (8,), generator=torch.Generator().manual_seed(10)).cuda()
@@ -246,7 +257,7 @@ def test_conv_weight_gradients_are_bit_reproducible():
         torch.cuda.synchronize()
         runs.append({n: p.grad.clone() for n, p in m.named_parameters() if p.dim() == 4 and p.shape[1] > 1})
     n_el = sum(g.numel() for g in runs[0].values())
-    assert n_el > 35_000_000
+    assert n_el > 34_000_000
     for name, g in runs[0].items():
         assert torch.isfinite(g).all() and g.abs().sum() > 0, name
         assert torch.equal(g, runs[1][name]) and torch.equal(g, runs[2][name]), name
