@@ -417,16 +417,20 @@ TEDM_API int tedm_debug_umma_probe(const void* A, const void* Bm, const int* shi
 
 /* The same block with every GEMM on tcgen05 (csrc/attention_tc.cu): LayerNorm -> k / q projections as 128-pixel UMMA tiles
  * -> softmaxes by the thread that owns the pixel -> context / to_out as UMMAs again; v is never materialised and the to_out
- * conv is folded into a per-image matrix.  shift_log2[128] = log2(e) * an upper bound of k per (head, d) that depends on
- * the weights only (||w_hd * g_pre||_2 * sqrt(C), Cauchy-Schwarz), which removes the running maximum from the softmax over
- * pixels; the caller must route blocks whose bound exceeds ~40 to tedm_linear_attention_fused_fwd instead.
- * n % 512 == 0, C = 64 / 128, 4 heads x 32. */
+ * conv is folded into a per-image matrix.
+ *   wqkv_g     = to_qkv weight with the pre-norm gain folded in: bf16 [384][C], row r = W[r] * g_pre (the kernel's
+ *                LayerNorm then has no gain)
+ *   shift_log2 = log2(e) * B, B >= every |q| and |k| logit; a WEIGHT-ONLY bound does (max_r ||wqkv_g[r]||_2 * sqrt(C), by
+ *                Cauchy-Schwarz, since ||LayerNorm(x)||_2 <= sqrt(C)).  It replaces the running maximum of the softmax over
+ *                pixels (a per-column constant cancels) and lets the softmax over d skip its maximum; the caller routes
+ *                blocks with B > ~40 (exp(-2B) must stay a normal fp32 number) to tedm_linear_attention_fused_fwd.
+ * n % 512 == 0, C = 64 / 128, 4 heads x 32.  workspace: tedm_linear_attention_tc_workspace() fp32 elements; it starts with
+ * the folded per-image matrices M [batch][C][128] bf16. */
 TEDM_API int tedm_linear_attention_tc_supported(int n, int channels, int heads, int dim_head);
 TEDM_API int64_t tedm_linear_attention_tc_workspace(int batch, int n, int channels);   /* fp32 elements */
-TEDM_API int tedm_linear_attention_tc_fwd(const void* x, const void* wqkv, const float* g_pre, const float* shift_log2,
-                                 const void* wout, const float* b_out, const float* g_out, void* out, float* workspace,
-                                 int batch, int n, int channels, int heads, int dim_head, float scale, float eps,
-                                 tedm_stream_t stream);
+TEDM_API int tedm_linear_attention_tc_fwd(const void* x, const void* wqkv_g, float shift_log2, const void* wout, const float* b_out,
+                                 const float* g_out, void* out, float* workspace, int batch, int n, int channels, int heads,
+                                 int dim_head, float scale, float eps, tedm_stream_t stream);
 
 /* ---- fp32 precision mode (north star: "1e-4 in fp32 mode"; the reference's default arithmetic, config.py:15) --------
  * Inference only.  Activations are fp32 NHWC between kernels.  Convolutions run on tedm_conv_igemm_fwd with every operand

@@ -40,3 +40,7 @@ except Exception as e:
     print("bench parse failed:", e)
 PY
 fi
+if [ "${NCU_LINATTN:-0}" = "1" ]; then
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/${tag}_linattn_launches.csv python scripts/prof_linattn.py 128 > gpurun_out/${tag}_ncu_linattn.log 2>&1
+  python scripts/summarize_launches.py gpurun_out/${tag}_linattn_launches.csv 2>/dev/null | head -30
+fi

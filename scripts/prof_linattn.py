@@ -26,10 +26,10 @@ for (H, C) in [(128, 64), (64, 128)]:
     t1 = timeit(lambda i: N.linear_attention_block_fused(xs[i % nset], wq, g1, wo, bo, g2))
     nb = B * H * H * C * 2
     print(f"B={B} {H}x{H}x{C}: unfused {t0*1e3:.0f} us, fused {t1*1e3:.0f} us ({3*nb/t1/1e6:.0f} GB/s algorithmic)")
-    shift, bound = N.linear_attention_tc_shift(wq, g1)
+    wg, shift, bound = N.linear_attention_tc_weights(wq, g1)
     try:
-        t2 = timeit(lambda i: N.linear_attention_block_tc(xs[i % nset], wq, g1, shift, wo, bo, g2))
-        a = N.linear_attention_block_tc(xs[0], wq, g1, shift, wo, bo, g2).float()
+        t2 = timeit(lambda i: N.linear_attention_block_tc(xs[i % nset], wg, shift, wo, bo, g2))
+        a = N.linear_attention_block_tc(xs[0], wg, shift, wo, bo, g2).float()
         b = N.linear_attention_block_fused(xs[0], wq, g1, wo, bo, g2).float()
         d = ((a - xs[0].float()) - (b - xs[0].float())).norm() / (b - xs[0].float()).norm()
         print(f"B={B} {H}x{H}x{C}: tcgen05 {t2*1e3:.0f} us ({3*nb/t2/1e6:.0f} GB/s algorithmic), shift bound {bound:.1f}, "

@@ -95,10 +95,11 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// LayerNorm of one pixel row held as C/64 swizzled blocks at `src` (block stride BLK): y = (x - mean) rstd g -> bf16 at `dst`
-// (dst may equal src).  Two passes over registers.  Optionally keeps the fp32 input row in `keep` (C values).
+// LayerNorm of one pixel row held as C/64 swizzled blocks at `src` (block stride BLK): xhat = (x - mean) rstd -> bf16 at `dst`
+// (dst may equal src).  The gain g is folded into the projection weights by the caller (W' = W diag(g)).  One pass,
+// four independent accumulators per statistic (a 64-deep dependent FADD chain would cost more than the arithmetic).
 template <int C>
-__device__ __forceinline__ void ln_row(uint32_t src, uint32_t dst, int row, const float* g_s, float eps) {
+__device__ __forceinline__ void ln_row(uint32_t src, uint32_t dst, int row, float eps) {
   float v[C];
 #pragma unroll
   for (int b = 0; b < C / 64; ++b)
@@ -109,24 +110,23 @@ __device__ __forceinline__ void ln_row(uint32_t src, uint32_t dst, int row, cons
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[b * 64 + c * 8 + j] = f[j];
     }
-  float s = 0.0f;
-#pragma unroll
-  for (int i = 0; i < C; ++i) s += v[i];
-  const float mean = s * (1.0f / C);
-  float q = 0.0f;
+  float s4[4] = {0.0f, 0.0f, 0.0f, 0.0f}, q4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
   for (int i = 0; i < C; ++i) {
-    v[i] -= mean;
-    q = fmaf(v[i], v[i], q);
+    s4[i & 3] += v[i];
+    q4[i & 3] = fmaf(v[i], v[i], q4[i & 3]);
   }
-  const float rstd = rsqrtf(q * (1.0f / C) + eps);
+  const float mean = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / C);
+  const float var = fmaxf(((q4[0] + q4[1]) + (q4[2] + q4[3])) * (1.0f / C) - mean * mean, 0.0f);
+  const float rstd = rsqrtf(var + eps);
+  const float nm = -mean * rstd;
 #pragma unroll
   for (int b = 0; b < C / 64; ++b)
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       float f[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = v[b * 64 + c * 8 + j] * rstd * g_s[b * 64 + c * 8 + j];
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(v[b * 64 + c * 8 + j], rstd, nm);
       sts128(sw_addr(dst + b * BLK, row, c), pack8(f));
     }
 }
@@ -142,8 +142,7 @@ struct TcParams {
   int items;             // K-A: work items = batch * (tiles_per_image / chunk_tiles)
   int total_tiles;       // K-B
   float eps;
-  const float* g_pre;    // [C]
-  const float* shift;    // [128] log2(e) * upper bound of k per (head, d)   (K-A)
+  float shift_log2;      // log2(e) * an upper bound of every k logit          (K-A)
   float* part;           // [items][128][C + 16] fp32                          (K-A)
   const float* b_out;    // [C]                                                (K-B)
   const float* g_out;    // [C]                                                (K-B)
@@ -166,7 +165,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_ctx_kernel(const __g
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_w, x_full[NS], x_empty[NS], y_ready[2], d1_full[2], p_ready[2], d2_full, d2_empty;
   __shared__ uint32_t tmem_slot;
-  __shared__ float g_s[C], sh_s[HID];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -193,8 +191,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_ctx_kernel(const __g
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
-  for (int i = threadIdx.x; i < C; i += TC_THREADS) g_s[i] = p.g_pre[i];
-  for (int i = threadIdx.x; i < HID; i += TC_THREADS) sh_s[i] = p.shift[i];
   for (int i = threadIdx.x; i < BLK / 16; i += TC_THREADS)
     sts128(one_s + i * 16, make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u));
   fence_proxy_async_smem();
@@ -278,22 +274,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_ctx_kernel(const __g
       const int st = i % NS;
       const uint32_t yb = x_s + st * XBUF;
       mbar_wait(smem_u32(&x_full[st]), (uint32_t)((i / NS) & 1));
-      ln_row<C>(yb, yb, row, g_s, p.eps);
+      ln_row<C>(yb, yb, row, p.eps);
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&y_ready[grp]));
       mbar_wait(smem_u32(&d1_full[grp]), ph);
       tc_fence_after();
       const uint32_t pb = p_s + grp * 2 * BLK;
+      const float nsh = -p.shift_log2;
+      // one shift for all columns: a per-column constant cancels in G / S, so the scalar maximum of the bounds will do
+      uint32_t r[2][32];
+      tmem_ld32(lane_addr + (uint32_t)(grp * HID), r[0]);
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {                     // 32 columns (= one head) at a time
-        uint32_t r[32];
-        tmem_ld32(lane_addr + (uint32_t)(grp * HID + ch * 32), r);
+      for (int ch = 0; ch < 4; ++ch) {                     // 32 columns (= one head) at a time; the next load is in flight
         tmem_ld_wait();
+        if (ch < 3) tmem_ld32(lane_addr + (uint32_t)(grp * HID + (ch + 1) * 32), r[(ch + 1) & 1]);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = ex2f(fmaf(__uint_as_float(r[c * 8 + j]), kLog2e, -sh_s[ch * 32 + c * 8 + j]));
+          for (int j = 0; j < 8; ++j) f[j] = ex2f(fmaf(__uint_as_float(r[ch & 1][c * 8 + j]), kLog2e, nsh));
           sts128(sw_addr(pb + (ch >> 1) * BLK, row, (ch & 1) * 4 + c), pack8(f));
         }
       }
@@ -333,37 +332,45 @@ template <int C>
 __global__ void __launch_bounds__(256) linattn_tc_combine_kernel(const float* __restrict__ part, const bf16* __restrict__ wqkv,
                                                                  const bf16* __restrict__ wout, bf16* __restrict__ mimg,
                                                                  int chunks, int n, float scale) {
-  constexpr int N2 = C + 16;
-  extern __shared__ float cs[];              // G [128][C + 1] | ctx [128][33]
-  float* G = cs;
-  float* ctx = cs + HID * (C + 1);
-  __shared__ float S[HID];
-  const int b = blockIdx.x;
-  const float* src = part + (size_t)b * chunks * HID * N2;
-  for (int i = threadIdx.x; i < HID * N2; i += 256) {
-    const int hd = i / N2, c = i % N2;
-    if (c > C) continue;
+  // CTA = (image, head): G_h [32 d][C], S_h [32] summed over the chunks; ctx_h = G_h Wv_h^T / (S n); M[c'][h*32+d]
+  constexpr int N2 = C + 16, GP = C + 1;
+  __shared__ float buf[2 * 32 * GP], S[32], ctx[32][33];      // G | Wv_h first, then Wo_h in the same storage
+  float* G = buf;
+  float* wv = buf + 32 * GP;
+  float* wo = buf;                                             // [C][33] <= 2 * 32 * (C + 1) floats
+  const int b = blockIdx.x, h = blockIdx.y;
+  const float* src = part + ((size_t)b * chunks * HID + h * 32) * N2;
+  for (int i = threadIdx.x; i < 32 * GP; i += 256) {               // consecutive threads -> consecutive columns of a row
+    const int d = i / GP, c = i % GP;
     float acc = 0.0f;
-    for (int k = 0; k < chunks; ++k) acc += src[(size_t)k * HID * N2 + i];
-    if (c < C) G[hd * (C + 1) + c] = acc;
-    else S[hd] = acc;
+    for (int k = 0; k < chunks; ++k) acc += src[((size_t)k * HID + d) * N2 + c];
+    if (c < C) G[d * GP + c] = acc;
+    else S[d] = acc;
+  }
+  for (int i = threadIdx.x; i < 32 * C; i += 256) {
+    const int e = i / C, c = i % C;
+    wv[e * GP + c] = __bfloat162float(wqkv[(size_t)(2 * HID + h * 32 + e) * C + c]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < HID * 32; i += 256) {
-    const int hd = i >> 5, e = i & 31, h = hd >> 5;
-    const bf16* wv = wqkv + (size_t)(2 * HID + h * 32 + e) * C;
+  for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+    const int d = i >> 5, e = i & 31;
     float acc = 0.0f;
-    for (int c = 0; c < C; ++c) acc = fmaf(G[hd * (C + 1) + c], __bfloat162float(wv[c]), acc);
-    ctx[hd * 33 + e] = acc / (S[hd] * (float)n);
+#pragma unroll 8
+    for (int c = 0; c < C; ++c) acc = fmaf(G[d * GP + c], wv[e * GP + c], acc);
+    ctx[d][e] = acc / (S[d] * (float)n);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C * HID; i += 256) {
-    const int c = i / HID, hd = i % HID, h = hd >> 5;
-    const bf16* wo = wout + (size_t)c * HID + h * 32;
+  for (int i = threadIdx.x; i < C * 32; i += 256) {
+    const int c = i >> 5, e = i & 31;
+    wo[c * 33 + e] = __bfloat162float(wout[(size_t)c * HID + h * 32 + e]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 32; i += 256) {
+    const int c = i >> 5, d = i & 31;
     float acc = 0.0f;
 #pragma unroll
-    for (int e = 0; e < 32; ++e) acc = fmaf(ctx[hd * 33 + e], __bfloat162float(wo[e]), acc);
-    mimg[((size_t)b * C + c) * HID + hd] = __float2bfloat16_rn(acc * scale);
+    for (int e = 0; e < 32; ++e) acc = fmaf(ctx[d][e], wo[c * 33 + e], acc);
+    mimg[((size_t)b * C + c) * HID + h * 32 + d] = __float2bfloat16_rn(acc * scale);
   }
 }
 
@@ -382,7 +389,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_out_kernel(const __g
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_w, x_full[NS], x_empty[NS], y_ready[2], d1_full[2], q_ready[2], d3_full[2], m_full, m_empty;
   __shared__ uint32_t tmem_slot;
-  __shared__ float g_s[C], bo_s[C], go_s[C];
+  __shared__ float bo_s[C], go_s[C];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -413,7 +420,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_out_kernel(const __g
   }
   if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
   for (int i = threadIdx.x; i < C; i += TC_THREADS) {
-    g_s[i] = p.g_pre[i];
     bo_s[i] = p.b_out[i];
     go_s[i] = p.g_out[i];
   }
@@ -509,28 +515,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_out_kernel(const __g
       if (gtid == 0) tma_store_wait_read<0>();
       named_bar_sync(1 + grp, 128);
       mbar_wait(smem_u32(&x_full[st]), (uint32_t)((i / NS) & 1));
-      ln_row<C>(xb, wb, row, g_s, p.eps);
+      ln_row<C>(xb, wb, row, p.eps);
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&y_ready[grp]));
       // ---- q -> softmax over the 32 channels of each head -> Q tile (K-major, 2 blocks of 64 (h,d))
       mbar_wait(smem_u32(&d1_full[grp]), ph);
       tc_fence_after();
+      // |q| is bounded by the same weight-only bound as k (<= 40): exp(q) stays inside fp32 without subtracting a maximum
+      uint32_t r[2][32];
+      tmem_ld32(lane_addr, r[0]);
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
-        uint32_t r[32];
-        tmem_ld32(lane_addr + (uint32_t)(h * 32), r);
         tmem_ld_wait();
-        float m = __uint_as_float(r[0]);
-#pragma unroll
-        for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
-        const float ml = m * kLog2e;
-        float e[32], s = 0.0f;
+        if (h < 3) tmem_ld32(lane_addr + (uint32_t)((h + 1) * 32), r[(h + 1) & 1]);
+        float e[32], s4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          e[j] = ex2f(fmaf(__uint_as_float(r[j]), kLog2e, -ml));
-          s += e[j];
+          e[j] = ex2f(__uint_as_float(r[h & 1][j]) * kLog2e);
+          s4[j & 3] += e[j];
         }
-        const float inv = __fdividef(1.0f, s);
+        const float inv = __fdividef(1.0f, (s4[0] + s4[1]) + (s4[2] + s4[3]));
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           float f[8];
@@ -548,24 +552,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_out_kernel(const __g
       float o[C];
 #pragma unroll
       for (int c0 = 0; c0 < C; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(lane_addr + (uint32_t)(HID + c0), r);
+        uint32_t ro[32];
+        tmem_ld32(lane_addr + (uint32_t)(HID + c0), ro);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) o[c0 + j] = __uint_as_float(r[j]) + bo_s[c0 + j];
+        for (int j = 0; j < 32; ++j) o[c0 + j] = __uint_as_float(ro[j]) + bo_s[c0 + j];
       }
       tc_fence_before();
-      float s = 0.0f;
-#pragma unroll
-      for (int c = 0; c < C; ++c) s += o[c];
-      const float mean = s * (1.0f / C);
-      float qv = 0.0f;
+      float s4[4] = {0.0f, 0.0f, 0.0f, 0.0f}, q4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        o[c] -= mean;
-        qv = fmaf(o[c], o[c], qv);
+        s4[c & 3] += o[c];
+        q4[c & 3] = fmaf(o[c], o[c], q4[c & 3]);
       }
-      const float rstd = rsqrtf(qv * (1.0f / C) + p.eps);
+      const float mean = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / C);
+      const float var = fmaxf(((q4[0] + q4[1]) + (q4[2] + q4[3])) * (1.0f / C) - mean * mean, 0.0f);
+      const float rstd = rsqrtf(var + p.eps);
 #pragma unroll
       for (int b = 0; b < KB; ++b)
 #pragma unroll
@@ -573,7 +575,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_out_kernel(const __g
           float res[8], f[8];
           unpack8(lds128(sw_addr(xb + b * BLK, row, c)), res);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = fmaf(o[b * 64 + c * 8 + j] * rstd, go_s[b * 64 + c * 8 + j], res[j]);
+          for (int j = 0; j < 8; ++j) f[j] = fmaf((o[b * 64 + c * 8 + j] - mean) * rstd, go_s[b * 64 + c * 8 + j], res[j]);
           sts128(sw_addr(wb + b * BLK, row, c), pack8(f));
         }
       fence_proxy_async_smem();
@@ -592,8 +594,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_out_kernel(const __g
 }
 
 template <int C>
-int launch_tc(const bf16* x, const bf16* wqkv, const float* g_pre, const float* shift, const bf16* wout, const float* b_out,
-              const float* g_out, bf16* out, float* workspace, int batch, int n, float scale, float eps, cudaStream_t s) {
+int launch_tc(const bf16* x, const bf16* wqkv, float shift_log2, const bf16* wout, const float* b_out, const float* g_out, bf16* out,
+              float* workspace, int batch, int n, float scale, float eps, cudaStream_t s) {
   constexpr int KB = C / 64, N2 = C + 16;
   const int tpi = n / TM, sms = tedm_num_sms();
   // K-A work items: chunks of consecutive tiles of one image; the chunk length that wastes the least of the last wave
@@ -629,26 +631,23 @@ int launch_tc(const bf16* x, const bf16* wqkv, const float* g_pre, const float* 
   p.items = (int)items;
   p.total_tiles = batch * tpi;
   p.eps = eps;
-  p.g_pre = g_pre;
-  p.shift = shift;
+  p.shift_log2 = shift_log2;
   p.part = part;
   p.b_out = b_out;
   p.g_out = g_out;
 
   const int smem_a = 1024 + KB * BLK + BLK + (C == 64 ? 6 : 3) * KB * BLK + 2 * 2 * BLK;
   const int smem_b = 1024 + KB * BLK + 2 * C * 128 + (C == 64 ? 4 : 3) * KB * BLK + 2 * 2 * BLK;
-  const int smem_c = (HID * (C + 1) + HID * 33) * (int)sizeof(float);
   static bool configured = false;
   if (!configured) {
     TEDM_CUDA(cudaFuncSetAttribute(linattn_tc_ctx_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a));
     TEDM_CUDA(cudaFuncSetAttribute(linattn_tc_out_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b));
-    TEDM_CUDA(cudaFuncSetAttribute(linattn_tc_combine_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c));
     configured = true;
   }
   const int grid_a = items < sms ? (int)items : sms;
   linattn_tc_ctx_kernel<C><<<grid_a, TC_THREADS, smem_a, s>>>(maps, p);
   TEDM_LAUNCH_CHECK();
-  linattn_tc_combine_kernel<C><<<batch, 256, smem_c, s>>>(part, wqkv, wout, mimg, chunks, n, scale);
+  linattn_tc_combine_kernel<C><<<dim3((unsigned)batch, 4), 256, 0, s>>>(part, wqkv, wout, mimg, chunks, n, scale);
   TEDM_LAUNCH_CHECK();
   const int grid_b = p.total_tiles < sms ? p.total_tiles : sms;
   linattn_tc_out_kernel<C><<<grid_b, TC_THREADS, smem_b, s>>>(maps, p);
@@ -669,20 +668,20 @@ extern "C" int64_t tedm_linear_attention_tc_workspace(int batch, int n, int chan
   return items * HID * (channels + 16) + (int64_t)batch * channels * HID / 2 + 64;
 }
 
-extern "C" int tedm_linear_attention_tc_fwd(const void* x, const void* wqkv, const float* g_pre, const float* shift_log2,
-                                            const void* wout, const float* b_out, const float* g_out, void* out, float* workspace,
-                                            int batch, int n, int channels, int heads, int dim_head, float scale, float eps,
-                                            tedm_stream_t stream) {
-  TEDM_CHECK_ARG(x && wqkv && g_pre && shift_log2 && wout && b_out && g_out && out && workspace && batch > 0,
+extern "C" int tedm_linear_attention_tc_fwd(const void* x, const void* wqkv_g, float shift_log2, const void* wout, const float* b_out,
+                                            const float* g_out, void* out, float* workspace, int batch, int n, int channels,
+                                            int heads, int dim_head, float scale, float eps, tedm_stream_t stream) {
+  TEDM_CHECK_ARG(x && wqkv_g && wout && b_out && g_out && out && workspace && batch > 0 && batch <= 65535,
                  "tedm_linear_attention_tc_fwd: bad arguments");
+  TEDM_CHECK_ARG(shift_log2 >= 0.0f && shift_log2 <= 60.0f, "tedm_linear_attention_tc_fwd: shift_log2=%f outside [0, 60]", shift_log2);
   TEDM_UNSUPPORTED(!tedm_linear_attention_tc_supported(n, channels, heads, dim_head),
                    "tedm_linear_attention_tc_fwd: n=%d channels=%d heads=%d dim_head=%d (needs 4 x 32 heads, 64 or 128 channels, "
                    "n a multiple of 512)", n, channels, heads, dim_head);
   TEDM_CHECK_ARG((long long)batch * n < 2147483647LL, "tedm_linear_attention_tc_fwd: too many pixels");
   cudaStream_t s = (cudaStream_t)stream;
   if (channels == 64)
-    return launch_tc<64>((const bf16*)x, (const bf16*)wqkv, g_pre, shift_log2, (const bf16*)wout, b_out, g_out, (bf16*)out, workspace,
+    return launch_tc<64>((const bf16*)x, (const bf16*)wqkv_g, shift_log2, (const bf16*)wout, b_out, g_out, (bf16*)out, workspace,
                          batch, n, scale, eps, s);
-  return launch_tc<128>((const bf16*)x, (const bf16*)wqkv, g_pre, shift_log2, (const bf16*)wout, b_out, g_out, (bf16*)out, workspace,
+  return launch_tc<128>((const bf16*)x, (const bf16*)wqkv_g, shift_log2, (const bf16*)wout, b_out, g_out, (bf16*)out, workspace,
                         batch, n, scale, eps, s);
 }

@@ -249,11 +249,10 @@ class UnetEngine:
                 n_pix, c, att.heads, att.dim_head):
             # the same block with every GEMM on tcgen05; its softmax over pixels uses a weight-only bound of the k logits
             # instead of a running maximum, so blocks with extreme projection weights stay on the mma.sync kernels below
-            shift, bound = self.cache.get(key + ":kshift", (att.to_qkv.weight, pre.g),
-                                          lambda w, g: N.linear_attention_tc_shift(w.to(torch.bfloat16), g, att.heads, att.dim_head))
+            wg, shift_log2, bound = self.cache.get(key + ":tcw", (att.to_qkv.weight, pre.g),
+                                                   lambda w, g: N.linear_attention_tc_weights(w, g, att.heads, att.dim_head))
             if bound <= N.LINATTN_TC_MAX_SHIFT:
-                return N.linear_attention_block_tc(x, self._w(key + ".to_qkv"), self._f32(pre.g).reshape(-1), shift,
-                                                   self._w(key + ".to_out"), self._f32(att.to_out[0].bias),
+                return N.linear_attention_block_tc(x, wg, shift_log2, self._w(key + ".to_out"), self._f32(att.to_out[0].bias),
                                                    self._f32(att.to_out[1].g).reshape(-1), att.heads, att.dim_head, att.scale,
                                                    self.ln_eps)
         if (tape is None and self.fuse_linear_attention

@@ -69,7 +69,7 @@ SIGNATURES = {
     "tedm_linear_attention_fused_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _p]),
     "tedm_linear_attention_tc_supported": (_i, [_i, _i, _i, _i]),
     "tedm_linear_attention_tc_workspace": (_i64, [_i, _i, _i]),
-    "tedm_linear_attention_tc_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _p]),
+    "tedm_linear_attention_tc_fwd": (_i, [_p, _p, _f, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _p]),
     "tedm_upsample2x": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "tedm_final_conv1x1": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "tedm_nchw_f32_to_nhwc_bf16": (_i, [_p, _p, _i, _i, _i, _p]),
@@ -460,30 +460,30 @@ def linear_attention_tc_supported(n: int, channels: int, heads: int = 4, dim_hea
     return bool(load().tedm_linear_attention_tc_supported(n, channels, heads, dim_head))
 
 
-def linear_attention_tc_shift(wqkv: torch.Tensor, g_pre: torch.Tensor, heads: int = 4, dim_head: int = 32):
-    """Weight-only upper bound of the k logits of a LinearAttention block: k = w . y with y = LN(x) * g, ||LN(x)||_2 <=
-    sqrt(C), hence |k_hd| <= ||w_hd * g||_2 sqrt(C) (+ 2 % for the bf16 rounding of y).  -> (log2(e) * bound [128] fp32,
-    largest bound as a float)."""
+def linear_attention_tc_weights(wqkv: torch.Tensor, g_pre: torch.Tensor, heads: int = 4, dim_head: int = 32):
+    """Operands of the tcgen05 LinearAttention block derived from the to_qkv weight (fp32 or bf16, [384][C] or OIHW) and the
+    pre-norm gain: (wqkv_g bf16 [384][C] = W * g, log2(e) * bound, bound) where bound >= |q|, |k| for every pixel:
+    q = w . (LN(x) * g) with ||LN(x)||_2 <= sqrt(C), hence |q_r| <= ||w_r * g||_2 sqrt(C) (+ 2 % for the bf16 rounding)."""
     hid = heads * dim_head
     c = wqkv.numel() // (3 * hid)
-    wk = wqkv.reshape(3 * hid, c)[hid:2 * hid].float()
-    bound = (wk * g_pre.reshape(1, c).float()).norm(dim=1) * (c ** 0.5) * 1.02 + 1e-3
-    return (bound * 1.4426950408889634).contiguous(), float(bound.max().item())
+    wg = (wqkv.reshape(3 * hid, c).float() * g_pre.reshape(1, c).float()).to(torch.bfloat16).contiguous()
+    bound = float((wg[:2 * hid].float().norm(dim=1).max() * (c ** 0.5) * 1.02 + 1e-3).item())
+    return wg, bound * 1.4426950408889634, bound
 
 
-def linear_attention_block_tc(x, wqkv, g_pre, shift_log2, wout, b_out, g_out, heads: int = 4, dim_head: int = 32,
+def linear_attention_block_tc(x, wqkv_g, shift_log2: float, wout, b_out, g_out, heads: int = 4, dim_head: int = 32,
                               scale: Optional[float] = None, eps: float = 1e-5, want_workspace: bool = False):
-    """Residual(PreNorm(LinearAttention)) inference forward on tcgen05 (csrc/attention_tc.cu); x NHWC bf16 -> same shape."""
+    """Residual(PreNorm(LinearAttention)) inference forward on tcgen05 (csrc/attention_tc.cu); x NHWC bf16 -> same shape.
+    wqkv_g / shift_log2 come from linear_attention_tc_weights."""
     if x.dim() != 4 or not x.is_contiguous():
         raise ValueError("x must be a contiguous NHWC tensor")
     b, h, w, c = x.shape
     scale = dim_head ** -0.5 if scale is None else scale
     out = torch.empty_like(x)
     ws = torch.empty(load().tedm_linear_attention_tc_workspace(b, h * w, c), device=x.device, dtype=torch.float32)
-    _call("tedm_linear_attention_tc_fwd", _ptr(x, torch.bfloat16, "x"), _ptr(wqkv, torch.bfloat16, "wqkv"),
-          _ptr(g_pre, torch.float32, "g_pre"), _ptr(shift_log2, torch.float32, "shift"), _ptr(wout, torch.bfloat16, "wout"),
-          _ptr(b_out, torch.float32, "b_out"), _ptr(g_out, torch.float32, "g_out"), _ptr(out), _ptr(ws), b, h * w, c, heads,
-          dim_head, float(scale), float(eps), _stream())
+    _call("tedm_linear_attention_tc_fwd", _ptr(x, torch.bfloat16, "x"), _ptr(wqkv_g, torch.bfloat16, "wqkv_g"), float(shift_log2),
+          _ptr(wout, torch.bfloat16, "wout"), _ptr(b_out, torch.float32, "b_out"), _ptr(g_out, torch.float32, "g_out"), _ptr(out),
+          _ptr(ws), b, h * w, c, heads, dim_head, float(scale), float(eps), _stream())
     return (out, ws) if want_workspace else out
 
 

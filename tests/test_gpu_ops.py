@@ -231,10 +231,10 @@ def test_linear_attention_block_tc(C, hw, B):
     wo = sd["a.fn.fn.to_out.0.weight"].reshape(C, 128).to(torch.bfloat16).cuda()
     g1, g2 = sd["a.fn.norm.g"].reshape(-1).cuda(), sd["a.fn.fn.to_out.1.g"].reshape(-1).cuda()
     bo = sd["a.fn.fn.to_out.0.bias"].cuda()
-    shift, bound = N.linear_attention_tc_shift(wq, g1)
+    wg, shift_log2, bound = N.linear_attention_tc_weights(sd["a.fn.fn.to_qkv.weight"].cuda(), g1)
     assert bound < N.LINATTN_TC_MAX_SHIFT
     xh = _nhwc(x)
-    got, ws = N.linear_attention_block_tc(xh, wq, g1, shift, wo, bo, g2, want_workspace=True)
+    got, ws = N.linear_attention_block_tc(xh, wg, shift_log2, wo, bo, g2, want_workspace=True)
     torch.cuda.synchronize()
     # (1) the folded per-image matrix M[c][hd] = scale * sum_e ctx[h][d][e] Wo[c][h*32+e], recomputed in fp32 torch
     y = O._chan_layernorm(x, sd["a.fn.norm.g"], 1e-5)

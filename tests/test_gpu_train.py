@@ -231,33 +231,32 @@ def test_unet_backward_with_1024_mid_tokens():
     assert float((mid - mid_ref).norm() / mid_ref.norm()) < 5e-2       # measured 2.2e-2
 
 
-def test_conv_weight_gradients_are_bit_reproducible():
-    """In deterministic mode (`native.set_deterministic()` / TEDM_DETERMINISTIC=1) both tcgen05 weight-gradient kernels add
-    their split-K slices in a fixed order (csrc/conv_igemm.cu): the same step run twice gives bit-identical gradients for
-    every convolution weight (94 % of the 36 M parameters).  The small per-channel reductions (norm gains, biases) still
-    use fp32 atomics."""
+def test_conv_weight_gradient_kernels_are_bit_reproducible_in_deterministic_mode():
+    """`native.set_deterministic()` / TEDM_DETERMINISTIC=1: both tcgen05 weight-gradient kernels add their split-K slices in
+    a fixed order (csrc/conv_igemm.cu), so the same (x, dy) gives a bit-identical dW on every run -- for the halo-tile 3x3
+    kernel always, for the generic kernel (1x1, 4x4-s2, folded upsample, the widest 3x3) when the mode is on.  (A whole
+    backward pass is not bit-reproducible yet: the GroupNorm backward reduces its per-channel sums with fp32 atomics, and
+    those feed the data gradient.)"""
     from tedm_b200 import native as N
+    gen = torch.Generator().manual_seed(12)
+    cases = [(N.MODE_1X1, 64, 0, 384, 64, 8), (N.MODE_1X1, 512, 0, 384, 16, 8), (N.MODE_3X3, 64, 0, 64, 64, 8),
+             (N.MODE_3X3, 512, 256, 512, 16, 8), (N.MODE_4X4S2, 64, 0, 128, 64, 8), (N.MODE_UP3X3, 256, 0, 128, 32, 8),
+             (N.MODE_1X1, 128, 64, 128, 64, 8)]
     N.set_deterministic(True)
     try:
-        _check_reproducible()
+        for mode, c0, c1, cout, size, b in cases:
+            x0 = torch.randn(b, size, size, c0, generator=gen).to(torch.bfloat16).cuda()
+            x1 = torch.randn(b, size, size, c1, generator=gen).to(torch.bfloat16).cuda() if c1 else None
+            osz = size // 2 if mode == N.MODE_4X4S2 else (2 * size if mode == N.MODE_UP3X3 else size)
+            dy = torch.randn(b, osz, osz, cout, generator=gen).to(torch.bfloat16).cuda()
+            khw = {N.MODE_1X1: 1, N.MODE_3X3: 9, N.MODE_4X4S2: 16, N.MODE_UP3X3: 9}[mode]
+            outs = []
+            for _ in range(4):
+                g = torch.zeros(cout, c0 + c1, khw, device="cuda")
+                N.conv_wgrad(x0, dy, mode, src1=x1, grad_oihw=g)
+                outs.append(g)
+            torch.cuda.synchronize()
+            assert outs[0].abs().sum() > 0 and torch.isfinite(outs[0]).all()
+            assert all(torch.equal(outs[0], o) for o in outs[1:]), (mode, c0, c1, cout, size)
     finally:
         N.set_deterministic(False)
-
-
-def _check_reproducible():
-    m = _model()
-    x = torch.rand(8, 1, 64, 64, generator=torch.Generator().manual_seed(9)).cuda()
-    t = torch.randint(0, 1000, (8,), generator=torch.Generator().manual_seed(10)).cuda()
-    nz = torch.randn(8, 1, 64, 64, generator=torch.Generator().manual_seed(11)).cuda()
-    runs = []
-    for _ in range(3):
-        for p in m.parameters():
-            p.grad = None
-        m.train_step(x, t=t, noise=nz).backward()
-        torch.cuda.synchronize()
-        runs.append({n: p.grad.clone() for n, p in m.named_parameters() if p.dim() == 4 and p.shape[1] > 1})
-    n_el = sum(g.numel() for g in runs[0].values())
-    assert n_el > 34_000_000
-    for name, g in runs[0].items():
-        assert torch.isfinite(g).all() and g.abs().sum() > 0, name
-        assert torch.equal(g, runs[1][name]) and torch.equal(g, runs[2][name]), name
