@@ -419,7 +419,7 @@ TEDM_API int tedm_debug_umma_probe(const void* A, const void* Bm, const int* shi
  * -> softmaxes by the thread that owns the pixel -> context / to_out as UMMAs again; v is never materialised and the to_out
  * conv is folded into a per-image matrix.
  *   wqkv_g     = to_qkv weight with the pre-norm gain folded in: bf16 [384][C], row r = W[r] * g_pre (the kernel's
- *                LayerNorm then has no gain)
+ *                LayerNorm then has no gain); the 128 q rows additionally times log2(e) (the softmax over d is an exp2)
  *   shift_log2 = log2(e) * B, B >= every |q| and |k| logit; a WEIGHT-ONLY bound does (max_r ||wqkv_g[r]||_2 * sqrt(C), by
  *                Cauchy-Schwarz, since ||LayerNorm(x)||_2 <= sqrt(C)).  It replaces the running maximum of the softmax over
  *                pixels (a per-column constant cancels) and lets the softmax over d skip its maximum; the caller routes

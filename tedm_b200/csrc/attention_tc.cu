@@ -58,7 +58,6 @@ int encode_2d(CUtensorMap* map, const void* ptr, long long rows, long long cols,
 constexpr int TM = 128;                 // pixels per tile = UMMA M
 constexpr int HID = 128;                // heads * dim_head
 constexpr int BLK = TM * 128;           // bytes of one [128 rows][64 bf16] swizzled block
-constexpr int TC_THREADS = 320;
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -95,40 +94,68 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// LayerNorm of one pixel row held as C/64 swizzled blocks at `src` (block stride BLK): xhat = (x - mean) rstd -> bf16 at `dst`
-// (dst may equal src).  The gain g is folded into the projection weights by the caller (W' = W diag(g)).  One pass,
-// four independent accumulators per statistic (a 64-deep dependent FADD chain would cost more than the arithmetic).
-template <int C>
-__device__ __forceinline__ void ln_row(uint32_t src, uint32_t dst, int row, float eps) {
-  float v[C];
+// TPP threads share a pixel (1: the thread owns the whole row; 2: thread h2 owns channels [h2 C/2, (h2+1) C/2)).  A row is
+// C/8 16-byte chunks over C/64 swizzled blocks; thread h2 owns chunks h2 * C/(8 TPP) ... of that linear order.
+template <int C, int TPP>
+__device__ __forceinline__ uint32_t part_addr(uint32_t base, int row, int h2, int i) {
+  const int l = h2 * (C / 8 / TPP) + i;
+  return sw_addr(base + (l >> 3) * BLK, row, l & 7);
+}
+
+// Per-pixel LayerNorm statistics.  TPP = 2: the two half-row partial sums are exchanged through two 8-byte shared-memory
+// slots (`mine` written, `theirs` read) around one named barrier of the group's threads.  REUSE: the slots lie inside a
+// buffer the caller is about to overwrite (no spare shared memory at C = 128), so a second barrier keeps the partner's
+// read ahead of that overwrite.  -> (rstd, -mean * rstd)
+template <int C, int TPP, bool REUSE>
+__device__ __forceinline__ float2 ln_stats(float s, float q, uint32_t mine, uint32_t theirs, int bar_id, float eps) {
+  if constexpr (TPP == 2) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(mine), "f"(s), "f"(q) : "memory");
+    named_bar_sync(bar_id, 256);
+    float ox, oy;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(ox), "=f"(oy) : "r"(theirs) : "memory");
+    if (REUSE) named_bar_sync(bar_id, 256);
+    s += ox;
+    q += oy;
+  }
+  const float mean = s * (1.0f / C);
+  const float var = fmaxf(q * (1.0f / C) - mean * mean, 0.0f);
+  const float rstd = rsqrtf(var + eps);
+  return make_float2(rstd, -mean * rstd);
+}
+
+// LayerNorm (no gain: folded into the projection weights, W' = W diag(g)) of this thread's part of pixel `row`:
+// src tile -> bf16 xhat at dst (may equal src).  One pass, four independent accumulators per statistic.
+template <int C, int TPP, bool REUSE>
+__device__ __forceinline__ void ln_part(uint32_t src, uint32_t dst, int row, int h2, uint32_t mine, uint32_t theirs, int bar_id,
+                                        float eps) {
+  constexpr int NCH = C / 8 / TPP;                 // 16-byte chunks of this thread
+  float v[NCH * 8];
 #pragma unroll
-  for (int b = 0; b < C / 64; ++b)
+  for (int i = 0; i < NCH; ++i) {
+    float f[8];
+    unpack8(lds128(part_addr<C, TPP>(src, row, h2, i)), f);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float f[8];
-      unpack8(lds128(sw_addr(src + b * BLK, row, c)), f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[b * 64 + c * 8 + j] = f[j];
-    }
+    for (int j = 0; j < 8; ++j) v[i * 8 + j] = f[j];
+  }
   float s4[4] = {0.0f, 0.0f, 0.0f, 0.0f}, q4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-  for (int i = 0; i < C; ++i) {
+  for (int i = 0; i < NCH * 8; ++i) {
     s4[i & 3] += v[i];
     q4[i & 3] = fmaf(v[i], v[i], q4[i & 3]);
   }
-  const float mean = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / C);
-  const float var = fmaxf(((q4[0] + q4[1]) + (q4[2] + q4[3])) * (1.0f / C) - mean * mean, 0.0f);
-  const float rstd = rsqrtf(var + eps);
-  const float nm = -mean * rstd;
+  const float2 st = ln_stats<C, TPP, REUSE>((s4[0] + s4[1]) + (s4[2] + s4[3]), (q4[0] + q4[1]) + (q4[2] + q4[3]), mine, theirs,
+                                            bar_id, eps);
 #pragma unroll
-  for (int b = 0; b < C / 64; ++b)
+  for (int i = 0; i < NCH; ++i) {
+    float f[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float f[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaf(v[b * 64 + c * 8 + j], rstd, nm);
-      sts128(sw_addr(dst + b * BLK, row, c), pack8(f));
-    }
+    for (int j = 0; j < 8; ++j) f[j] = fmaf(v[i * 8 + j], st.x, st.y);
+    sts128(part_addr<C, TPP>(dst, row, h2, i), pack8(f));
+  }
+}
+
+__device__ __forceinline__ uint64_t desc_mn_lbo(uint32_t addr, uint32_t lbo_bytes) {   // MN-major SW128 with an explicit block stride
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
 struct TcMaps {
@@ -151,27 +178,31 @@ struct TcParams {
 // ==========================================================================================================
 // K-A: per (image, chunk of tiles):  G[hd][c] = sum_px P[px][hd] y[px][c],  S[hd] = sum_px P[px][hd]
 // ==========================================================================================================
-template <int C>
-__global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_ctx_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+template <int C, int NG, int TPP>
+__global__ void __launch_bounds__(64 + NG * 128 * TPP, 1) linattn_tc_ctx_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+  constexpr int GT = 128 * TPP;                    // threads of a compute group: TPP threads per pixel
+  constexpr int TC_THREADS = 64 + NG * GT;         // producer warp, issuer warp, NG compute groups
   constexpr int KB = C / 64;                       // 64-channel blocks of a pixel row
   constexpr int N2 = C + 16;                       // G columns + 16 columns of S (the ones block)
   constexpr int NS = C == 64 ? 6 : 3;              // x / y ring: tiles in flight towards this SM (HBM latency is ~2 tile times)
   constexpr int XBUF = KB * BLK;
+  constexpr bool MERGE_S = C == 64;                // one 64-column block: [y | ones] is a single B operand (explicit block stride)
   constexpr uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-  constexpr uint32_t IDESC_G = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(C >> 3) << 17) |
-                               ((uint32_t)(HID >> 4) << 24);
+  constexpr uint32_t IDESC_G = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)((MERGE_S ? N2 : C) >> 3) << 17) | ((uint32_t)(HID >> 4) << 24);
   constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(16 >> 3) << 17) |
                                ((uint32_t)(HID >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_w, x_full[NS], x_empty[NS], y_ready[2], d1_full[2], p_ready[2], d2_full, d2_empty;
+  __shared__ __align__(8) uint64_t bar_w, x_full[NS], x_empty[NS], y_ready[NG], d1_full[NG], p_ready[NG], d2_full, d2_empty;
   __shared__ uint32_t tmem_slot;
+  __shared__ float2 exch[TPP == 2 ? NG : 1][TPP == 2 ? 2 * TM : 1];   // LayerNorm partial sums: [group][half][pixel]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_s = base;                                  // Wk: KB blocks of [128 hd][64 c]
-  const uint32_t one_s = w_s + KB * BLK;                      // a block of bf16 ones: B operand of the S product
-  const uint32_t x_s = one_s + BLK;                           // ring of NS tiles, LayerNormed in place
-  const uint32_t p_s = x_s + NS * XBUF;                       // [2] x P: two MN blocks [128 px][64 hd]
+  const uint32_t x_s = w_s + KB * BLK;                        // ring of NS tiles, LayerNormed in place
+  const uint32_t one_s = x_s + NS * XBUF;                     // a block of bf16 ones (after the ring: a positive block stride)
+  const uint32_t p_s = one_s + BLK;                           // [NG] x P: two MN blocks [128 px][64 hd]
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&maps.x);
@@ -181,13 +212,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_ctx_kernel(const __g
       mbar_init(smem_u32(&x_full[s]), 1);
       mbar_init(smem_u32(&x_empty[s]), 1);
     }
-    for (int g = 0; g < 2; ++g) {
-      mbar_init(smem_u32(&y_ready[g]), 128);
+    for (int g = 0; g < NG; ++g) {
+      mbar_init(smem_u32(&y_ready[g]), GT);
       mbar_init(smem_u32(&d1_full[g]), 1);
-      mbar_init(smem_u32(&p_ready[g]), 128);
+      mbar_init(smem_u32(&p_ready[g]), GT);
     }
     mbar_init(smem_u32(&d2_full), 1);
-    mbar_init(smem_u32(&d2_empty), 128);
+    mbar_init(smem_u32(&d2_empty), GT);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
@@ -198,10 +229,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_ctx_kernel(const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t d2_col = 256;                                // D1[g] at columns g * 128; G at 256 .. 256 + C; S at 256 + C .. + 16
+  const uint32_t d2_col = NG * HID;                           // D1[g] at columns g * 128; then G (C columns) and S (16)
 
   // tiles of this CTA: items blockIdx.x, + gridDim.x, ...; local tile index i counts across items.
-  // tile i: ring stage i % NS, compute group i & 1
+  // tile i: ring stage i % NS, compute group i % NG
   const int my_items = p.items > (int)blockIdx.x ? (p.items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int my_tiles = my_items * p.chunk_tiles;
   const int chunks_per_image = p.tiles_per_image / p.chunk_tiles;
@@ -234,25 +265,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_ctx_kernel(const __g
       mbar_wait(smem_u32(&bar_w), 0);
       tc_fence_after();
       auto gemm2 = [&](int j) {                     // G (+)= P_j^T y_j ;  S (+)= P_j^T 1
-        const int g = j & 1, tl = j % p.chunk_tiles, st = j % NS;
+        const int g = j % NG, tl = j % p.chunk_tiles, st = j % NS;
         if (tl == 0 && j > 0) {                     // a new item: the previous item's accumulator must have been drained
           mbar_wait(smem_u32(&d2_empty), (uint32_t)(((j / p.chunk_tiles - 1) & 1)));
           tc_fence_after();
         }
-        mbar_wait(smem_u32(&p_ready[g]), (uint32_t)((j >> 1) & 1));
+        mbar_wait(smem_u32(&p_ready[g]), (uint32_t)((j / NG) & 1));
         tc_fence_after();
-        const uint64_t adesc = desc_mn(p_s + g * 2 * BLK), bdesc = desc_mn(x_s + st * XBUF), sdesc = desc_mn(one_s);
+        const uint32_t yb = x_s + st * XBUF;
+        const uint64_t adesc = desc_mn(p_s + g * 2 * BLK);
+        if constexpr (MERGE_S) {
+          const uint64_t bdesc = desc_mn_lbo(yb, one_s - yb);          // block 0 = y, "block 1" = the shared ones block
 #pragma unroll
-        for (int k = 0; k < TM / 16; ++k) {
-          umma_bf16(tmem + d2_col, adesc + 128ull * k, bdesc + 128ull * k, IDESC_G, (tl | k) != 0 ? 1u : 0u);
-          umma_bf16(tmem + d2_col + C, adesc + 128ull * k, sdesc + 128ull * k, IDESC_S, (tl | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < TM / 16; ++k) umma_bf16(tmem + d2_col, adesc + 128ull * k, bdesc + 128ull * k, IDESC_G, (tl | k) != 0 ? 1u : 0u);
+        } else {
+          const uint64_t bdesc = desc_mn(yb), sdesc = desc_mn(one_s);
+#pragma unroll
+          for (int k = 0; k < TM / 16; ++k) {
+            umma_bf16(tmem + d2_col, adesc + 128ull * k, bdesc + 128ull * k, IDESC_G, (tl | k) != 0 ? 1u : 0u);
+            umma_bf16(tmem + d2_col + C, adesc + 128ull * k, sdesc + 128ull * k, IDESC_S, (tl | k) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(smem_u32(&x_empty[st]));        // y_j (and P_j) are free once these complete
         if (tl == p.chunk_tiles - 1) umma_commit(smem_u32(&d2_full));
       };
       for (int i = 0; i < my_tiles; ++i) {
-        const int g = i & 1, st = i % NS;
-        mbar_wait(smem_u32(&y_ready[g]), (uint32_t)((i >> 1) & 1));
+        const int g = i % NG, st = i % NS;
+        mbar_wait(smem_u32(&y_ready[g]), (uint32_t)((i / NG) & 1));
         tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
@@ -267,33 +306,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_ctx_kernel(const __g
     }
     __syncwarp();
   } else {
-    const int grp = (warp - 2) >> 2, q = warp & 3, row = q * 32 + lane;
+    const int grp = (warp - 2) / (4 * TPP), h2 = TPP == 2 ? ((warp - 2) >> 2) & 1 : 0, q = warp & 3, row = q * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-    for (int i = grp; i < my_tiles; i += 2) {
-      const uint32_t ph = (uint32_t)((i >> 1) & 1);
+    const float nsh = -p.shift_log2;
+    for (int i = grp; i < my_tiles; i += NG) {
+      const uint32_t ph = (uint32_t)((i / NG) & 1);
       const int st = i % NS;
       const uint32_t yb = x_s + st * XBUF;
       mbar_wait(smem_u32(&x_full[st]), (uint32_t)((i / NS) & 1));
-      ln_row<C>(yb, yb, row, p.eps);
+      ln_part<C, TPP, false>(yb, yb, row, h2, TPP == 2 ? smem_u32(&exch[TPP == 2 ? grp : 0][TPP == 2 ? h2 * TM + row : 0]) : 0u,
+                             TPP == 2 ? smem_u32(&exch[TPP == 2 ? grp : 0][TPP == 2 ? (h2 ^ 1) * TM + row : 0]) : 0u, 1 + grp, p.eps);
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&y_ready[grp]));
       mbar_wait(smem_u32(&d1_full[grp]), ph);
       tc_fence_after();
-      const uint32_t pb = p_s + grp * 2 * BLK;
-      const float nsh = -p.shift_log2;
-      // one shift for all columns: a per-column constant cancels in G / S, so the scalar maximum of the bounds will do
+      // this thread's 4 / TPP heads (32 columns each).  One shift for all columns: a per-column constant cancels in G / S.
+      constexpr int NH = 4 / TPP;
+      const uint32_t pbase = p_s + grp * 2 * BLK;
       uint32_t r[2][32];
-      tmem_ld32(lane_addr + (uint32_t)(grp * HID), r[0]);
+      tmem_ld32(lane_addr + (uint32_t)(grp * HID + h2 * NH * 32), r[0]);
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {                     // 32 columns (= one head) at a time; the next load is in flight
+      for (int hh = 0; hh < NH; ++hh) {                    // the next head's load is in flight while this one is processed
         tmem_ld_wait();
-        if (ch < 3) tmem_ld32(lane_addr + (uint32_t)(grp * HID + (ch + 1) * 32), r[(ch + 1) & 1]);
+        if (hh + 1 < NH) tmem_ld32(lane_addr + (uint32_t)(grp * HID + (h2 * NH + hh + 1) * 32), r[(hh + 1) & 1]);
+        const int gh = h2 * NH + hh;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = ex2f(fmaf(__uint_as_float(r[ch & 1][c * 8 + j]), kLog2e, nsh));
-          sts128(sw_addr(pb + (ch >> 1) * BLK, row, (ch & 1) * 4 + c), pack8(f));
+          for (int j = 0; j < 8; ++j) f[j] = ex2f(fmaf(__uint_as_float(r[hh & 1][c * 8 + j]), kLog2e, nsh));
+          sts128(sw_addr(pbase + (gh >> 1) * BLK, row, (gh & 1) * 4 + c), pack8(f));
         }
       }
       tc_fence_before();
@@ -305,15 +347,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_ctx_kernel(const __g
         tc_fence_after();
         const int item = blockIdx.x + it * gridDim.x;
         float* dst = p.part + ((size_t)item * HID + row) * N2;
+        constexpr int N16 = N2 / 16, SPLIT = TPP == 2 ? (N16 + 1) / 2 : N16;  // 16-column chunks: the first SPLIT to thread 0 of the pixel
 #pragma unroll 1
-        for (int c0 = 0; c0 < N2; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(lane_addr + d2_col + (uint32_t)c0, r);
+        for (int cc = h2 ? SPLIT : 0; cc < (h2 ? N16 : SPLIT); ++cc) {
+          uint32_t rr[16];
+          tmem_ld16(lane_addr + d2_col + (uint32_t)(cc * 16), rr);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float4*>(dst + c0 + 4 * j) = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                                                       __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            *reinterpret_cast<float4*>(dst + cc * 16 + 4 * j) = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]),
+                                                                            __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
         }
         tc_fence_before();
         mbar_arrive(smem_u32(&d2_empty));
@@ -377,26 +420,34 @@ __global__ void __launch_bounds__(256) linattn_tc_combine_kernel(const float* __
 // ==========================================================================================================
 // K-B: out = LN_out( softmax_d(LN(x) Wq^T) M^T + b_o ) g_o + x
 // ==========================================================================================================
-template <int C>
-__global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_out_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+template <int C, int NG, int TPP>
+__global__ void __launch_bounds__(64 + NG * 128 * TPP, 1) linattn_tc_out_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+  constexpr int GT = 128 * TPP;                    // threads of a compute group: TPP threads per pixel
+  constexpr int TC_THREADS = 64 + NG * GT;
   constexpr int KB = C / 64;
-  constexpr int NS = C == 64 ? 4 : 3;              // x ring (a tile stays until its residual has been added)
+  constexpr int NS = C == 64 ? (NG >= 3 ? 4 : 6) : 3;   // x ring (a tile stays until its residual has been added)
   constexpr int XBUF = KB * BLK;
   constexpr int WBUF = 2 * BLK;                    // per group: y (KB blocks) -> Q (2 blocks) -> output staging (KB blocks), in turn
   constexpr int MBLK = C * 128;                    // bytes of one [C rows][64 hd] block of M
+  constexpr int HC = C / TPP;                      // channels per thread
   constexpr uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
   constexpr uint32_t IDESC3 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_w, x_full[NS], x_empty[NS], y_ready[2], d1_full[2], q_ready[2], d3_full[2], m_full, m_empty;
+  __shared__ __align__(8) uint64_t bar_w, x_full[NS], x_empty[NS], y_ready[NG], d1_full[NG], q_ready[NG], d3_full[NG], m_full, m_empty;
   __shared__ uint32_t tmem_slot;
   __shared__ float bo_s[C], go_s[C];
+  // LayerNorm partial sums of the two threads of a pixel: at C = 64 a static [group][half][pixel] array; at C = 128 every
+  // byte of shared memory is taken, so the slots are the first 8 bytes of each thread's own destination in the work buffer
+  constexpr bool EXCH_IN_WB = C == 128;
+  constexpr bool EXCH_STATIC = TPP == 2 && !EXCH_IN_WB;
+  __shared__ float2 exch[EXCH_STATIC ? NG : 1][EXCH_STATIC ? 2 * TM : 1];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_s = base;                                  // Wq: KB blocks of [128 hd][64 c]
   const uint32_t m_s = w_s + KB * BLK;                        // M of the current image: 2 blocks of [C][64 hd]
   const uint32_t x_s = m_s + 2 * MBLK;                        // ring of NS x tiles
-  const uint32_t b_s = x_s + NS * XBUF;                       // [2] work buffers
+  const uint32_t b_s = x_s + NS * XBUF;                       // [NG] work buffers
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&maps.x);
@@ -406,12 +457,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_out_kernel(const __g
     mbar_init(smem_u32(&bar_w), 1);
     for (int s = 0; s < NS; ++s) {
       mbar_init(smem_u32(&x_full[s]), 1);
-      mbar_init(smem_u32(&x_empty[s]), 128);
+      mbar_init(smem_u32(&x_empty[s]), GT);
     }
-    for (int g = 0; g < 2; ++g) {
-      mbar_init(smem_u32(&y_ready[g]), 128);
+    for (int g = 0; g < NG; ++g) {
+      mbar_init(smem_u32(&y_ready[g]), GT);
       mbar_init(smem_u32(&d1_full[g]), 1);
-      mbar_init(smem_u32(&q_ready[g]), 128);
+      mbar_init(smem_u32(&q_ready[g]), GT);
       mbar_init(smem_u32(&d3_full[g]), 1);
     }
     mbar_init(smem_u32(&m_full), 1);
@@ -426,10 +477,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_out_kernel(const __g
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_slot;                            // group g: q at columns g * 256, o at g * 256 + 128
+  const uint32_t tmem = tmem_slot;                            // group g: columns g * 128 hold q, then (q consumed) o
 
   // a contiguous range of tiles per CTA (consecutive tiles share an image, so M is reloaded rarely).
-  // tile i of the range: ring stage i % NS, compute group i & 1
+  // tile i of the range: ring stage i % NS, compute group i % NG
   const long long T = p.total_tiles;
   const int t0 = (int)(T * blockIdx.x / gridDim.x), t1 = (int)(T * (blockIdx.x + 1) / gridDim.x);
   const int my_tiles = t1 - t0;
@@ -468,33 +519,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_out_kernel(const __g
       mbar_wait(smem_u32(&bar_w), 0);
       tc_fence_after();
       int n_img = 0;
-      auto gemm2 = [&](int j) {                     // o_j = Q_j M^T
-        const int g = j & 1, tile = t0 + j, img = tile / p.tiles_per_image;
+      auto gemm2 = [&](int j) {                     // o_j = Q_j M^T  (into the columns q_j occupied: it has been consumed)
+        const int g = j % NG, tile = t0 + j, img = tile / p.tiles_per_image;
         if (j == 0 || (tile - 1) / p.tiles_per_image != img) {        // first tile of an image: its M must have landed
           mbar_wait(smem_u32(&m_full), (uint32_t)(n_img & 1));
           ++n_img;
         }
-        mbar_wait(smem_u32(&q_ready[g]), (uint32_t)((j >> 1) & 1));
+        mbar_wait(smem_u32(&q_ready[g]), (uint32_t)((j / NG) & 1));
         tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
           const uint64_t adesc = desc_k(b_s + g * WBUF + kb * BLK), bdesc = desc_k(m_s + kb * MBLK);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem + g * 256 + HID, adesc + 2ull * k, bdesc + 2ull * k, IDESC3, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(tmem + g * HID, adesc + 2ull * k, bdesc + 2ull * k, IDESC3, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(smem_u32(&d3_full[g]));
         if (j == my_tiles - 1 || (tile + 1) / p.tiles_per_image != img) umma_commit(smem_u32(&m_empty));   // last tile of the image here
       };
       for (int i = 0; i < my_tiles; ++i) {
-        const int g = i & 1;
-        mbar_wait(smem_u32(&y_ready[g]), (uint32_t)((i >> 1) & 1));
+        const int g = i % NG;
+        mbar_wait(smem_u32(&y_ready[g]), (uint32_t)((i / NG) & 1));
         tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
           const uint64_t adesc = desc_k(b_s + g * WBUF + kb * BLK), bdesc = desc_k(w_s + kb * BLK);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem + g * 256, adesc + 2ull * k, bdesc + 2ull * k, IDESC1, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem + g * HID, adesc + 2ull * k, bdesc + 2ull * k, IDESC1, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(smem_u32(&d1_full[g]));
         if (i > 0) gemm2(i - 1);
@@ -503,44 +554,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_out_kernel(const __g
     }
     __syncwarp();
   } else {
-    const int grp = (warp - 2) >> 2, q = warp & 3, row = q * 32 + lane;
-    const int gtid = threadIdx.x - 64 - grp * 128;            // 0..127 inside the group
-    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * 256);
+    const int grp = (warp - 2) / (4 * TPP), h2 = TPP == 2 ? ((warp - 2) >> 2) & 1 : 0, q = warp & 3, row = q * 32 + lane;
+    const int gtid = threadIdx.x - 64 - grp * GT;             // index inside the group
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * HID);
     const uint32_t wb = b_s + grp * WBUF;
-    for (int i = grp; i < my_tiles; i += 2) {
-      const uint32_t ph = (uint32_t)((i >> 1) & 1);
+    for (int i = grp; i < my_tiles; i += NG) {
+      const uint32_t ph = (uint32_t)((i / NG) & 1);
       const int st = i % NS;
       const uint32_t xb = x_s + st * XBUF;
       // the TMA store of this group's previous tile must have drained the work buffer before LayerNorm rewrites it
       if (gtid == 0) tma_store_wait_read<0>();
-      named_bar_sync(1 + grp, 128);
+      named_bar_sync(1 + grp, GT);
       mbar_wait(smem_u32(&x_full[st]), (uint32_t)((i / NS) & 1));
-      ln_row<C>(xb, wb, row, p.eps);
+      const uint32_t ex_mine = EXCH_IN_WB ? part_addr<C, TPP>(wb, row, h2, 0) : smem_u32(&exch[EXCH_STATIC ? grp : 0][EXCH_STATIC ? h2 * TM + row : 0]);
+      const uint32_t ex_theirs = EXCH_IN_WB ? part_addr<C, TPP>(wb, row, h2 ^ 1, 0)
+                                            : smem_u32(&exch[EXCH_STATIC ? grp : 0][EXCH_STATIC ? (h2 ^ 1) * TM + row : 0]);
+      // (one static slot pair serves both normalisations of a tile: y_ready / d1_full lie between them, and those complete
+      // only after all 256 threads have read their partner's value)
+      ln_part<C, TPP, EXCH_IN_WB>(xb, wb, row, h2, ex_mine, ex_theirs, 1 + grp, p.eps);
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&y_ready[grp]));
-      // ---- q -> softmax over the 32 channels of each head -> Q tile (K-major, 2 blocks of 64 (h,d))
+      // ---- q -> softmax over the 32 channels of each of this thread's two heads -> Q block h2 (K-major)
       mbar_wait(smem_u32(&d1_full[grp]), ph);
       tc_fence_after();
-      // |q| is bounded by the same weight-only bound as k (<= 40): exp(q) stays inside fp32 without subtracting a maximum
-      uint32_t r[2][32];
-      tmem_ld32(lane_addr, r[0]);
+      {
+        // |q| is bounded by the same weight-only bound as k (<= 40): exp(q) stays inside fp32 without subtracting a maximum
+        constexpr int NH = 4 / TPP;
+        uint32_t r[2][32];
+        tmem_ld32(lane_addr + (uint32_t)(h2 * NH * 32), r[0]);
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        tmem_ld_wait();
-        if (h < 3) tmem_ld32(lane_addr + (uint32_t)((h + 1) * 32), r[(h + 1) & 1]);
-        float e[32], s4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (int hh = 0; hh < NH; ++hh) {
+          tmem_ld_wait();
+          if (hh + 1 < NH) tmem_ld32(lane_addr + (uint32_t)((h2 * NH + hh + 1) * 32), r[(hh + 1) & 1]);
+          const int gh = h2 * NH + hh;
+          float e[32], s4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          e[j] = ex2f(__uint_as_float(r[h & 1][j]) * kLog2e);
-          s4[j & 3] += e[j];
-        }
-        const float inv = __fdividef(1.0f, (s4[0] + s4[1]) + (s4[2] + s4[3]));
+          for (int j = 0; j < 32; ++j) {
+            e[j] = ex2f(__uint_as_float(r[hh & 1][j]));          // log2(e) is folded into the q rows of wqkv_g
+            s4[j & 3] += e[j];
+          }
+          const float inv = __fdividef(1.0f, (s4[0] + s4[1]) + (s4[2] + s4[3]));
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float f[8];
+          for (int c = 0; c < 4; ++c) {
+            float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = e[c * 8 + j] * inv;
-          sts128(sw_addr(wb + (h >> 1) * BLK, row, (h & 1) * 4 + c), pack8(f));
+            for (int j = 0; j < 8; ++j) f[j] = e[c * 8 + j] * inv;
+            sts128(sw_addr(wb + (gh >> 1) * BLK, row, (gh & 1) * 4 + c), pack8(f));
+          }
         }
       }
       tc_fence_before();
@@ -549,38 +609,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linattn_tc_out_kernel(const __g
       // ---- o -> + bias -> LayerNorm over C -> * g_out + x -> bf16 staging tile -> TMA store
       mbar_wait(smem_u32(&d3_full[grp]), ph);
       tc_fence_after();
-      float o[C];
+      float o[HC];
 #pragma unroll
-      for (int c0 = 0; c0 < C; c0 += 32) {
+      for (int c0 = 0; c0 < HC; c0 += 32) {
         uint32_t ro[32];
-        tmem_ld32(lane_addr + (uint32_t)(HID + c0), ro);
+        tmem_ld32(lane_addr + (uint32_t)(h2 * HC + c0), ro);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) o[c0 + j] = __uint_as_float(ro[j]) + bo_s[c0 + j];
+        for (int j = 0; j < 32; ++j) o[c0 + j] = __uint_as_float(ro[j]) + bo_s[h2 * HC + c0 + j];
       }
       tc_fence_before();
       float s4[4] = {0.0f, 0.0f, 0.0f, 0.0f}, q4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
+      for (int c = 0; c < HC; ++c) {
         s4[c & 3] += o[c];
         q4[c & 3] = fmaf(o[c], o[c], q4[c & 3]);
       }
-      const float mean = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / C);
-      const float var = fmaxf(((q4[0] + q4[1]) + (q4[2] + q4[3])) * (1.0f / C) - mean * mean, 0.0f);
-      const float rstd = rsqrtf(var + p.eps);
+      const float2 stt = ln_stats<C, TPP, EXCH_IN_WB>((s4[0] + s4[1]) + (s4[2] + s4[3]), (q4[0] + q4[1]) + (q4[2] + q4[3]), ex_mine, ex_theirs,
+                                                 1 + grp, p.eps);
 #pragma unroll
-      for (int b = 0; b < KB; ++b)
+      for (int c = 0; c < HC / 8; ++c) {
+        float res[8], f[8];
+        unpack8(lds128(part_addr<C, TPP>(xb, row, h2, c)), res);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float res[8], f[8];
-          unpack8(lds128(sw_addr(xb + b * BLK, row, c)), res);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = fmaf((o[b * 64 + c * 8 + j] - mean) * rstd, go_s[b * 64 + c * 8 + j], res[j]);
-          sts128(sw_addr(wb + b * BLK, row, c), pack8(f));
-        }
+        for (int j = 0; j < 8; ++j) f[j] = fmaf(fmaf(o[c * 8 + j], stt.x, stt.y), go_s[h2 * HC + c * 8 + j], res[j]);
+        sts128(part_addr<C, TPP>(wb, row, h2, c), pack8(f));
+      }
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&x_empty[st]));                   // the residual has been read: the ring stage may be refilled
-      named_bar_sync(1 + grp, 128);
+      named_bar_sync(1 + grp, GT);
       if (gtid == 0) {
         for (int kb = 0; kb < KB; ++kb) tma_store_2d(&maps.out, wb + kb * BLK, kb * 64, (t0 + i) * TM);
         tma_store_commit();
@@ -636,21 +693,24 @@ int launch_tc(const bf16* x, const bf16* wqkv, float shift_log2, const bf16* wou
   p.b_out = b_out;
   p.g_out = g_out;
 
-  const int smem_a = 1024 + KB * BLK + BLK + (C == 64 ? 6 : 3) * KB * BLK + 2 * 2 * BLK;
-  const int smem_b = 1024 + KB * BLK + 2 * C * 128 + (C == 64 ? 4 : 3) * KB * BLK + 2 * 2 * BLK;
+  // measured on B200 (profiles/r02_linattn_tc.txt): at C = 64 three groups with one thread per pixel, at C = 128 (where
+  // shared memory leaves room for two groups only) two threads per pixel
+  constexpr int NG = C == 64 ? 3 : 2, TPP = C == 64 ? 1 : 2;
+  const int smem_a = 1024 + KB * BLK + BLK + (C == 64 ? 6 : 3) * KB * BLK + NG * 2 * BLK;
+  const int smem_b = 1024 + KB * BLK + 2 * C * 128 + (C == 64 ? (NG >= 3 ? 4 : 6) : 3) * KB * BLK + NG * 2 * BLK;
   static bool configured = false;
   if (!configured) {
-    TEDM_CUDA(cudaFuncSetAttribute(linattn_tc_ctx_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a));
-    TEDM_CUDA(cudaFuncSetAttribute(linattn_tc_out_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b));
+    TEDM_CUDA(cudaFuncSetAttribute(linattn_tc_ctx_kernel<C, NG, TPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a));
+    TEDM_CUDA(cudaFuncSetAttribute(linattn_tc_out_kernel<C, NG, TPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b));
     configured = true;
   }
   const int grid_a = items < sms ? (int)items : sms;
-  linattn_tc_ctx_kernel<C><<<grid_a, TC_THREADS, smem_a, s>>>(maps, p);
+  linattn_tc_ctx_kernel<C, NG, TPP><<<grid_a, 64 + NG * 128 * TPP, smem_a, s>>>(maps, p);
   TEDM_LAUNCH_CHECK();
   linattn_tc_combine_kernel<C><<<dim3((unsigned)batch, 4), 256, 0, s>>>(part, wqkv, wout, mimg, chunks, n, scale);
   TEDM_LAUNCH_CHECK();
   const int grid_b = p.total_tiles < sms ? p.total_tiles : sms;
-  linattn_tc_out_kernel<C><<<grid_b, TC_THREADS, smem_b, s>>>(maps, p);
+  linattn_tc_out_kernel<C, NG, TPP><<<grid_b, 64 + NG * 128 * TPP, smem_b, s>>>(maps, p);
   TEDM_LAUNCH_CHECK();
   return TEDM_OK;
 }

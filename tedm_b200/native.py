@@ -466,9 +466,10 @@ def linear_attention_tc_weights(wqkv: torch.Tensor, g_pre: torch.Tensor, heads: 
     q = w . (LN(x) * g) with ||LN(x)||_2 <= sqrt(C), hence |q_r| <= ||w_r * g||_2 sqrt(C) (+ 2 % for the bf16 rounding)."""
     hid = heads * dim_head
     c = wqkv.numel() // (3 * hid)
-    wg = (wqkv.reshape(3 * hid, c).float() * g_pre.reshape(1, c).float()).to(torch.bfloat16).contiguous()
-    bound = float((wg[:2 * hid].float().norm(dim=1).max() * (c ** 0.5) * 1.02 + 1e-3).item())
-    return wg, bound * 1.4426950408889634, bound
+    wf = wqkv.reshape(3 * hid, c).float() * g_pre.reshape(1, c).float()
+    bound = float((wf[:2 * hid].to(torch.bfloat16).float().norm(dim=1).max() * (c ** 0.5) * 1.02 + 1e-3).item())
+    wf[:hid] *= 1.4426950408889634                      # the q rows carry log2(e): the kernel's softmax over d is exp2(q')
+    return wf.to(torch.bfloat16).contiguous(), bound * 1.4426950408889634, bound
 
 
 def linear_attention_block_tc(x, wqkv_g, shift_log2: float, wout, b_out, g_out, heads: int = 4, dim_head: int = 32,
