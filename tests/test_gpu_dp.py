@@ -44,10 +44,13 @@ def _worker(rank, world, port, out):
     lo, hi = rank * 4, rank * 4 + 4
     loss = m.train_step(x[lo:hi].cuda(), t=t[lo:hi].cuda(), noise=nz[lo:hi].cuda())
     loss.backward()
+    grad = opt.flat_grad().clone()
+    dist.all_reduce(grad)                              # what dp_optimizer_step hands to Adam (with grad_scale = 1 / world)
+    grad /= world
     dp_optimizer_step(opt, world)
     torch.cuda.synchronize()
     if rank == 0:
-        torch.save({"flat": opt.flat_param.cpu(), "loss": loss.item()}, out)
+        torch.save({"flat": opt.flat_param.cpu(), "loss": loss.item(), "grad": grad.cpu()}, out)
     dist.destroy_process_group()
 
 
@@ -64,10 +67,17 @@ def test_two_gpu_step_matches_single_gpu_on_the_full_batch(tmp_path):
     before = opt.flat_param.clone()
     x, t, nz = _data()
     m.train_step(x.cuda(), t=t.cuda(), noise=nz.cuda()).backward()
+    grad_ref = opt.flat_grad().clone().cpu()
     opt.step()
     ref = opt.flat_param.cpu()
+    # the mean gradient over the two shards IS the full-batch gradient: per-image arithmetic does not depend on the batch
+    # split, only the fp32 summation order of the weight gradients does
+    g_rel = ((dp["grad"].double() - grad_ref.double()).norm() / grad_ref.double().norm()).item()
+    print(f"DP vs single-GPU gradient: relative difference {g_rel:.3g}")
+    assert g_rel < 1e-3, g_rel
     delta_ref, delta_dp = ref - before.cpu(), dp["flat"] - before.cpu()
-    # Adam's first step moves every weight by lr * sign(g) (up to eps): compare the update directions and sizes
+    # Adam's first step moves every weight by lr * sign(g) (up to eps): a gradient that is zero to rounding can land on
+    # either side, and every such flip costs 2 lr -- hence the looser bound on the update than on the gradient
     agree = (torch.sign(delta_ref) == torch.sign(delta_dp)).float().mean().item()
     rel = ((delta_ref - delta_dp).norm() / delta_ref.norm()).item()
     print(f"DP vs single-GPU update: sign agreement {agree:.5f}, relative difference {rel:.4f}")
@@ -190,7 +200,7 @@ def test_head_training_two_gpus_vs_one(tmp_path, sync):
     errs["loss"] = abs(dp["loss"] - ref["loss"]) / abs(ref["loss"])
     print(f"head training, 2 GPUs vs 1 (sync_bn={sync}):", errs)
     if sync:
-        assert errs["loss"] < 1e-5 and errs["rm"] < 1e-5 and errs["rv"] < 1e-4 and errs["grads"] < 2e-2 and errs["flat"] < 1e-4, errs
+        assert errs["loss"] < 1e-5 and errs["rm"] < 1e-5 and errs["rv"] < 1e-4 and errs["grads"] < 1e-3 and errs["flat"] < 1e-3, errs
     else:
         # per-replica statistics: running buffers are rank 0's shard's, the loss differs in the third digit
         assert errs["loss"] < 5e-2 and errs["grads"] < 0.5, errs
