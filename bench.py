@@ -457,12 +457,19 @@ def run_ours(args):
                 fh.write(f"{shp} | {cnt:3d} {t_ms:9.3f} {fl / (t_ms * 1e-3) / 1e12:8.1f} {100 * t_ms / conv_ms:6.1f}%\n")
     pk = peaks()
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    # DRAM traffic of the dominant conv launch (3x3 64->64 @128x128, 128 images): dram__bytes_read + write of ONE launch from
+    # an `ncu --set full` capture of this very command, parsed into profiles/r02_conv_traffic.json by
+    # scripts/conv_traffic.py (null when that file is absent -- never a literal)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r02_conv_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj
     roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (all conv launches of one step)", "achieved": achieved,
                 "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
                 "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
-                # ncu --set full, dominant launch (3x3 64->64 @128x128, 128 images): dram read + write per launch; the
-                # algorithmic in+out of that launch is 536.9 MB (profiles/r01_h_ncu_full_conv_kernels.txt)
-                "traffic": 496.1e6, "traffic_unit": "bytes/launch (conv_igemm_kernel<64,WS,GN>, B*S=128)",
+                "traffic": traffic, "traffic_unit": "bytes/launch of the dominant launch (see traffic_source)",
+                "traffic_source": traffic_src,
                 "conv_launches_per_step": len(records), "conv_ms_per_step": conv_ms,
                 "conv_share_of_step": conv_ms / (ms / args.steps) if ms > 0 else None,
                 "conv_gflop_per_step": conv_fl / 1e9}
@@ -488,6 +495,19 @@ def run_ours(args):
                        "executed_conv_gflop_per_image": conv_flops_step / B / 1e9,
                        "frac_of_sustained_peak_minimal_form": value * GFLOP_TEDM_MIN / 1e3 / (pk["tflops_sustained"] * world)},
             "roofline": roofline, "roofline_hbm": roofline_hbm, "clocks": clocks.summary()}
+    # ---- the same workload in the fp32 precision mode (the reference's default arithmetic; 1e-4 parity, tests/test_gpu_fp32.py)
+    if rank == 0 and world == 1 and not args.no_fp32:
+        model.set_precision("fp32")
+        try:
+            for i in range(2):
+                step_resident(i)
+            n32 = max(2, args.steps // 2)
+            ms32 = timed(step_resident, n32)
+            line["fp32_mode"] = {"dtype": "f32", "value": B * n32 / (ms32 * 1e-3), "unit": "images/s", "ms_per_step": ms32 / n32,
+                                 "steps": n32, "arithmetic": "fp32 storage; convs as split-bf16 (hi*hi + lo*hi + hi*lo) on tcgen05, "
+                                 "fp32 accumulation; GroupNorm / LayerNorm / attention / head in fp32"}
+        finally:
+            model.set_precision("bf16")
     # ---- second half of BASELINE.json's metric: the DDPM pre-training step (UNet fwd+bwd TFLOP/s vs bf16 peak) ----
     del model, resident, noise
     torch.cuda.empty_cache()
@@ -592,6 +612,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step (config.py:58 default 16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the DDPM training-step leg")
+    ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-precision-mode leg")
     ap.add_argument("--train-batches", type=int, nargs="+", default=[16, 64, 128],
                     help="per-GPU batch sizes of the training leg (config.py:58 default is 16)")
     args = ap.parse_args()

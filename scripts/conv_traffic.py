@@ -1,0 +1,36 @@
+#!/usr/bin/env python
+"""profiles/r02_conv_traffic.json from an `ncu --set full` raw CSV of the bench command restricted to conv_igemm_kernel:
+the launch with the longest duration (the dominant 3x3 64->64 @128x128 weight-stationary conv), its DRAM bytes and the
+algorithmic bytes of that launch.   usage: python scripts/conv_traffic.py gpurun_out/<tag>_raw.csv [out.json]"""
+import csv
+import json
+import sys
+
+
+def main(path, out):
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    ix = {h: i for i, h in enumerate(hdr)}
+
+    def val(r, key):
+        v, u = float(r[ix[key]].replace(",", "")), units[ix[key]]
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6, "usecond": 1, "nsecond": 1e-3, "msecond": 1e3}.get(u, 1)
+        return v * scale
+
+    convs = [r for r in rows[2:] if "conv_igemm_kernel" in r[ix["Kernel Name"]]]
+    best = max(convs, key=lambda r: val(r, "gpu__time_duration.sum"))
+    rd, wr = val(best, "dram__bytes_read.sum"), val(best, "dram__bytes_write.sum")
+    grid = best[ix["launch__grid_size"]]
+    res = {"kernel": best[ix["Kernel Name"]].strip(), "launches_captured": len(convs), "grid": grid,
+           "duration_us_under_ncu": val(best, "gpu__time_duration.sum"), "dram_bytes_read": rd, "dram_bytes_write": wr,
+           "dram_bytes_per_launch": rd + wr,
+           "algorithmic_bytes_per_launch": 2 * 128 * 128 * 128 * 64 * 2,
+           "algorithmic": "in + out of a 3x3 64->64 conv at 128x128 over 128 (image, timestep) pairs, bf16: 2 x 268.4 MB",
+           "source": "ncu --set full --clock-control none of `bench.py --steps 1 --warmup 1 --no-train --no-cpu-baseline --no-fp32` "
+                     "(scripts/profile_round2.sh); the dominant launch = the longest conv_igemm_kernel launch captured"}
+    json.dump(res, open(out, "w"), indent=1)
+    print(json.dumps(res, indent=1))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else "profiles/r02_conv_traffic.json")

@@ -113,7 +113,7 @@ class DatasetDM(nn.Module):
     def _segment_graphed(self, x: Tensor, noise: Optional[Tensor]):
         if not x.is_cuda:
             raise RuntimeError("tedm_b200.DatasetDM runs on CUDA (sm_100a) only; there is no CPU fallback")
-        sig = (tuple(x.shape), noise is not None,
+        sig = (tuple(x.shape), noise is not None, self.precision,
                tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers())))
         g = getattr(self, "_seg_graph", None)
         if g is None or g["sig"] != sig:
