@@ -593,6 +593,7 @@ def train_leg(args, dev, world, rank, pk, barrier):
             "tflops_fwd_bwd": ips * GFLOP_TRAIN / 1e3, "frac_of_sustained_bf16_peak": ips * GFLOP_TRAIN / 1e3 / (pk["tflops_sustained"] * world),
             "e2e_images_per_s": world * B * args.steps / (ms_e2e * 1e-3), "h2d_bytes_per_step": B * IMG * IMG * 4,
             "d2h_bytes_per_step": 4, "native_calls_per_step": step.native_calls_per_step, "loss_last": losses[-1]}
+        step.close()
         del step
         torch.cuda.empty_cache()
     best = max((k for k in out if k.startswith("batch")), key=lambda k: out[k]["tflops_fwd_bwd"])

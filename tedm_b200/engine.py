@@ -102,6 +102,9 @@ class UnetEngine:
             off += rb.time_mlp[1].weight.shape[0]
         self._ss_total = off
         self.last_grad_arena: Optional[GradArena] = None
+        # data parallelism: an object with early(flat_slice) / late(tensors) that sums gradient regions over ranks WHILE the
+        # backward is still running (tedm_b200/train.py: GradReducer); None = the caller reduces afterwards
+        self.grad_reducer = None
         # every implicit-GEMM conv weight of the net: key -> (parameter, forward mode); re-laid out in ONE launch
         self._wspec: Dict[str, Tuple[nn.Parameter, int]] = {}
         self._wsig = None
@@ -516,6 +519,14 @@ class UnetEngine:
         dh, _ = self._resblock_bwd("mid_block2", m.mid_block2, dh, tape, G, tproj, dss)
         dh = self._mid_attention_bwd("mid_attn", m.mid_attn, dh, tape, G)
         dh, _ = self._resblock_bwd("mid_block1", m.mid_block1, dh, tape, G, tproj, dss)
+        tail_lo = None
+        if self.grad_reducer is not None:
+            # every parameter from `ups` to the end of the arena (decoder, mid blocks, output convs) has its gradient now,
+            # except the per-block time projections, which are reduced separately below: start summing that region over
+            # the ranks while the encoder's backward runs.  Weight gradients live on the side stream, so the reducer's
+            # stream has to wait for both.
+            tail_lo = G.offsets[id(next(m.ups.parameters()))][0]
+            self.grad_reducer.early(G.flat[tail_lo:], self._side if self._keep else None)
         for i in reversed(range(len(m.downs))):
             b1, b2, attn, down = m.downs[i]
             k = f"downs.{i}"
@@ -530,15 +541,23 @@ class UnetEngine:
             dh, _ = self._resblock_bwd(k + ".0", b1, dh, tape, G, tproj, dss)
         dstem = N.add_bf16(dh, dstem_skip)
         N.stem_conv7x7_wgrad(x, dstem, G.of(m.init_conv.weight), G.of(m.init_conv.bias))
-        if tproj is not None:
-            self._time_bwd(tape, dss, G)
+        tgrads = self._time_bwd(tape, dss, G) if tproj is not None else None
         if self._side is not None and self._keep:
             torch.cuda.current_stream().wait_stream(self._side)            # join: every weight gradient has landed
         self._keep.clear()
+        if self.grad_reducer is not None:
+            # the encoder half of the arena + the concatenated time-projection gradients; then (after both regions have
+            # been summed) the time projections are scattered to their owners inside the arena
+            late = [G.flat[:tail_lo]] + ([tgrads[0].view(-1), tgrads[1]] if tgrads is not None else [])
+            self.grad_reducer.late(late)
+        if tgrads is not None:
+            self._time_scatter(tgrads, G)
         self.last_grad_arena = G
         return G
 
-    def _time_bwd(self, tape: Tape, dss: Tensor, G: GradArena) -> None:
+    def _time_bwd(self, tape: Tape, dss: Tensor, G: GradArena):
+        """Backward of the time MLPs; returns the gradients of the CONCATENATED per-block projections (weight, bias) for
+        `_time_scatter` -- kept apart so that a data-parallel reducer can sum them before they are scattered."""
         m = self.m
         emb, hid, temb = tape.saved["time"]
         wcat, _ = self._time_cat()
@@ -550,6 +569,10 @@ class UnetEngine:
                           G.of(m.time_mlp[3].weight), G.of(m.time_mlp[3].bias))
         N.linear_bwd(d2, hid, N.ACT_GELU, emb, N.ACT_NONE, self._f32(m.time_mlp[1].weight),
                      G.of(m.time_mlp[1].weight), G.of(m.time_mlp[1].bias), want_dx=False)
+        return dwcat, dbcat
+
+    def _time_scatter(self, tgrads, G: GradArena) -> None:
+        dwcat, dbcat = tgrads
         off = 0
         for rb in self._resblocks:      # scatter the concatenated projection gradient back to its owners
             lin = rb.time_mlp[1]

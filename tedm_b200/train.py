@@ -6,8 +6,11 @@ reference's batch size of 16 the GPU finishes them faster than Python can issue 
 launch-bound sequence is captured once and replayed:
 
     graph A: zero_grad -> weight re-layout -> q_sample -> UNet fwd -> L1/p2 loss -> UNet bwd   (gradient arena)
-    [world > 1] ONE NCCL all-reduce of the flat gradient arena (sum; the 1/world goes into Adam's grad_scale)
+             [world > 1] the gradient all-reduce is INSIDE this graph, on a communication stream, in two regions: the
+             decoder / mid / output half of the arena is summed over the ranks while the encoder's backward still runs,
+             the encoder half (+ the time projections) at the end (sum; the 1/world goes into Adam's grad_scale)
     graph B: fused Adam over the flat parameter / moment arenas -> version bump
+If NCCL cannot be captured on this build, the step falls back to ONE all-reduce of the whole arena between the two graphs.
 
 Shapes are static (batch, image size); timesteps and noise are drawn inside the graph by torch's
 graph-safe Philox generator, exactly where the reference draws them (diffusion_model.py:126-129,193).
@@ -22,6 +25,33 @@ from torch import Tensor
 
 from .models.diffusion_model import DiffusionModel
 from .optim import FusedAdam
+
+
+class GradReducer:
+    """Sums regions of the gradient arena over the ranks on its own stream while the backward pass is still producing the
+    rest (hooked into tedm_b200.engine.UnetEngine.backward).  Bucket sizes follow the backward's structure, not a link
+    count: NVSwitch gives every pair of GPUs full bandwidth, so two large collectives cost two launch latencies."""
+
+    def __init__(self, device):
+        self.comm = torch.cuda.Stream(device=device)
+        self.collectives = 0
+
+    def early(self, flat_slice: Tensor, side: Optional[torch.cuda.Stream]) -> None:
+        self.comm.wait_stream(torch.cuda.current_stream())
+        if side is not None:
+            self.comm.wait_stream(side)                       # weight gradients are written on the engine's side stream
+        with torch.cuda.stream(self.comm):
+            dist.all_reduce(flat_slice, op=dist.ReduceOp.SUM)
+        self.collectives += 1
+
+    def late(self, tensors) -> None:
+        cur = torch.cuda.current_stream()
+        self.comm.wait_stream(cur)
+        with torch.cuda.stream(self.comm):
+            for t in tensors:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                self.collectives += 1
+        cur.wait_stream(self.comm)                            # join: Adam (and the time-projection scatter) see reduced gradients
 
 
 class GraphedTrainStep:
@@ -39,21 +69,41 @@ class GraphedTrainStep:
         self._params = [p for p in model.parameters() if p.requires_grad]
         self._flat: Optional[Tensor] = None      # the gradient arena graph A writes and graph B reads (fixed at capture)
         self._hyper = None                       # optimiser hyper-parameters frozen into graph B
+        # overlapped, in-graph gradient reduction (world > 1); TEDM_DP_OVERLAP=0 keeps the single all-reduce between the graphs
+        import os
+        self.reducer: Optional[GradReducer] = None
+        if self.world > 1 and os.environ.get("TEDM_DP_OVERLAP", "1") != "0":
+            self.reducer = GradReducer(example.device)
         if use_graph:
-            self._capture(warmup)
+            try:
+                self._capture(warmup)
+            except Exception as e:                                   # NCCL not capturable here: fall back, loudly
+                if self.reducer is None:
+                    raise
+                print(f"GraphedTrainStep: in-graph gradient reduction unavailable ({type(e).__name__}: {str(e)[:120]}); "
+                      "using one all-reduce between the graphs")
+                torch.cuda.synchronize()
+                self.reducer = None
+                self._ga = self._gb = None
+                self._capture(warmup)
 
     # -- the two halves of a step ---------------------------------------------------------------
     def _fwd_bwd(self) -> None:
         self.opt.zero_grad(set_to_none=True)
         loss = self.model.train_step(self.x)
-        loss.backward()
+        eng = self.model.model.engine
+        eng.grad_reducer = self.reducer
+        try:
+            loss.backward()
+        finally:
+            eng.grad_reducer = None
         self.loss.copy_(loss.detach())
 
     def _update(self, flat: Optional[Tensor] = None) -> None:
         self.opt.step(grad_scale=1.0 / self.world, flat_grad=flat)
 
     def _allreduce(self, flat: Optional[Tensor] = None) -> None:
-        if self.world > 1:
+        if self.world > 1 and self.reducer is None:              # with a reducer the sums happened inside _fwd_bwd
             dist.all_reduce(self.opt.flat_grad() if flat is None else flat, op=dist.ReduceOp.SUM)
 
     def _hyper_sig(self):
@@ -114,6 +164,13 @@ class GraphedTrainStep:
         self.native_calls_per_step = N.launches - l0     # native entry points inside one replayed step
 
     # -- public ---------------------------------------------------------------------------------
+    def close(self) -> None:
+        """Release the CUDA graphs.  With the in-graph gradient reduction they hold captured NCCL operations, and
+        `dist.destroy_process_group()` waits for those: close the step (or drop it) BEFORE tearing the process group down."""
+        torch.cuda.synchronize()
+        self._ga = self._gb = None
+        self._flat = None
+
     def __call__(self, x: Tensor) -> Tensor:
         """One optimiser step on batch x (same shape as the example); returns the loss (device scalar)."""
         if x.shape != self.x.shape:

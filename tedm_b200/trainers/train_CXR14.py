@@ -58,6 +58,8 @@ def train(config, model, optimizer, train_loader, val_loader, logger, scaler=Non
                         save(model, optimizer, config, os.path.join(str(config.log_dir), "best_model.pt"), step)
 
             if step >= config.max_steps or config.debug:
+                if graphed is not None:
+                    graphed.close()             # captured NCCL work must be gone before the process group is torn down
                 return model
 
 

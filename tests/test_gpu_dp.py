@@ -111,7 +111,9 @@ def _worker_graphed(rank, world, port, out):
     gathered = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
     if rank == 0:
-        torch.save({"equal": all(torch.equal(gathered[0], g) for g in gathered[1:]), "step": opt._step}, out)
+        torch.save({"equal": all(torch.equal(gathered[0], g) for g in gathered[1:]), "step": opt._step,
+                    "in_graph_reduction": step.reducer is not None}, out)
+    step.close()                                    # the graphs hold captured NCCL work: release them before the group
     dist.destroy_process_group()
 
 
@@ -124,6 +126,7 @@ def test_graphed_dp_replicas_stay_bit_identical_across_an_eager_step(tmp_path):
     out = str(tmp_path / "dpg.pt")
     mp.spawn(_worker_graphed, args=(2, _free_port(), out), nprocs=2, join=True)
     res = torch.load(out)
+    print("graphed DP:", res)
     assert res["equal"] and res["step"] == 7, res
 
 
