@@ -527,6 +527,7 @@ class UnetEngine:
             # stream has to wait for both.
             tail_lo = G.offsets[id(next(m.ups.parameters()))][0]
             self.grad_reducer.early(G.flat[tail_lo:], self._side if self._keep else None)
+        level_hi = tail_lo
         for i in reversed(range(len(m.downs))):
             b1, b2, attn, down = m.downs[i]
             k = f"downs.{i}"
@@ -539,6 +540,12 @@ class UnetEngine:
             dh, _ = self._resblock_bwd(k + ".1", b2, dh, tape, G, tproj, dss)
             dh = N.add_bf16(dh, d_b1_skip)
             dh, _ = self._resblock_bwd(k + ".0", b1, dh, tape, G, tproj, dss)
+            if self.grad_reducer is not None:
+                # this encoder level's slice of the arena is complete (its time projections aside): the deepest level,
+                # which holds most of the encoder's parameters, finishes first
+                lo = G.offsets[id(next(m.downs[i].parameters()))][0]
+                self.grad_reducer.early(G.flat[lo:level_hi], self._side if self._keep else None)
+                level_hi = lo
         dstem = N.add_bf16(dh, dstem_skip)
         N.stem_conv7x7_wgrad(x, dstem, G.of(m.init_conv.weight), G.of(m.init_conv.bias))
         tgrads = self._time_bwd(tape, dss, G) if tproj is not None else None
@@ -546,9 +553,9 @@ class UnetEngine:
             torch.cuda.current_stream().wait_stream(self._side)            # join: every weight gradient has landed
         self._keep.clear()
         if self.grad_reducer is not None:
-            # the encoder half of the arena + the concatenated time-projection gradients; then (after both regions have
-            # been summed) the time projections are scattered to their owners inside the arena
-            late = [G.flat[:tail_lo]] + ([tgrads[0].view(-1), tgrads[1]] if tgrads is not None else [])
+            # what is left: the stem and the time MLP at the head of the arena + the concatenated time-projection gradients;
+            # then (after every region has been summed) the time projections are scattered to their owners in the arena
+            late = [G.flat[:level_hi]] + ([tgrads[0].view(-1), tgrads[1]] if tgrads is not None else [])
             self.grad_reducer.late(late)
         if tgrads is not None:
             self._time_scatter(tgrads, G)
