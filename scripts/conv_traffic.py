@@ -21,11 +21,17 @@ def main(path, out):
     best = max(convs, key=lambda r: val(r, "gpu__time_duration.sum"))
     rd, wr = val(best, "dram__bytes_read.sum"), val(best, "dram__bytes_write.sum")
     grid = best[ix["launch__grid_size"]]
+    t = 128 * 128 * 128 * 64 * 2          # one 64-channel bf16 map at 128 x 128 over 128 (image, timestep) pairs: 268.4 MB
+    # conv_igemm_kernel<64, WS, GN> serves two shapes at 128 x 128: 64 -> 64 (one input map) and the decoder's (64 + 64) -> 64
+    # (two input maps, the skip concat that is never materialised); the DRAM read volume tells which one the longest launch is
+    n_in = 2 if rd > 1.5 * t else 1
     res = {"kernel": best[ix["Kernel Name"]].strip(), "launches_captured": len(convs), "grid": grid,
            "duration_us_under_ncu": val(best, "gpu__time_duration.sum"), "dram_bytes_read": rd, "dram_bytes_write": wr,
            "dram_bytes_per_launch": rd + wr,
-           "algorithmic_bytes_per_launch": 2 * 128 * 128 * 128 * 64 * 2,
-           "algorithmic": "in + out of a 3x3 64->64 conv at 128x128 over 128 (image, timestep) pairs, bf16: 2 x 268.4 MB",
+           "algorithmic_bytes_per_launch": (n_in + 1) * t,
+           "traffic_over_algorithmic": (rd + wr) / ((n_in + 1) * t),
+           "algorithmic": f"{n_in} input map(s) + 1 output map of a 3x3 conv to 64 channels at 128x128 over 128 (image, timestep) "
+                          f"pairs, bf16: {n_in + 1} x 268.4 MB",
            "source": "ncu --set full --clock-control none of `bench.py --steps 1 --warmup 1 --no-train --no-cpu-baseline --no-fp32` "
                      "(scripts/profile_round2.sh); the dominant launch = the longest conv_igemm_kernel launch captured"}
     json.dump(res, open(out, "w"), indent=1)
