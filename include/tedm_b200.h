@@ -157,6 +157,10 @@ TEDM_API int64_t tedm_conv_igemm_wgrad_workspace(void);
 /* 1: every convolution weight gradient is bit-reproducible from run to run (torch.use_deterministic_algorithms-style
  * opt-in); 0 (default): the generic kernel's split-K slices add in arrival order. */
 TEDM_API int tedm_conv_set_deterministic(int enable);
+/* 1 (default): 3x3 / 4x4 / folded-upsample convolutions over >= 128 input channels whose N tile is <= 128 run as CTA pairs
+ * (tcgen05 cta_group::2, clusters of two SMs: M = 256, each CTA stages its own pixels and half of the weight tile);
+ * 0: one CTA per tile everywhere; 2: pairs wherever the geometry allows (tests, A/B runs). */
+TEDM_API int tedm_conv_set_cta_pairs(int enable);
 /* number of partial-statistics slots per image that tedm_conv_igemm_fwd writes for this output extent */
 TEDM_API int tedm_conv_gn_parts(int out_height, int out_width);
 /* tuning/debug: force the N tile (64/128/256; 0 = automatic) of tedm_conv_igemm_fwd */

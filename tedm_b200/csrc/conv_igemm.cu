@@ -58,6 +58,7 @@ struct ConvParams {
   int src_blocks[MAX_SRC], src_C[MAX_SRC];
   int src_center[MAX_SRC];       // 1: feeds only the centre tap of a 3x3 (a folded 1x1 branch)
   int num_kb;                    // k-blocks per tile
+  int cg;                        // host only: 2 = launch as CTA pairs (cta_group::2)
   int tileW, tileH, tileB, tiles_x, tiles_y;
   int B, Ho, Wo;                 // tile space extent (output pixels; source pixels for mode 3)
   int OH, OW, osy, osx;          // output tensor extent and tile->output coordinate scale
@@ -119,14 +120,17 @@ __device__ __forceinline__ void butterfly_sum(float (&vals)[NV], int lane, int w
 struct TileCoord {
   int b0, y0, x0, n0, par, trem;
 };
-__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, int bn) {
+// `tile` counts the tiles of one CTA, or (CG = 2) of a CTA pair: the pair shares the N tile and the parity and takes two
+// consecutive M tiles, one per CTA (`rank`).
+template <int CG>
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, int bn, int rank) {
   TileCoord t;
   // one real division (n_tiles may be 3, 6, 12); everything else is a power of two -- the producer thread decodes a
   // tile per handful of k-blocks on the 1x1 convolutions
   const int rest = tile / p.n_tiles;
   const int nt = tile - rest * p.n_tiles;
   t.par = rest & (p.zdim - 1);
-  const int mt = rest >> p.z_shift;
+  const int mt = (rest >> p.z_shift) * CG + rank;
   const int bg = mt >> p.tpg_shift;
   t.trem = mt & ((1 << p.tpg_shift) - 1);
   t.b0 = bg * p.tileB;
@@ -149,16 +153,22 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, 
 constexpr int EPI_THREADS = 256;   // 8 epilogue warps
 constexpr int CONV_THREADS = 64 + EPI_THREADS;
 
-template <int BN, bool WS, int CPG, bool RES>
+//   CG = 2: CTA PAIRS (cta_group::2, cluster of two SMs of one TPC).  One tcgen05.mma spans both SMs: M = 256 = the two
+//               CTAs' 128-pixel tiles, each CTA feeds its own A rows and HALF of the weight tile (N / 2 rows), the
+//               hardware shares the halves.  Per SM and UMMA the shared-memory read drops from A 4 KB + B (BN / 32) KB to
+//               A 4 KB + B (BN / 64) KB -- what bounds the N = 64 / 128 tiles.  Only the leader CTA (rank 0) issues MMAs;
+//               both issue TMA, all transaction bytes land on the leader's barriers; tcgen05.commit multicasts to both.
+template <int BN, bool WS, int CPG, bool RES, int CG>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   const CUtensorMap& mapW = maps.w;
   const CUtensorMap& mapOut = maps.out;
   const CUtensorMap& mapOut2 = maps.out2;
-  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int BNC = BN / CG;                     // weight rows (output channels) this CTA stages per tile
+  constexpr int B_BYTES = BNC * BK * 2;
   constexpr int STAGE_BYTES = WS ? A_ROW_BYTES : A_BYTES + B_BYTES;
   constexpr int OUT_BYTES = (BN / 64) * A_BYTES;
-  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[MAX_STAGES];
@@ -188,38 +198,54 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bar_acc_full[i]), 1);
-      mbar_init(smem_u32(&bar_acc_empty[i]), EPI_THREADS / 32);
+      mbar_init(smem_u32(&bar_acc_empty[i]), CG * (EPI_THREADS / 32));     // the leader's copy hears both CTAs' epilogues
     }
     mbar_init(smem_u32(&bar_w), 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<2 * BN>(smem_u32(&tmem_slot));
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_alloc_pair<2 * BN>(smem_u32(&tmem_slot));
+    else tmem_alloc<2 * BN>(smem_u32(&tmem_slot));
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();        // the peer's barriers exist before anything is sent to them
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG, tile_end = p.num_tiles / CG;
 
   if (warp == 0) {
     // ===== TMA producer =====================================================================
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      // CG = 2: both CTAs load (their A rows, their half of the weights); the bytes are counted on the LEADER's barrier,
+      // which only the leader arms
+      auto load5 = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+        if constexpr (CG == 2) tma_load_5d_pair(dst, m, bar, c0, c1, c2, c3, c4);
+        else tma_load_5d(dst, m, bar, c0, c1, c2, c3, c4);
+      };
+      auto load2 = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+        if constexpr (CG == 2) tma_load_2d_pair(dst, m, bar, c0, c1);
+        else tma_load_2d(dst, m, bar, c0, c1);
+      };
       if (WS) {
         const uint32_t bw = smem_u32(&bar_w);
-        mbar_expect_tx(bw, w_bytes);
-        for (int i = 0; i < 9 * cb_total; ++i) tma_load_2d(smem_base + (uint32_t)i * B_BYTES, &mapW, bw, i * BK, 0);
+        if (rank == 0) mbar_expect_tx(bw, CG * w_bytes);
+        for (int i = 0; i < 9 * cb_total; ++i) load2(smem_base + (uint32_t)i * B_BYTES, &mapW, bw, i * BK, rank * BNC);
       }
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile, BN);
+      for (int tile = tile0; tile < tile_end; tile += tile_step) {
+        const TileCoord t = decode_tile<CG>(p, tile, BN, rank);
         if (WS) {
           for (int dy = 0; dy < 3; ++dy)
             for (int cb = 0; cb < cb_total; ++cb) {
               mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
               const uint32_t full = smem_u32(&bar_full[stage]);
-              mbar_expect_tx(full, ROW_PIX * BK * 2);
+              if (rank == 0) mbar_expect_tx(full, CG * ROW_PIX * BK * 2);
               const bool second = cb >= p.c0_blocks;
-              tma_load_5d(stage_base + stage * STAGE_BYTES, &maps.a[second ? 1 : 0], full,
-                          (second ? cb - p.c0_blocks : cb) * BK, t.x0 - 1, 0, t.y0 + dy - 1, t.b0);
+              load5(stage_base + stage * STAGE_BYTES, &maps.a[second ? 1 : 0], full,
+                    (second ? cb - p.c0_blocks : cb) * BK, t.x0 - 1, 0, t.y0 + dy - 1, t.b0);
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1u;
@@ -253,10 +279,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                 for (int cblk = 0; cblk < p.src_blocks[si]; ++cblk, ++kb) {
                   mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
                   const uint32_t full = smem_u32(&bar_full[stage]);
-                  mbar_expect_tx(full, STAGE_BYTES);
+                  if (rank == 0) mbar_expect_tx(full, CG * STAGE_BYTES);
                   const uint32_t a_dst = stage_base + stage * STAGE_BYTES;
-                  tma_load_5d(a_dst, mapA, full, chan_off + cblk * BK, t.x0 + offx, pc, t.y0 + offy, t.b0);
-                  tma_load_2d(a_dst + A_BYTES, &mapW, full, kb * BK, t.par * p.cout + t.n0);
+                  load5(a_dst, mapA, full, chan_off + cblk * BK, t.x0 + offx, pc, t.y0 + offy, t.b0);
+                  load2(a_dst + A_BYTES, &mapW, full, kb * BK, t.par * p.cout + t.n0 + rank * BNC);
                   if (++stage == p.stages) {
                     stage = 0;
                     phase ^= 1u;
@@ -269,15 +295,23 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer =========================================================================
-    if (elect_one()) {
+    // ===== MMA issuer (CG = 2: the leader CTA's, for the pair) ================================
+    auto umma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+      if constexpr (CG == 2) umma_bf16_pair(d, a, b, IDESC, acc);
+      else umma_bf16(d, a, b, IDESC, acc);
+    };
+    auto commit = [&](uint32_t bar) {
+      if constexpr (CG == 2) umma_commit_pair(bar);
+      else umma_commit(bar);
+    };
+    if (rank == 0 && elect_one()) {
       int stage = 0, it = 0;
       uint32_t phase = 0;
       if (WS) {
         mbar_wait(smem_u32(&bar_w), 0);
         tc_fence_after();
       }
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < tile_end; tile += tile_step, ++it) {
         const int buf = it & 1;
         mbar_wait(smem_u32(&bar_acc_empty[buf]), (uint32_t)(((it >> 1) & 1) ^ 1));
         tc_fence_after();
@@ -293,10 +327,9 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                 const uint64_t adesc = make_sw128_desc(a_addr + (uint32_t)dx * 128u);
                 const uint64_t bdesc = make_sw128_desc(smem_base + (uint32_t)(((dy * 3 + dx) * cb_total + cb) * B_BYTES));
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)
-                  umma_bf16(d_tmem, adesc + 2ull * k, bdesc + 2ull * k, IDESC, (dy | cb | dx | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < BK / 16; ++k) umma(d_tmem, adesc + 2ull * k, bdesc + 2ull * k, (dy | cb | dx | k) != 0 ? 1u : 0u);
               }
-              umma_commit(smem_u32(&bar_empty[stage]));
+              commit(smem_u32(&bar_empty[stage]));
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1u;
@@ -310,16 +343,15 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
             const uint32_t a_addr = stage_base + stage * STAGE_BYTES;
             const uint64_t adesc = make_sw128_desc(a_addr), bdesc = make_sw128_desc(a_addr + A_BYTES);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_bf16(d_tmem, adesc + 2ull * k, bdesc + 2ull * k, IDESC, (kb | k) != 0 ? 1u : 0u);
-            umma_commit(smem_u32(&bar_empty[stage]));
+            for (int k = 0; k < BK / 16; ++k) umma(d_tmem, adesc + 2ull * k, bdesc + 2ull * k, (kb | k) != 0 ? 1u : 0u);
+            commit(smem_u32(&bar_empty[stage]));
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1u;
             }
           }
         }
-        umma_commit(smem_u32(&bar_acc_full[buf]));
+        commit(smem_u32(&bar_acc_full[buf]));
       }
     }
     __syncwarp();
@@ -340,8 +372,8 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     const int ty = rrem / p.tileW, tx = rrem % p.tileW;
     const int seg_size = hwt < 32 ? hwt : 32;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const TileCoord t = decode_tile(p, tile, BN);
+    for (int tile = tile0; tile < tile_end; tile += tile_step, ++it) {
+      const TileCoord t = decode_tile<CG>(p, tile, BN, rank);
       const int par_y = t.par >> 1, par_x = t.par & 1;
       const int b = t.b0 + tb, y = t.y0 + ty, x = t.x0 + tx;
       const bool valid = b < p.B;
@@ -448,7 +480,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
       // this accumulator buffer is free for the MMA issuer again
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[buf]));
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_leader(smem_u32(&bar_acc_empty[buf]));
+        else mbar_arrive(smem_u32(&bar_acc_empty[buf]));
+      }
       if (CPG) {
         butterfly_sum<NV>(gv, lane, seg_size);
         const int ls = lane & (seg_size - 1);
@@ -497,7 +532,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<2 * BN>(tmem_base);
+  if constexpr (CG == 2) cluster_sync_all();        // neither CTA leaves (or frees TMEM) while the pair's MMAs can still touch it
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_dealloc_pair<2 * BN>(tmem_base);
+    else tmem_dealloc<2 * BN>(tmem_base);
+  }
 }
 
 int encode_act_map(CUtensorMap* map, const void* ptr, int B, int H, int W, int C, long long image_stride, int mode,
@@ -538,12 +577,13 @@ int encode_weight_map(CUtensorMap* map, const void* ptr, long long rows, long lo
   return TEDM_OK;
 }
 
-template <int BN, bool WS, int CPG, bool RES>
-int launch_conv_res(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
+template <int BN, bool WS, int CPG, bool RES, int CG>
+int launch_conv_cg(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
   const int cb_total = p.c0_blocks + p.c1_blocks;
-  const int stage_bytes = WS ? A_ROW_BYTES : A_BYTES + BN * BK * 2;
+  const int b_bytes = (BN / CG) * BK * 2;            // per-CTA share of a weight tile
+  const int stage_bytes = WS ? A_ROW_BYTES : A_BYTES + b_bytes;
   const int out_bytes = (BN / 64) * A_BYTES;
-  const int base = 1024 + (WS ? 9 * cb_total * BN * BK * 2 : 0);
+  const int base = 1024 + (WS ? 9 * cb_total * b_bytes : 0);
   // double-buffer the output staging tile when that still leaves >= 4 pipeline slots
   p.out_bufs = (DYN_SMEM_MAX - base - 2 * out_bytes) / stage_bytes >= 4 ? 2 : 1;
   const int fixed = base + p.out_bufs * out_bytes;
@@ -554,13 +594,38 @@ int launch_conv_res(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
   const int smem = fixed + stages * stage_bytes;
   static int configured = 0;
   if (configured < smem) {
-    TEDM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, WS, CPG, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TEDM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, WS, CPG, RES, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  int grid = p.num_tiles < tedm_num_sms() ? p.num_tiles : tedm_num_sms();
-  conv_igemm_kernel<BN, WS, CPG, RES><<<grid, CONV_THREADS, smem, stream>>>(maps, p);
+  const int work = p.num_tiles / CG;                   // tiles per CTA (pair)
+  int grid = (work < tedm_num_sms() / CG ? work : tedm_num_sms() / CG) * CG;
+  if constexpr (CG == 1) {
+    conv_igemm_kernel<BN, WS, CPG, RES, 1><<<grid, CONV_THREADS, smem, stream>>>(maps, p);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(CONV_THREADS);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TEDM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, WS, CPG, RES, 2>, maps, p));
+  }
   TEDM_LAUNCH_CHECK();
   return TEDM_OK;
+}
+
+template <int BN, bool WS, int CPG, bool RES>
+int launch_conv_res(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
+  if constexpr (BN <= 128) {
+    if (p.cg == 2) return launch_conv_cg<BN, WS, CPG, RES, 2>(maps, p, stream);
+  }
+  return launch_conv_cg<BN, WS, CPG, RES, 1>(maps, p, stream);
 }
 
 // residual / split-output epilogues exist only without GroupNorm statistics (they never co-occur in the net)
@@ -1062,6 +1127,7 @@ int g_enable_wgrad3 = 1;  // tedm_conv_set_wgrad_halo: 0 off, 1 automatic, 2 whe
 int g_deterministic = 0;  // tedm_conv_set_deterministic
 
 int g_enable_ws = 1;  // tedm_conv_set_ws
+int g_enable_pairs = 1;  // tedm_conv_set_cta_pairs
 int g_force_bn = 0;  // debug/tuning override (tedm_conv_set_tile_n)
 
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -1081,6 +1147,11 @@ extern "C" int tedm_conv_set_wgrad_halo(int enable) {
 
 extern "C" int tedm_conv_set_deterministic(int enable) {
   g_deterministic = enable != 0;
+  return TEDM_OK;
+}
+
+extern "C" int tedm_conv_set_cta_pairs(int enable) {
+  g_enable_pairs = enable;                // 0 off, 1 automatic, 2 wherever the geometry allows
   return TEDM_OK;
 }
 
@@ -1205,6 +1276,13 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   const bool ws = g_enable_ws && a->mode == 1 && p.tileH == 1 && p.tileB == 1 && p.tileW == BM && a->cout == 64 && bn == 64 &&
                   (a->c0 + a->c1) <= 128 && a->n_extra == 0;
 
+  // CTA pairs (cta_group::2) where shared-memory bandwidth bounds the tile: N <= 128, a real K loop (3x3 / 4x4 / folded
+  // upsample over >= 128 input channels).  Measured on B200 (profiles/r02_conv_pairs_ab.txt): 4-8 % faster there; the
+  // HBM-bound 1x1 convolutions lose 20-70 % in lock-step pairs and the single-channel-block 64 -> 64 layers 30 %, so those
+  // stay one CTA per tile.
+  p.cg = (g_enable_pairs && bn <= 128 && m_tiles % 2 == 0 && tedm_num_sms() >= 2 && a->mode != 0 && ktot / p.taps >= 128) ? 2 : 1;
+  if (g_enable_pairs == 2 && bn <= 128 && m_tiles % 2 == 0) p.cg = 2;       // forced (tests)
+
   alignas(64) ConvMaps maps;
   CUtensorMap& mapW = maps.w;
   CUtensorMap& mapOut = maps.out;
@@ -1220,7 +1298,7 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
       maps.a[i] = maps.a[0];
     }
   }
-  rc = encode_weight_map(&mapW, a->weight, (long long)zdim * a->cout, ktot, bn);
+  rc = encode_weight_map(&mapW, a->weight, (long long)zdim * a->cout, ktot, bn / p.cg);
   if (rc) return rc;
   if (!p.out_f32) {
     // bf16 outputs leave through a TMA store; the upsample mode scatters each parity through the same

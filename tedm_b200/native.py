@@ -57,6 +57,7 @@ SIGNATURES = {
     "tedm_conv_set_ws": (_i, [_i]),
     "tedm_conv_set_wgrad_halo": (_i, [_i]),
     "tedm_conv_set_deterministic": (_i, [_i]),
+    "tedm_conv_set_cta_pairs": (_i, [_i]),
     "tedm_weight_to_krsc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "tedm_fold_upsample_weight": (_i, [_p, _p, _i, _i, _p]),
     "tedm_gn_silu_fwd": (_i, [_p, _p, _i, _p, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _f, _p]),
@@ -137,6 +138,8 @@ def load() -> C.CDLL:
         _lib = lib
         if os.environ.get("TEDM_DETERMINISTIC", "0") == "1":
             lib.tedm_conv_set_deterministic(1)
+        if os.environ.get("TEDM_CTA_PAIRS", "1") != "1":        # A/B runs: 0 = one CTA per conv tile everywhere, 2 = pairs wherever possible
+            lib.tedm_conv_set_cta_pairs(int(os.environ["TEDM_CTA_PAIRS"]))
     return _lib
 
 
@@ -268,6 +271,11 @@ def set_deterministic(enable: bool = True) -> None:
     """Bit-reproducible convolution weight gradients (the generic weight-gradient kernel then adds its split-K slices in
     slice order instead of arrival order).  Also switched on by TEDM_DETERMINISTIC=1 in the environment."""
     load().tedm_conv_set_deterministic(int(bool(enable)))
+
+
+def set_cta_pairs(mode: int = 1) -> None:
+    """0: one CTA per conv tile; 1 (default): CTA pairs (tcgen05 cta_group::2) where they pay; 2: wherever the geometry allows."""
+    load().tedm_conv_set_cta_pairs(int(mode))
 
 
 def conv_gn_parts(oh: int, ow: int) -> int:

@@ -151,3 +151,35 @@ def test_conv_fp32_output():
     assert got.dtype == torch.float32
     ref = _ref_conv([x], w, None, 0)
     assert _rel(got.permute(0, 3, 1, 2), ref) < 1e-5
+
+
+@pytest.mark.parametrize("case", [
+    # (B, H, W, c0, c1, cout, mode, gn)
+    (2, 16, 16, 64, 0, 64, 0, 0), (2, 16, 16, 128, 64, 128, 1, 8), (2, 128, 128, 64, 64, 64, 1, 8), (4, 128, 128, 64, 0, 64, 1, 8),
+    (2, 64, 64, 64, 0, 128, 2, 0), (2, 16, 16, 128, 0, 64, 3, 0), (6, 8, 8, 256, 128, 128, 1, 8), (3, 16, 16, 192, 0, 64, 1, 0)])
+def test_cta_pairs_equal_single_cta(case):
+    """CTA pairs (tcgen05 cta_group::2: one MMA over two SMs, M = 256, each CTA staging its own pixels and half of the weight
+    tile) accumulate every output in the same K order as one CTA per tile: outputs and GroupNorm partials are bit-identical.
+    Forced on (mode 2) for shapes the default heuristic would leave on single CTAs too (1x1, 64 input channels, WS rows)."""
+    from tedm_b200 import native as N
+    B, H, W, c0, c1, cout, mode, gn = case
+    k = {0: 1, 1: 3, 2: 4, 3: 3}[mode]
+    ctot = c0 + c1
+    x0, x1 = _rand((B, c0, H, W), 1), (_rand((B, c1, H, W), 2) if c1 else None)
+    w, b = _rand((cout, ctot, k, k), 3, (ctot * k * k) ** -0.5), _rand((cout,), 4, 0.1)
+    wk = N.fold_upsample_weight(w.cuda()) if mode == 3 else N.weight_to_krsc(w.cuda())
+    outs = []
+    try:
+        for pairs in (0, 2):
+            N.set_cta_pairs(pairs)
+            outs.append(N.conv_igemm(_nhwc(x0), wk.reshape(-1), mode, cout, bias=b.cuda(), src1=_nhwc(x1) if c1 else None, gn_groups=gn))
+    finally:
+        N.set_cta_pairs(1)
+    torch.cuda.synchronize()
+    single, paired = outs
+    if gn:
+        assert torch.equal(single[1], paired[1])
+        single, paired = single[0], paired[0]
+    assert torch.equal(single, paired)
+    ref = _ref_conv([x0] + ([x1] if c1 else []), w, b, mode)
+    assert _rel(paired.float().permute(0, 3, 1, 2), ref) < 6e-3
