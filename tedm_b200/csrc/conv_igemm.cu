@@ -659,6 +659,262 @@ int launch_conv(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
 
 
 // ==========================================================================================
+// 3x3, 64 -> 64 channels on full 128-pixel rows: FOUR output rows per tile, weights resident.
+//
+// conv_igemm_kernel<64, WS> on these layers is bound by shared-memory bandwidth, not by the tensor core: a
+// 128 x 64 x 16 UMMA reads A 4 KB + B 2 KB for 32 tensor-cycles (192 B/clk against 128 B/clk of shared memory), every
+// input row is fetched three times (once per output row it feeds) and read nine times by the tensor core.  Here an input
+// row is fetched ONCE per tile and multiplied by the weights of every vertical tap at once:
+//     D[pixel][out row r-1 | out row r | out row r+1]  +=  in_row(r)[pixel + dx][ci] * [W(dy=2) | W(dy=1) | W(dy=0)][ci]
+// i.e. one N = 192 UMMA whose 64-column thirds are the accumulators of three DIFFERENT output rows, which sit side by
+// side in TMEM (a0..a3 = output rows y0..y0+3, 64 columns each).  Six input rows feed a tile:
+//     row y0+1 -> a0 a1 a2 (N = 192, starts them)      row y0+4 -> a3 (N = 64, W(dy=2), starts it)
+//     row y0+2 -> a1 a2 a3 (N = 192)                   row y0   -> a0 a1 (N = 128, [W1|W0])
+//     row y0+3 -> a2 a3    (N = 128, [W2|W1])          row y0-1 -> a0 (N = 64, W0)
+// every window of the resident [W2|W1|W0] tile is contiguous, so each is one descriptor.  Per output row the tensor core
+// now reads 144 KB of operands instead of 216 KB and TMA writes 25 KB instead of 50 KB; the tensor-cycle floor
+// (1152 cycles per row) and the shared-memory floor (1125) meet.
+//
+// warps: 0 = TMA producer, 1 = MMA issuer, 2..5 / 6..9 = two epilogue groups (one output row each at a time: TMEM ->
+// registers -> bias, GroupNorm partial sums -> bf16 -> swizzled staging tile -> TMA store); two TMEM accumulator sets
+// (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+struct Ws4Params {
+  int B, H, tiles_x, rows4;      // rows4 = H / 4
+  int num_tiles, stages;
+  const float* bias;
+  float* gn_partial;
+  int gn_groups, gn_parts;
+};
+
+constexpr int WS4_W_BYTES = 9 * 64 * BK * 2;        // [dx][dy = 2,1,0][64 cout][64 cin] bf16 = 72 KB
+constexpr int WS4_THREADS = 64 + 256;
+
+template <int CPG>
+__global__ void __launch_bounds__(WS4_THREADS, 1)
+conv_ws4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
+                const __grid_constant__ CUtensorMap mapOut, const Ws4Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_acc_full[2];
+  __shared__ __align__(8) uint64_t bar_acc_empty[2];
+  __shared__ __align__(8) uint64_t bar_w;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float red[2][4][16];     // [epilogue group][warp][(sum, sumsq) of 8 GroupNorm groups]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_base = smem_base + WS4_W_BYTES;
+  const uint32_t out_base = stage_base + (uint32_t)p.stages * A_ROW_BYTES;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapW);
+    tma_prefetch_desc(&mapOut);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar_acc_full[i]), 1);
+      mbar_init(smem_u32(&bar_acc_empty[i]), 8);
+    }
+    mbar_init(smem_u32(&bar_w), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  // the six input rows of a tile in issue order: row offset, first accumulator, N, first row of the weight window
+  constexpr int R_OFF[6] = {1, 4, 2, 0, 3, -1};
+  constexpr int A_FIRST[6] = {0, 3, 1, 0, 2, 0};
+  constexpr int N_COLS[6] = {192, 64, 192, 128, 128, 64};
+  constexpr int W_ROW[6] = {0, 0, 0, 64, 0, 128};
+
+  if (warp == 0) {
+    // ===== TMA producer =====================================================================
+    if (elect_one()) {
+      const uint32_t bw = smem_u32(&bar_w);
+      mbar_expect_tx(bw, WS4_W_BYTES);
+      for (int dx = 0; dx < 3; ++dx)
+        for (int j = 0; j < 3; ++j)            // j-th 64-row block of the resident tile = vertical tap 2 - j
+          tma_load_2d(smem_base + (uint32_t)((dx * 3 + j) * 64 * BK * 2), &mapW, bw, ((2 - j) * 3 + dx) * BK, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int tx = tile % p.tiles_x, rest = tile / p.tiles_x;
+        const int y0 = (rest % p.rows4) * 4, b = rest / p.rows4;
+#pragma unroll
+        for (int s = 0; s < 6; ++s) {
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          const uint32_t full = smem_u32(&bar_full[stage]);
+          mbar_expect_tx(full, ROW_PIX * BK * 2);
+          tma_load_5d(stage_base + stage * A_ROW_BYTES, &mapA, full, 0, tx * BM - 1, 0, y0 + R_OFF[s], b);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer =========================================================================
+    if (elect_one()) {
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      mbar_wait(smem_u32(&bar_w), 0);
+      tc_fence_after();
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int set = it & 1;
+        mbar_wait(smem_u32(&bar_acc_empty[set]), (uint32_t)(((it >> 1) & 1) ^ 1));
+        tc_fence_after();
+#pragma unroll
+        for (int s = 0; s < 6; ++s) {
+          constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BM >> 4) << 24);
+          const uint32_t idesc = IDESC_BASE | ((uint32_t)(N_COLS[s] >> 3) << 17);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(set * 256 + A_FIRST[s] * 64);
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          tc_fence_after();
+          const uint32_t a_addr = stage_base + stage * A_ROW_BYTES;
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const uint64_t adesc = make_sw128_desc(a_addr + (uint32_t)dx * 128u);
+            const uint64_t bdesc = make_sw128_desc(smem_base + (uint32_t)(dx * 3 * 64 * BK * 2 + W_ROW[s] * BK * 2));
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(d_tmem, adesc + 2ull * k, bdesc + 2ull * k, idesc, (s >= 2 || (dx | k) != 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&bar_empty[stage]));
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(smem_u32(&bar_acc_full[set]));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: group g = warps 2+4g .. 5+4g takes output rows g and g + 2 of every tile ================
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;                         // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;                  // pixel inside the 128-pixel row
+    const int eg = threadIdx.x - 64 - g * 128;      // 0..127 inside the group
+    const uint32_t out_buf = out_base + (uint32_t)g * A_BYTES;
+    const int bar_a = 1 + 2 * g, bar_b = 2 + 2 * g;
+    float bias_r[64];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      bias_r[4 * j] = bv.x;
+      bias_r[4 * j + 1] = bv.y;
+      bias_r[4 * j + 2] = bv.z;
+      bias_r[4 * j + 3] = bv.w;
+    }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int tx = tile % p.tiles_x, rest = tile / p.tiles_x;
+      const int y0 = (rest % p.rows4) * 4, b = rest / p.rows4;
+      const int set = it & 1;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int a = g + 2 * half;                 // accumulator = output row y0 + a
+        // the TMA store that last read this group's staging tile must be done with it; `red` of the previous row too
+        if (eg == 0) tma_store_wait_read<0>();
+        named_bar_sync(bar_a, 128);
+        if (half == 0) {
+          mbar_wait(smem_u32(&bar_acc_full[set]), (uint32_t)((it >> 1) & 1));
+          tc_fence_after();
+        }
+        float gv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) gv[i] = 0.0f;
+#pragma unroll
+        for (int chunk = 0; chunk < 2; ++chunk) {
+          uint32_t r0[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * 256 + a * 64 + chunk * 32), r0);
+          tmem_ld_wait();
+          if (half == 1 && chunk == 1) {
+            // both rows of this warp are in registers: the accumulator set is free for the MMA issuer again
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[set]));
+          }
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + bias_r[chunk * 32 + j];
+          if (CPG) {
+#pragma unroll
+            for (int sg = 0; sg < 4; ++sg) {
+              float s_ = 0.0f, q_ = 0.0f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                s_ += v[sg * 8 + j];
+                q_ = fmaf(v[sg * 8 + j], v[sg * 8 + j], q_);
+              }
+              gv[2 * (chunk * 4 + sg)] = s_;
+              gv[2 * (chunk * 4 + sg) + 1] = q_;
+            }
+          }
+          const uint32_t sub = out_buf + (uint32_t)row * 128u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t c16 = (uint32_t)(chunk * 4 + j);
+            const uint32_t dst = sub + ((c16 ^ (uint32_t)(row & 7)) << 4);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pack_bf16x2(v[8 * j], v[8 * j + 1])),
+                         "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])), "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])),
+                         "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7])) : "memory");
+          }
+        }
+        if (CPG) {
+          butterfly_sum<16>(gv, lane, 32);         // lane l: value index l >> 1
+          if ((lane & 1) == 0) red[g][q][lane >> 1] = gv[0];
+        }
+        fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+        named_bar_sync(bar_b, 128);
+        if (eg == 0) {
+          tma_store_5d(&mapOut, out_buf, 0, tx * BM, 0, y0 + a, b);
+          tma_store_commit();
+        }
+        if (CPG && eg < 16) {
+          const float tot = red[g][0][eg] + red[g][1][eg] + red[g][2][eg] + red[g][3][eg];
+          const int part = (y0 + a) * p.tiles_x + tx;
+          p.gn_partial[((size_t)b * p.gn_parts + part) * p.gn_groups * 2 + eg] = tot;
+        }
+      }
+    }
+    if (eg == 0) tma_store_wait_all<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+template <int CPG>
+int launch_ws4(const CUtensorMap& mapA, const CUtensorMap& mapW, const CUtensorMap& mapOut, Ws4Params& p, cudaStream_t stream) {
+  const int fixed = 1024 + WS4_W_BYTES + 2 * A_BYTES;
+  int stages = (DYN_SMEM_MAX - fixed) / A_ROW_BYTES;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  TEDM_UNSUPPORTED(stages < 3, "tedm_conv_igemm_fwd: shared memory too small for the 4-row weight-stationary kernel");
+  p.stages = stages;
+  const int smem = fixed + stages * A_ROW_BYTES;
+  static int configured = 0;
+  if (configured < smem) {
+    TEDM_CUDA(cudaFuncSetAttribute(conv_ws4_kernel<CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  const int grid = p.num_tiles < tedm_num_sms() ? p.num_tiles : tedm_num_sms();
+  conv_ws4_kernel<CPG><<<grid, WS4_THREADS, smem, stream>>>(mapA, mapW, mapOut, p);
+  TEDM_LAUNCH_CHECK();
+  return TEDM_OK;
+}
+
+
+// ==========================================================================================
 // weight gradient:  dW[co][tap][ci] = sum_pixels dY[pixel][co] * X[pixel + tap offset][ci]
 //
 // The contraction runs over pixels, which are the ROWS of both NHWC operands, so both are fed to the
@@ -1156,7 +1412,7 @@ extern "C" int tedm_conv_set_cta_pairs(int enable) {
 }
 
 extern "C" int tedm_conv_set_ws(int enable) {
-  g_enable_ws = enable != 0;
+  g_enable_ws = enable;                   // 0 off, 1 on (four-row tiles where they apply), 2 single-row tiles only
   return TEDM_OK;
 }
 
@@ -1280,8 +1536,12 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   // upsample over >= 128 input channels).  Measured on B200 (profiles/r02_conv_pairs_ab.txt): 4-8 % faster there; the
   // HBM-bound 1x1 convolutions lose 20-70 % in lock-step pairs and the single-channel-block 64 -> 64 layers 30 %, so those
   // stay one CTA per tile.
+  // four output rows per tile (conv_ws4_kernel): one 64-channel source, plain bf16 output, GroupNorm groups of 8 or none
+  const bool ws4 = ws && g_enable_ws == 1 && p.n_src == 1 && a->c0 == 64 && p.Ho % 4 == 0 && !p.out_f32 && !p.residual && !p.split &&
+                   (!p.gn_partial || p.gn_cpg == 8);
   p.cg = (g_enable_pairs && bn <= 128 && m_tiles % 2 == 0 && tedm_num_sms() >= 2 && a->mode != 0 && ktot / p.taps >= 128) ? 2 : 1;
   if (g_enable_pairs == 2 && bn <= 128 && m_tiles % 2 == 0) p.cg = 2;       // forced (tests)
+  if (ws4) p.cg = 1;
 
   alignas(64) ConvMaps maps;
   CUtensorMap& mapW = maps.w;
@@ -1318,6 +1578,19 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   }
 
   cudaStream_t s = (cudaStream_t)stream;
+  if (ws4) {
+    Ws4Params q{};
+    q.B = p.B;
+    q.H = p.Ho;
+    q.tiles_x = p.tiles_x;
+    q.rows4 = p.Ho / 4;
+    q.num_tiles = p.B * q.rows4 * p.tiles_x;
+    q.bias = p.bias;
+    q.gn_partial = p.gn_partial;
+    q.gn_groups = p.gn_groups;
+    q.gn_parts = p.gn_parts;
+    return p.gn_partial ? launch_ws4<8>(maps.a[0], mapW, mapOut, q, s) : launch_ws4<0>(maps.a[0], mapW, mapOut, q, s);
+  }
   if (ws) return launch_conv<64, true>(maps, p, s);
   switch (bn) {
     case 64: return launch_conv<64, false>(maps, p, s);

@@ -140,6 +140,8 @@ def load() -> C.CDLL:
             lib.tedm_conv_set_deterministic(1)
         if os.environ.get("TEDM_CTA_PAIRS", "1") != "1":        # A/B runs: 0 = one CTA per conv tile everywhere, 2 = pairs wherever possible
             lib.tedm_conv_set_cta_pairs(int(os.environ["TEDM_CTA_PAIRS"]))
+        if os.environ.get("TEDM_WS", "1") != "1":               # A/B runs: 0 = no weight-stationary tiles, 2 = single-row tiles only
+            lib.tedm_conv_set_ws(int(os.environ["TEDM_WS"]))
     return _lib
 
 

@@ -144,6 +144,33 @@ def test_conv_ws_path_matches_generic_path():
     assert _rel(p_ws.sum(1), p_g.sum(1)) < 1e-4
 
 
+@pytest.mark.parametrize("case", [(3, 128, 128, True, 8), (2, 8, 256, False, 0), (150, 4, 128, True, 8), (1, 128, 128, True, 0)])
+def test_conv_ws4_tiles_match_single_row_tiles(case):
+    """64 -> 64 on 128-pixel rows: four output rows per tile (every input row multiplied by the three vertical taps at once,
+    N = 192) against one output row per tile (mode 2) and against F.conv2d; image borders, more tiles than SMs, two x tiles."""
+    from tedm_b200 import native as N
+    B, H, W, use_bias, gn = case
+    x, w = _rand((B, 64, H, W), 11), _rand((64, 64, 3, 3), 12, 576 ** -0.5)
+    b = _rand((64,), 13, 0.1).cuda() if use_bias else None
+    xh, wk = _nhwc(x), N.weight_to_krsc(w.cuda())
+    outs = []
+    try:
+        for mode in (1, 2):
+            N.load().tedm_conv_set_ws(mode)
+            outs.append(N.conv_igemm(xh, wk, 1, 64, bias=b, gn_groups=gn))
+    finally:
+        N.load().tedm_conv_set_ws(1)
+    torch.cuda.synchronize()
+    four, one = outs
+    if gn:
+        assert _rel(four[1].sum(1), one[1].sum(1)) < 1e-5
+        assert _rel(four[1], one[1]) < 1e-4                      # per-row partials keep their layout
+        four, one = four[0], one[0]
+    assert _rel(four.float(), one.float()) < 2e-3                # same products, different accumulation order
+    ref = _ref_conv([x], w, b.cpu() if use_bias else None, 1)
+    assert _rel(four.float().permute(0, 3, 1, 2), ref) < 6e-3
+
+
 def test_conv_fp32_output():
     from tedm_b200 import native as N
     x, w = _rand((3, 128, 16, 16), 1), _rand((128, 128, 1, 1), 2, 128 ** -0.5)
@@ -170,11 +197,13 @@ def test_cta_pairs_equal_single_cta(case):
     wk = N.fold_upsample_weight(w.cuda()) if mode == 3 else N.weight_to_krsc(w.cuda())
     outs = []
     try:
+        N.load().tedm_conv_set_ws(2)          # single-row weight-stationary tiles (the four-row kernel is never paired)
         for pairs in (0, 2):
             N.set_cta_pairs(pairs)
             outs.append(N.conv_igemm(_nhwc(x0), wk.reshape(-1), mode, cout, bias=b.cuda(), src1=_nhwc(x1) if c1 else None, gn_groups=gn))
     finally:
         N.set_cta_pairs(1)
+        N.load().tedm_conv_set_ws(1)
     torch.cuda.synchronize()
     single, paired = outs
     if gn:
