@@ -678,21 +678,34 @@ int launch_conv(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
 // warps: 0 = TMA producer, 1 = MMA issuer, 2..5 / 6..9 = two epilogue groups (one output row each at a time: TMEM ->
 // registers -> bias, GroupNorm partial sums -> bf16 -> swizzled staging tile -> TMA store); two TMEM accumulator sets
 // (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+// CB = 2: 128 input channels (one 128-channel source or two 64-channel ones): a slot is one (row, channel block), the
+//         resident weights take 144 KB, which leaves three slots and ONE staging tile, so the eight epilogue warps share a row.
+// W64:    64-pixel rows (64 -> 64 at 64 x 64): M = 128 is the same row of TWO images, which makes vertical neighbours whole
+//         tiles again; the horizontal taps cannot be row-shifted windows of one box here (the second image would have to
+//         start 64 rows after the first, inside its halo), so a slot is one (row, dx) box of 2 x 64 pixels loaded at x = dx - 1.
 struct Ws4Params {
-  int B, H, tiles_x, rows4;      // rows4 = H / 4
-  int num_tiles, stages;
+  int B, tiles_x, rows4;         // rows4 = H / 4
+  int num_tiles, stages, c0_blocks;
   const float* bias;
   float* gn_partial;
   int gn_groups, gn_parts;
 };
 
-constexpr int WS4_W_BYTES = 9 * 64 * BK * 2;        // [dx][dy = 2,1,0][64 cout][64 cin] bf16 = 72 KB
 constexpr int WS4_THREADS = 64 + 256;
 
-template <int CPG>
+template <int CPG, int CB, bool W64>
 __global__ void __launch_bounds__(WS4_THREADS, 1)
-conv_ws4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
-                const __grid_constant__ CUtensorMap mapOut, const Ws4Params p) {
+conv_ws4_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapOut, const Ws4Params p) {
+  static_assert(!(W64 && CB != 1), "64-pixel rows: one channel block");
+  constexpr int W_TILE = 192 * BK * 2;               // [W(dy=2) | W(dy=1) | W(dy=0)] of one (dx, channel block): 24 KB
+  constexpr int W_BYTES = 3 * CB * W_TILE;
+  constexpr int SLOT_BYTES = W64 ? A_BYTES : A_ROW_BYTES;
+  constexpr int SLOT_TX = W64 ? A_BYTES : ROW_PIX * BK * 2;
+  constexpr int G = CB == 1 ? 2 : 1;                 // epilogue groups (each with its own staging tile)
+  constexpr int GT = 256 / G;                        // threads per group
+  constexpr int WCH = G == 2 ? 2 : 1;                // 32-column chunks per warp
+  constexpr int NV = 8 * WCH;                        // (sum, sumsq) of the GroupNorm groups a warp covers
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_empty[MAX_STAGES];
@@ -700,15 +713,16 @@ conv_ws4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   __shared__ __align__(8) uint64_t bar_acc_empty[2];
   __shared__ __align__(8) uint64_t bar_w;
   __shared__ uint32_t tmem_slot;
-  __shared__ float red[2][4][16];     // [epilogue group][warp][(sum, sumsq) of 8 GroupNorm groups]
+  __shared__ float red[2][4][16];     // [group, or column half when one group][lane quarter][values]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stage_base = smem_base + WS4_W_BYTES;
-  const uint32_t out_base = stage_base + (uint32_t)p.stages * A_ROW_BYTES;
+  const uint32_t stage_base = smem_base + W_BYTES;
+  const uint32_t out_base = stage_base + (uint32_t)p.stages * SLOT_BYTES;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapA0);
+    tma_prefetch_desc(&mapA1);
     tma_prefetch_desc(&mapW);
     tma_prefetch_desc(&mapOut);
     for (int s = 0; s < p.stages; ++s) {
@@ -733,29 +747,46 @@ conv_ws4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   constexpr int A_FIRST[6] = {0, 3, 1, 0, 2, 0};
   constexpr int N_COLS[6] = {192, 64, 192, 128, 128, 64};
   constexpr int W_ROW[6] = {0, 0, 0, 64, 0, 128};
+  auto tile_coord = [&](int tile, int& b, int& y0, int& x0) {
+    const int tx = tile % p.tiles_x, rest = tile / p.tiles_x;
+    y0 = (rest % p.rows4) * 4;
+    b = (rest / p.rows4) * (W64 ? 2 : 1);
+    x0 = tx * BM;
+  };
 
   if (warp == 0) {
     // ===== TMA producer =====================================================================
     if (elect_one()) {
       const uint32_t bw = smem_u32(&bar_w);
-      mbar_expect_tx(bw, WS4_W_BYTES);
+      mbar_expect_tx(bw, W_BYTES);
       for (int dx = 0; dx < 3; ++dx)
-        for (int j = 0; j < 3; ++j)            // j-th 64-row block of the resident tile = vertical tap 2 - j
-          tma_load_2d(smem_base + (uint32_t)((dx * 3 + j) * 64 * BK * 2), &mapW, bw, ((2 - j) * 3 + dx) * BK, 0);
+        for (int cb = 0; cb < CB; ++cb)
+          for (int j = 0; j < 3; ++j)            // j-th 64-row block of the resident tile = vertical tap 2 - j
+            tma_load_2d(smem_base + (uint32_t)((dx * CB + cb) * W_TILE + j * 64 * BK * 2), &mapW, bw,
+                        (((2 - j) * 3 + dx) * CB + cb) * BK, 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int tx = tile % p.tiles_x, rest = tile / p.tiles_x;
-        const int y0 = (rest % p.rows4) * 4, b = rest / p.rows4;
+        int b, y0, x0;
+        tile_coord(tile, b, y0, x0);
 #pragma unroll
         for (int s = 0; s < 6; ++s) {
-          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-          const uint32_t full = smem_u32(&bar_full[stage]);
-          mbar_expect_tx(full, ROW_PIX * BK * 2);
-          tma_load_5d(stage_base + stage * A_ROW_BYTES, &mapA, full, 0, tx * BM - 1, 0, y0 + R_OFF[s], b);
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1u;
+#pragma unroll
+          for (int u = 0; u < (W64 ? 3 : CB); ++u) {     // u = dx (64-pixel rows) or channel block
+            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+            const uint32_t full = smem_u32(&bar_full[stage]);
+            mbar_expect_tx(full, SLOT_TX);
+            if (W64) {
+              tma_load_5d(stage_base + stage * SLOT_BYTES, &mapA0, full, 0, u - 1, 0, y0 + R_OFF[s], b);
+            } else {
+              const bool second = u >= p.c0_blocks;
+              tma_load_5d(stage_base + stage * SLOT_BYTES, second ? &mapA1 : &mapA0, full, (second ? u - p.c0_blocks : u) * BK,
+                          x0 - 1, 0, y0 + R_OFF[s], b);
+            }
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
         }
       }
@@ -777,21 +808,25 @@ conv_ws4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BM >> 4) << 24);
           const uint32_t idesc = IDESC_BASE | ((uint32_t)(N_COLS[s] >> 3) << 17);
           const uint32_t d_tmem = tmem_base + (uint32_t)(set * 256 + A_FIRST[s] * 64);
-          mbar_wait(smem_u32(&bar_full[stage]), phase);
-          tc_fence_after();
-          const uint32_t a_addr = stage_base + stage * A_ROW_BYTES;
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            const uint64_t adesc = make_sw128_desc(a_addr + (uint32_t)dx * 128u);
-            const uint64_t bdesc = make_sw128_desc(smem_base + (uint32_t)(dx * 3 * 64 * BK * 2 + W_ROW[s] * BK * 2));
+          for (int u = 0; u < (W64 ? 3 : CB); ++u) {
+            mbar_wait(smem_u32(&bar_full[stage]), phase);
+            tc_fence_after();
+            const uint32_t a_addr = stage_base + stage * SLOT_BYTES;
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_bf16(d_tmem, adesc + 2ull * k, bdesc + 2ull * k, idesc, (s >= 2 || (dx | k) != 0) ? 1u : 0u);
-          }
-          umma_commit(smem_u32(&bar_empty[stage]));
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1u;
+            for (int d = 0; d < (W64 ? 1 : 3); ++d) {
+              const int dx = W64 ? u : d, cb = W64 ? 0 : u;
+              const uint64_t adesc = make_sw128_desc(a_addr + (W64 ? 0u : (uint32_t)dx * 128u));
+              const uint64_t bdesc = make_sw128_desc(smem_base + (uint32_t)((dx * CB + cb) * W_TILE + W_ROW[s] * BK * 2));
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                umma_bf16(d_tmem, adesc + 2ull * k, bdesc + 2ull * k, idesc, (s >= 2 || (u | d | k) != 0) ? 1u : 0u);
+            }
+            umma_commit(smem_u32(&bar_empty[stage]));
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
         }
         umma_commit(smem_u32(&bar_acc_full[set]));
@@ -799,17 +834,20 @@ conv_ws4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
     __syncwarp();
   } else {
-    // ===== epilogue: group g = warps 2+4g .. 5+4g takes output rows g and g + 2 of every tile ================
-    const int g = (warp - 2) >> 2;
+    // ===== epilogue ===========================================================================
+    // two groups (warps 2..5 / 6..9; 64 columns per thread; group g takes output rows 2g, 2g+1) or one group of eight warps
+    // (32 columns per thread, rows 0..3)
+    const int g = G == 2 ? (warp - 2) >> 2 : 0;
+    const int hsel = G == 2 ? 0 : (warp - 2) >> 2;  // column half (one group)
     const int q = warp & 3;                         // TMEM lane quarter this warp may read
-    const int row = q * 32 + lane;                  // pixel inside the 128-pixel row
-    const int eg = threadIdx.x - 64 - g * 128;      // 0..127 inside the group
+    const int row = q * 32 + lane;                  // M row: pixel of the 128-pixel row, or (image, pixel) of two 64-pixel rows
+    const int eg = threadIdx.x - 64 - g * GT;       // index inside the group
     const uint32_t out_buf = out_base + (uint32_t)g * A_BYTES;
     const int bar_a = 1 + 2 * g, bar_b = 2 + 2 * g;
-    float bias_r[64];
+    float bias_r[32 * WCH];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < 8 * WCH; ++j) {
+      const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias) + hsel * 8 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
       bias_r[4 * j] = bv.x;
       bias_r[4 * j + 1] = bv.y;
       bias_r[4 * j + 2] = bv.z;
@@ -817,36 +855,39 @@ conv_ws4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int tx = tile % p.tiles_x, rest = tile / p.tiles_x;
-      const int y0 = (rest % p.rows4) * 4, b = rest / p.rows4;
+      int b, y0, x0;
+      tile_coord(tile, b, y0, x0);
       const int set = it & 1;
+      float gv[NV];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int a = g + 2 * half;                 // accumulator = output row y0 + a
+      for (int half = 0; half < 4 / G; ++half) {
+        const int a = (4 / G) * g + half;           // accumulator = output row y0 + a
         // the TMA store that last read this group's staging tile must be done with it; `red` of the previous row too
         if (eg == 0) tma_store_wait_read<0>();
-        named_bar_sync(bar_a, 128);
+        named_bar_sync(bar_a, GT);
         if (half == 0) {
           mbar_wait(smem_u32(&bar_acc_full[set]), (uint32_t)((it >> 1) & 1));
           tc_fence_after();
         }
-        float gv[16];
+        if (!W64 || (half & 1) == 0) {              // 64-pixel rows: a GroupNorm partial covers a PAIR of rows
 #pragma unroll
-        for (int i = 0; i < 16; ++i) gv[i] = 0.0f;
+          for (int i = 0; i < NV; ++i) gv[i] = 0.0f;
+        }
 #pragma unroll
-        for (int chunk = 0; chunk < 2; ++chunk) {
+        for (int ch = 0; ch < WCH; ++ch) {
+          const int chunk = G == 2 ? ch : hsel;     // 32-column chunk of the 64 output channels
           uint32_t r0[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * 256 + a * 64 + chunk * 32), r0);
           tmem_ld_wait();
-          if (half == 1 && chunk == 1) {
-            // both rows of this warp are in registers: the accumulator set is free for the MMA issuer again
+          if (half == 4 / G - 1 && ch == WCH - 1) {
+            // every row of this warp is in registers: the accumulator set is free for the MMA issuer again
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[set]));
           }
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + bias_r[chunk * 32 + j];
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + bias_r[ch * 32 + j];
           if (CPG) {
 #pragma unroll
             for (int sg = 0; sg < 4; ++sg) {
@@ -856,8 +897,8 @@ conv_ws4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 s_ += v[sg * 8 + j];
                 q_ = fmaf(v[sg * 8 + j], v[sg * 8 + j], q_);
               }
-              gv[2 * (chunk * 4 + sg)] = s_;
-              gv[2 * (chunk * 4 + sg) + 1] = q_;
+              gv[2 * (ch * 4 + sg)] += s_;
+              gv[2 * (ch * 4 + sg) + 1] += q_;
             }
           }
           const uint32_t sub = out_buf + (uint32_t)row * 128u;
@@ -870,20 +911,35 @@ conv_ws4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                          "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7])) : "memory");
           }
         }
-        if (CPG) {
-          butterfly_sum<16>(gv, lane, 32);         // lane l: value index l >> 1
-          if ((lane & 1) == 0) red[g][q][lane >> 1] = gv[0];
+        const bool emit = CPG != 0 && (!W64 || (half & 1) == 1);
+        if (emit) {
+          float t[NV];
+#pragma unroll
+          for (int i = 0; i < NV; ++i) t[i] = gv[i];
+          butterfly_sum<NV>(t, lane, 32);           // lane l: value index l >> (NV == 16 ? 1 : 2)
+          constexpr int SH = NV == 16 ? 1 : 2;
+          if ((lane & ((1 << SH) - 1)) == 0) red[G == 2 ? g : hsel][q][lane >> SH] = t[0];
         }
         fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
-        named_bar_sync(bar_b, 128);
+        named_bar_sync(bar_b, GT);
         if (eg == 0) {
-          tma_store_5d(&mapOut, out_buf, 0, tx * BM, 0, y0 + a, b);
+          tma_store_5d(&mapOut, out_buf, 0, W64 ? 0 : x0, 0, y0 + a, b);
           tma_store_commit();
         }
-        if (CPG && eg < 16) {
-          const float tot = red[g][0][eg] + red[g][1][eg] + red[g][2][eg] + red[g][3][eg];
-          const int part = (y0 + a) * p.tiles_x + tx;
-          p.gn_partial[((size_t)b * p.gn_parts + part) * p.gn_groups * 2 + eg] = tot;
+        if (emit) {
+          // value index i = 2 * GroupNorm group + (sum, sumsq) = the float offset inside one (image, part) record
+          if (W64) {
+            if (eg < 32) {
+              const int img = eg >> 4, i = eg & 15;
+              if (b + img < p.B)
+                p.gn_partial[((size_t)(b + img) * p.gn_parts + ((y0 + a) >> 1)) * p.gn_groups * 2 + i] =
+                    red[g][2 * img][i] + red[g][2 * img + 1][i];
+            }
+          } else if (eg < 16) {
+            const int rsel = G == 2 ? g : eg >> 3, i = G == 2 ? eg : eg & 7;
+            const float tot = red[rsel][0][i] + red[rsel][1][i] + red[rsel][2][i] + red[rsel][3][i];
+            p.gn_partial[((size_t)b * p.gn_parts + (y0 + a) * p.tiles_x + x0 / BM) * p.gn_groups * 2 + eg] = tot;
+          }
         }
       }
     }
@@ -894,25 +950,33 @@ conv_ws4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-template <int CPG>
-int launch_ws4(const CUtensorMap& mapA, const CUtensorMap& mapW, const CUtensorMap& mapOut, Ws4Params& p, cudaStream_t stream) {
-  const int fixed = 1024 + WS4_W_BYTES + 2 * A_BYTES;
-  int stages = (DYN_SMEM_MAX - fixed) / A_ROW_BYTES;
+template <int CPG, int CB, bool W64>
+int launch_ws4(const CUtensorMap& mapA0, const CUtensorMap& mapA1, const CUtensorMap& mapW, const CUtensorMap& mapOut,
+               Ws4Params& p, cudaStream_t stream) {
+  const int slot = W64 ? A_BYTES : A_ROW_BYTES;
+  const int fixed = 1024 + 3 * CB * 192 * BK * 2 + (CB == 1 ? 2 : 1) * A_BYTES;
+  int stages = (DYN_SMEM_MAX - fixed) / slot;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   TEDM_UNSUPPORTED(stages < 3, "tedm_conv_igemm_fwd: shared memory too small for the 4-row weight-stationary kernel");
   p.stages = stages;
-  const int smem = fixed + stages * A_ROW_BYTES;
+  const int smem = fixed + stages * slot;
   static int configured = 0;
   if (configured < smem) {
-    TEDM_CUDA(cudaFuncSetAttribute(conv_ws4_kernel<CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TEDM_CUDA(cudaFuncSetAttribute(conv_ws4_kernel<CPG, CB, W64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
   const int grid = p.num_tiles < tedm_num_sms() ? p.num_tiles : tedm_num_sms();
-  conv_ws4_kernel<CPG><<<grid, WS4_THREADS, smem, stream>>>(mapA, mapW, mapOut, p);
+  conv_ws4_kernel<CPG, CB, W64><<<grid, WS4_THREADS, smem, stream>>>(mapA0, mapA1, mapW, mapOut, p);
   TEDM_LAUNCH_CHECK();
   return TEDM_OK;
 }
 
+template <int CB, bool W64>
+int launch_ws4_cpg(const CUtensorMap& mapA0, const CUtensorMap& mapA1, const CUtensorMap& mapW, const CUtensorMap& mapOut,
+                   Ws4Params& p, cudaStream_t stream) {
+  return p.gn_partial ? launch_ws4<8, CB, W64>(mapA0, mapA1, mapW, mapOut, p, stream)
+                      : launch_ws4<0, CB, W64>(mapA0, mapA1, mapW, mapOut, p, stream);
+}
 
 // ==========================================================================================
 // weight gradient:  dW[co][tap][ci] = sum_pixels dY[pixel][co] * X[pixel + tap offset][ci]
@@ -1536,9 +1600,11 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   // upsample over >= 128 input channels).  Measured on B200 (profiles/r02_conv_pairs_ab.txt): 4-8 % faster there; the
   // HBM-bound 1x1 convolutions lose 20-70 % in lock-step pairs and the single-channel-block 64 -> 64 layers 30 %, so those
   // stay one CTA per tile.
-  // four output rows per tile (conv_ws4_kernel): one 64-channel source, plain bf16 output, GroupNorm groups of 8 or none
-  const bool ws4 = ws && g_enable_ws == 1 && p.n_src == 1 && a->c0 == 64 && p.Ho % 4 == 0 && !p.out_f32 && !p.residual && !p.split &&
-                   (!p.gn_partial || p.gn_cpg == 8);
+  // four output rows per tile (conv_ws4_kernel): 64 or 128 input channels on 128-pixel rows, or 64 on 64-pixel rows (two
+  // images per tile); plain bf16 output, GroupNorm groups of 8 or none
+  const bool ws4_epilogue = g_enable_ws == 1 && p.Ho % 4 == 0 && !p.out_f32 && !p.residual && !p.split && (!p.gn_partial || p.gn_cpg == 8);
+  const bool w64 = ws4_epilogue && a->mode == 1 && p.Wo == 64 && a->c0 == 64 && a->c1 == 0 && a->n_extra == 0 && a->cout == 64;
+  const bool ws4 = (ws && ws4_epilogue) || w64;
   p.cg = (g_enable_pairs && bn <= 128 && m_tiles % 2 == 0 && tedm_num_sms() >= 2 && a->mode != 0 && ktot / p.taps >= 128) ? 2 : 1;
   if (g_enable_pairs == 2 && bn <= 128 && m_tiles % 2 == 0) p.cg = 2;       // forced (tests)
   if (ws4) p.cg = 1;
@@ -1548,6 +1614,10 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   CUtensorMap& mapOut = maps.out;
   CUtensorMap& mapOut2 = maps.out2;
   const int boxW = ws ? ROW_PIX : p.tileW;
+  if (w64) {                                 // M = one 64-pixel row of two images
+    p.tileH = 1;
+    p.tileB = 2;
+  }
   int rc = TEDM_OK;
   for (int i = 0; i < MAX_SRC; ++i) {
     if (i < p.n_src) {
@@ -1581,15 +1651,18 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   if (ws4) {
     Ws4Params q{};
     q.B = p.B;
-    q.H = p.Ho;
-    q.tiles_x = p.tiles_x;
+    q.tiles_x = w64 ? 1 : p.tiles_x;
     q.rows4 = p.Ho / 4;
-    q.num_tiles = p.B * q.rows4 * p.tiles_x;
+    q.num_tiles = (w64 ? (p.B + 1) / 2 : p.B) * q.rows4 * q.tiles_x;
+    q.c0_blocks = p.c0_blocks;
     q.bias = p.bias;
     q.gn_partial = p.gn_partial;
     q.gn_groups = p.gn_groups;
     q.gn_parts = p.gn_parts;
-    return p.gn_partial ? launch_ws4<8>(maps.a[0], mapW, mapOut, q, s) : launch_ws4<0>(maps.a[0], mapW, mapOut, q, s);
+    const CUtensorMap& a1 = maps.a[p.n_src > 1 ? 1 : 0];
+    if (w64) return launch_ws4_cpg<1, true>(maps.a[0], a1, mapW, mapOut, q, s);
+    if (a->c0 + a->c1 == 64) return launch_ws4_cpg<1, false>(maps.a[0], a1, mapW, mapOut, q, s);
+    return launch_ws4_cpg<2, false>(maps.a[0], a1, mapW, mapOut, q, s);
   }
   if (ws) return launch_conv<64, true>(maps, p, s);
   switch (bn) {

@@ -58,6 +58,9 @@ CASES = [
     (1, 128, 128, 64, 64, 64, 1, True, False, 8, 0),
     (2, 4, 256, 64, 0, 64, 1, True, False, 8, 0),
     (1, 128, 128, 128, 0, 64, 1, False, False, 0, 0),
+    # four-row tiles on 64-pixel rows (two images per tile; odd batch; 8 rows)
+    (3, 64, 64, 64, 0, 64, 1, True, False, 8, 0),
+    (2, 8, 64, 64, 0, 64, 1, False, False, 0, 0),
     # persistent loop with more tiles than SMs on the generic path
     (40, 16, 16, 128, 0, 128, 1, True, False, 8, 64),
     (6, 64, 64, 64, 0, 384, 0, False, False, 0, 0),
@@ -144,30 +147,38 @@ def test_conv_ws_path_matches_generic_path():
     assert _rel(p_ws.sum(1), p_g.sum(1)) < 1e-4
 
 
-@pytest.mark.parametrize("case", [(3, 128, 128, True, 8), (2, 8, 256, False, 0), (150, 4, 128, True, 8), (1, 128, 128, True, 0)])
+@pytest.mark.parametrize("case", [(3, 128, 128, 64, 0, True, 8), (2, 8, 256, 64, 0, False, 0), (150, 4, 128, 64, 0, True, 8),
+                                  (1, 128, 128, 64, 0, True, 0), (2, 128, 128, 64, 64, True, 8), (2, 16, 128, 128, 0, False, 0),
+                                  (75, 4, 128, 64, 64, True, 8), (5, 64, 64, 64, 0, True, 8), (2, 16, 64, 64, 0, False, 0),
+                                  (301, 4, 64, 64, 0, True, 8)])
 def test_conv_ws4_tiles_match_single_row_tiles(case):
-    """64 -> 64 on 128-pixel rows: four output rows per tile (every input row multiplied by the three vertical taps at once,
-    N = 192) against one output row per tile (mode 2) and against F.conv2d; image borders, more tiles than SMs, two x tiles."""
+    """3x3 into 64 channels with resident weights and four output rows per tile (every input row multiplied by the three
+    vertical taps at once, N = 192) against the one-row / generic tiles (tedm_conv_set_ws(2)) and against F.conv2d: 64 and
+    128 input channels, one or two sources, 64-pixel rows (two images per tile, odd batches), image borders, more tiles
+    than SMs, two x tiles."""
     from tedm_b200 import native as N
-    B, H, W, use_bias, gn = case
-    x, w = _rand((B, 64, H, W), 11), _rand((64, 64, 3, 3), 12, 576 ** -0.5)
+    B, H, W, c0, c1, use_bias, gn = case
+    ctot = c0 + c1
+    x0, x1 = _rand((B, c0, H, W), 11), (_rand((B, c1, H, W), 14) if c1 else None)
+    w = _rand((64, ctot, 3, 3), 12, (9 * ctot) ** -0.5)
     b = _rand((64,), 13, 0.1).cuda() if use_bias else None
-    xh, wk = _nhwc(x), N.weight_to_krsc(w.cuda())
+    wk = N.weight_to_krsc(w.cuda())
     outs = []
     try:
         for mode in (1, 2):
             N.load().tedm_conv_set_ws(mode)
-            outs.append(N.conv_igemm(xh, wk, 1, 64, bias=b, gn_groups=gn))
+            outs.append(N.conv_igemm(_nhwc(x0), wk, 1, 64, bias=b, src1=_nhwc(x1) if c1 else None, gn_groups=gn))
     finally:
         N.load().tedm_conv_set_ws(1)
     torch.cuda.synchronize()
     four, one = outs
     if gn:
+        assert four[1].shape == one[1].shape
         assert _rel(four[1].sum(1), one[1].sum(1)) < 1e-5
-        assert _rel(four[1], one[1]) < 1e-4                      # per-row partials keep their layout
+        assert _rel(four[1], one[1]) < 1e-4                      # the partials keep their layout
         four, one = four[0], one[0]
     assert _rel(four.float(), one.float()) < 2e-3                # same products, different accumulation order
-    ref = _ref_conv([x], w, b.cpu() if use_bias else None, 1)
+    ref = _ref_conv([x0] + ([x1] if c1 else []), w, b.cpu() if use_bias else None, 1)
     assert _rel(four.float().permute(0, 3, 1, 2), ref) < 6e-3
 
 
