@@ -136,6 +136,10 @@ typedef struct {
   int extra_c[4];
   int64_t extra_image_stride[4];    /* elements; 0 = dense */
   int extra_center[4];
+  /* NULL, or fp32 [B][cout][2] from tedm_gn_affine: the residual then enters as SiLU(a * residual + b), i.e. `residual` is
+   * the raw output of block2's conv and this call is ResnetBlock's `block2(h) + res_conv(x)` (models/unet_model.py:174-175)
+   * with GroupNorm, SiLU and the add done in the 1x1 conv's epilogue (needs tiles inside one image: Ho * Wo >= 128). */
+  const float* residual_affine;
 } tedm_conv_args;
 TEDM_API int tedm_conv_igemm_fwd(const tedm_conv_args* args, tedm_stream_t stream);
 /* Weight gradient of the same convolution (backward of models/unet_model.py:43,49,122,157,185,188,226,227,308,324):
@@ -194,6 +198,13 @@ TEDM_API int tedm_gn_silu_fwd(const void* x, const float* gn_partial, int gn_par
                      const float* beta, const float* scale_shift, int ss_stride, int ss_offset,
                      const void* residual, void* out, int batch, int hw, int channels, int groups,
                      float eps, tedm_stream_t stream);
+
+/* The per-(image, channel) affine of tedm_gn_silu_fwd on its own: affine[b][c] = (a / 2, b / 2) with
+ * GroupNorm(x)[c] * (scale + 1) + shift = a * x + b (models/unet_model.py:128-133), for consumers that apply the
+ * normalisation themselves (tedm_conv_args.residual_affine).  fp32 [B][C][2]. */
+TEDM_API int tedm_gn_affine(const float* gn_partial, int gn_parts, const float* gamma, const float* beta,
+                   const float* scale_shift, int ss_stride, int ss_offset, float* affine, int batch, int hw,
+                   int channels, int groups, float eps, tedm_stream_t stream);
 
 /* Per-pixel channel LayerNorm with gain only (+ residual): models/unet_model.py:52-61, and the
  * Residual wrapper (:29-36) when `residual` is given. */

@@ -78,6 +78,7 @@ struct ConvParams {
   bf16* out2;
   const bf16* residual2;
   long long out2_image_stride;
+  const float2* res_affine;      // [B][cout] (a/2, b/2): the residual enters as SiLU(a * r + b)  (tiles inside one image)
 };
 
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
@@ -179,6 +180,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   __shared__ uint32_t tmem_slot;
   __shared__ float red[2][4][2][4][2];   // [column half][lane quarter][segment][group][sum, sumsq]
   __shared__ __align__(16) float sbias[256];
+  __shared__ __align__(16) float2 saff[RES ? 256 : 1];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cb_total = p.c0_blocks + p.c1_blocks;
@@ -371,6 +373,47 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     const int tb = row / hwt, rrem = row % hwt;
     const int ty = rrem / p.tileW, tx = rrem % p.tileW;
     const int seg_size = hwt < 32 ? hwt : 32;
+    // the residual rows of a thread for one tile.  With a split output, 64-channel sub-tile cp belongs to
+    // (residual, `split` channels per pixel) or (residual2, cout - split channels per pixel).
+    auto fetch_res = [&](const TileCoord& tt, uint4* dst, bool* has) {
+      const int b_ = tt.b0 + tb, y_ = tt.y0 + ty, x_ = tt.x0 + tx;
+      const size_t pixoff_ = (size_t)(y_ * p.osy + (tt.par >> 1)) * p.OW + (x_ * p.osx + (tt.par & 1));
+      const size_t opix_ = (size_t)b_ * p.out_image_stride + pixoff_ * p.cout + tt.n0;
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const int chunk = hsel * CH + i, c = tt.n0 + (chunk >> 1) * 64;
+        const bf16* rsub;
+        if (p.split == 0) rsub = p.residual ? p.residual + opix_ + (chunk >> 1) * 64 : nullptr;
+        else if (c < p.split) rsub = p.residual ? p.residual + (size_t)b_ * p.out_image_stride + pixoff_ * p.split + c : nullptr;
+        else rsub = p.residual2 ? p.residual2 + (size_t)b_ * p.out2_image_stride + pixoff_ * (p.cout - p.split) + (c - p.split) : nullptr;
+        has[i] = rsub != nullptr && b_ < p.B;
+        if (has[i]) {
+          const uint4* rp = reinterpret_cast<const uint4*>(rsub + (chunk & 1) * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[i * 4 + j] = __ldg(rp + j);
+        }
+      }
+    };
+    // N tiles <= 128: the residual rows, bias and residual affine of tile i+1 are requested while tile i is processed -- the
+    // 1x1 convolutions have no main loop to hide a global-memory round trip behind
+    constexpr bool PIPE = RES && CH <= 2;
+    uint4 rnext[PIPE ? CH * 4 : 1];
+    bool hnext[PIPE ? CH : 1];
+    float bias_next = 0.0f;
+    float2 aff_next = make_float2(0.0f, 0.0f);
+    auto fetch_consts = [&](const TileCoord& tt) {
+      if (e < BN) {
+        bias_next = p.bias ? __ldg(p.bias + tt.n0 + e) : 0.0f;
+        if (p.res_affine) aff_next = __ldg(p.res_affine + (size_t)tt.b0 * p.cout + tt.n0 + e);
+      }
+    };
+    if constexpr (PIPE) {
+      if (tile0 < tile_end) {
+        const TileCoord t0 = decode_tile<CG>(p, tile0, BN, rank);
+        fetch_res(t0, rnext, hnext);
+        fetch_consts(t0);
+      }
+    }
     int it = 0;
     for (int tile = tile0; tile < tile_end; tile += tile_step, ++it) {
       const TileCoord t = decode_tile<CG>(p, tile, BN, rank);
@@ -388,28 +431,35 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
         if (p.out_bufs == 2) tma_store_wait_read<1>();
         else tma_store_wait_read<0>();
       }
-      for (int i = e; i < BN; i += EPI_THREADS) sbias[i] = p.bias ? __ldg(p.bias + t.n0 + i) : 0.0f;
+      if constexpr (PIPE) {
+        if (e < BN) {
+          sbias[e] = bias_next;
+          saff[e] = aff_next;
+        }
+      } else {
+        for (int i = e; i < BN; i += EPI_THREADS) sbias[i] = p.bias ? __ldg(p.bias + t.n0 + i) : 0.0f;
+        if constexpr (RES) {
+          if (p.res_affine)
+            for (int i = e; i < BN; i += EPI_THREADS) saff[i] = __ldg(p.res_affine + (size_t)t.b0 * p.cout + t.n0 + i);
+        }
+      }
       named_bar_sync(1, EPI_THREADS);
-      // the residual values of this thread are fetched BEFORE waiting for the accumulator: their latency hides
-      // behind the main loop of this tile.  With a split output, 64-channel sub-tile cp belongs to
-      // (residual, `split` channels per pixel) or (residual2, cout - split channels per pixel).
+      // without the one-tile-ahead pipeline the residual values are fetched BEFORE waiting for the accumulator: their
+      // latency hides behind the main loop of this tile
       uint4 rpre[RES ? CH * 4 : 1];
       bool has_res[RES ? CH : 1];
-      if constexpr (RES) {
+      if constexpr (PIPE) {
 #pragma unroll
-        for (int i = 0; i < CH; ++i) {
-          const int chunk = hsel * CH + i, c = t.n0 + (chunk >> 1) * 64;
-          const bf16* rsub;
-          if (p.split == 0) rsub = p.residual ? p.residual + opix + (chunk >> 1) * 64 : nullptr;
-          else if (c < p.split) rsub = p.residual ? p.residual + (size_t)b * p.out_image_stride + pixoff * p.split + c : nullptr;
-          else rsub = p.residual2 ? p.residual2 + (size_t)b * p.out2_image_stride + pixoff * (p.cout - p.split) + (c - p.split) : nullptr;
-          has_res[i] = rsub != nullptr && valid;
-          if (has_res[i]) {
-            const uint4* rp = reinterpret_cast<const uint4*>(rsub + (chunk & 1) * 32);
+        for (int i = 0; i < CH * 4; ++i) rpre[i] = rnext[i];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) rpre[i * 4 + j] = __ldg(rp + j);
-          }
+        for (int i = 0; i < CH; ++i) has_res[i] = hnext[i];
+        if (tile + tile_step < tile_end) {
+          const TileCoord tn = decode_tile<CG>(p, tile + tile_step, BN, rank);
+          fetch_res(tn, rnext, hnext);
+          fetch_consts(tn);
         }
+      } else if constexpr (RES) {
+        fetch_res(t, rpre, has_res);
       }
       mbar_wait(smem_u32(&bar_acc_full[buf]), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
@@ -452,6 +502,13 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
             for (int j = 0; j < 4; ++j) {
               float f[8];
               unpack8(rpre[i * 4 + j], f);
+              if (p.res_affine) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  const float2 ab = saff[chunk * 32 + 8 * j + c];
+                  f[c] = silu_half(fmaf(f[c], ab.x, ab.y));
+                }
+              }
 #pragma unroll
               for (int c = 0; c < 8; ++c) v[8 * j + c] += f[c];
             }
@@ -1555,6 +1612,12 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
     p.out2_image_stride = (long long)p.OH * p.OW * (a->cout - a->split);
   }
   p.out_image_stride = a->out_image_stride ? a->out_image_stride : (long long)p.OH * p.OW * (a->split ? a->split : a->cout);
+  if (a->residual_affine) {
+    TEDM_CHECK_ARG(a->residual != nullptr, "tedm_conv_igemm_fwd: residual_affine without a residual");
+    TEDM_UNSUPPORTED(a->split != 0 || p.tileB != 1 || a->cout > 256 * 1024,
+                     "tedm_conv_igemm_fwd: residual_affine needs a single output and tiles inside one image (Ho * Wo >= 128)");
+    p.res_affine = reinterpret_cast<const float2*>(a->residual_affine);
+  }
   p.gn_partial = a->gn_partial;
   if (a->gn_partial) {
     TEDM_CHECK_ARG(a->gn_groups > 0 && a->cout % a->gn_groups == 0, "tedm_conv_igemm_fwd: gn_groups=%d", a->gn_groups);
@@ -1572,6 +1635,7 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   const long long m_tiles = (long long)ceil_div(p.B, p.tileB) * p.tiles_x * p.tiles_y;
   const int zdim = a->mode == 3 ? 4 : 1;
   auto legal = [&](int c) {
+    if (a->residual_affine && c == 256) return false;    // the one-tile-ahead residual pipeline exists for N <= 128
     return a->cout % c == 0 && (!p.gn_partial || (c % p.gn_cpg == 0 && c / p.gn_cpg <= 8));
   };
   int bn = 0;

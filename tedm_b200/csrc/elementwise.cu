@@ -484,6 +484,63 @@ __global__ void __launch_bounds__(256) gn_silu_kernel(const bf16* __restrict__ x
   }
 }
 
+// The prologue of gn_silu_kernel alone: per-(image, channel) halved affine for consumers that normalise on the fly.
+__global__ void __launch_bounds__(256) gn_affine_kernel(const float* __restrict__ partial, int parts,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        const float* __restrict__ ss, int ss_stride, int ss_offset,
+                                                        float2* __restrict__ affine, int hw, int C, int groups, float eps) {
+  __shared__ float s_mean[32], s_rstd[32];
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cpg = C / groups;
+  for (int g = warp; g < groups; g += 8) {
+    double s = 0.0, q = 0.0;
+    for (int p = lane; p < parts; p += 32) {
+      const float2 v = *reinterpret_cast<const float2*>(partial + (((size_t)b * parts + p) * groups + g) * 2);
+      s += (double)v.x;
+      q += (double)v.y;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0) {
+      const double n = (double)hw * (double)cpg;
+      const double mean = s / n;
+      double var = q / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[g] = (float)mean;
+      s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const int g = c / cpg;
+    float a = s_rstd[g] * gamma[c];
+    float bb = beta[c] - s_mean[g] * a;
+    if (ss) {
+      const float sc = ss[(size_t)b * ss_stride + ss_offset + c] + 1.0f;
+      const float sh = ss[(size_t)b * ss_stride + ss_offset + C + c];
+      a *= sc;
+      bb = bb * sc + sh;
+    }
+    affine[(size_t)b * C + c] = make_float2(0.5f * a, 0.5f * bb);
+  }
+}
+
+extern "C" int tedm_gn_affine(const float* gn_partial, int gn_parts, const float* gamma, const float* beta,
+                              const float* scale_shift, int ss_stride, int ss_offset, float* affine, int batch, int hw,
+                              int channels, int groups, float eps, tedm_stream_t stream) {
+  TEDM_CHECK_ARG(gn_partial && gamma && beta && affine, "tedm_gn_affine: null pointer");
+  TEDM_CHECK_ARG(batch > 0 && hw > 0 && gn_parts > 0, "tedm_gn_affine: bad sizes");
+  TEDM_UNSUPPORTED(groups <= 0 || groups > 32 || channels % groups != 0 || channels > GN_MAX_C,
+                   "tedm_gn_affine: channels=%d groups=%d unsupported", channels, groups);
+  gn_affine_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(gn_partial, gn_parts, gamma, beta, scale_shift, ss_stride, ss_offset,
+                                                           reinterpret_cast<float2*>(affine), hw, channels, groups, eps);
+  TEDM_LAUNCH_CHECK();
+  return TEDM_OK;
+}
+
 extern "C" int tedm_gn_silu_fwd(const void* x, const float* gn_partial, int gn_parts, const float* gamma,
                                 const float* beta, const float* scale_shift, int ss_stride, int ss_offset,
                                 const void* residual, void* out, int batch, int hw, int channels, int groups, float eps,

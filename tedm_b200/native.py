@@ -24,7 +24,7 @@ class ConvArgs(C.Structure):  # tedm_conv_args
                 ("cout", _i), ("mode", _i), ("gn_groups", _i), ("out_dtype", _i), ("src0_image_stride", _i64),
                 ("src1_image_stride", _i64), ("out_image_stride", _i64), ("split", _i), ("out2", _p), ("residual2", _p),
                 ("n_extra", _i), ("extra_src", _p * 4), ("extra_c", _i * 4), ("extra_image_stride", _i64 * 4),
-                ("extra_center", _i * 4)]
+                ("extra_center", _i * 4), ("residual_affine", _p)]
 
 
 class WeightEntry(C.Structure):  # tedm_weight_entry
@@ -53,6 +53,7 @@ SIGNATURES = {
     "tedm_conv_igemm_wgrad_workspace": (_i64, []),
     "tedm_prepare_weights": (_i, [_p, _i, _i, _p]),
     "tedm_conv_gn_parts": (_i, [_i, _i]),
+    "tedm_gn_affine": (_i, [_p, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _f, _p]),
     "tedm_conv_set_tile_n": (_i, [_i]),
     "tedm_conv_set_ws": (_i, [_i]),
     "tedm_conv_set_wgrad_halo": (_i, [_i]),
@@ -298,12 +299,13 @@ def _nhwc(t: Optional[torch.Tensor], name: str, dtype=torch.bfloat16):
 
 def conv_igemm(src0: torch.Tensor, weight: torch.Tensor, mode: int, cout: int, bias=None, src1=None, residual=None,
                gn_groups: int = 0, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16, split: int = 0,
-               residual2=None, extra: Sequence = ()):
+               residual2=None, extra: Sequence = (), residual_affine=None):
     """Returns out (B, Ho, Wo, cout) bf16 (or fp32) [, gn_partial (B, parts, groups, 2) fp32 if gn_groups > 0].
     src0/src1/out may be batch-strided views (e.g. x[s::S]); residual must share out's strides.
     split > 0: returns (out[..., :split], out2[..., split:]) as two dense tensors (+ residual / residual2).
     extra: up to four more A sources [(tensor, centre_only)], walked after src0/src1 inside every tap (centre_only: a
-    1x1 branch folded into the centre tap of a 3x3)."""
+    1x1 branch folded into the centre tap of a 3x3).
+    residual_affine: (B, cout, 2) fp32 from gn_affine(): the residual enters as SiLU(GroupNorm(residual))."""
     b, h, w, c0 = src0.shape
     c1 = src1.shape[3] if src1 is not None else 0
     if src1 is not None and src1.shape[:3] != src0.shape[:3]:
@@ -341,6 +343,10 @@ def conv_igemm(src0: torch.Tensor, weight: torch.Tensor, mode: int, cout: int, b
     a = ConvArgs(p0, p1, _ptr(weight, torch.bfloat16, "weight"), _ptr(bias, torch.float32, "bias"), pr, po, _ptr(gnp),
                  b, h, w, c0, c1, cout, mode, gn_groups, 1 if out.dtype == torch.float32 else 0, s0, s1,
                  0 if split else so, split, _ptr(out2), _ptr(residual2, torch.bfloat16, "residual2"))
+    if residual_affine is not None:
+        if residual is None or tuple(residual_affine.shape) != (b, cout, 2):
+            raise ValueError("conv_igemm: residual_affine is (B, cout, 2) and needs a residual")
+        a.residual_affine = _ptr(residual_affine, torch.float32, "residual_affine")
     a.n_extra = len(extra)
     for i, (t, ctr) in enumerate(extra):
         if t.shape[:3] != src0.shape[:3]:
@@ -419,6 +425,16 @@ def gn_silu(x, gn_partial, gamma, beta, groups: int, eps: float = 1e-5, scale_sh
             _call(*args)
     else:
         _call(*args)
+    return out
+
+
+def gn_affine(gn_partial, gamma, beta, groups: int, hw: int, eps: float = 1e-5, scale_shift=None, ss_offset: int = 0):
+    """(B, C, 2) fp32: the halved per-(image, channel) affine (a / 2, b / 2) of gn_silu, for conv_igemm(residual_affine=...)."""
+    b, c = gn_partial.shape[0], gamma.numel()
+    out = torch.empty(b, c, 2, device=gn_partial.device, dtype=torch.float32)
+    _call("tedm_gn_affine", _ptr(gn_partial, torch.float32), gn_partial.shape[1], _ptr(gamma, torch.float32),
+          _ptr(beta, torch.float32), _ptr(scale_shift, torch.float32), scale_shift.shape[1] if scale_shift is not None else 0,
+          ss_offset, _ptr(out), b, hw, c, groups, eps, _stream())
     return out
 
 

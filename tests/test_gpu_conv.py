@@ -182,6 +182,43 @@ def test_conv_ws4_tiles_match_single_row_tiles(case):
     assert _rel(four.float().permute(0, 3, 1, 2), ref) < 6e-3
 
 
+@pytest.mark.parametrize("case", [(2, 128, 128, 64, 64, 64), (3, 16, 16, 256, 0, 512), (2, 32, 32, 128, 0, 256), (5, 64, 64, 128, 64, 128)])
+def test_conv_residual_affine_is_resnet_block_tail(case):
+    """ResnetBlock's tail `SiLU(GroupNorm(h2)) + res_conv(x)` (reference models/unet_model.py:174-175) in ONE kernel -- the 1x1
+    conv reads the raw output of block2's conv as a residual that is normalised in its epilogue -- against the two passes
+    (1x1 conv, then GroupNorm + SiLU + add) and against torch."""
+    from tedm_b200 import native as N
+    B, H, W, c0, c1, cout = case
+    groups = 8
+    x0, x1 = _rand((B, c0, H, W), 21), (_rand((B, c1, H, W), 22) if c1 else None)
+    hin = _rand((B, cout, H, W), 23)
+    w3, b3 = _rand((cout, cout, 3, 3), 24, (9 * cout) ** -0.5), _rand((cout,), 25, 0.1)
+    wr, br = _rand((cout, c0 + c1, 1, 1), 26, (c0 + c1) ** -0.5), _rand((cout,), 27, 0.1)
+    gamma, beta = (1.0 + _rand((cout,), 28, 0.2)).cuda(), _rand((cout,), 29, 0.2).cuda()
+    h2, part = N.conv_igemm(_nhwc(hin), N.weight_to_krsc(w3.cuda()), 1, cout, bias=b3.cuda(), gn_groups=groups)
+    wrk = N.weight_to_krsc(wr.cuda())
+    s1 = _nhwc(x1) if c1 else None
+    res = N.conv_igemm(_nhwc(x0), wrk, 0, cout, bias=br.cuda(), src1=s1)
+    two = N.gn_silu(h2, part, gamma, beta, groups, residual=res)
+    aff = N.gn_affine(part, gamma, beta, groups, H * W)
+    one = N.conv_igemm(_nhwc(x0), wrk, 0, cout, bias=br.cuda(), src1=s1, residual=h2, residual_affine=aff)
+    torch.cuda.synchronize()
+    assert _rel(one.float(), two.float()) < 4e-3            # one bf16 rounding fewer than the two-pass form
+    hf = h2.float().permute(0, 3, 1, 2)
+    ref = F.silu(F.group_norm(hf, groups, gamma, beta, 1e-5)) + _ref_conv([x0] + ([x1] if c1 else []), wr, br, 0)
+    assert _rel(one.float().permute(0, 3, 1, 2), ref) < 5e-3
+    assert _rel(one.float().permute(0, 3, 1, 2), ref) <= _rel(two.float().permute(0, 3, 1, 2), ref) * 1.05
+
+
+def test_conv_residual_affine_needs_tiles_inside_one_image():
+    from tedm_b200 import native as N
+    x = torch.zeros(4, 8, 8, 64, dtype=torch.bfloat16, device="cuda")
+    w = torch.zeros(64, 1, 1, 64, dtype=torch.bfloat16, device="cuda")
+    aff = torch.zeros(4, 64, 2, device="cuda")
+    with pytest.raises(RuntimeError, match="inside one image"):
+        N.conv_igemm(x, w, 0, 64, residual=x, residual_affine=aff)
+
+
 def test_conv_fp32_output():
     from tedm_b200 import native as N
     x, w = _rand((3, 128, 16, 16), 1), _rand((128, 128, 1, 1), 2, 128 ** -0.5)
