@@ -679,9 +679,7 @@ int launch_conv_cg(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
 
 template <int BN, bool WS, int CPG, bool RES>
 int launch_conv_res(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
-  if constexpr (BN <= 128) {
-    if (p.cg == 2) return launch_conv_cg<BN, WS, CPG, RES, 2>(maps, p, stream);
-  }
+  if (p.cg == 2) return launch_conv_cg<BN, WS, CPG, RES, 2>(maps, p, stream);
   return launch_conv_cg<BN, WS, CPG, RES, 1>(maps, p, stream);
 }
 
@@ -1660,17 +1658,18 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   const bool ws = g_enable_ws && a->mode == 1 && p.tileH == 1 && p.tileB == 1 && p.tileW == BM && a->cout == 64 && bn == 64 &&
                   (a->c0 + a->c1) <= 128 && a->n_extra == 0;
 
-  // CTA pairs (cta_group::2) where shared-memory bandwidth bounds the tile: N <= 128, a real K loop (3x3 / 4x4 / folded
-  // upsample over >= 128 input channels).  Measured on B200 (profiles/r02_conv_pairs_ab.txt): 4-8 % faster there; the
-  // HBM-bound 1x1 convolutions lose 20-70 % in lock-step pairs and the single-channel-block 64 -> 64 layers 30 %, so those
-  // stay one CTA per tile.
+  // CTA pairs (cta_group::2): a real K loop (3x3 / 4x4 / folded upsample over >= 128 input channels).  Shared memory serves
+  // the tensor core's operand reads AND the TMA's writes; a pair halves the weight half of both.  Measured on B200
+  // (profiles/r02_conv_pairs_ab.txt): +4-8 % on N <= 128 tiles, +8-10 % on N = 256 tiles; the HBM-bound 1x1 convolutions
+  // lose 20-70 % in lock-step pairs and single-channel-block layers 30 %, so those stay one CTA per tile.
   // four output rows per tile (conv_ws4_kernel): 64 or 128 input channels on 128-pixel rows, or 64 on 64-pixel rows (two
   // images per tile); plain bf16 output, GroupNorm groups of 8 or none
   const bool ws4_epilogue = g_enable_ws == 1 && p.Ho % 4 == 0 && !p.out_f32 && !p.residual && !p.split && (!p.gn_partial || p.gn_cpg == 8);
   const bool w64 = ws4_epilogue && a->mode == 1 && p.Wo == 64 && a->c0 == 64 && a->c1 == 0 && a->n_extra == 0 && a->cout == 64;
   const bool ws4 = (ws && ws4_epilogue) || w64;
-  p.cg = (g_enable_pairs && bn <= 128 && m_tiles % 2 == 0 && tedm_num_sms() >= 2 && a->mode != 0 && ktot / p.taps >= 128) ? 2 : 1;
-  if (g_enable_pairs == 2 && bn <= 128 && m_tiles % 2 == 0) p.cg = 2;       // forced (tests)
+  p.cg = (g_enable_pairs && m_tiles % 2 == 0 && tedm_num_sms() >= 2 && a->mode != 0 && ktot / p.taps >= 128) ? 2 : 1;
+  if (g_enable_pairs == 3 && bn == 256) p.cg = 1;                           // A/B: pairs on N <= 128 tiles only
+  if (g_enable_pairs == 2 && m_tiles % 2 == 0) p.cg = 2;                    // forced (tests)
   if (ws4) p.cg = 1;
 
   alignas(64) ConvMaps maps;

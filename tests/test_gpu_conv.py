@@ -147,6 +147,25 @@ def test_conv_ws_path_matches_generic_path():
     assert _rel(p_ws.sum(1), p_g.sum(1)) < 1e-4
 
 
+def test_cta_pairs_with_n256_tiles():
+    """CTA pairs on the widest N tile (256 columns: each CTA stages 128 weight rows): bit-identical to single CTAs."""
+    from tedm_b200 import native as N
+    x, w, b = _rand((6, 256, 16, 16), 31), _rand((512, 256, 3, 3), 32, 2304 ** -0.5), _rand((512,), 33, 0.1)
+    xh, wk = _nhwc(x), N.weight_to_krsc(w.cuda())
+    outs = []
+    try:
+        N.load().tedm_conv_set_tile_n(256)
+        for pairs in (0, 2):
+            N.set_cta_pairs(pairs)
+            outs.append(N.conv_igemm(xh, wk, 1, 512, bias=b.cuda(), gn_groups=8))
+    finally:
+        N.set_cta_pairs(1)
+        N.load().tedm_conv_set_tile_n(0)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert _rel(outs[1][0].float().permute(0, 3, 1, 2), _ref_conv([x], w, b, 1)) < 6e-3
+
+
 @pytest.mark.parametrize("case", [(3, 128, 128, 64, 0, True, 8), (2, 8, 256, 64, 0, False, 0), (150, 4, 128, 64, 0, True, 8),
                                   (1, 128, 128, 64, 0, True, 0), (2, 128, 128, 64, 64, True, 8), (2, 16, 128, 128, 0, False, 0),
                                   (75, 4, 128, 64, 64, True, 8), (5, 64, 64, 64, 0, True, 8), (2, 16, 64, 64, 0, False, 0),
