@@ -41,6 +41,11 @@ constexpr int A_ROW_BYTES = 17 * 1024;   // row mode: 130 pixels x 128 B = 16640
 constexpr int ROW_PIX = BM + 2;
 constexpr int NGMAX = 32;        // max GroupNorm groups touched by one N tile
 constexpr int MAX_STAGES = 8;
+constexpr int HALO_W = 8, HALO_H = 16;                         // halo mode: a tile is 8 pixels x 16 rows of one image
+constexpr int HALO_PITCH = (HALO_W + 2) * BK * 2;              // bytes between image rows of the 10 x 18-pixel halo box
+constexpr int HALO_TX = (HALO_W + 2) * (HALO_H + 2) * BK * 2;  // 23040 B
+constexpr int HALO_BYTES = 23 * 1024;                          // padded to the 1 KB swizzle atom
+constexpr int MAX_HALO_STAGES = 3;
 constexpr int DYN_SMEM_MAX = 221 * 1024;  // + ~3.3 KB static <= 227 KB per CTA
 
 constexpr int MAX_SRC = 6;
@@ -63,7 +68,7 @@ struct ConvParams {
   int B, Ho, Wo;                 // tile space extent (output pixels; source pixels for mode 3)
   int OH, OW, osy, osx;          // output tensor extent and tile->output coordinate scale
   int cout;
-  int n_tiles, zdim, num_tiles, stages, out_bufs;
+  int n_tiles, zdim, num_tiles, stages, out_bufs, a_stages;
   int z_shift, tpg_shift, tx_shift;   // log2 of zdim, tiles_x * tiles_y, tiles_x (all powers of two)
   const float* bias;
   const bf16* residual;
@@ -87,6 +92,10 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   // is a function of the absolute shared-memory address, so row-shifted windows of a TMA-written
   // buffer are valid operands with base_offset = 0.
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// the same with the 8-row groups `sbo_bytes` apart instead of packed (a tile whose rows of 8 pixels sit in a wider buffer)
+__device__ __forceinline__ uint64_t make_sw128_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
 // Sum NV per-thread values over the `width` (32 or 16) lanes of a segment with a transposing butterfly:
@@ -159,15 +168,21 @@ constexpr int CONV_THREADS = 64 + EPI_THREADS;
 //               hardware shares the halves.  Per SM and UMMA the shared-memory read drops from A 4 KB + B (BN / 32) KB to
 //               A 4 KB + B (BN / 64) KB -- what bounds the N = 64 / 128 tiles.  Only the leader CTA (rank 0) issues MMAs;
 //               both issue TMA, all transaction bytes land on the leader's barriers; tcgen05.commit multicasts to both.
-template <int BN, bool WS, int CPG, bool RES, int CG>
+//   AM = 2 (HALO; 3x3 on images of at least 16 rows): a tile is 8 pixels x 16 rows, and its 10 x 18-pixel halo box of one
+//               64-channel block is loaded ONCE and serves all nine taps: tap (ky, kx) is the window that starts (ky, kx)
+//               pixels into the box, its 8-pixel rows 1280 B apart (the descriptor's stride between 8-row groups) instead of
+//               packed.  Shared memory carries the tensor core's operand reads AND the TMA's writes; this removes 8/9 of
+//               the activation writes (a slot of the main ring then holds only the weight tile of one (tap, channel block)).
+template <int BN, int AM, int CPG, bool RES, int CG>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
+  constexpr bool WS = AM == 1, HALO = AM == 2;
   const CUtensorMap& mapW = maps.w;
   const CUtensorMap& mapOut = maps.out;
   const CUtensorMap& mapOut2 = maps.out2;
   constexpr int BNC = BN / CG;                     // weight rows (output channels) this CTA stages per tile
   constexpr int B_BYTES = BNC * BK * 2;
-  constexpr int STAGE_BYTES = WS ? A_ROW_BYTES : A_BYTES + B_BYTES;
+  constexpr int STAGE_BYTES = WS ? A_ROW_BYTES : (HALO ? B_BYTES : A_BYTES + B_BYTES);
   constexpr int OUT_BYTES = (BN / 64) * A_BYTES;
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
 
@@ -177,6 +192,8 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   __shared__ __align__(8) uint64_t bar_acc_full[2];
   __shared__ __align__(8) uint64_t bar_acc_empty[2];
   __shared__ __align__(8) uint64_t bar_w;
+  __shared__ __align__(8) uint64_t bar_afull[MAX_HALO_STAGES];
+  __shared__ __align__(8) uint64_t bar_aempty[MAX_HALO_STAGES];
   __shared__ uint32_t tmem_slot;
   __shared__ float red[2][4][2][4][2];   // [column half][lane quarter][segment][group][sum, sumsq]
   __shared__ __align__(16) float sbias[256];
@@ -187,7 +204,8 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_bytes = WS ? (uint32_t)(9 * cb_total * B_BYTES) : 0u;
   const uint32_t stage_base = smem_base + w_bytes;
-  const uint32_t out_base = stage_base + (uint32_t)p.stages * STAGE_BYTES;
+  const uint32_t halo_base = stage_base + (uint32_t)p.stages * STAGE_BYTES;
+  const uint32_t out_base = halo_base + (HALO ? (uint32_t)p.a_stages * HALO_BYTES : 0u);
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.n_src; ++i) tma_prefetch_desc(&maps.a[i]);
@@ -203,6 +221,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
       mbar_init(smem_u32(&bar_acc_empty[i]), CG * (EPI_THREADS / 32));     // the leader's copy hears both CTAs' epilogues
     }
     mbar_init(smem_u32(&bar_w), 1);
+    for (int i = 0; i < MAX_HALO_STAGES; ++i) {
+      mbar_init(smem_u32(&bar_afull[i]), 1);
+      mbar_init(smem_u32(&bar_aempty[i]), 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -220,8 +242,9 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   if (warp == 0) {
     // ===== TMA producer =====================================================================
     if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, astage = 0;
+      uint32_t phase = 0, aphase = 0;
+      const int cb_all = p.num_kb / p.taps;        // 64-channel blocks over all sources (halo mode: no centre-only sources)
       // CG = 2: both CTAs load (their A rows, their half of the weights); the bytes are counted on the LEADER's barrier,
       // which only the leader arms
       auto load5 = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
@@ -253,6 +276,41 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                 phase ^= 1u;
               }
             }
+        } else if (HALO) {
+          // per 64-channel block: the halo box once, then the nine weight tiles; the next block's box is requested after
+          // the second weight tile, so that it lands while this block is multiplied
+          auto load_halo = [&](int si, int cblk) {
+            mbar_wait(smem_u32(&bar_aempty[astage]), aphase ^ 1u);
+            const uint32_t afull = smem_u32(&bar_afull[astage]);
+            if (rank == 0) mbar_expect_tx(afull, CG * HALO_TX);
+            load5(halo_base + astage * HALO_BYTES, &maps.a[si], afull, cblk * BK, t.x0 - 1, 0, t.y0 - 1, t.b0);
+            if (++astage == p.a_stages) {
+              astage = 0;
+              aphase ^= 1u;
+            }
+          };
+          load_halo(0, 0);
+          int si = 0, cblk = 0;
+          for (int cbg = 0; cbg < cb_all; ++cbg) {
+            int nsi = si, ncblk = cblk + 1;            // the block after this one
+            if (ncblk == p.src_blocks[si]) {
+              ncblk = 0;
+              ++nsi;
+            }
+            for (int tap = 0; tap < 9; ++tap) {
+              if (tap == 2 && cbg + 1 < cb_all) load_halo(nsi, ncblk);
+              mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+              const uint32_t full = smem_u32(&bar_full[stage]);
+              if (rank == 0) mbar_expect_tx(full, CG * STAGE_BYTES);
+              load2(stage_base + stage * STAGE_BYTES, &mapW, full, (tap * cb_all + cbg) * BK, t.n0 + rank * BNC);
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+            si = nsi;
+            cblk = ncblk;
+          }
         } else {
           const int par_y = t.par >> 1, par_x = t.par & 1;
           // nested counters instead of kb / cb_total etc.: this single thread paces the whole pipeline, and at N = 64 a
@@ -307,8 +365,8 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
       else umma_commit(bar);
     };
     if (rank == 0 && elect_one()) {
-      int stage = 0, it = 0;
-      uint32_t phase = 0;
+      int stage = 0, it = 0, astage = 0;
+      uint32_t phase = 0, aphase = 0;
       if (WS) {
         mbar_wait(smem_u32(&bar_w), 0);
         tc_fence_after();
@@ -337,6 +395,32 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                 phase ^= 1u;
               }
             }
+        } else if (HALO) {
+          const int cb_all = p.num_kb / p.taps;
+          for (int cbg = 0; cbg < cb_all; ++cbg) {
+            mbar_wait(smem_u32(&bar_afull[astage]), aphase);
+            tc_fence_after();
+            const uint32_t h_addr = halo_base + astage * HALO_BYTES;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(smem_u32(&bar_full[stage]), phase);
+              tc_fence_after();
+              const uint64_t adesc = make_sw128_desc_sbo(h_addr + (uint32_t)((tap / 3) * HALO_PITCH + (tap % 3) * BK * 2), HALO_PITCH);
+              const uint64_t bdesc = make_sw128_desc(stage_base + stage * STAGE_BYTES);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma(d_tmem, adesc + 2ull * k, bdesc + 2ull * k, (cbg | tap | k) != 0 ? 1u : 0u);
+              commit(smem_u32(&bar_empty[stage]));
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+            commit(smem_u32(&bar_aempty[astage]));
+            if (++astage == p.a_stages) {
+              astage = 0;
+              aphase ^= 1u;
+            }
+          }
         } else {
           const int num_kb = p.num_kb;
           for (int kb = 0; kb < num_kb; ++kb) {
@@ -634,13 +718,15 @@ int encode_weight_map(CUtensorMap* map, const void* ptr, long long rows, long lo
   return TEDM_OK;
 }
 
-template <int BN, bool WS, int CPG, bool RES, int CG>
+template <int BN, int AM, int CPG, bool RES, int CG>
 int launch_conv_cg(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
+  constexpr bool WS = AM == 1, HALO = AM == 2;
   const int cb_total = p.c0_blocks + p.c1_blocks;
   const int b_bytes = (BN / CG) * BK * 2;            // per-CTA share of a weight tile
-  const int stage_bytes = WS ? A_ROW_BYTES : A_BYTES + b_bytes;
+  const int stage_bytes = WS ? A_ROW_BYTES : (HALO ? b_bytes : A_BYTES + b_bytes);
   const int out_bytes = (BN / 64) * A_BYTES;
-  const int base = 1024 + (WS ? 9 * cb_total * b_bytes : 0);
+  p.a_stages = HALO ? (p.num_kb / p.taps > 1 ? 2 : 1) + 1 : 0;      // one box per 64-channel block in flight + one being consumed
+  const int base = 1024 + (WS ? 9 * cb_total * b_bytes : 0) + p.a_stages * HALO_BYTES;
   // double-buffer the output staging tile when that still leaves >= 4 pipeline slots
   p.out_bufs = (DYN_SMEM_MAX - base - 2 * out_bytes) / stage_bytes >= 4 ? 2 : 1;
   const int fixed = base + p.out_bufs * out_bytes;
@@ -651,13 +737,13 @@ int launch_conv_cg(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
   const int smem = fixed + stages * stage_bytes;
   static int configured = 0;
   if (configured < smem) {
-    TEDM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, WS, CPG, RES, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TEDM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, AM, CPG, RES, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
   const int work = p.num_tiles / CG;                   // tiles per CTA (pair)
   int grid = (work < tedm_num_sms() / CG ? work : tedm_num_sms() / CG) * CG;
   if constexpr (CG == 1) {
-    conv_igemm_kernel<BN, WS, CPG, RES, 1><<<grid, CONV_THREADS, smem, stream>>>(maps, p);
+    conv_igemm_kernel<BN, AM, CPG, RES, 1><<<grid, CONV_THREADS, smem, stream>>>(maps, p);
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
@@ -671,43 +757,43 @@ int launch_conv_cg(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    TEDM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, WS, CPG, RES, 2>, maps, p));
+    TEDM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, AM, CPG, RES, 2>, maps, p));
   }
   TEDM_LAUNCH_CHECK();
   return TEDM_OK;
 }
 
-template <int BN, bool WS, int CPG, bool RES>
+template <int BN, int AM, int CPG, bool RES>
 int launch_conv_res(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
-  if (p.cg == 2) return launch_conv_cg<BN, WS, CPG, RES, 2>(maps, p, stream);
-  return launch_conv_cg<BN, WS, CPG, RES, 1>(maps, p, stream);
+  if (p.cg == 2) return launch_conv_cg<BN, AM, CPG, RES, 2>(maps, p, stream);
+  return launch_conv_cg<BN, AM, CPG, RES, 1>(maps, p, stream);
 }
 
 // residual / split-output epilogues exist only without GroupNorm statistics (they never co-occur in the net)
-template <int BN, bool WS, int CPG>
+template <int BN, int AM, int CPG>
 int launch_conv_cpg(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
   if constexpr (CPG == 0) {
-    if (p.residual || p.residual2 || p.split) return launch_conv_res<BN, WS, 0, true>(maps, p, stream);
+    if (p.residual || p.residual2 || p.split) return launch_conv_res<BN, AM, 0, true>(maps, p, stream);
   }
-  return launch_conv_res<BN, WS, CPG, false>(maps, p, stream);
+  return launch_conv_res<BN, AM, CPG, false>(maps, p, stream);
 }
 
-template <int BN, bool WS>
+template <int BN, int AM>
 int launch_conv(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
   const int cpg = p.gn_partial ? p.gn_cpg : 0;
-  if (cpg == 0) return launch_conv_cpg<BN, WS, 0>(maps, p, stream);
+  if (cpg == 0) return launch_conv_cpg<BN, AM, 0>(maps, p, stream);
   if constexpr (BN / 8 <= 8) {
-    if (cpg == 8) return launch_conv_cpg<BN, WS, 8>(maps, p, stream);
+    if (cpg == 8) return launch_conv_cpg<BN, AM, 8>(maps, p, stream);
   }
   if constexpr (BN / 16 <= 8) {
-    if (cpg == 16) return launch_conv_cpg<BN, WS, 16>(maps, p, stream);
+    if (cpg == 16) return launch_conv_cpg<BN, AM, 16>(maps, p, stream);
   }
-  if (cpg == 32) return launch_conv_cpg<BN, WS, 32>(maps, p, stream);
+  if (cpg == 32) return launch_conv_cpg<BN, AM, 32>(maps, p, stream);
   if constexpr (BN >= 64) {
-    if (cpg == 64) return launch_conv_cpg<BN, WS, 64>(maps, p, stream);
+    if (cpg == 64) return launch_conv_cpg<BN, AM, 64>(maps, p, stream);
   }
   if constexpr (BN >= 128) {
-    if (cpg == 128) return launch_conv_cpg<BN, WS, 128>(maps, p, stream);
+    if (cpg == 128) return launch_conv_cpg<BN, AM, 128>(maps, p, stream);
   }
   return tedm_set_error(TEDM_ERR_UNSUPPORTED, "tedm_conv_igemm_fwd: %d channels per GroupNorm group with N tile %d", cpg, BN);
 }
@@ -1502,6 +1588,7 @@ int g_enable_wgrad3 = 1;  // tedm_conv_set_wgrad_halo: 0 off, 1 automatic, 2 whe
 int g_deterministic = 0;  // tedm_conv_set_deterministic
 
 int g_enable_ws = 1;  // tedm_conv_set_ws
+int g_enable_halo = 1;  // tedm_conv_set_halo
 int g_enable_pairs = 1;  // tedm_conv_set_cta_pairs
 int g_force_bn = 0;  // debug/tuning override (tedm_conv_set_tile_n)
 
@@ -1532,6 +1619,11 @@ extern "C" int tedm_conv_set_cta_pairs(int enable) {
 
 extern "C" int tedm_conv_set_ws(int enable) {
   g_enable_ws = enable;                   // 0 off, 1 on (four-row tiles where they apply), 2 single-row tiles only
+  return TEDM_OK;
+}
+
+extern "C" int tedm_conv_set_halo(int enable) {
+  g_enable_halo = enable != 0;
   return TEDM_OK;
 }
 
@@ -1594,6 +1686,21 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   p.tileB = BM / (p.tileW * p.tileH);
   p.tiles_x = p.Wo / p.tileW;
   p.tiles_y = p.Ho / p.tileH;
+  // halo mode (3x3 whose nine taps read one 10 x 18-pixel box per 64-channel block): tiles of 8 pixels x 16 rows.  The layers
+  // the weight-stationary kernels take (whole 128-pixel rows into 64 channels; 64 -> 64 on 64-pixel rows) keep those.
+  const bool ws_geom = g_enable_ws && a->mode == 1 && p.Wo >= BM && a->cout == 64 && (a->c0 + a->c1) <= 128 && a->n_extra == 0;
+  const bool w64_geom = g_enable_ws == 1 && a->mode == 1 && p.Wo == 64 && p.Ho % 4 == 0 && a->c0 == 64 && a->c1 == 0 &&
+                        a->n_extra == 0 && a->cout == 64 && a->out_dtype == 0 && !a->residual && !a->split &&
+                        (!a->gn_partial || a->cout / a->gn_groups == 8);
+  const bool halo = g_enable_halo && a->mode == 1 && a->n_extra == 0 && p.Wo % HALO_W == 0 && p.Ho % HALO_H == 0 && !ws_geom &&
+                    !w64_geom;
+  if (halo) {
+    p.tileW = HALO_W;
+    p.tileH = HALO_H;
+    p.tileB = 1;
+    p.tiles_x = p.Wo / HALO_W;
+    p.tiles_y = p.Ho / HALO_H;
+  }
   p.cout = a->cout;
   p.bias = a->bias;
   p.residual = (const bf16*)a->residual;
@@ -1676,7 +1783,7 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   CUtensorMap& mapW = maps.w;
   CUtensorMap& mapOut = maps.out;
   CUtensorMap& mapOut2 = maps.out2;
-  const int boxW = ws ? ROW_PIX : p.tileW;
+  const int boxW = ws ? ROW_PIX : (halo ? HALO_W + 2 : p.tileW);
   if (w64) {                                 // M = one 64-pixel row of two images
     p.tileH = 1;
     p.tileB = 2;
@@ -1685,7 +1792,7 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   for (int i = 0; i < MAX_SRC; ++i) {
     if (i < p.n_src) {
       rc = encode_act_map(&maps.a[i], src_ptr[i], a->batch, a->height, a->width, p.src_C[i], src_stride[i], a->mode, boxW,
-                          p.tileH, p.tileB);
+                          halo ? HALO_H + 2 : p.tileH, p.tileB);
       if (rc) return rc;
     } else {
       maps.a[i] = maps.a[0];
@@ -1727,11 +1834,18 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
     if (a->c0 + a->c1 == 64) return launch_ws4_cpg<1, false>(maps.a[0], a1, mapW, mapOut, q, s);
     return launch_ws4_cpg<2, false>(maps.a[0], a1, mapW, mapOut, q, s);
   }
-  if (ws) return launch_conv<64, true>(maps, p, s);
+  if (ws) return launch_conv<64, 1>(maps, p, s);
+  if (halo) {
+    switch (bn) {
+      case 64: return launch_conv<64, 2>(maps, p, s);
+      case 128: return launch_conv<128, 2>(maps, p, s);
+      default: return launch_conv<256, 2>(maps, p, s);
+    }
+  }
   switch (bn) {
-    case 64: return launch_conv<64, false>(maps, p, s);
-    case 128: return launch_conv<128, false>(maps, p, s);
-    default: return launch_conv<256, false>(maps, p, s);
+    case 64: return launch_conv<64, 0>(maps, p, s);
+    case 128: return launch_conv<128, 0>(maps, p, s);
+    default: return launch_conv<256, 0>(maps, p, s);
   }
 }
 

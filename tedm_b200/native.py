@@ -56,6 +56,7 @@ SIGNATURES = {
     "tedm_gn_affine": (_i, [_p, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _f, _p]),
     "tedm_conv_set_tile_n": (_i, [_i]),
     "tedm_conv_set_ws": (_i, [_i]),
+    "tedm_conv_set_halo": (_i, [_i]),
     "tedm_conv_set_wgrad_halo": (_i, [_i]),
     "tedm_conv_set_deterministic": (_i, [_i]),
     "tedm_conv_set_cta_pairs": (_i, [_i]),
@@ -141,6 +142,8 @@ def load() -> C.CDLL:
             lib.tedm_conv_set_deterministic(1)
         if os.environ.get("TEDM_CTA_PAIRS", "1") != "1":        # A/B runs: 0 = one CTA per conv tile everywhere, 2 = pairs wherever possible
             lib.tedm_conv_set_cta_pairs(int(os.environ["TEDM_CTA_PAIRS"]))
+        if os.environ.get("TEDM_HALO", "1") != "1":             # A/B runs: 0 = one activation box per tap in every 3x3 conv
+            lib.tedm_conv_set_halo(int(os.environ["TEDM_HALO"]))
         if os.environ.get("TEDM_WS", "1") != "1":               # A/B runs: 0 = no weight-stationary tiles, 2 = single-row tiles only
             lib.tedm_conv_set_ws(int(os.environ["TEDM_WS"]))
     return _lib

@@ -147,6 +147,47 @@ def test_conv_ws_path_matches_generic_path():
     assert _rel(p_ws.sum(1), p_g.sum(1)) < 1e-4
 
 
+@pytest.mark.parametrize("case", [
+    # (B, H, W, c0, c1, cout, bias, gn, residual, force_bn)
+    (3, 16, 16, 64, 0, 128, True, 8, False, 0), (2, 64, 64, 128, 64, 128, True, 8, False, 0), (5, 16, 16, 512, 256, 512, True, 8, False, 256),
+    (2, 32, 32, 256, 0, 256, False, 0, True, 0), (1, 128, 128, 64, 0, 128, True, 0, True, 0), (40, 16, 32, 128, 0, 128, True, 8, False, 64),
+    (2, 16, 8, 192, 0, 64, True, 8, False, 0), (3, 32, 64, 64, 0, 320, False, 0, False, 0)])
+def test_conv_halo_tiles_match_per_tap_tiles(case):
+    """3x3 convs on 8 x 16-pixel tiles whose 10 x 18 halo box is loaded once per 64-channel block (nine windows of it feed the
+    tensor core, rows 1280 B apart) against one 128-pixel box per tap (tedm_conv_set_halo(0)) and F.conv2d: image borders,
+    two sources, every N tile, GroupNorm partials, residual epilogue, more tiles than SMs, CTA pairs and single CTAs."""
+    from tedm_b200 import native as N
+    B, H, W, c0, c1, cout, use_bias, gn, use_res, force_bn = case
+    ctot = c0 + c1
+    x0, x1 = _rand((B, c0, H, W), 41), (_rand((B, c1, H, W), 42) if c1 else None)
+    w = _rand((cout, ctot, 3, 3), 43, (9 * ctot) ** -0.5)
+    b = _rand((cout,), 44, 0.1).cuda() if use_bias else None
+    res = _nhwc(_rand((B, cout, H, W), 45)) if use_res else None
+    wk = N.weight_to_krsc(w.cuda())
+    outs = []
+    try:
+        N.load().tedm_conv_set_tile_n(force_bn)
+        for halo, pairs in ((1, 1), (0, 1), (1, 0)):
+            N.load().tedm_conv_set_halo(halo)
+            N.set_cta_pairs(pairs)
+            outs.append(N.conv_igemm(_nhwc(x0), wk, 1, cout, bias=b, src1=_nhwc(x1) if c1 else None, gn_groups=gn, residual=res))
+    finally:
+        N.load().tedm_conv_set_halo(1)
+        N.set_cta_pairs(1)
+        N.load().tedm_conv_set_tile_n(0)
+    torch.cuda.synchronize()
+    if gn:
+        assert _rel(outs[0][1].sum(1), outs[1][1].sum(1)) < 1e-5
+        assert torch.equal(outs[0][1], outs[2][1])               # pairs and single CTAs add in the same order
+        outs = [o[0] for o in outs]
+    assert torch.equal(outs[0], outs[2])
+    assert _rel(outs[0].float(), outs[1].float()) < 2e-3         # same products, different accumulation order
+    ref = _ref_conv([x0] + ([x1] if c1 else []), w, b.cpu() if use_bias else None, 1)
+    if use_res:
+        ref = ref + res.float().permute(0, 3, 1, 2)
+    assert _rel(outs[0].float().permute(0, 3, 1, 2), ref) < 6e-3
+
+
 def test_cta_pairs_with_n256_tiles():
     """CTA pairs on the widest N tile (256 columns: each CTA stages 128 weight rows): bit-identical to single CTAs."""
     from tedm_b200 import native as N
@@ -194,7 +235,8 @@ def test_conv_ws4_tiles_match_single_row_tiles(case):
     if gn:
         assert four[1].shape == one[1].shape
         assert _rel(four[1].sum(1), one[1].sum(1)) < 1e-5
-        assert _rel(four[1], one[1]) < 1e-4                      # the partials keep their layout
+        if W >= 128:
+            assert _rel(four[1], one[1]) < 1e-4                  # the partials keep their layout (one per 128-pixel row)
         four, one = four[0], one[0]
     assert _rel(four.float(), one.float()) < 2e-3                # same products, different accumulation order
     ref = _ref_conv([x0] + ([x1] if c1 else []), w, b.cpu() if use_bias else None, 1)

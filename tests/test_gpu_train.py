@@ -33,7 +33,21 @@ def _model():
     return m.cuda()
 
 
-def _compare_grads(named_grads, g, tag):
+def _l1_sign_flips(m, gs):
+    """The L1 loss hands the backward sign(prediction - noise) / N: a prediction that bf16 rounding puts on the other side of its
+    target flips one of the N = 2048 entries of d loss / d output, which alone moves that vector by 2 / sqrt(N) = 4.4 % of its
+    norm.  Count those entries against the reference's prediction (fixture `unet_out`) so that the gradient tolerance can state
+    what it depends on instead of passing or failing with the rounding of one pixel."""
+    x0, t, nz = T(gs["x0"]).cuda(), T(gs["t"]).cuda(), T(gs["noise"]).cuda()
+    pred, noise = m(x0, t, noise=nz)                   # autograd-enabled: the training forward
+    ref = T(gs["unet_out"]).cuda()
+    flips = int((torch.sign(pred.detach().float() - noise) != torch.sign(ref - noise)).sum())
+    print("L1 sign flips against the reference prediction:", flips, "of", ref.numel())
+    assert flips <= 4                                   # measured 0-1
+    return flips
+
+
+def _compare_grads(named_grads, g, tag, flips=0):
     total_ref = np.sqrt(sum(float(g[f"norm/{n}"]) ** 2 for n, _ in named_grads))
     num = den = 0.0
     worst = []
@@ -49,22 +63,25 @@ def _compare_grads(named_grads, g, tag):
     worst.sort(reverse=True)
     overall = (num / den) ** 0.5
     print(f"[{tag}] whole-gradient rel err (sampled) {overall:.4f}; worst tensors:", [(round(a, 4), round(b, 4), n) for a, b, n in worst[:6]])
-    assert overall < 1.5e-2, overall
-    assert worst[0][0] < 9e-2, worst[:5]
-    assert max(w[1] for w in worst) < 2e-2, sorted(worst, key=lambda w: -w[1])[:5]
+    n_out = 2 * 32 * 32
+    assert overall < 1.5e-2 + 1.5 * 2 * flips ** 0.5 / n_out ** 0.5, (overall, flips)   # measured 0.6-1.2 % without a flip, 3.6 % with one
+    # (a flipped sign moves the bias gradients, plain sums of d loss / d output, by 2 of ~25)
+    assert worst[0][0] < 9e-2 + 0.1 * flips, worst[:5]
+    assert max(w[1] for w in worst) < 2e-2 + 0.1 * flips, sorted(worst, key=lambda w: -w[1])[:5]
 
 
 def test_train_step_gradients_match_reference(golden):
     g, gs = golden["ddpm_small_grads"], golden["ddpm_small"]
     m = _model()
     x0, t, nz = T(gs["x0"]).cuda(), T(gs["t"]).cuda(), T(gs["noise"]).cuda()
+    flips = _l1_sign_flips(m, gs)
     loss = m.train_step(x0, t=t, noise=nz)
     assert abs(loss.item() - float(g["loss"])) < 2e-2 * float(g["loss"])
     loss.backward()
     torch.cuda.synchronize()
     named = [(n, p.grad) for n, p in m.named_parameters()]
     assert all(gr is not None for _, gr in named)
-    _compare_grads(named, g, "ddpm_small")
+    _compare_grads(named, g, "ddpm_small", flips)
     # the gradients are slices of ONE arena in parameter order (what FusedAdam / the DP all-reduce rely on)
     base = named[0][1].data_ptr()
     off = 0
@@ -139,6 +156,7 @@ def test_fused_adam_step_matches_reference(golden):
     opt = FusedAdam(m.parameters(), lr=1e-4)
     x0, t, nz = T(gs["x0"]).cuda(), T(gs["t"]).cuda(), T(gs["noise"]).cuda()
     before = {n: p.detach().clone() for n, p in m.named_parameters()}
+    flips = _l1_sign_flips(m, gs)
     opt.zero_grad()
     m.train_step(x0, t=t, noise=nz).backward()
     opt.step()
@@ -155,7 +173,7 @@ def test_fused_adam_step_matches_reference(golden):
         agree += int((torch.sign(delta[big]) == torch.sign(delta_ref[big])).sum())
         total += int(big.sum())
     print("Adam step sign agreement", agree / total, total)
-    assert agree / total > 0.99                      # measured 0.9953
+    assert agree / total > 0.99 - 0.01 * flips       # measured 0.9953 without a flipped L1 sign, 0.9872 with one
     # a second forward must see the updated weights (derived bf16 weight caches invalidated by the step)
     with torch.no_grad():
         l2 = m.train_step(x0, t=t, noise=nz)
