@@ -1003,9 +1003,6 @@ conv_ws4_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 #pragma unroll
       for (int half = 0; half < 4 / G; ++half) {
         const int a = (4 / G) * g + half;           // accumulator = output row y0 + a
-        // the TMA store that last read this group's staging tile must be done with it; `red` of the previous row too
-        if (eg == 0) tma_store_wait_read<0>();
-        named_bar_sync(bar_a, GT);
         if (half == 0) {
           mbar_wait(smem_u32(&bar_acc_full[set]), (uint32_t)((it >> 1) & 1));
           tc_fence_after();
@@ -1014,6 +1011,9 @@ conv_ws4_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 #pragma unroll
           for (int i = 0; i < NV; ++i) gv[i] = 0.0f;
         }
+        // TMEM -> registers -> bias, GroupNorm sums, bf16: all of it BEFORE waiting for the staging tile, so that the TMA
+        // store of the previous row drains under this row's arithmetic
+        uint32_t pk[16 * WCH];
 #pragma unroll
         for (int ch = 0; ch < WCH; ++ch) {
           const int chunk = G == 2 ? ch : hsel;     // 32-column chunk of the 64 output channels
@@ -1042,22 +1042,32 @@ conv_ws4_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
               gv[2 * (ch * 4 + sg) + 1] += q_;
             }
           }
-          const uint32_t sub = out_buf + (uint32_t)row * 128u;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[ch * 16 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        }
+        const bool emit = CPG != 0 && (!W64 || (half & 1) == 1);
+        float t[NV];
+        if (emit) {
+#pragma unroll
+          for (int i = 0; i < NV; ++i) t[i] = gv[i];
+          butterfly_sum<NV>(t, lane, 32);           // lane l: value index l >> (NV == 16 ? 1 : 2)
+        }
+        // the TMA store that last read this group's staging tile must be done with it; `red` of the previous row too
+        if (eg == 0) tma_store_wait_read<0>();
+        named_bar_sync(bar_a, GT);
+        const uint32_t sub = out_buf + (uint32_t)row * 128u;
+#pragma unroll
+        for (int ch = 0; ch < WCH; ++ch) {
+          const int chunk = G == 2 ? ch : hsel;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t c16 = (uint32_t)(chunk * 4 + j);
             const uint32_t dst = sub + ((c16 ^ (uint32_t)(row & 7)) << 4);
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pack_bf16x2(v[8 * j], v[8 * j + 1])),
-                         "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])), "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])),
-                         "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7])) : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pk[ch * 16 + 4 * j]), "r"(pk[ch * 16 + 4 * j + 1]),
+                         "r"(pk[ch * 16 + 4 * j + 2]), "r"(pk[ch * 16 + 4 * j + 3]) : "memory");
           }
         }
-        const bool emit = CPG != 0 && (!W64 || (half & 1) == 1);
         if (emit) {
-          float t[NV];
-#pragma unroll
-          for (int i = 0; i < NV; ++i) t[i] = gv[i];
-          butterfly_sum<NV>(t, lane, 32);           // lane l: value index l >> (NV == 16 ? 1 : 2)
           constexpr int SH = NV == 16 ? 1 : 2;
           if ((lane & ((1 << SH) - 1)) == 0) red[G == 2 ? g : hsel][q][lane >> SH] = t[0];
         }
