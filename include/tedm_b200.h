@@ -140,6 +140,11 @@ typedef struct {
    * the raw output of block2's conv and this call is ResnetBlock's `block2(h) + res_conv(x)` (models/unet_model.py:174-175)
    * with GroupNorm, SiLU and the add done in the 1x1 conv's epilogue (needs tiles inside one image: Ho * Wo >= 128). */
   const float* residual_affine;
+  /* NULL, or fp32 [B][c0][2] from tedm_gn_affine: the conv's input is SiLU(a * src0 + b), i.e. src0 is the raw output of
+   * block1's conv and this call is Block.forward's GroupNorm + scale/shift + SiLU (models/unet_model.py:128-134) fused into
+   * block2's conv: the halo boxes are normalised in shared memory, the activation never reaches HBM.  Single-source 3x3 convs
+   * on the halo-tile path only (tedm_conv_src_affine_supported). */
+  const float* src0_affine;
 } tedm_conv_args;
 TEDM_API int tedm_conv_igemm_fwd(const tedm_conv_args* args, tedm_stream_t stream);
 /* Weight gradient of the same convolution (backward of models/unet_model.py:43,49,122,157,185,188,226,227,308,324):
@@ -165,6 +170,8 @@ TEDM_API int tedm_conv_set_deterministic(int enable);
  * (tcgen05 cta_group::2, clusters of two SMs: M = 256, each CTA stages its own pixels and half of the weight tile);
  * 0: one CTA per tile everywhere; 2: pairs wherever the geometry allows (tests, A/B runs). */
 TEDM_API int tedm_conv_set_cta_pairs(int enable);
+/* 1 if a 3x3 conv of this shape accepts tedm_conv_args.src0_affine */
+TEDM_API int tedm_conv_src_affine_supported(int height, int width, int c0, int cout);
 /* number of partial-statistics slots per image that tedm_conv_igemm_fwd writes for this output extent */
 TEDM_API int tedm_conv_gn_parts(int out_height, int out_width);
 /* tuning/debug: force the N tile (64/128/256; 0 = automatic) of tedm_conv_igemm_fwd */

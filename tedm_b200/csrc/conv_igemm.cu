@@ -45,7 +45,7 @@ constexpr int HALO_W = 8, HALO_H = 16;                         // halo mode: a t
 constexpr int HALO_PITCH = (HALO_W + 2) * BK * 2;              // bytes between image rows of the 10 x 18-pixel halo box
 constexpr int HALO_TX = (HALO_W + 2) * (HALO_H + 2) * BK * 2;  // 23040 B
 constexpr int HALO_BYTES = 23 * 1024;                          // padded to the 1 KB swizzle atom
-constexpr int MAX_HALO_STAGES = 3;
+constexpr int MAX_HALO_STAGES = 4;
 constexpr int DYN_SMEM_MAX = 221 * 1024;  // + ~3.3 KB static <= 227 KB per CTA
 
 constexpr int MAX_SRC = 6;
@@ -84,6 +84,7 @@ struct ConvParams {
   const bf16* residual2;
   long long out2_image_stride;
   const float2* res_affine;      // [B][cout] (a/2, b/2): the residual enters as SiLU(a * r + b)  (tiles inside one image)
+  const float* src_affine;       // AM = 3: [B][c0][2] (a/2, b/2): the conv's input is SiLU(a * src0 + b)
 };
 
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
@@ -162,6 +163,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, 
 //               weights once instead of once per tile.
 constexpr int EPI_THREADS = 256;   // 8 epilogue warps
 constexpr int CONV_THREADS = 64 + EPI_THREADS;
+constexpr int XF_THREADS = 128;    // AM = 3: four more warps that normalise the halo boxes in place
 
 //   CG = 2: CTA PAIRS (cta_group::2, cluster of two SMs of one TPC).  One tcgen05.mma spans both SMs: M = 256 = the two
 //               CTAs' 128-pixel tiles, each CTA feeds its own A rows and HALF of the weight tile (N / 2 rows), the
@@ -173,10 +175,16 @@ constexpr int CONV_THREADS = 64 + EPI_THREADS;
 //               pixels into the box, its 8-pixel rows 1280 B apart (the descriptor's stride between 8-row groups) instead of
 //               packed.  Shared memory carries the tensor core's operand reads AND the TMA's writes; this removes 8/9 of
 //               the activation writes (a slot of the main ring then holds only the weight tile of one (tap, channel block)).
+//   AM = 3 (halo mode with a fused input transform): the conv's input is SiLU(a * x + b) of the tensor the boxes are loaded
+//               from, (a, b) per (image, channel) from tedm_gn_affine -- Block's GroupNorm + scale/shift + SiLU
+//               (models/unet_model.py:128-134) applied to the halo box in shared memory by four extra warps, between the
+//               TMA's arrival and the tensor core's reads, so the normalised activation never exists in HBM.  A halo box is
+//               1.4 tiles of pixels and is loaded once, so the transform costs 1.4 MUFU per element (a per-tap A tile
+//               would need 9).  Pixels outside the image stay the TMA's zero fill (the conv pads the ACTIVATION).
 template <int BN, int AM, int CPG, bool RES, int CG>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+__global__ void __launch_bounds__(AM == 3 ? CONV_THREADS + XF_THREADS : CONV_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
-  constexpr bool WS = AM == 1, HALO = AM == 2;
+  constexpr bool WS = AM == 1, HALO = AM >= 2, XF = AM == 3;
   const CUtensorMap& mapW = maps.w;
   const CUtensorMap& mapOut = maps.out;
   const CUtensorMap& mapOut2 = maps.out2;
@@ -194,6 +202,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   __shared__ __align__(8) uint64_t bar_w;
   __shared__ __align__(8) uint64_t bar_afull[MAX_HALO_STAGES];
   __shared__ __align__(8) uint64_t bar_aempty[MAX_HALO_STAGES];
+  __shared__ __align__(8) uint64_t bar_aready[MAX_HALO_STAGES];   // AM = 3: box normalised (the pair's leader hears both CTAs)
   __shared__ uint32_t tmem_slot;
   __shared__ float red[2][4][2][4][2];   // [column half][lane quarter][segment][group][sum, sumsq]
   __shared__ __align__(16) float sbias[256];
@@ -224,6 +233,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     for (int i = 0; i < MAX_HALO_STAGES; ++i) {
       mbar_init(smem_u32(&bar_afull[i]), 1);
       mbar_init(smem_u32(&bar_aempty[i]), 1);
+      mbar_init(smem_u32(&bar_aready[i]), CG * (XF_THREADS / 32));
     }
     fence_barrier_init();
   }
@@ -255,6 +265,27 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
         if constexpr (CG == 2) tma_load_2d_pair(dst, m, bar, c0, c1);
         else tma_load_2d(dst, m, bar, c0, c1);
       };
+      int h_tile = tile0, h_cbg = 0;                // AM = 3: the next box to request
+      auto request_halo = [&]() {
+        if (h_tile >= tile_end) return;
+        const TileCoord th = decode_tile<CG>(p, h_tile, BN, rank);
+        mbar_wait(smem_u32(&bar_aempty[astage]), aphase ^ 1u);
+        const uint32_t afull = smem_u32(&bar_afull[astage]);
+        mbar_expect_tx(afull, HALO_TX);              // each CTA's transform warps wait for their OWN box: local barrier
+        tma_load_5d(halo_base + astage * HALO_BYTES, &maps.a[0], afull, h_cbg * BK, th.x0 - 1, 0, th.y0 - 1, th.b0);
+        if (++astage == p.a_stages) {
+          astage = 0;
+          aphase ^= 1u;
+        }
+        if (++h_cbg == cb_all) {
+          h_cbg = 0;
+          h_tile += tile_step;
+        }
+      };
+      if constexpr (XF) {
+        request_halo();
+        request_halo();
+      }
       if (WS) {
         const uint32_t bw = smem_u32(&bar_w);
         if (rank == 0) mbar_expect_tx(bw, CG * w_bytes);
@@ -271,6 +302,21 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
               const bool second = cb >= p.c0_blocks;
               load5(stage_base + stage * STAGE_BYTES, &maps.a[second ? 1 : 0], full,
                     (second ? cb - p.c0_blocks : cb) * BK, t.x0 - 1, 0, t.y0 + dy - 1, t.b0);
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+        } else if (XF) {
+          // boxes are requested TWO blocks ahead of the weight tiles, across tile boundaries (request_halo): a box has to
+          // land and be normalised before the tensor core reaches its block
+          for (int cbg = 0; cbg < cb_all; ++cbg)
+            for (int tap = 0; tap < 9; ++tap) {
+              if (tap == 0) request_halo();
+              mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+              const uint32_t full = smem_u32(&bar_full[stage]);
+              if (rank == 0) mbar_expect_tx(full, CG * STAGE_BYTES);
+              load2(stage_base + stage * STAGE_BYTES, &mapW, full, (tap * cb_all + cbg) * BK, t.n0 + rank * BNC);
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1u;
@@ -398,7 +444,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
         } else if (HALO) {
           const int cb_all = p.num_kb / p.taps;
           for (int cbg = 0; cbg < cb_all; ++cbg) {
-            mbar_wait(smem_u32(&bar_afull[astage]), aphase);
+            mbar_wait(smem_u32(XF ? &bar_aready[astage] : &bar_afull[astage]), aphase);
             tc_fence_after();
             const uint32_t h_addr = halo_base + astage * HALO_BYTES;
 #pragma unroll
@@ -441,6 +487,68 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
       }
     }
     __syncwarp();
+  } else if (XF && warp >= CONV_THREADS / 32) {
+    // ===== input transform (AM = 3): 128 threads; thread = (16-byte channel chunk, pixel row mod 16) ========
+    if constexpr (XF) {
+      const int tt = threadIdx.x - CONV_THREADS;
+      const int c8 = tt & 7, prow = tt >> 3;
+      const int cb_all = p.num_kb / p.taps;
+      const int csrc = p.src_C[0];
+      int astage = 0;
+      uint32_t aphase = 0;
+      for (int tile = tile0; tile < tile_end; tile += tile_step) {
+        const TileCoord t = decode_tile<CG>(p, tile, BN, rank);
+        for (int cbg = 0; cbg < cb_all; ++cbg) {
+          // (a / 2, b / 2) of this thread's 8 channels of image b0 (requested before the box is waited for)
+          const float4* ap = reinterpret_cast<const float4*>(p.src_affine + 2 * ((size_t)t.b0 * csrc + cbg * BK + c8 * 8));
+          float ca[8], cb[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 v = __ldg(ap + j);
+            ca[2 * j] = v.x;
+            cb[2 * j] = v.y;
+            ca[2 * j + 1] = v.z;
+            cb[2 * j + 1] = v.w;
+          }
+          mbar_wait(smem_u32(&bar_afull[astage]), aphase);
+          const uint32_t box = halo_base + astage * HALO_BYTES;
+          // pixel px = prow + 16 i of the 10 x 18 box: (px & 7) and with it the swizzled chunk position never change
+          int hy = prow / (HALO_W + 2), hx = prow - hy * (HALO_W + 2);
+          const uint32_t addr0 = box + (uint32_t)prow * 128u + ((uint32_t)(c8 ^ (prow & 7)) << 4);
+#pragma unroll 4
+          for (int i = 0; i < ((HALO_W + 2) * (HALO_H + 2) + 15) / 16; ++i) {
+            const int iy = t.y0 - 1 + hy, ix = t.x0 - 1 + hx;
+            const bool inside = prow + 16 * i < (HALO_W + 2) * (HALO_H + 2) && iy >= 0 && iy < p.Ho && ix >= 0 && ix < p.Wo;
+            hx += 6;                                   // 16 pixels further = one row and six pixels
+            hy += 1;
+            if (hx >= HALO_W + 2) {
+              hx -= HALO_W + 2;
+              hy += 1;
+            }
+            if (!inside) continue;                     // zero padding of the activation stays zero
+            const uint32_t addr = addr0 + (uint32_t)i * 2048u;
+            uint4 raw;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "r"(addr));
+            float f[8];
+            unpack8(raw, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = silu_half(fmaf(f[j], ca[j], cb[j]));
+            const uint4 o = pack8(f);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+          }
+          fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's (async proxy) reads
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_leader(smem_u32(&bar_aready[astage]));
+            else mbar_arrive(smem_u32(&bar_aready[astage]));
+          }
+          if (++astage == p.a_stages) {
+            astage = 0;
+            aphase ^= 1u;
+          }
+        }
+      }
+    }
   } else {
     // ===== epilogue: 8 warps; warp w reads TMEM lane quarter (w & 3) and half of the tile's columns ==========
     constexpr int CH = BN / 64;                 // 32-column chunks per warp
@@ -720,12 +828,14 @@ int encode_weight_map(CUtensorMap* map, const void* ptr, long long rows, long lo
 
 template <int BN, int AM, int CPG, bool RES, int CG>
 int launch_conv_cg(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
-  constexpr bool WS = AM == 1, HALO = AM == 2;
+  constexpr bool WS = AM == 1, HALO = AM >= 2;
+  constexpr int NTHREADS = AM == 3 ? CONV_THREADS + XF_THREADS : CONV_THREADS;
   const int cb_total = p.c0_blocks + p.c1_blocks;
   const int b_bytes = (BN / CG) * BK * 2;            // per-CTA share of a weight tile
   const int stage_bytes = WS ? A_ROW_BYTES : (HALO ? b_bytes : A_BYTES + b_bytes);
   const int out_bytes = (BN / 64) * A_BYTES;
-  p.a_stages = HALO ? (p.num_kb / p.taps > 1 ? 2 : 1) + 1 : 0;      // one box per 64-channel block in flight + one being consumed
+  // one box per 64-channel block in flight + one being consumed (AM = 3: requested two blocks ahead, one being normalised)
+  p.a_stages = HALO ? (AM == 3 ? 4 : (p.num_kb / p.taps > 1 ? 2 : 1) + 1) : 0;
   const int base = 1024 + (WS ? 9 * cb_total * b_bytes : 0) + p.a_stages * HALO_BYTES;
   // double-buffer the output staging tile when that still leaves >= 4 pipeline slots
   p.out_bufs = (DYN_SMEM_MAX - base - 2 * out_bytes) / stage_bytes >= 4 ? 2 : 1;
@@ -743,11 +853,11 @@ int launch_conv_cg(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
   const int work = p.num_tiles / CG;                   // tiles per CTA (pair)
   int grid = (work < tedm_num_sms() / CG ? work : tedm_num_sms() / CG) * CG;
   if constexpr (CG == 1) {
-    conv_igemm_kernel<BN, AM, CPG, RES, 1><<<grid, CONV_THREADS, smem, stream>>>(maps, p);
+    conv_igemm_kernel<BN, AM, CPG, RES, 1><<<grid, NTHREADS, smem, stream>>>(maps, p);
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(CONV_THREADS);
+    cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -772,7 +882,7 @@ int launch_conv_res(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
 // residual / split-output epilogues exist only without GroupNorm statistics (they never co-occur in the net)
 template <int BN, int AM, int CPG>
 int launch_conv_cpg(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
-  if constexpr (CPG == 0) {
+  if constexpr (CPG == 0 && AM != 3) {
     if (p.residual || p.residual2 || p.split) return launch_conv_res<BN, AM, 0, true>(maps, p, stream);
   }
   return launch_conv_res<BN, AM, CPG, false>(maps, p, stream);
@@ -1637,6 +1747,14 @@ extern "C" int tedm_conv_set_halo(int enable) {
   return TEDM_OK;
 }
 
+extern "C" int tedm_conv_src_affine_supported(int height, int width, int c0, int cout) {
+  // mirrors the halo-mode selection of tedm_conv_igemm_fwd for a single-source 3x3 conv with GroupNorm groups of cout / 8
+  if (!g_enable_halo || width % HALO_W != 0 || height % HALO_H != 0 || !is_pow2(height) || !is_pow2(width)) return 0;
+  const bool ws_geom = g_enable_ws && width >= BM && cout == 64 && c0 <= 128;
+  const bool w64_geom = g_enable_ws == 1 && width == 64 && height % 4 == 0 && c0 == 64 && cout == 64;
+  return (!ws_geom && !w64_geom && c0 % BK == 0 && cout % 64 == 0) ? 1 : 0;
+}
+
 extern "C" int tedm_conv_gn_parts(int out_height, int out_width) {
   const long long hw = (long long)out_height * out_width;
   return hw >= BM ? (int)(hw / BM) : 1;
@@ -1704,6 +1822,12 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
                         (!a->gn_partial || a->cout / a->gn_groups == 8);
   const bool halo = g_enable_halo && a->mode == 1 && a->n_extra == 0 && p.Wo % HALO_W == 0 && p.Ho % HALO_H == 0 && !ws_geom &&
                     !w64_geom;
+  if (a->src0_affine) {
+    TEDM_UNSUPPORTED(!halo || a->src1 || a->residual || a->split || a->out_dtype != 0,
+                     "tedm_conv_igemm_fwd: src0_affine needs a single-source 3x3 conv on the halo-tile path, plain bf16 output "
+                     "(see tedm_conv_src_affine_supported)");
+    p.src_affine = a->src0_affine;
+  }
   if (halo) {
     p.tileW = HALO_W;
     p.tileH = HALO_H;
@@ -1845,6 +1969,13 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
     return launch_ws4_cpg<2, false>(maps.a[0], a1, mapW, mapOut, q, s);
   }
   if (ws) return launch_conv<64, 1>(maps, p, s);
+  if (halo && p.src_affine) {
+    switch (bn) {
+      case 64: return launch_conv<64, 3>(maps, p, s);
+      case 128: return launch_conv<128, 3>(maps, p, s);
+      default: return launch_conv<256, 3>(maps, p, s);
+    }
+  }
   if (halo) {
     switch (bn) {
       case 64: return launch_conv<64, 2>(maps, p, s);

@@ -83,6 +83,8 @@ class UnetEngine:
         self.linear_attention_tc = os.environ.get("TEDM_LINATTN_TC", "1") != "0"
         # inference: res_conv + GroupNorm + SiLU + add of a ResnetBlock's tail in one kernel; TEDM_FUSE_RES=0 keeps the two passes
         self.fuse_res_conv = os.environ.get("TEDM_FUSE_RES", "1") != "0"
+        # inference: block1's GroupNorm + SiLU applied to block2's conv input in shared memory; TEDM_FUSE_GN=0 keeps the pass
+        self.fuse_gn_into_conv = os.environ.get("TEDM_FUSE_GN", "1") != "0"
         # backward: weight gradients run on a side stream next to the data-gradient chain (they only meet in the optimiser);
         # at the low-resolution levels neither kernel fills the 148 SMs on its own
         self.overlap_wgrad = True
@@ -235,6 +237,28 @@ class UnetEngine:
     def _resblock(self, key: str, rb: nn.Module, x0: Tensor, x1: Optional[Tensor], tproj: Optional[Tensor],
                   tape: Optional[Tape] = None) -> Tensor:
         ss_off = self._ss_offset[id(rb)]
+        b2 = rb.block2
+        c_mid, c_out = b2.proj.weight.shape[1], b2.proj.weight.shape[0]
+        if (tape is None and self.fuse_gn_into_conv and N.conv_src_affine_supported(x0.shape[1], x0.shape[2], c_mid, c_out)):
+            # inference: block1's GroupNorm + scale/shift + SiLU is applied to block2's halo boxes in shared memory
+            b1 = rb.block1
+            h1, part1 = N.conv_igemm(x0, self._w(key + ".block1.proj"), N.MODE_3X3, c_mid, bias=self._f32(b1.proj.bias), src1=x1,
+                                     gn_groups=b1.norm.num_groups)
+            aff1 = N.gn_affine(part1, self._f32(b1.norm.weight), self._f32(b1.norm.bias), b1.norm.num_groups,
+                               h1.shape[1] * h1.shape[2], eps=b1.norm.eps, scale_shift=tproj, ss_offset=ss_off)
+            h2, part2 = N.conv_igemm(h1, self._w(key + ".block2.proj"), N.MODE_3X3, c_out, bias=self._f32(b2.proj.bias),
+                                     gn_groups=b2.norm.num_groups, src0_affine=aff1)
+            if isinstance(rb.res_conv, nn.Conv2d) and self.fuse_res_conv:
+                aff2 = N.gn_affine(part2, self._f32(b2.norm.weight), self._f32(b2.norm.bias), b2.norm.num_groups,
+                                   h2.shape[1] * h2.shape[2], eps=b2.norm.eps)
+                return N.conv_igemm(x0, self._w(key + ".res_conv"), N.MODE_1X1, c_out, bias=self._f32(rb.res_conv.bias), src1=x1,
+                                    residual=h2, residual_affine=aff2)
+            if isinstance(rb.res_conv, nn.Conv2d):
+                res = N.conv_igemm(x0, self._w(key + ".res_conv"), N.MODE_1X1, c_out, bias=self._f32(rb.res_conv.bias), src1=x1)
+            else:
+                res = x0
+            return N.gn_silu(h2, part2, self._f32(b2.norm.weight), self._f32(b2.norm.bias), b2.norm.num_groups, eps=b2.norm.eps,
+                             residual=res)
         h = self._block(key + ".block1", rb.block1, x0, x1, tproj, ss_off, None, tape)
         if isinstance(rb.res_conv, nn.Conv2d) and tape is None and self.fuse_res_conv and h.shape[1] * h.shape[2] >= 128:
             # inference: block2's GroupNorm + SiLU and the residual add happen in the epilogue of the 1x1 res_conv, which

@@ -24,7 +24,7 @@ class ConvArgs(C.Structure):  # tedm_conv_args
                 ("cout", _i), ("mode", _i), ("gn_groups", _i), ("out_dtype", _i), ("src0_image_stride", _i64),
                 ("src1_image_stride", _i64), ("out_image_stride", _i64), ("split", _i), ("out2", _p), ("residual2", _p),
                 ("n_extra", _i), ("extra_src", _p * 4), ("extra_c", _i * 4), ("extra_image_stride", _i64 * 4),
-                ("extra_center", _i * 4), ("residual_affine", _p)]
+                ("extra_center", _i * 4), ("residual_affine", _p), ("src0_affine", _p)]
 
 
 class WeightEntry(C.Structure):  # tedm_weight_entry
@@ -53,6 +53,7 @@ SIGNATURES = {
     "tedm_conv_igemm_wgrad_workspace": (_i64, []),
     "tedm_prepare_weights": (_i, [_p, _i, _i, _p]),
     "tedm_conv_gn_parts": (_i, [_i, _i]),
+    "tedm_conv_src_affine_supported": (_i, [_i, _i, _i, _i]),
     "tedm_gn_affine": (_i, [_p, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _f, _p]),
     "tedm_conv_set_tile_n": (_i, [_i]),
     "tedm_conv_set_ws": (_i, [_i]),
@@ -302,13 +303,14 @@ def _nhwc(t: Optional[torch.Tensor], name: str, dtype=torch.bfloat16):
 
 def conv_igemm(src0: torch.Tensor, weight: torch.Tensor, mode: int, cout: int, bias=None, src1=None, residual=None,
                gn_groups: int = 0, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16, split: int = 0,
-               residual2=None, extra: Sequence = (), residual_affine=None):
+               residual2=None, extra: Sequence = (), residual_affine=None, src0_affine=None):
     """Returns out (B, Ho, Wo, cout) bf16 (or fp32) [, gn_partial (B, parts, groups, 2) fp32 if gn_groups > 0].
     src0/src1/out may be batch-strided views (e.g. x[s::S]); residual must share out's strides.
     split > 0: returns (out[..., :split], out2[..., split:]) as two dense tensors (+ residual / residual2).
     extra: up to four more A sources [(tensor, centre_only)], walked after src0/src1 inside every tap (centre_only: a
     1x1 branch folded into the centre tap of a 3x3).
-    residual_affine: (B, cout, 2) fp32 from gn_affine(): the residual enters as SiLU(GroupNorm(residual))."""
+    residual_affine: (B, cout, 2) fp32 from gn_affine(): the residual enters as SiLU(GroupNorm(residual)).
+    src0_affine: (B, c0, 2) fp32 from gn_affine(): the conv reads SiLU(GroupNorm(src0)) (conv_src_affine_supported())."""
     b, h, w, c0 = src0.shape
     c1 = src1.shape[3] if src1 is not None else 0
     if src1 is not None and src1.shape[:3] != src0.shape[:3]:
@@ -350,6 +352,10 @@ def conv_igemm(src0: torch.Tensor, weight: torch.Tensor, mode: int, cout: int, b
         if residual is None or tuple(residual_affine.shape) != (b, cout, 2):
             raise ValueError("conv_igemm: residual_affine is (B, cout, 2) and needs a residual")
         a.residual_affine = _ptr(residual_affine, torch.float32, "residual_affine")
+    if src0_affine is not None:
+        if tuple(src0_affine.shape) != (b, c0, 2):
+            raise ValueError("conv_igemm: src0_affine is (B, c0, 2)")
+        a.src0_affine = _ptr(src0_affine, torch.float32, "src0_affine")
     a.n_extra = len(extra)
     for i, (t, ctr) in enumerate(extra):
         if t.shape[:3] != src0.shape[:3]:
@@ -429,6 +435,10 @@ def gn_silu(x, gn_partial, gamma, beta, groups: int, eps: float = 1e-5, scale_sh
     else:
         _call(*args)
     return out
+
+
+def conv_src_affine_supported(h: int, w: int, c0: int, cout: int) -> bool:
+    return bool(load().tedm_conv_src_affine_supported(h, w, c0, cout))
 
 
 def gn_affine(gn_partial, gamma, beta, groups: int, hw: int, eps: float = 1e-5, scale_shift=None, ss_offset: int = 0):

@@ -188,6 +188,57 @@ def test_conv_halo_tiles_match_per_tap_tiles(case):
     assert _rel(outs[0].float().permute(0, 3, 1, 2), ref) < 6e-3
 
 
+@pytest.mark.parametrize("case", [(2, 64, 64, 128, 128, True, 0), (3, 16, 16, 512, 512, True, 0), (2, 32, 32, 256, 256, False, 0),
+                                  (1, 16, 16, 64, 128, True, 64), (40, 16, 16, 128, 128, True, 0), (2, 128, 128, 128, 128, False, 0)])
+def test_conv_input_groupnorm_fused_into_halo_boxes(case):
+    """Block.forward's GroupNorm + (scale + 1) / shift + SiLU (reference models/unet_model.py:128-134) applied to the conv's
+    halo boxes in shared memory (src0_affine) against the separate pass followed by the same conv: the normalised values are
+    rounded to bf16 by the same expression in both, so the outputs are bit-identical; pairs and single CTAs."""
+    from tedm_b200 import native as N
+    B, H, W, c, cout, with_ss, force_bn = case
+    groups = 8
+    assert N.conv_src_affine_supported(H, W, c, cout)
+    xin = _rand((B, c, H, W), 51)
+    w1, b1 = _rand((c, c, 3, 3), 52, (9 * c) ** -0.5), _rand((c,), 53, 0.1)
+    w2, b2 = _rand((cout, c, 3, 3), 54, (9 * c) ** -0.5), _rand((cout,), 55, 0.1)
+    gamma, beta = (1.0 + _rand((c,), 56, 0.2)).cuda(), _rand((c,), 57, 0.2).cuda()
+    ss = _rand((B, 2 * c + 6), 58, 0.3).cuda() if with_ss else None
+    h1, part = N.conv_igemm(_nhwc(xin), N.weight_to_krsc(w1.cuda()), 1, c, bias=b1.cuda(), gn_groups=groups)
+    a1 = N.gn_silu(h1, part, gamma, beta, groups, scale_shift=ss, ss_offset=3)
+    aff = N.gn_affine(part, gamma, beta, groups, H * W, scale_shift=ss, ss_offset=3)
+    w2k = N.weight_to_krsc(w2.cuda())
+    outs = []
+    try:
+        N.load().tedm_conv_set_tile_n(force_bn)
+        for pairs in (1, 0):
+            N.set_cta_pairs(pairs)
+            two = N.conv_igemm(a1, w2k, 1, cout, bias=b2.cuda(), gn_groups=groups)
+            one = N.conv_igemm(h1, w2k, 1, cout, bias=b2.cuda(), gn_groups=groups, src0_affine=aff)
+            outs.append((two, one))
+    finally:
+        N.set_cta_pairs(1)
+        N.load().tedm_conv_set_tile_n(0)
+    torch.cuda.synchronize()
+    for two, one in outs:
+        assert _rel(one[0].float(), two[0].float()) < 1e-6, _rel(one[0].float(), two[0].float())
+        assert torch.equal(one[0], two[0]) and torch.equal(one[1], two[1])
+    hf = h1.float().permute(0, 3, 1, 2)
+    y = F.group_norm(hf, groups, gamma, beta, 1e-5)
+    if with_ss:
+        y = y * (ss[:, 3:3 + c, None, None] + 1) + ss[:, 3 + c:3 + 2 * c, None, None]
+    ref = F.conv2d(F.silu(y).to(torch.bfloat16).float(), w2.to(torch.bfloat16).float().cuda(), b2.cuda(), padding=1)
+    assert _rel(outs[0][1][0].float().permute(0, 3, 1, 2), ref) < 8e-3
+
+
+def test_conv_src_affine_is_refused_off_the_halo_path():
+    from tedm_b200 import native as N
+    assert not N.conv_src_affine_supported(128, 128, 64, 64) and not N.conv_src_affine_supported(8, 8, 256, 256)
+    x = torch.zeros(2, 8, 8, 64, dtype=torch.bfloat16, device="cuda")
+    w = torch.zeros(64, 3, 3, 64, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(RuntimeError, match="src0_affine"):
+        N.conv_igemm(x, w, 1, 64, src0_affine=torch.zeros(2, 64, 2, device="cuda"))
+
+
 def test_cta_pairs_with_n256_tiles():
     """CTA pairs on the widest N tile (256 columns: each CTA stages 128 weight rows): bit-identical to single CTAs."""
     from tedm_b200 import native as N
