@@ -128,6 +128,25 @@ __device__ __forceinline__ void butterfly_sum(float (&vals)[NV], int lane, int w
   }
 }
 
+// SiLU(a * x + b) on the 8 bf16 values of a 16-byte chunk, (a, b) already halved (silu(z) = z/2 + z/2 * tanh(z/2)): the exact
+// expression of gn_silu_kernel, so that a fused consumer and the separate pass round to the same bf16 values
+__device__ __forceinline__ uint4 affine_silu8(const uint4& raw, const float (&ca)[8], const float (&cb)[8]) {
+  float f[8];
+  unpack8(raw, f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = silu_half(fmaf(f[j], ca[j], cb[j]));
+  return pack8(f);
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128_if(bool pred, uint32_t addr, const uint4& v) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %5, 0;\n @p st.shared.v4.u32 [%0], {%1,%2,%3,%4};\n}" ::"r"(addr), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w), "r"((int)pred) : "memory");
+}
+
 struct TileCoord {
   int b0, y0, x0, n0, par, trem;
 };
@@ -512,29 +531,32 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
           }
           mbar_wait(smem_u32(&bar_afull[astage]), aphase);
           const uint32_t box = halo_base + astage * HALO_BYTES;
-          // pixel px = prow + 16 i of the 10 x 18 box: (px & 7) and with it the swizzled chunk position never change
-          int hy = prow / (HALO_W + 2), hx = prow - hy * (HALO_W + 2);
+          // pixel px = prow + 16 i of the 10 x 18 box: (px & 7) and with it the swizzled chunk position never change.
+          // Straight-line code, six chunks at a time: all loads first (shared memory is busy feeding the tensor core, a
+          // dependent load costs hundreds of cycles), predicated stores instead of branches.
+          constexpr int NPX = (HALO_W + 2) * (HALO_H + 2), NIT = (NPX + 15) / 16;
           const uint32_t addr0 = box + (uint32_t)prow * 128u + ((uint32_t)(c8 ^ (prow & 7)) << 4);
-#pragma unroll 4
-          for (int i = 0; i < ((HALO_W + 2) * (HALO_H + 2) + 15) / 16; ++i) {
-            const int iy = t.y0 - 1 + hy, ix = t.x0 - 1 + hx;
-            const bool inside = prow + 16 * i < (HALO_W + 2) * (HALO_H + 2) && iy >= 0 && iy < p.Ho && ix >= 0 && ix < p.Wo;
-            hx += 6;                                   // 16 pixels further = one row and six pixels
-            hy += 1;
-            if (hx >= HALO_W + 2) {
-              hx -= HALO_W + 2;
-              hy += 1;
-            }
-            if (!inside) continue;                     // zero padding of the activation stays zero
-            const uint32_t addr = addr0 + (uint32_t)i * 2048u;
-            uint4 raw;
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "r"(addr));
-            float f[8];
-            unpack8(raw, f);
+          int hy = prow / (HALO_W + 2), hx = prow - hy * (HALO_W + 2);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = silu_half(fmaf(f[j], ca[j], cb[j]));
-            const uint4 o = pack8(f);
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+          for (int i0 = 0; i0 < NIT; i0 += 6) {
+            uint4 raw[6];
+            bool inside[6];
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+              const int i = i0 + u;
+              const int iy = t.y0 - 1 + hy, ix = t.x0 - 1 + hx;
+              inside[u] = i < NIT && prow + 16 * i < NPX && iy >= 0 && iy < p.Ho && ix >= 0 && ix < p.Wo;
+              hx += 6;                                 // 16 pixels further = one row and six pixels
+              hy += 1;
+              if (hx >= HALO_W + 2) {
+                hx -= HALO_W + 2;
+                hy += 1;
+              }
+              raw[u] = lds128(addr0 + (uint32_t)(inside[u] ? i : 0) * 2048u);
+            }
+#pragma unroll
+            for (int u = 0; u < 6; ++u)                // pixels outside the image keep the TMA's zero fill
+              sts128_if(inside[u], addr0 + (uint32_t)(inside[u] ? i0 + u : 0) * 2048u, affine_silu8(raw[u], ca, cb));
           }
           fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's (async proxy) reads
           __syncwarp();
@@ -940,15 +962,21 @@ struct Ws4Params {
   const float* bias;
   float* gn_partial;
   int gn_groups, gn_parts;
+  int H, W;
+  const float* src_affine;       // XF: [B][64][2] (a/2, b/2): the conv's input is SiLU(a * src + b)
 };
 
 constexpr int WS4_THREADS = 64 + 256;
 
-template <int CPG, int CB, bool W64>
-__global__ void __launch_bounds__(WS4_THREADS, 1)
+// XF (one channel block, 128-pixel rows): the input rows are normalised in place -- SiLU(a * x + b), the GroupNorm + scale/shift
+// + SiLU of the Block that produced them -- by four extra warps between the TMA's arrival and the tensor core's reads (see
+// conv_igemm_kernel AM = 3); an input row is fetched once per tile, so this costs 1.5 MUFU per element.
+template <int CPG, int CB, bool W64, bool XF>
+__global__ void __launch_bounds__(XF ? WS4_THREADS + XF_THREADS : WS4_THREADS, 1)
 conv_ws4_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                 const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapOut, const Ws4Params p) {
   static_assert(!(W64 && CB != 1), "64-pixel rows: one channel block");
+  static_assert(!XF || (CB == 1 && !W64), "input transform: one channel block, 128-pixel rows");
   constexpr int W_TILE = 192 * BK * 2;               // [W(dy=2) | W(dy=1) | W(dy=0)] of one (dx, channel block): 24 KB
   constexpr int W_BYTES = 3 * CB * W_TILE;
   constexpr int SLOT_BYTES = W64 ? A_BYTES : A_ROW_BYTES;
@@ -965,6 +993,8 @@ conv_ws4_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   __shared__ __align__(8) uint64_t bar_w;
   __shared__ uint32_t tmem_slot;
   __shared__ float red[2][4][16];     // [group, or column half when one group][lane quarter][values]
+  __shared__ __align__(8) uint64_t bar_ready[XF ? MAX_STAGES : 1];   // XF: row normalised
+  __shared__ __align__(16) float sbias[XF ? 64 : 4];                 // XF: the bias lives here instead of in registers
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -985,7 +1015,12 @@ conv_ws4_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       mbar_init(smem_u32(&bar_acc_empty[i]), 8);
     }
     mbar_init(smem_u32(&bar_w), 1);
+    if constexpr (XF)
+      for (int s = 0; s < p.stages; ++s) mbar_init(smem_u32(&bar_ready[s]), XF_THREADS / 32);
     fence_barrier_init();
+  }
+  if constexpr (XF) {
+    if (threadIdx.x < 64) sbias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.0f;
   }
   if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
   tc_fence_before();
@@ -1061,7 +1096,7 @@ conv_ws4_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           const uint32_t d_tmem = tmem_base + (uint32_t)(set * 256 + A_FIRST[s] * 64);
 #pragma unroll
           for (int u = 0; u < (W64 ? 3 : CB); ++u) {
-            mbar_wait(smem_u32(&bar_full[stage]), phase);
+            mbar_wait(smem_u32(XF ? &bar_ready[stage] : &bar_full[stage]), phase);
             tc_fence_after();
             const uint32_t a_addr = stage_base + stage * SLOT_BYTES;
 #pragma unroll
@@ -1084,6 +1119,56 @@ conv_ws4_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       }
     }
     __syncwarp();
+  } else if (XF && warp >= WS4_THREADS / 32) {
+    // ===== input transform (XF): 128 threads; thread = (16-byte channel chunk, pixel mod 16) ================
+    if constexpr (XF) {
+      const int tt = threadIdx.x - WS4_THREADS;
+      const int c8 = tt & 7, prow = tt >> 3;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int b, y0, x0;
+        tile_coord(tile, b, y0, x0);
+        const float4* ap = reinterpret_cast<const float4*>(p.src_affine + 2 * ((size_t)b * 64 + c8 * 8));
+        float ca[8], cb[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 v = __ldg(ap + j);
+          ca[2 * j] = v.x;
+          cb[2 * j] = v.y;
+          ca[2 * j + 1] = v.z;
+          cb[2 * j + 1] = v.w;
+        }
+#pragma unroll 1
+        for (int s = 0; s < 6; ++s) {
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          const int y = y0 + R_OFF[s];
+          if (y >= 0 && y < p.H) {                  // rows outside the image stay the TMA's zero fill
+            // straight-line: all nine loads first (shared memory is busy feeding the tensor core), predicated stores
+            constexpr int NIT = (ROW_PIX + 15) / 16;
+            const uint32_t addr0 = stage_base + stage * SLOT_BYTES + (uint32_t)prow * 128u + ((uint32_t)(c8 ^ (prow & 7)) << 4);
+            uint4 raw[NIT];
+            bool inside[NIT];
+#pragma unroll
+            for (int i = 0; i < NIT; ++i) {
+              const int px = prow + 16 * i, x = x0 - 1 + px;
+              inside[i] = px < ROW_PIX && x >= 0 && x < p.W;
+              raw[i] = lds128(addr0 + (uint32_t)(inside[i] ? i : 0) * 2048u);
+            }
+#pragma unroll
+            for (int i = 0; i < NIT; ++i)
+              sts128_if(inside[i], addr0 + (uint32_t)(inside[i] ? i : 0) * 2048u, affine_silu8(raw[i], ca, cb));
+          }
+          fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's (async proxy) reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bar_ready[stage]));
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
   } else {
     // ===== epilogue ===========================================================================
     // two groups (warps 2..5 / 6..9; 64 columns per thread; group g takes output rows 2g, 2g+1) or one group of eight warps
@@ -1095,14 +1180,16 @@ conv_ws4_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     const int eg = threadIdx.x - 64 - g * GT;       // index inside the group
     const uint32_t out_buf = out_base + (uint32_t)g * A_BYTES;
     const int bar_a = 1 + 2 * g, bar_b = 2 + 2 * g;
-    float bias_r[32 * WCH];
+    float bias_r[XF ? 1 : 32 * WCH];
+    if constexpr (!XF) {
 #pragma unroll
-    for (int j = 0; j < 8 * WCH; ++j) {
-      const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias) + hsel * 8 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-      bias_r[4 * j] = bv.x;
-      bias_r[4 * j + 1] = bv.y;
-      bias_r[4 * j + 2] = bv.z;
-      bias_r[4 * j + 3] = bv.w;
+      for (int j = 0; j < 8 * WCH; ++j) {
+        const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias) + hsel * 8 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bias_r[4 * j] = bv.x;
+        bias_r[4 * j + 1] = bv.y;
+        bias_r[4 * j + 2] = bv.z;
+        bias_r[4 * j + 3] = bv.w;
+      }
     }
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -1138,7 +1225,7 @@ conv_ws4_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           }
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + bias_r[ch * 32 + j];
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + (XF ? sbias[chunk * 32 + j] : bias_r[XF ? 0 : ch * 32 + j]);
           if (CPG) {
 #pragma unroll
             for (int sg = 0; sg < 4; ++sg) {
@@ -1211,7 +1298,7 @@ conv_ws4_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-template <int CPG, int CB, bool W64>
+template <int CPG, int CB, bool W64, bool XF>
 int launch_ws4(const CUtensorMap& mapA0, const CUtensorMap& mapA1, const CUtensorMap& mapW, const CUtensorMap& mapOut,
                Ws4Params& p, cudaStream_t stream) {
   const int slot = W64 ? A_BYTES : A_ROW_BYTES;
@@ -1223,11 +1310,11 @@ int launch_ws4(const CUtensorMap& mapA0, const CUtensorMap& mapA1, const CUtenso
   const int smem = fixed + stages * slot;
   static int configured = 0;
   if (configured < smem) {
-    TEDM_CUDA(cudaFuncSetAttribute(conv_ws4_kernel<CPG, CB, W64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TEDM_CUDA(cudaFuncSetAttribute(conv_ws4_kernel<CPG, CB, W64, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
   const int grid = p.num_tiles < tedm_num_sms() ? p.num_tiles : tedm_num_sms();
-  conv_ws4_kernel<CPG, CB, W64><<<grid, WS4_THREADS, smem, stream>>>(mapA0, mapA1, mapW, mapOut, p);
+  conv_ws4_kernel<CPG, CB, W64, XF><<<grid, XF ? WS4_THREADS + XF_THREADS : WS4_THREADS, smem, stream>>>(mapA0, mapA1, mapW, mapOut, p);
   TEDM_LAUNCH_CHECK();
   return TEDM_OK;
 }
@@ -1235,8 +1322,13 @@ int launch_ws4(const CUtensorMap& mapA0, const CUtensorMap& mapA1, const CUtenso
 template <int CB, bool W64>
 int launch_ws4_cpg(const CUtensorMap& mapA0, const CUtensorMap& mapA1, const CUtensorMap& mapW, const CUtensorMap& mapOut,
                    Ws4Params& p, cudaStream_t stream) {
-  return p.gn_partial ? launch_ws4<8, CB, W64>(mapA0, mapA1, mapW, mapOut, p, stream)
-                      : launch_ws4<0, CB, W64>(mapA0, mapA1, mapW, mapOut, p, stream);
+  if constexpr (CB == 1 && !W64) {
+    if (p.src_affine)
+      return p.gn_partial ? launch_ws4<8, CB, W64, true>(mapA0, mapA1, mapW, mapOut, p, stream)
+                          : launch_ws4<0, CB, W64, true>(mapA0, mapA1, mapW, mapOut, p, stream);
+  }
+  return p.gn_partial ? launch_ws4<8, CB, W64, false>(mapA0, mapA1, mapW, mapOut, p, stream)
+                      : launch_ws4<0, CB, W64, false>(mapA0, mapA1, mapW, mapOut, p, stream);
 }
 
 // ==========================================================================================
@@ -1749,10 +1841,11 @@ extern "C" int tedm_conv_set_halo(int enable) {
 
 extern "C" int tedm_conv_src_affine_supported(int height, int width, int c0, int cout) {
   // mirrors the halo-mode selection of tedm_conv_igemm_fwd for a single-source 3x3 conv with GroupNorm groups of cout / 8
-  if (!g_enable_halo || width % HALO_W != 0 || height % HALO_H != 0 || !is_pow2(height) || !is_pow2(width)) return 0;
+  if (!is_pow2(height) || !is_pow2(width) || c0 % BK != 0 || cout % 64 != 0) return 0;
   const bool ws_geom = g_enable_ws && width >= BM && cout == 64 && c0 <= 128;
   const bool w64_geom = g_enable_ws == 1 && width == 64 && height % 4 == 0 && c0 == 64 && cout == 64;
-  return (!ws_geom && !w64_geom && c0 % BK == 0 && cout % 64 == 0) ? 1 : 0;
+  if (ws_geom) return (g_enable_ws == 1 && c0 == 64 && height % 4 == 0) ? 1 : 0;     // conv_ws4_kernel<.., XF>
+  return (g_enable_halo && width % HALO_W == 0 && height % HALO_H == 0 && !w64_geom) ? 1 : 0;
 }
 
 extern "C" int tedm_conv_gn_parts(int out_height, int out_width) {
@@ -1823,9 +1916,11 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   const bool halo = g_enable_halo && a->mode == 1 && a->n_extra == 0 && p.Wo % HALO_W == 0 && p.Ho % HALO_H == 0 && !ws_geom &&
                     !w64_geom;
   if (a->src0_affine) {
-    TEDM_UNSUPPORTED(!halo || a->src1 || a->residual || a->split || a->out_dtype != 0,
-                     "tedm_conv_igemm_fwd: src0_affine needs a single-source 3x3 conv on the halo-tile path, plain bf16 output "
-                     "(see tedm_conv_src_affine_supported)");
+    // the halo-tile path, or the four-row weight-stationary kernel with one channel block on 128-pixel rows
+    const bool ws4_xf = ws_geom && g_enable_ws == 1 && a->c0 == 64 && p.Ho % 4 == 0 && (!a->gn_partial || a->cout / a->gn_groups == 8);
+    TEDM_UNSUPPORTED((!halo && !ws4_xf) || a->src1 || a->residual || a->split || a->out_dtype != 0,
+                     "tedm_conv_igemm_fwd: src0_affine needs a single-source 3x3 conv on the halo-tile or four-row path, plain "
+                     "bf16 output (see tedm_conv_src_affine_supported)");
     p.src_affine = a->src0_affine;
   }
   if (halo) {
@@ -1963,6 +2058,9 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
     q.gn_partial = p.gn_partial;
     q.gn_groups = p.gn_groups;
     q.gn_parts = p.gn_parts;
+    q.H = p.Ho;
+    q.W = p.Wo;
+    q.src_affine = p.src_affine;
     const CUtensorMap& a1 = maps.a[p.n_src > 1 ? 1 : 0];
     if (w64) return launch_ws4_cpg<1, true>(maps.a[0], a1, mapW, mapOut, q, s);
     if (a->c0 + a->c1 == 64) return launch_ws4_cpg<1, false>(maps.a[0], a1, mapW, mapOut, q, s);

@@ -85,6 +85,8 @@ class UnetEngine:
         self.fuse_res_conv = os.environ.get("TEDM_FUSE_RES", "1") != "0"
         # inference: block1's GroupNorm + SiLU applied to block2's conv input in shared memory; TEDM_FUSE_GN=0 keeps the pass
         self.fuse_gn_into_conv = os.environ.get("TEDM_FUSE_GN", "1") != "0"
+        self.fuse_gn_min_bytes = int(os.environ.get("TEDM_FUSE_GN_MIN_MB", "0")) << 20    # A/B: only tensors at least this large
+        self.fuse_gn_ws4 = os.environ.get("TEDM_FUSE_GN_WS4", "1") != "0"                # A/B: the four-row kernel's variant
         # backward: weight gradients run on a side stream next to the data-gradient chain (they only meet in the optimiser);
         # at the low-resolution levels neither kernel fills the 148 SMs on its own
         self.overlap_wgrad = True
@@ -239,7 +241,9 @@ class UnetEngine:
         ss_off = self._ss_offset[id(rb)]
         b2 = rb.block2
         c_mid, c_out = b2.proj.weight.shape[1], b2.proj.weight.shape[0]
-        if (tape is None and self.fuse_gn_into_conv and N.conv_src_affine_supported(x0.shape[1], x0.shape[2], c_mid, c_out)):
+        if (tape is None and self.fuse_gn_into_conv and N.conv_src_affine_supported(x0.shape[1], x0.shape[2], c_mid, c_out)
+                and x0.shape[0] * x0.shape[1] * x0.shape[2] * c_mid * 2 >= self.fuse_gn_min_bytes
+                and (self.fuse_gn_ws4 or not (x0.shape[2] >= 128 and c_out == 64))):
             # inference: block1's GroupNorm + scale/shift + SiLU is applied to block2's halo boxes in shared memory
             b1 = rb.block1
             h1, part1 = N.conv_igemm(x0, self._w(key + ".block1.proj"), N.MODE_3X3, c_mid, bias=self._f32(b1.proj.bias), src1=x1,

@@ -189,11 +189,13 @@ def test_conv_halo_tiles_match_per_tap_tiles(case):
 
 
 @pytest.mark.parametrize("case", [(2, 64, 64, 128, 128, True, 0), (3, 16, 16, 512, 512, True, 0), (2, 32, 32, 256, 256, False, 0),
-                                  (1, 16, 16, 64, 128, True, 64), (40, 16, 16, 128, 128, True, 0), (2, 128, 128, 128, 128, False, 0)])
+                                  (1, 16, 16, 64, 128, True, 64), (40, 16, 16, 128, 128, True, 0), (2, 128, 128, 128, 128, False, 0),
+                                  (3, 128, 128, 64, 64, True, 0), (150, 4, 128, 64, 64, True, 0), (2, 8, 256, 64, 64, False, 0)])
 def test_conv_input_groupnorm_fused_into_halo_boxes(case):
     """Block.forward's GroupNorm + (scale + 1) / shift + SiLU (reference models/unet_model.py:128-134) applied to the conv's
-    halo boxes in shared memory (src0_affine) against the separate pass followed by the same conv: the normalised values are
-    rounded to bf16 by the same expression in both, so the outputs are bit-identical; pairs and single CTAs."""
+    halo boxes in shared memory (src0_affine; the input rows of the four-row weight-stationary kernel for 64 -> 64 on 128-pixel
+    rows) against the separate pass followed by the same conv: the normalised values are rounded to bf16 by the same expression
+    in both, so the outputs are bit-identical; pairs and single CTAs."""
     from tedm_b200 import native as N
     B, H, W, c, cout, with_ss, force_bn = case
     groups = 8
@@ -232,7 +234,8 @@ def test_conv_input_groupnorm_fused_into_halo_boxes(case):
 
 def test_conv_src_affine_is_refused_off_the_halo_path():
     from tedm_b200 import native as N
-    assert not N.conv_src_affine_supported(128, 128, 64, 64) and not N.conv_src_affine_supported(8, 8, 256, 256)
+    assert not N.conv_src_affine_supported(64, 64, 64, 64) and not N.conv_src_affine_supported(8, 8, 256, 256)
+    assert not N.conv_src_affine_supported(128, 128, 128, 64)
     x = torch.zeros(2, 8, 8, 64, dtype=torch.bfloat16, device="cuda")
     w = torch.zeros(64, 3, 3, 64, dtype=torch.bfloat16, device="cuda")
     with pytest.raises(RuntimeError, match="src0_affine"):
