@@ -83,8 +83,11 @@ class UnetEngine:
         self.linear_attention_tc = os.environ.get("TEDM_LINATTN_TC", "1") != "0"
         # inference: res_conv + GroupNorm + SiLU + add of a ResnetBlock's tail in one kernel; TEDM_FUSE_RES=0 keeps the two passes
         self.fuse_res_conv = os.environ.get("TEDM_FUSE_RES", "1") != "0"
-        # inference: block1's GroupNorm + SiLU applied to block2's conv input in shared memory; TEDM_FUSE_GN=0 keeps the pass
-        self.fuse_gn_into_conv = os.environ.get("TEDM_FUSE_GN", "1") != "0"
+        # inference: block1's GroupNorm + SiLU applied to block2's conv input in shared memory instead of a pass of its own
+        # (bit-identical).  OFF by default: measured on B200 it removes 0.33 ms of GroupNorm passes per step and adds about as
+        # much to the convs (the transform's LDS / STS / MUFU compete with the tensor core for shared memory and issue slots):
+        # 8.88-8.96 ms against 8.99-9.08 ms, inside the box-to-box noise; TEDM_FUSE_GN=1 turns it on
+        self.fuse_gn_into_conv = os.environ.get("TEDM_FUSE_GN", "0") != "0"
         self.fuse_gn_min_bytes = int(os.environ.get("TEDM_FUSE_GN_MIN_MB", "0")) << 20    # A/B: only tensors at least this large
         self.fuse_gn_ws4 = os.environ.get("TEDM_FUSE_GN_WS4", "1") != "0"                # A/B: the four-row kernel's variant
         # backward: weight gradients run on a side stream next to the data-gradient chain (they only meet in the optimiser);

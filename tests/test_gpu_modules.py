@@ -57,6 +57,30 @@ def test_walking_the_submodules_equals_unet_forward(with_t):
     assert walked.shape == ref.shape and _rel(walked, ref) < TOL and _rel(walked, fused) < TOL
 
 
+def test_groupnorm_fused_into_conv_is_bit_identical_through_the_unet():
+    """engine.fuse_gn_into_conv (Block's GroupNorm + SiLU applied to the next conv's input in shared memory) and
+    engine.fuse_res_conv (ResnetBlock's tail in the res_conv epilogue) against the plain schedule: the first is bit-identical,
+    the second rounds once less."""
+    m, sd = _unet()
+    x = synth_images(3, 64, 5).cuda()
+    t = synth_timesteps(3, seed=5).cuda()
+    eng = m.engine
+    saved = (eng.fuse_gn_into_conv, eng.fuse_res_conv)
+    try:
+        outs = {}
+        for gn, res in ((False, False), (True, False), (False, True), (True, True)):
+            eng.fuse_gn_into_conv, eng.fuse_res_conv = gn, res
+            with torch.no_grad():
+                outs[(gn, res)] = m(x, t)
+    finally:
+        eng.fuse_gn_into_conv, eng.fuse_res_conv = saved
+    assert torch.equal(outs[(True, False)], outs[(False, False)])
+    assert torch.equal(outs[(True, True)], outs[(False, True)])
+    ref = O.unet_forward(sd, x.cpu(), t.cpu())
+    assert _rel(outs[(False, True)], outs[(False, False)]) < 5e-3
+    assert _rel(outs[(True, True)], ref) < TOL and _rel(outs[(False, False)], ref) < TOL
+
+
 def test_each_submodule_against_the_oracle():
     m, sd = _unet()
     g = torch.Generator().manual_seed(1)
