@@ -53,6 +53,7 @@ constexpr int MAX_SRC = 6;
 struct ConvMaps {                // every tensor map of a launch (one __grid_constant__ parameter: its elements are addressable)
   CUtensorMap a[MAX_SRC];
   CUtensorMap w, out, out2;
+  CUtensorMap res;               // res_tma: the residual tensor, same geometry as `out`
 };
 
 struct ConvParams {
@@ -85,6 +86,7 @@ struct ConvParams {
   long long out2_image_stride;
   const float2* res_affine;      // [B][cout] (a/2, b/2): the residual enters as SiLU(a * r + b)  (tiles inside one image)
   const float* src_affine;       // AM = 3: [B][c0][2] (a/2, b/2): the conv's input is SiLU(a * src0 + b)
+  int res_tma;                   // 1: the residual tile is TMA-loaded into the output staging tile one tile ahead (3 buffers)
 };
 
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
@@ -222,6 +224,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   __shared__ __align__(8) uint64_t bar_afull[MAX_HALO_STAGES];
   __shared__ __align__(8) uint64_t bar_aempty[MAX_HALO_STAGES];
   __shared__ __align__(8) uint64_t bar_aready[MAX_HALO_STAGES];   // AM = 3: box normalised (the pair's leader hears both CTAs)
+  __shared__ __align__(8) uint64_t bar_res[3];                    // res_tma: residual tile landed in staging buffer i
   __shared__ uint32_t tmem_slot;
   __shared__ float red[2][4][2][4][2];   // [column half][lane quarter][segment][group][sum, sumsq]
   __shared__ __align__(16) float sbias[256];
@@ -254,6 +257,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
       mbar_init(smem_u32(&bar_aempty[i]), 1);
       mbar_init(smem_u32(&bar_aready[i]), CG * (XF_THREADS / 32));
     }
+    for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&bar_res[i]), 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -621,15 +625,26 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
         if (p.res_affine) aff_next = __ldg(p.res_affine + (size_t)tt.b0 * p.cout + tt.n0 + e);
       }
     };
+    // res_tma (1x1 convs with a residual): the residual tile of tile i + 1 is TMA-loaded into the staging buffer tile i + 1 will
+    // leave through -- coalesced, no registers, a whole tile of lead time -- and added in place; three staging buffers, so the
+    // buffer being refilled is the one whose store (tile i - 2) has certainly been read
+    const bool res_tma = RES && p.res_tma;
+    auto load_res_tile = [&](const TileCoord& tt, int slot) {
+      const uint32_t bar = smem_u32(&bar_res[slot]);
+      mbar_expect_tx(bar, OUT_BYTES);
+      for (int sidx = 0; sidx < BN / 64; ++sidx)
+        tma_load_5d(out_base + (uint32_t)(slot * OUT_BYTES + sidx * A_BYTES), &maps.res, bar, tt.n0 + sidx * 64, tt.x0, 0, tt.y0, tt.b0);
+    };
     if constexpr (PIPE) {
       if (tile0 < tile_end) {
         const TileCoord t0 = decode_tile<CG>(p, tile0, BN, rank);
-        fetch_res(t0, rnext, hnext);
+        if (!res_tma) fetch_res(t0, rnext, hnext);
+        else if (e == 0) load_res_tile(t0, 0);
         fetch_consts(t0);
       }
     }
-    int it = 0;
-    for (int tile = tile0; tile < tile_end; tile += tile_step, ++it) {
+    int it = 0, obuf = 0;                       // obuf = it % out_bufs
+    for (int tile = tile0; tile < tile_end; tile += tile_step, ++it, obuf = obuf + 1 == p.out_bufs ? 0 : obuf + 1) {
       const TileCoord t = decode_tile<CG>(p, tile, BN, rank);
       const int par_y = t.par >> 1, par_x = t.par & 1;
       const int b = t.b0 + tb, y = t.y0 + ty, x = t.x0 + tx;
@@ -638,12 +653,17 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
       const size_t pixoff = (size_t)oy * p.OW + ox;
       const size_t opix = (size_t)b * p.out_image_stride + pixoff * p.cout + t.n0;
       const int buf = it & 1;
-      const uint32_t out_buf = out_base + (p.out_bufs == 2 ? (uint32_t)(buf * OUT_BYTES) : 0u);
+      const uint32_t out_buf = out_base + (uint32_t)(obuf * OUT_BYTES);
+      const int obuf_next = obuf + 1 == p.out_bufs ? 0 : obuf + 1;
       // the TMA store that last used this staging buffer must have drained it; every thread must be done
       // with the previous tile's `red` / `sbias` before this tile overwrites them (barrier below)
       if (e == 0 && !p.out_f32) {
-        if (p.out_bufs == 2) tma_store_wait_read<1>();
+        if (p.out_bufs >= 2) tma_store_wait_read<1>();
         else tma_store_wait_read<0>();
+        if constexpr (PIPE) {
+          // at most the store of tile i - 1 is still reading: buffer (i + 1) % 3, last used by tile i - 2, is free
+          if (res_tma && tile + tile_step < tile_end) load_res_tile(decode_tile<CG>(p, tile + tile_step, BN, rank), obuf_next);
+        }
       }
       if constexpr (PIPE) {
         if (e < BN) {
@@ -669,7 +689,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
         for (int i = 0; i < CH; ++i) has_res[i] = hnext[i];
         if (tile + tile_step < tile_end) {
           const TileCoord tn = decode_tile<CG>(p, tile + tile_step, BN, rank);
-          fetch_res(tn, rnext, hnext);
+          if (!res_tma) fetch_res(tn, rnext, hnext);
           fetch_consts(tn);
         }
       } else if constexpr (RES) {
@@ -677,6 +697,9 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
       }
       mbar_wait(smem_u32(&bar_acc_full[buf]), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
+      if constexpr (PIPE) {
+        if (res_tma) mbar_wait(smem_u32(&bar_res[obuf]), (uint32_t)((it / 3) & 1));
+      }
       float gv[NV];
 #pragma unroll
       for (int i = 0; i < NV; ++i) gv[i] = 0.0f;
@@ -711,11 +734,16 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
           }
         }
         if constexpr (RES) {
-          if (has_res[i]) {
+          if (res_tma || has_res[i]) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float f[8];
-              unpack8(rpre[i * 4 + j], f);
+              if (res_tma) {                       // the residual sits where this thread's result will go
+                const uint32_t c16 = (uint32_t)(half * 4 + j);
+                unpack8(lds128(out_buf + (uint32_t)cp * A_BYTES + (uint32_t)row * 128u + ((c16 ^ (uint32_t)(row & 7)) << 4)), f);
+              } else {
+                unpack8(rpre[i * 4 + j], f);
+              }
               if (p.res_affine) {
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -861,6 +889,10 @@ int launch_conv_cg(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
   const int base = 1024 + (WS ? 9 * cb_total * b_bytes : 0) + p.a_stages * HALO_BYTES;
   // double-buffer the output staging tile when that still leaves >= 4 pipeline slots
   p.out_bufs = (DYN_SMEM_MAX - base - 2 * out_bytes) / stage_bytes >= 4 ? 2 : 1;
+  if (p.res_tma) {
+    if (RES && BN <= 128 && (DYN_SMEM_MAX - base - 3 * out_bytes) / stage_bytes >= 3) p.out_bufs = 3;
+    else p.res_tma = 0;
+  }
   const int fixed = base + p.out_bufs * out_bytes;
   int stages = (DYN_SMEM_MAX - fixed) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -1801,6 +1833,7 @@ int g_deterministic = 0;  // tedm_conv_set_deterministic
 
 int g_enable_ws = 1;  // tedm_conv_set_ws
 int g_enable_halo = 1;  // tedm_conv_set_halo
+int g_enable_res_tma = 1;   // tedm_conv_set_halo(2) turns it off (A/B)
 int g_enable_pairs = 1;  // tedm_conv_set_cta_pairs
 int g_force_bn = 0;  // debug/tuning override (tedm_conv_set_tile_n)
 
@@ -1835,6 +1868,7 @@ extern "C" int tedm_conv_set_ws(int enable) {
 }
 
 extern "C" int tedm_conv_set_halo(int enable) {
+  g_enable_res_tma = enable != 2;         // 2 = halo tiles on, residual tiles of the 1x1 convs through registers (A/B)
   g_enable_halo = enable != 0;
   return TEDM_OK;
 }
@@ -2044,6 +2078,14 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
     if (rc) return rc;
   } else {
     mapOut2 = mapOut;
+  }
+  // 1x1 convs with a residual: the residual tile travels by TMA into the output staging tile (launch_conv_cg decides whether
+  // three staging buffers fit)
+  maps.res = mapOut;
+  if (g_enable_res_tma && a->mode == 0 && a->residual && !a->split && !p.out_f32 && bn <= 128) {
+    rc = encode_act_map(&maps.res, a->residual, a->batch, p.OH, p.OW, a->cout, p.out_image_stride, 0, p.tileW, p.tileH, p.tileB);
+    if (rc) return rc;
+    p.res_tma = 1;
   }
 
   cudaStream_t s = (cudaStream_t)stream;
