@@ -465,7 +465,7 @@ def run_ours(args):
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj
-    roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (all conv launches of one step)", "achieved": achieved,
+    roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_ws4_kernel (all conv launches of one step)", "achieved": achieved,
                 "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
                 "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
                 "traffic": traffic, "traffic_unit": "bytes/launch of the dominant launch (see traffic_source)",
