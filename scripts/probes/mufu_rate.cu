@@ -1,3 +1,4 @@
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/probes/mufu_rate scripts/probes/mufu_rate.cu   (measured on B200: 16 tanh / ex2 per clock per SM)
 // MUFU throughput probe: tanh.approx.f32 vs ex2.approx.f32 vs rcp.approx.f32 per SM per clock (B200).
 #include <cstdio>
 #include <cuda_runtime.h>
