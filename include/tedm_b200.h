@@ -181,7 +181,8 @@ TEDM_API int tedm_conv_set_wgrad_halo(int enable);
 /* tuning/debug: enable (default) / disable the weight-stationary row path of the 3x3 conv */
 TEDM_API int tedm_conv_set_ws(int enable);
 /* 3x3 convolutions on images of >= 16 rows run on 8 x 16-pixel tiles whose 10 x 18 halo box serves all nine taps (1, default);
- * 0 = one activation box per tap everywhere (A/B runs, tests). */
+ * 0 = one activation box per tap everywhere; 2 = 1 with the residual tiles of the 1x1 convs fetched through registers instead
+ * of TMA; 3 = 1 plus halo tiles for the folded upsample conv (measured slower) -- A/B runs and tests. */
 TEDM_API int tedm_conv_set_halo(int enable);
 
 /* fp32 OIHW [Cout][Cin][kh][kw] -> bf16 KRSC [Cout][kh][kw][Cin] (derived weight cache). */

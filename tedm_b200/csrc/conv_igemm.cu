@@ -271,6 +271,18 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   const uint32_t tmem_base = tmem_slot;
   const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
   const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG, tile_end = p.num_tiles / CG;
+  // halo mode on the folded upsample conv (mode 3): the four parity tiles of an M tile read the SAME 10 x 18 box (their 2 x 2
+  // taps are the windows (ky + parity_y, kx + parity_x) of it), so a CTA takes them in a row -- with one N tile they are
+  // consecutive tile indices -- and the boxes of all channel blocks stay resident for the four of them
+  const bool quad = HALO && p.mode == 3;
+  auto seq_tile = [&](int k) -> int {        // the k-th tile of this CTA (pair), or -1
+    if (quad) {
+      const int g4 = (tile0 + (k >> 2) * tile_step) * 4;
+      return g4 < tile_end ? g4 + (k & 3) : -1;
+    }
+    const int tl = tile0 + k * tile_step;
+    return tl < tile_end ? tl : -1;
+  };
 
   if (warp == 0) {
     // ===== TMA producer =====================================================================
@@ -314,7 +326,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
         if (rank == 0) mbar_expect_tx(bw, CG * w_bytes);
         for (int i = 0; i < 9 * cb_total; ++i) load2(smem_base + (uint32_t)i * B_BYTES, &mapW, bw, i * BK, rank * BNC);
       }
-      for (int tile = tile0; tile < tile_end; tile += tile_step) {
+      for (int k = 0, tile; (tile = seq_tile(k)) >= 0; ++k) {
         const TileCoord t = decode_tile<CG>(p, tile, BN, rank);
         if (WS) {
           for (int dy = 0; dy < 3; ++dy)
@@ -346,8 +358,8 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
               }
             }
         } else if (HALO) {
-          // per 64-channel block: the halo box once, then the nine weight tiles; the next block's box is requested after
-          // the second weight tile, so that it lands while this block is multiplied
+          // per 64-channel block: the halo box once, then the weight tiles of its taps; the next block's box is requested
+          // after the second weight tile, so that it lands while this block is multiplied
           auto load_halo = [&](int si, int cblk) {
             mbar_wait(smem_u32(&bar_aempty[astage]), aphase ^ 1u);
             const uint32_t afull = smem_u32(&bar_afull[astage]);
@@ -358,7 +370,21 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
               aphase ^= 1u;
             }
           };
-          load_halo(0, 0);
+          const int ntap = p.taps;                    // 9, or the 2 x 2 of one parity of the folded upsample conv
+          if (quad) {
+            if ((k & 3) == 0) {                       // the boxes of every channel block, kept for the four parities
+              int si = 0, cblk = 0;
+              for (int cbg = 0; cbg < cb_all; ++cbg) {
+                load_halo(si, cblk);
+                if (++cblk == p.src_blocks[si]) {
+                  cblk = 0;
+                  ++si;
+                }
+              }
+            }
+          } else {
+            load_halo(0, 0);
+          }
           int si = 0, cblk = 0;
           for (int cbg = 0; cbg < cb_all; ++cbg) {
             int nsi = si, ncblk = cblk + 1;            // the block after this one
@@ -366,12 +392,12 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
               ncblk = 0;
               ++nsi;
             }
-            for (int tap = 0; tap < 9; ++tap) {
-              if (tap == 2 && cbg + 1 < cb_all) load_halo(nsi, ncblk);
+            for (int tap = 0; tap < ntap; ++tap) {
+              if (!quad && tap == 2 && cbg + 1 < cb_all) load_halo(nsi, ncblk);
               mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
               const uint32_t full = smem_u32(&bar_full[stage]);
               if (rank == 0) mbar_expect_tx(full, CG * STAGE_BYTES);
-              load2(stage_base + stage * STAGE_BYTES, &mapW, full, (tap * cb_all + cbg) * BK, t.n0 + rank * BNC);
+              load2(stage_base + stage * STAGE_BYTES, &mapW, full, (tap * cb_all + cbg) * BK, t.par * p.cout + t.n0 + rank * BNC);
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1u;
@@ -440,7 +466,9 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
         mbar_wait(smem_u32(&bar_w), 0);
         tc_fence_after();
       }
-      for (int tile = tile0; tile < tile_end; tile += tile_step, ++it) {
+      int g_astage = 0;
+      uint32_t g_aphase = 0;
+      for (int tile; (tile = seq_tile(it)) >= 0; ++it) {
         const int buf = it & 1;
         mbar_wait(smem_u32(&bar_acc_empty[buf]), (uint32_t)(((it >> 1) & 1) ^ 1));
         tc_fence_after();
@@ -466,15 +494,30 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
             }
         } else if (HALO) {
           const int cb_all = p.num_kb / p.taps;
+          const int ntap = p.taps;
+          int par_y = 0, par_x = 0;
+          if (quad) {
+            // the same boxes for the four parities: walk the group's slots again from where its first tile found them
+            if ((it & 3) == 0) {
+              g_astage = astage;
+              g_aphase = aphase;
+            } else {
+              astage = g_astage;
+              aphase = g_aphase;
+            }
+            const int par = tile & 3;                 // one N tile: the parity is the fastest tile index
+            par_y = par >> 1;
+            par_x = par & 1;
+          }
           for (int cbg = 0; cbg < cb_all; ++cbg) {
             mbar_wait(smem_u32(XF ? &bar_aready[astage] : &bar_afull[astage]), aphase);
             tc_fence_after();
             const uint32_t h_addr = halo_base + astage * HALO_BYTES;
-#pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int tap = 0; tap < ntap; ++tap) {
               mbar_wait(smem_u32(&bar_full[stage]), phase);
               tc_fence_after();
-              const uint64_t adesc = make_sw128_desc_sbo(h_addr + (uint32_t)((tap / 3) * HALO_PITCH + (tap % 3) * BK * 2), HALO_PITCH);
+              const int wy = quad ? (tap >> 1) + par_y : tap / 3, wx = quad ? (tap & 1) + par_x : tap % 3;
+              const uint64_t adesc = make_sw128_desc_sbo(h_addr + (uint32_t)(wy * HALO_PITCH + wx * BK * 2), HALO_PITCH);
               const uint64_t bdesc = make_sw128_desc(stage_base + stage * STAGE_BYTES);
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) umma(d_tmem, adesc + 2ull * k, bdesc + 2ull * k, (cbg | tap | k) != 0 ? 1u : 0u);
@@ -484,7 +527,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                 phase ^= 1u;
               }
             }
-            commit(smem_u32(&bar_aempty[astage]));
+            if (!quad || (it & 3) == 3) commit(smem_u32(&bar_aempty[astage]));
             if (++astage == p.a_stages) {
               astage = 0;
               aphase ^= 1u;
@@ -636,15 +679,15 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
         tma_load_5d(out_base + (uint32_t)(slot * OUT_BYTES + sidx * A_BYTES), &maps.res, bar, tt.n0 + sidx * 64, tt.x0, 0, tt.y0, tt.b0);
     };
     if constexpr (PIPE) {
-      if (tile0 < tile_end) {
-        const TileCoord t0 = decode_tile<CG>(p, tile0, BN, rank);
+      if (seq_tile(0) >= 0) {
+        const TileCoord t0 = decode_tile<CG>(p, seq_tile(0), BN, rank);
         if (!res_tma) fetch_res(t0, rnext, hnext);
         else if (e == 0) load_res_tile(t0, 0);
         fetch_consts(t0);
       }
     }
     int it = 0, obuf = 0;                       // obuf = it % out_bufs
-    for (int tile = tile0; tile < tile_end; tile += tile_step, ++it, obuf = obuf + 1 == p.out_bufs ? 0 : obuf + 1) {
+    for (int tile; (tile = seq_tile(it)) >= 0; ++it, obuf = obuf + 1 == p.out_bufs ? 0 : obuf + 1) {
       const TileCoord t = decode_tile<CG>(p, tile, BN, rank);
       const int par_y = t.par >> 1, par_x = t.par & 1;
       const int b = t.b0 + tb, y = t.y0 + ty, x = t.x0 + tx;
@@ -662,7 +705,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
         else tma_store_wait_read<0>();
         if constexpr (PIPE) {
           // at most the store of tile i - 1 is still reading: buffer (i + 1) % 3, last used by tile i - 2, is free
-          if (res_tma && tile + tile_step < tile_end) load_res_tile(decode_tile<CG>(p, tile + tile_step, BN, rank), obuf_next);
+          if (res_tma && seq_tile(it + 1) >= 0) load_res_tile(decode_tile<CG>(p, seq_tile(it + 1), BN, rank), obuf_next);
         }
       }
       if constexpr (PIPE) {
@@ -687,8 +730,8 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
         for (int i = 0; i < CH * 4; ++i) rpre[i] = rnext[i];
 #pragma unroll
         for (int i = 0; i < CH; ++i) has_res[i] = hnext[i];
-        if (tile + tile_step < tile_end) {
-          const TileCoord tn = decode_tile<CG>(p, tile + tile_step, BN, rank);
+        if (seq_tile(it + 1) >= 0) {
+          const TileCoord tn = decode_tile<CG>(p, seq_tile(it + 1), BN, rank);
           if (!res_tma) fetch_res(tn, rnext, hnext);
           fetch_consts(tn);
         }
@@ -885,7 +928,9 @@ int launch_conv_cg(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
   const int stage_bytes = WS ? A_ROW_BYTES : (HALO ? b_bytes : A_BYTES + b_bytes);
   const int out_bytes = (BN / 64) * A_BYTES;
   // one box per 64-channel block in flight + one being consumed (AM = 3: requested two blocks ahead, one being normalised)
+  const int cb_all = p.taps ? p.num_kb / p.taps : 1;
   p.a_stages = HALO ? (AM == 3 ? 4 : (p.num_kb / p.taps > 1 ? 2 : 1) + 1) : 0;
+  if (HALO && p.mode == 3) p.a_stages = 2 * cb_all <= MAX_HALO_STAGES ? 2 * cb_all : cb_all;   // resident for four parity tiles
   const int base = 1024 + (WS ? 9 * cb_total * b_bytes : 0) + p.a_stages * HALO_BYTES;
   // double-buffer the output staging tile when that still leaves >= 4 pipeline slots
   p.out_bufs = (DYN_SMEM_MAX - base - 2 * out_bytes) / stage_bytes >= 4 ? 2 : 1;
@@ -904,7 +949,7 @@ int launch_conv_cg(const ConvMaps& maps, ConvParams& p, cudaStream_t stream) {
     TEDM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, AM, CPG, RES, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  const int work = p.num_tiles / CG;                   // tiles per CTA (pair)
+  const int work = p.num_tiles / CG / (HALO && p.mode == 3 ? 4 : 1);   // tiles (groups of four parity tiles) per CTA (pair)
   int grid = (work < tedm_num_sms() / CG ? work : tedm_num_sms() / CG) * CG;
   if constexpr (CG == 1) {
     conv_igemm_kernel<BN, AM, CPG, RES, 1><<<grid, NTHREADS, smem, stream>>>(maps, p);
@@ -1834,6 +1879,7 @@ int g_deterministic = 0;  // tedm_conv_set_deterministic
 int g_enable_ws = 1;  // tedm_conv_set_ws
 int g_enable_halo = 1;  // tedm_conv_set_halo
 int g_enable_res_tma = 1;   // tedm_conv_set_halo(2) turns it off (A/B)
+int g_enable_halo3 = 0;     // tedm_conv_set_halo(3): halo tiles for the folded upsample conv too (measured slower)
 int g_enable_pairs = 1;  // tedm_conv_set_cta_pairs
 int g_force_bn = 0;  // debug/tuning override (tedm_conv_set_tile_n)
 
@@ -1869,6 +1915,7 @@ extern "C" int tedm_conv_set_ws(int enable) {
 
 extern "C" int tedm_conv_set_halo(int enable) {
   g_enable_res_tma = enable != 2;         // 2 = halo tiles on, residual tiles of the 1x1 convs through registers (A/B)
+  g_enable_halo3 = enable == 3;           // 3 = halo tiles for the folded upsample conv as well (A/B, tests)
   g_enable_halo = enable != 0;
   return TEDM_OK;
 }
@@ -1947,8 +1994,14 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   const bool w64_geom = g_enable_ws == 1 && a->mode == 1 && p.Wo == 64 && p.Ho % 4 == 0 && a->c0 == 64 && a->c1 == 0 &&
                         a->n_extra == 0 && a->cout == 64 && a->out_dtype == 0 && !a->residual && !a->split &&
                         (!a->gn_partial || a->cout / a->gn_groups == 8);
-  const bool halo = g_enable_halo && a->mode == 1 && a->n_extra == 0 && p.Wo % HALO_W == 0 && p.Ho % HALO_H == 0 && !ws_geom &&
-                    !w64_geom;
+  // ... and, only with tedm_conv_set_halo(3), the folded upsample conv (mode 3) with one N tile and at most four channel blocks
+  // (their boxes stay resident for the four parity tiles of an M tile).  Measured on B200: 128 -> 64 @64x64 0.322 ms against
+  // 0.300 ms with one box per (parity, tap), 256 -> 128 @32x32 0.178 against 0.135: these tiles have K = 4 taps x 2-4 blocks
+  // and are bound by their epilogues, not by operand traffic, so the default keeps the per-tap tiles.
+  const bool halo3 = g_enable_halo3 && a->mode == 3 && a->n_extra == 0 && a->c1 == 0 && p.Wo % HALO_W == 0 && p.Ho % HALO_H == 0 &&
+                     a->c0 <= 4 * BK && (a->cout == 64 || a->cout == 128 || a->cout == 256) && g_force_bn == 0;
+  const bool halo = (g_enable_halo && a->mode == 1 && a->n_extra == 0 && p.Wo % HALO_W == 0 && p.Ho % HALO_H == 0 && !ws_geom &&
+                     !w64_geom) || halo3;
   if (a->src0_affine) {
     // the halo-tile path, or the four-row weight-stationary kernel with one channel block on 128-pixel rows
     const bool ws4_xf = ws_geom && g_enable_ws == 1 && a->c0 == 64 && p.Ho % 4 == 0 && (!a->gn_partial || a->cout / a->gn_groups == 8);
@@ -2013,6 +2066,7 @@ extern "C" int tedm_conv_igemm_fwd(const tedm_conv_args* a, tedm_stream_t stream
   for (int i = 2; i >= 0 && bn == 0; --i)  // nothing fills the machine: take the narrowest legal tile
     if (legal(cands[i])) bn = cands[i];
   if (g_force_bn && legal(g_force_bn)) bn = g_force_bn;
+  if (halo3) bn = a->cout;                   // one N tile: the four parities of an M tile are consecutive tile indices
   TEDM_UNSUPPORTED(bn == 0, "tedm_conv_igemm_fwd: no N tile for cout=%d with %d-channel GroupNorm groups", a->cout, p.gn_cpg);
   const long long num_tiles = m_tiles * zdim * (a->cout / bn);
   TEDM_CHECK_ARG(num_tiles <= 2147483647LL, "tedm_conv_igemm_fwd: too many tiles");

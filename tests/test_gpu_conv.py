@@ -242,6 +242,35 @@ def test_conv_src_affine_is_refused_off_the_halo_path():
         N.conv_igemm(x, w, 1, 64, src0_affine=torch.zeros(2, 64, 2, device="cuda"))
 
 
+@pytest.mark.parametrize("case", [(2, 16, 16, 128, 64, False), (1, 64, 64, 128, 64, False), (3, 32, 32, 256, 128, False), (2, 16, 16, 64, 64, True),
+                                  (20, 16, 8, 128, 256, False), (5, 32, 16, 64, 128, True)])
+def test_upsample_conv_halo_tiles_match_per_tap_tiles(case):
+    """The folded nearest-x2 upsample conv (mode 3) in halo mode: the four parity tiles of an M tile share the 10 x 18 boxes of
+    all channel blocks (2 x 2 windows each) against one box per (parity, tap); pairs and single CTAs; residual epilogue."""
+    from tedm_b200 import native as N
+    B, H, W, c, cout, use_res = case
+    x = _rand((B, c, H, W), 61)
+    w, b = _rand((cout, c, 3, 3), 62, (9 * c) ** -0.5), _rand((cout,), 63, 0.1)
+    res = _nhwc(_rand((B, cout, 2 * H, 2 * W), 64)) if use_res else None
+    wk = N.fold_upsample_weight(w.cuda())
+    outs = []
+    try:
+        for halo, pairs in ((3, 1), (1, 1), (3, 0)):       # 3 = halo tiles for mode 3 too (off by default: measured slower)
+            N.load().tedm_conv_set_halo(halo)
+            N.set_cta_pairs(pairs)
+            outs.append(N.conv_igemm(_nhwc(x), wk, 3, cout, bias=b.cuda(), residual=res))
+    finally:
+        N.load().tedm_conv_set_halo(1)
+        N.set_cta_pairs(1)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[2])
+    assert _rel(outs[0].float(), outs[1].float()) < 2e-3
+    ref = _ref_conv([x], w, b, 3)
+    if use_res:
+        ref = ref + res.float().permute(0, 3, 1, 2)
+    assert _rel(outs[0].float().permute(0, 3, 1, 2), ref) < 1.2e-2
+
+
 def test_cta_pairs_with_n256_tiles():
     """CTA pairs on the widest N tile (256 columns: each CTA stages 128 weight rows): bit-identical to single CTAs."""
     from tedm_b200 import native as N
