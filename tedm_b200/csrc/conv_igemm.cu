@@ -662,10 +662,14 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     bool hnext[PIPE ? CH : 1];
     float bias_next = 0.0f;
     float2 aff_next = make_float2(0.0f, 0.0f);
+    // the bias (and residual affine) of the NEXT tile are requested while this one is processed, in every variant: a global
+    // round trip at the head of each tile's epilogue is what bounds the tiles with short K loops (1x1, stride-2, upsample)
     auto fetch_consts = [&](const TileCoord& tt) {
       if (e < BN) {
         bias_next = p.bias ? __ldg(p.bias + tt.n0 + e) : 0.0f;
-        if (p.res_affine) aff_next = __ldg(p.res_affine + (size_t)tt.b0 * p.cout + tt.n0 + e);
+        if constexpr (RES) {
+          if (p.res_affine) aff_next = __ldg(p.res_affine + (size_t)tt.b0 * p.cout + tt.n0 + e);
+        }
       }
     };
     // res_tma (1x1 convs with a residual): the residual tile of tile i + 1 is TMA-loaded into the staging buffer tile i + 1 will
@@ -678,13 +682,13 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
       for (int sidx = 0; sidx < BN / 64; ++sidx)
         tma_load_5d(out_base + (uint32_t)(slot * OUT_BYTES + sidx * A_BYTES), &maps.res, bar, tt.n0 + sidx * 64, tt.x0, 0, tt.y0, tt.b0);
     };
-    if constexpr (PIPE) {
-      if (seq_tile(0) >= 0) {
-        const TileCoord t0 = decode_tile<CG>(p, seq_tile(0), BN, rank);
+    if (seq_tile(0) >= 0) {
+      const TileCoord t0 = decode_tile<CG>(p, seq_tile(0), BN, rank);
+      if constexpr (PIPE) {
         if (!res_tma) fetch_res(t0, rnext, hnext);
         else if (e == 0) load_res_tile(t0, 0);
-        fetch_consts(t0);
       }
+      fetch_consts(t0);
     }
     int it = 0, obuf = 0;                       // obuf = it % out_bufs
     for (int tile; (tile = seq_tile(it)) >= 0; ++it, obuf = obuf + 1 == p.out_bufs ? 0 : obuf + 1) {
@@ -708,17 +712,9 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
           if (res_tma && seq_tile(it + 1) >= 0) load_res_tile(decode_tile<CG>(p, seq_tile(it + 1), BN, rank), obuf_next);
         }
       }
-      if constexpr (PIPE) {
-        if (e < BN) {
-          sbias[e] = bias_next;
-          saff[e] = aff_next;
-        }
-      } else {
-        for (int i = e; i < BN; i += EPI_THREADS) sbias[i] = p.bias ? __ldg(p.bias + t.n0 + i) : 0.0f;
-        if constexpr (RES) {
-          if (p.res_affine)
-            for (int i = e; i < BN; i += EPI_THREADS) saff[i] = __ldg(p.res_affine + (size_t)t.b0 * p.cout + t.n0 + i);
-        }
+      if (e < BN) {
+        sbias[e] = bias_next;
+        if constexpr (RES) saff[e] = aff_next;
       }
       named_bar_sync(1, EPI_THREADS);
       // without the one-tile-ahead pipeline the residual values are fetched BEFORE waiting for the accumulator: their
@@ -735,8 +731,9 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
           if (!res_tma) fetch_res(tn, rnext, hnext);
           fetch_consts(tn);
         }
-      } else if constexpr (RES) {
-        fetch_res(t, rpre, has_res);
+      } else {
+        if constexpr (RES) fetch_res(t, rpre, has_res);
+        if (seq_tile(it + 1) >= 0) fetch_consts(decode_tile<CG>(p, seq_tile(it + 1), BN, rank));
       }
       mbar_wait(smem_u32(&bar_acc_full[buf]), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
