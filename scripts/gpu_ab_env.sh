@@ -9,7 +9,11 @@ import json, sys
 try:
     d = json.loads(open("gpurun_out/abenv.json").read().strip().splitlines()[-1])
     print(sys.argv[1], "->", round(d["value"], 1), "img/s", round(d["ms_per_step"], 3), "ms conv", round(d["roofline"]["frac"], 4), d["clocks"]["reasons"])
-    print("   ", open("gpurun_out/abenv_table.txt").read().splitlines()[1])
+    import os, re
+    rows = open("gpurun_out/abenv_table.txt").read().splitlines()[1:]
+    pat = os.environ.get("ROWS")
+    for r in (rows[:1] if not pat else [r for r in rows if re.search(pat, r)]):
+        print("   ", r)
 except Exception as e:
     print(sys.argv[1], "failed", e, open("gpurun_out/abenv.err").read()[-800:])
 PY
