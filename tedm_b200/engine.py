@@ -81,7 +81,8 @@ class UnetEngine:
         self.fuse_linear_attention = True
         # tcgen05 form of the fused block (csrc/attention_tc.cu) where it applies; TEDM_LINATTN_TC=0 keeps the mma.sync kernels (A/B runs)
         self.linear_attention_tc = os.environ.get("TEDM_LINATTN_TC", "1") != "0"
-        # inference: res_conv + GroupNorm + SiLU + add of a ResnetBlock's tail in one kernel; TEDM_FUSE_RES=0 keeps the two passes
+        # res_conv + GroupNorm + SiLU + add of a ResnetBlock's tail in one kernel (forward of inference and training);
+        # TEDM_FUSE_RES=0 keeps the two passes
         self.fuse_res_conv = os.environ.get("TEDM_FUSE_RES", "1") != "0"
         # inference: block1's GroupNorm + SiLU applied to block2's conv input in shared memory instead of a pass of its own
         # (bit-identical).  OFF by default: measured on B200 it removes 0.33 ms of GroupNorm passes per step and adds about as
@@ -267,12 +268,15 @@ class UnetEngine:
             return N.gn_silu(h2, part2, self._f32(b2.norm.weight), self._f32(b2.norm.bias), b2.norm.num_groups, eps=b2.norm.eps,
                              residual=res)
         h = self._block(key + ".block1", rb.block1, x0, x1, tproj, ss_off, None, tape)
-        if isinstance(rb.res_conv, nn.Conv2d) and tape is None and self.fuse_res_conv and h.shape[1] * h.shape[2] >= 128:
-            # inference: block2's GroupNorm + SiLU and the residual add happen in the epilogue of the 1x1 res_conv, which
-            # reads block2's raw conv output as its residual -- res_conv's own output is never written
+        if isinstance(rb.res_conv, nn.Conv2d) and self.fuse_res_conv and h.shape[1] * h.shape[2] >= 128:
+            # block2's GroupNorm + SiLU and the residual add happen in the epilogue of the 1x1 res_conv, which reads block2's
+            # raw conv output as its residual -- res_conv's own output is never written.  Training too: the backward needs
+            # block2's input, raw output and statistics (saved below), never res_conv's output
             blk, cout = rb.block2, rb.res_conv.weight.shape[0]
             h2, part = N.conv_igemm(h, self._w(key + ".block2.proj"), N.MODE_3X3, cout, bias=self._f32(blk.proj.bias),
                                     gn_groups=blk.norm.num_groups)
+            if tape is not None:
+                tape.saved[key + ".block2"] = (h, None, h2, part)
             aff = N.gn_affine(part, self._f32(blk.norm.weight), self._f32(blk.norm.bias), blk.norm.num_groups,
                               h2.shape[1] * h2.shape[2], eps=blk.norm.eps)
             return N.conv_igemm(x0, self._w(key + ".res_conv"), N.MODE_1X1, cout, bias=self._f32(rb.res_conv.bias), src1=x1,
