@@ -5,8 +5,8 @@
 //   M = 128 output pixels per CTA (a tileB x tileH x tileW box of the NHWC output),
 //   N = BN output channels (64/128/256), K = taps * (c0 + c1) in blocks of 64 channels.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+ TMEM owner),
-// warps 2..5 = epilogue (TMEM -> registers -> bias/residual/GroupNorm partials -> bf16 global).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+ TMEM owner),
+// warps 2..9 = epilogue (TMEM -> registers -> bias/residual/GroupNorm partials -> bf16 staging tile -> TMA store).
 // A tiles are fetched by 5-D tiled TMA straight from the NHWC activation tensor: the box is
 // (64 ch, tileW, 1, tileH, tileB) at a per-tap pixel offset, out-of-bounds pixels (the conv's zero
 // padding, and batch overhang) are zero-filled by the TMA unit, and the 128B swizzle makes the
@@ -14,6 +14,20 @@
 // decoder is a second A tensor map (the K loop walks src0's channels, then src1's); the stride-2
 // 4x4 Downsample reads a (2C, W/2, 2, H/2, B) view of the same memory so every tap is again a
 // dense box; the nearest-x2 Upsample+3x3 runs as four parity 2x2 convs on the source resolution.
+//
+// What is in this file, in order:
+//   conv_igemm_kernel<BN, AM, CPG, RES, CG>   the general kernel.  AM: 0 = one activation box per (tap, channel block);
+//                                             1 = weight-stationary rows (3x3 into 64 channels, resident weights);
+//                                             2 = halo tiles (3x3: one 10 x 18-pixel box serves all nine taps);
+//                                             3 = halo tiles whose boxes are normalised in shared memory (fused GroupNorm).
+//                                             CG = 2: CTA pairs (tcgen05 cta_group::2).  RES: residual / split epilogue,
+//                                             incl. the residual tile by TMA and SiLU(GroupNorm(residual)) (ResnetBlock tail).
+//   conv_ws4_kernel<CPG, CB, W64, XF>         3x3 into 64 channels on whole rows, four output rows per tile, the three
+//                                             vertical taps of an input row in ONE N = 192 UMMA.
+//   conv_wgrad_kernel / conv_wgrad3_kernel    weight gradients (generic; 3x3 halo-tile form) and their reduce kernels.
+//   tedm_conv_igemm_fwd / _wgrad              host side: shape checks, tile geometry, kernel selection, tensor maps.
+// Shared memory serves the tensor core's operand reads AND the TMA's writes (128 B/clk per SM): most of what distinguishes the
+// variants is how many bytes of each a FLOP costs (DESIGN.md sections 3 and 8).
 #include "common.cuh"
 
 namespace {
