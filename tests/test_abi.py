@@ -30,6 +30,29 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert sorted(native.SIGNATURES) == declared, "native.SIGNATURES and include/tedm_b200.h disagree"
 
 
+def test_conv_tile_selection_predicates_are_host_logic():
+    """Which 3x3 convs accept a fused input GroupNorm (tedm_conv_src_affine_supported mirrors the tile selection of
+    tedm_conv_igemm_fwd: halo tiles, or the four-row weight-stationary kernel) and how many GroupNorm partial slots a conv
+    writes: pure host functions, no device needed."""
+    from tedm_b200 import native
+    lib = native.load()
+    ok = lib.tedm_conv_src_affine_supported
+    assert ok(64, 64, 128, 128) == 1 and ok(16, 16, 512, 512) == 1 and ok(32, 32, 256, 256) == 1     # halo tiles
+    assert ok(128, 128, 64, 64) == 1                       # four-row weight-stationary kernel, one channel block
+    assert ok(128, 128, 128, 64) == 0                      # ... two channel blocks: no transform warps
+    assert ok(64, 64, 64, 64) == 0                         # 64-pixel rows of two images
+    assert ok(8, 8, 256, 256) == 0 and ok(16, 12, 64, 128) == 0 and ok(48, 48, 64, 128) == 0   # below a tile / not a power of two
+    try:
+        lib.tedm_conv_set_halo(0)
+        assert ok(64, 64, 128, 128) == 0 and ok(128, 128, 64, 64) == 1
+        lib.tedm_conv_set_ws(0)
+        assert ok(128, 128, 64, 64) == 0
+    finally:
+        lib.tedm_conv_set_halo(1)
+        lib.tedm_conv_set_ws(1)
+    assert lib.tedm_conv_gn_parts(128, 128) == 128 and lib.tedm_conv_gn_parts(16, 16) == 2 and lib.tedm_conv_gn_parts(8, 8) == 1
+
+
 def test_no_cpu_fallback():
     import torch
     from tedm_b200.models import Unet
