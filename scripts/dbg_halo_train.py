@@ -1,3 +1,4 @@
+"""Which half of the step the halo-tile convs perturb: gradients with halo tiles on/off in the forward and in the backward separately (found the flipped L1 sign)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))

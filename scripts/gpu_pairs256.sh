@@ -1,3 +1,5 @@
+#!/bin/bash
+# conv A/B: CTA pairs on N <= 128 tiles only (TEDM_CTA_PAIRS=3) against every N (1): pair tests, bench lines, per-shape tables
 timeout 300 python -m pytest tests/test_gpu_conv.py -m gpu -q --no-header -p no:cacheprovider -k "pairs" 2>&1 | tail -5
 for v in 1 3; do
   TEDM_CTA_PAIRS=$v TEDM_BENCH_CONV_TABLE=gpurun_out/r02s_conv_table_${v}.txt timeout 500 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-fp32 --no-train > gpurun_out/r02s_bench_${v}.json 2> gpurun_out/r02s_${v}.err
