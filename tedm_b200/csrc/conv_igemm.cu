@@ -53,7 +53,6 @@ constexpr int BK = 64;           // channels per k-block (128 bytes: one swizzle
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int A_ROW_BYTES = 17 * 1024;   // row mode: 130 pixels x 128 B = 16640 B, padded to the 1 KB swizzle atom
 constexpr int ROW_PIX = BM + 2;
-constexpr int NGMAX = 32;        // max GroupNorm groups touched by one N tile
 constexpr int MAX_STAGES = 8;
 constexpr int HALO_W = 8, HALO_H = 16;                         // halo mode: a tile is 8 pixels x 16 rows of one image
 constexpr int HALO_PITCH = (HALO_W + 2) * BK * 2;              // bytes between image rows of the 10 x 18-pixel halo box
